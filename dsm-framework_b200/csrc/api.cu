@@ -1,0 +1,1055 @@
+// api.cu -- the C ABI of include/dsmfm.h: host-side orchestration of the
+// sm_100a build kernels.  No CPU fallback: every computation on the data path
+// (histogram, packing, suffix sorting, BWT, wavelet tree, rank directories)
+// runs in the kernels of kernels.cu / radix_sort.cu; the host only builds the
+// <=256-entry Huffman code table and the tree shape, and writes files.
+#include "../../include/dsmfm.h"
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <vector>
+
+using namespace dsmfm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------
+// Huffman code table -- node::makecodetable / maketable, HuffWT.cpp:133-184.
+// Same container (std::priority_queue over std::vector with std::greater),
+// same push order (ascending byte value, counts > 0), same weight-only
+// comparison, so libstdc++'s heap resolves ties exactly as in the reference.
+// ---------------------------------------------------------------------------
+struct HuffNode {
+    uint64_t weight;
+    int id; // index into the tree arrays
+    bool operator>(const HuffNode &o) const { return weight > o.weight; }
+};
+
+struct HuffTree {
+    std::vector<int> child0, child1, value;
+};
+
+void huff_assign(const HuffTree &t, int node, uint32_t code, uint32_t bits, dsmfm_code *tab, uint32_t *maxbits)
+{
+    if (t.child0[node] >= 0) {
+        huff_assign(t, t.child0[node], code, bits + 1, tab, maxbits);
+        huff_assign(t, t.child1[node], bits < 32 ? (code | (1u << bits)) : code, bits + 1, tab, maxbits);
+    } else {
+        tab[t.value[node]].code = code;
+        tab[t.value[node]].bits = bits;
+        if (bits > *maxbits) *maxbits = bits;
+    }
+}
+
+uint32_t build_codetable(const uint64_t counts[256], dsmfm_code tab[256])
+{
+    HuffTree t;
+    std::priority_queue<HuffNode, std::vector<HuffNode>, std::greater<HuffNode>> q;
+    for (int i = 0; i < 256; ++i) {
+        tab[i].count = counts[i];
+        tab[i].bits = 0;
+        tab[i].code = 0;
+    }
+    for (int i = 0; i < 256; ++i) {
+        if (!counts[i]) continue;
+        t.child0.push_back(-1);
+        t.child1.push_back(-1);
+        t.value.push_back(i);
+        q.push(HuffNode{counts[i], (int)t.value.size() - 1});
+    }
+    if (q.empty()) return 0;
+    while (q.size() > 1) {
+        HuffNode c0 = q.top();
+        q.pop();
+        HuffNode c1 = q.top();
+        q.pop();
+        t.child0.push_back(c0.id);
+        t.child1.push_back(c1.id);
+        t.value.push_back(0);
+        q.push(HuffNode{c0.weight + c1.weight, (int)t.value.size() - 1});
+    }
+    uint32_t maxbits = 0;
+    huff_assign(t, q.top().id, 0u, 0u, tab, &maxbits);
+    return maxbits;
+}
+
+// ---------------------------------------------------------------------------
+// Wavelet tree shape from the code table, in the pre-order HuffWT::save uses
+// (HuffWT.cpp:73-86): a node at `level` holding the symbols whose code starts
+// with `prefix`; leaf iff a single symbol whose code ends here (HuffWT.cpp:35-40).
+// ---------------------------------------------------------------------------
+struct WtShape {
+    std::vector<dsmfm_node> nodes;       // pre-order; pointers filled after the device pass
+    std::vector<int> internal_of_node;   // node -> internal index or -1
+    std::vector<uint8_t> info;           // [n_internal][256] membership/branch table for the kernels
+    int n_internal = 0;
+};
+
+void shape_rec(const dsmfm_code *tab, uint32_t prefix, uint32_t level, WtShape &s)
+{
+    int members = 0, only = -1;
+    uint64_t total = 0;
+    const uint32_t pmask = level >= 32 ? 0xffffffffu : ((1u << level) - 1u);
+    for (int c = 0; c < 256; ++c) {
+        if (!tab[c].count || tab[c].bits < level || (tab[c].code & pmask) != prefix) continue;
+        ++members;
+        only = c;
+        total += tab[c].count;
+    }
+    dsmfm_node nd;
+    std::memset(&nd, 0, sizeof nd);
+    if (members == 1 && tab[only].bits == level) {
+        nd.leaf = 1;
+        nd.ch = (uint8_t)only; // a leaf's subsequence is one repeated symbol, so s[0] is that symbol
+        s.nodes.push_back(nd);
+        s.internal_of_node.push_back(-1);
+        return;
+    }
+    nd.leaf = 0;
+    nd.nbits = total;
+    nd.integers = total / 64 + 1; // == ceil((n+1)/64), BitRank.cpp:97-101
+    const int v = s.n_internal++;
+    s.info.resize((size_t)s.n_internal * 256, 0);
+    for (int c = 0; c < 256; ++c) {
+        if (!tab[c].count || tab[c].bits < level || (tab[c].code & pmask) != prefix) continue;
+        s.info[(size_t)v * 256 + c] = (uint8_t)(1u | (((tab[c].code >> level) & 1u) << 1));
+    }
+    s.nodes.push_back(nd);
+    s.internal_of_node.push_back(v);
+    shape_rec(tab, prefix, level + 1, s);
+    shape_rec(tab, prefix | (1u << level), level + 1, s);
+}
+
+size_t align8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+// Device-side wavelet tree + BitRank build for a byte sequence already in HBM.
+struct WaveletResult {
+    WtShape shape;
+    uint8_t *d_sections = nullptr; // [data | Rs | Rb] per internal node, 8-byte aligned pieces
+    size_t section_bytes = 0;
+    std::vector<size_t> off_data, off_rs, off_rb; // per internal node
+    uint8_t *d_ch = nullptr;                      // per internal node
+    // host copies (pinned), filled by fetch()
+    uint8_t *h_sections = nullptr;
+    std::vector<uint8_t> h_ch;
+
+    void release()
+    {
+        if (d_sections) cudaFree(d_sections);
+        if (d_ch) cudaFree(d_ch);
+        if (h_sections) cudaFreeHost(h_sections);
+        d_sections = d_ch = h_sections = nullptr;
+    }
+};
+
+void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, const dsmfm_code *tab, WaveletResult &r,
+                          uint32_t *launches, size_t *dev_bytes)
+{
+    r.shape = WtShape();
+    shape_rec(tab, 0u, 0u, r.shape);
+    const int m = r.shape.n_internal;
+    if (m == 0) return;
+    if (m > kWtMaxNodes) throw CudaError{cudaErrorInvalidValue, "too many wavelet tree nodes", __FILE__, __LINE__};
+    r.off_data.resize(m);
+    r.off_rs.resize(m);
+    r.off_rb.resize(m);
+    size_t off = 0;
+    uint64_t max_sb = 0;
+    for (size_t i = 0; i < r.shape.nodes.size(); ++i) {
+        const int v = r.shape.internal_of_node[i];
+        if (v < 0) continue;
+        const dsmfm_node &nd = r.shape.nodes[i];
+        r.off_data[v] = off;
+        off += nd.integers * 8;
+        r.off_rs[v] = off;
+        off += (nd.nbits / 256 + 1) * 8;
+        r.off_rb[v] = off;
+        off += align8(nd.nbits / 64 + 1);
+        max_sb = std::max<uint64_t>(max_sb, nd.nbits / 256 + 1);
+    }
+    r.section_bytes = off;
+    DSM_CUDA(cudaMalloc(&r.d_sections, off));
+    DSM_CUDA(cudaMalloc(&r.d_ch, (size_t)m));
+    DSM_CUDA(cudaMemsetAsync(r.d_sections, 0, off, st));
+    DSM_CUDA(cudaMemsetAsync(r.d_ch, 0, (size_t)m, st));
+
+    const uint64_t ntiles = div_up(n, kWtTile);
+    uint8_t *d_info = nullptr;
+    uint64_t *d_tile = nullptr, **d_ptrs = nullptr, *d_scratch = nullptr;
+    const size_t tile_bytes = sizeof(uint64_t) * (size_t)m * ntiles;
+    const size_t scratch_bytes = sizeof(uint64_t) * (div_up(max_sb, kRankChunk) + 1);
+    DSM_CUDA(cudaMalloc(&d_info, (size_t)m * 256));
+    DSM_CUDA(cudaMalloc(&d_tile, tile_bytes));
+    DSM_CUDA(cudaMalloc(&d_ptrs, sizeof(uint64_t *) * m));
+    DSM_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
+    if (dev_bytes) *dev_bytes = off + m + (size_t)m * 256 + tile_bytes + sizeof(uint64_t *) * m + scratch_bytes;
+    std::vector<uint64_t *> ptrs(m);
+    for (int v = 0; v < m; ++v) ptrs[v] = reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]);
+    try {
+        DSM_CUDA(cudaMemcpyAsync(d_info, r.shape.info.data(), (size_t)m * 256, cudaMemcpyHostToDevice, st));
+        DSM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(uint64_t *) * m, cudaMemcpyHostToDevice, st));
+        launch_wt_count(st, d_seq, n, d_info, m, ntiles, d_tile, launches);
+        launch_wt_scan(st, d_tile, m, ntiles, launches);
+        launch_wt_fill(st, d_seq, n, d_info, m, ntiles, d_tile, d_ptrs, r.d_ch, launches);
+        for (size_t i = 0; i < r.shape.nodes.size(); ++i) {
+            const int v = r.shape.internal_of_node[i];
+            if (v < 0) continue;
+            launch_bitrank(st, reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]), r.shape.nodes[i].nbits,
+                           reinterpret_cast<uint64_t *>(r.d_sections + r.off_rs[v]), r.d_sections + r.off_rb[v],
+                           d_scratch, launches);
+        }
+        DSM_CUDA(cudaStreamSynchronize(st)); // ptrs / info are host vectors: keep them alive until consumed
+    } catch (...) {
+        cudaFree(d_info); cudaFree(d_tile); cudaFree(d_ptrs); cudaFree(d_scratch);
+        throw;
+    }
+    cudaFree(d_info);
+    cudaFree(d_tile);
+    cudaFree(d_ptrs);
+    cudaFree(d_scratch);
+}
+
+void wavelet_fetch(cudaStream_t st, WaveletResult &r)
+{
+    const int m = r.shape.n_internal;
+    if (m > 0) {
+        DSM_CUDA(cudaMallocHost(&r.h_sections, r.section_bytes));
+        r.h_ch.resize(m);
+        DSM_CUDA(cudaMemcpyAsync(r.h_sections, r.d_sections, r.section_bytes, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaMemcpyAsync(r.h_ch.data(), r.d_ch, (size_t)m, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+    }
+    for (size_t i = 0; i < r.shape.nodes.size(); ++i) {
+        const int v = r.shape.internal_of_node[i];
+        if (v < 0) continue;
+        dsmfm_node &nd = r.shape.nodes[i];
+        nd.ch = r.h_ch[v];
+        nd.data = reinterpret_cast<const uint64_t *>(r.h_sections + r.off_data[v]);
+        nd.Rs = reinterpret_cast<const uint64_t *>(r.h_sections + r.off_rs[v]);
+        nd.Rb = r.h_sections + r.off_rb[v];
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// the builder handle
+// ---------------------------------------------------------------------------
+struct dsmfm_builder {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t samplerate = DSMFM_DEFAULT_SAMPLERATE;
+    uint32_t flags = 0;
+    uint64_t expected = 0;
+    std::string err;
+
+    // host staging for dsmfm_append (pinned, double buffered)
+    static constexpr size_t kStage = 64u << 20;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_free[2] = {nullptr, nullptr};
+    int cur = 0;
+    size_t cur_used = 0;
+
+    // text in HBM while it streams in
+    struct Chunk { uint8_t *d; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    uint64_t n = 0;
+
+    bool finished = false, built = false, fetched = false;
+
+    // device state of the build
+    uint8_t *d_raw = nullptr;
+    bool raw_is_chunk = false;
+    uint32_t *d_sa = nullptr;      // one of the value buffers of the sort (DSMFM_FLAG_KEEP_SA)
+    uint8_t *d_bwt = nullptr;      // lives in the first key buffer of the sort
+    WaveletResult wt;
+    uint8_t *h_bwt = nullptr;
+
+    uint64_t counts[256];
+    dsmfm_index index;
+    dsmfm_stats stats;
+    size_t dev_now = 0, dev_peak = 0;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int fail_cuda(const CudaError &e)
+    {
+        return fail(e.code == cudaErrorMemoryAllocation ? DSMFM_ENOMEM : DSMFM_ECUDA, "CUDA error %d (%s) in %s at %s:%d",
+                    (int)e.code, cudaGetErrorString(e.code), e.what, e.file, e.line);
+    }
+
+    // every device allocation of the builder is tracked so that a failed build leaks nothing
+    std::vector<std::pair<void *, size_t>> allocs;
+    void *dmalloc(size_t bytes)
+    {
+        void *p = nullptr;
+        DSM_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        allocs.emplace_back(p, bytes);
+        dev_now += bytes;
+        dev_peak = std::max(dev_peak, dev_now);
+        return p;
+    }
+    void dfree(void *p)
+    {
+        if (!p) return;
+        for (size_t i = 0; i < allocs.size(); ++i) {
+            if (allocs[i].first != p) continue;
+            dev_now -= std::min(dev_now, allocs[i].second);
+            allocs.erase(allocs.begin() + i);
+            cudaFree(p);
+            return;
+        }
+    }
+
+    void push_device(const void *src, size_t bytes, cudaMemcpyKind kind)
+    {
+        const uint8_t *s = static_cast<const uint8_t *>(src);
+        while (bytes) {
+            if (chunks.empty() || chunks.back().used == chunks.back().cap) {
+                size_t cap = chunks.empty() && expected ? (size_t)expected + 64 : (size_t)256 << 20;
+                if (cap < bytes && chunks.empty() && !expected) cap = bytes + 64;
+                Chunk c{static_cast<uint8_t *>(dmalloc(cap)), cap, 0};
+                chunks.push_back(c);
+            }
+            Chunk &c = chunks.back();
+            const size_t take = std::min(bytes, c.cap - c.used);
+            DSM_CUDA(cudaMemcpyAsync(c.d + c.used, s, take, kind, stream));
+            c.used += take;
+            s += take;
+            bytes -= take;
+            n += take;
+        }
+    }
+
+    void flush_stage()
+    {
+        if (!cur_used) return;
+        push_device(stage[cur], cur_used, cudaMemcpyHostToDevice);
+        DSM_CUDA(cudaEventRecord(stage_free[cur], stream));
+        cur ^= 1;
+        cur_used = 0;
+        DSM_CUDA(cudaEventSynchronize(stage_free[cur])); // the other buffer's copy has drained
+    }
+
+    void release_device()
+    {
+        for (auto &a : allocs) cudaFree(a.first);
+        allocs.clear();
+        chunks.clear();
+        d_raw = nullptr;
+        d_sa = nullptr;
+        d_bwt = nullptr;
+        dev_now = 0;
+        wt.release();
+    }
+
+    void build();
+    void fetch();
+};
+
+// ---------------------------------------------------------------------------
+// the device build
+// ---------------------------------------------------------------------------
+void dsmfm_builder::build()
+{
+    cudaStream_t st = stream;
+    uint32_t *L = &stats.kernel_launches;
+    std::memset(&stats, 0, sizeof stats);
+    cudaEvent_t ev[8];
+    for (auto &e : ev) DSM_CUDA(cudaEventCreate(&e));
+    cudaEvent_t ev_pass0, ev_pass1;
+    DSM_CUDA(cudaEventCreate(&ev_pass0));
+    DSM_CUDA(cudaEventCreate(&ev_pass1));
+
+    flush_stage();
+    bool empty_collection = false;
+    if (n == 0) { // TextCollectionBuilder.cpp:111-119: one empty text
+        const uint8_t z = 0;
+        push_device(&z, 1, cudaMemcpyHostToDevice);
+        DSM_CUDA(cudaStreamSynchronize(st));
+        empty_collection = true;
+    }
+    if (n >= (1ull << 32) - kRefCap - 64) {
+        throw CudaError{cudaErrorInvalidValue, "more than 2^32 symbols on one device (shard the collection)", __FILE__, __LINE__};
+    }
+
+    DSM_CUDA(cudaEventRecord(ev[0], st));
+    // contiguous text
+    if (chunks.size() == 1) {
+        d_raw = chunks[0].d;
+        raw_is_chunk = true;
+    } else {
+        d_raw = static_cast<uint8_t *>(dmalloc(n + 64));
+        raw_is_chunk = false;
+        size_t o = 0;
+        for (auto &c : chunks) {
+            DSM_CUDA(cudaMemcpyAsync(d_raw + o, c.d, c.used, cudaMemcpyDeviceToDevice, st));
+            o += c.used;
+        }
+        DSM_CUDA(cudaStreamSynchronize(st));
+        for (auto &c : chunks) dfree(c.d);
+        chunks.clear();
+    }
+
+    // ---- histogram, document statistics, alphabet --------------------------------
+    uint64_t *d_counts = static_cast<uint64_t *>(dmalloc(256 * 8));
+    const uint64_t nstat = div_up(n, kStatChunk);
+    ChunkStat *d_stat = static_cast<ChunkStat *>(dmalloc(nstat * sizeof(ChunkStat)));
+    DSM_CUDA(cudaMemsetAsync(d_counts, 0, 256 * 8, st));
+    launch_byte_hist(st, d_raw, n, d_counts, L);
+    launch_doc_stats(st, d_raw, n, d_stat, L);
+    std::vector<ChunkStat> hstat(nstat);
+    DSM_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(hstat.data(), d_stat, nstat * sizeof(ChunkStat), cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    dfree(d_counts);
+    dfree(d_stat);
+
+    uint64_t maxgap = 0, mingap = ~0ull;
+    int64_t prev = -1, lastz = -1;
+    for (const ChunkStat &c : hstat) {
+        if (c.last < 0) continue;
+        const uint64_t g = (uint64_t)(c.first - prev);
+        maxgap = std::max(maxgap, g);
+        mingap = std::min(mingap, g);
+        maxgap = std::max(maxgap, c.maxgap);
+        mingap = std::min(mingap, c.mingap);
+        prev = c.last;
+        lastz = c.last;
+    }
+    if (lastz != (int64_t)n - 1)
+        throw CudaError{cudaErrorInvalidValue, "text does not end with a document terminator", __FILE__, __LINE__};
+    if (mingap == 1 && !empty_collection)
+        throw CudaError{cudaErrorInvalidValue, "EMPTY", __FILE__, __LINE__};
+
+    uint8_t code_map[256];
+    std::memset(code_map, 0, sizeof code_map);
+    uint32_t sigma = 0;
+    for (int c = 1; c < 256; ++c)
+        if (counts[c]) code_map[c] = (uint8_t)++sigma;
+    const int bits = sigma <= 7 ? 3 : (sigma <= 15 ? 4 : 8);
+    const int spw = 64 / bits;
+
+    index.n = n;
+    index.samplerate = samplerate;
+    index.number_of_texts = (uint32_t)counts[0];
+    index.max_text_length = maxgap;
+    stats.n = n;
+    stats.bases = n - counts[0];
+    stats.bits_per_symbol = bits;
+    stats.sigma = sigma;
+
+    // ---- pack -----------------------------------------------------------------------
+    const uint64_t nwords = div_up(n, spw) + 2;
+    uint8_t *d_map = static_cast<uint8_t *>(dmalloc(256));
+    uint64_t *d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
+    DSM_CUDA(cudaMemcpyAsync(d_map, code_map, 256, cudaMemcpyHostToDevice, st));
+    launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
+    DSM_CUDA(cudaEventRecord(ev[1], st));
+
+    // ---- initial sort by the first SPW symbols ---------------------------------------
+    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(n * 8));
+    uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(n * 8));
+    uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
+    uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
+    RadixWorkspace ws;
+    ws.allocate(n);
+    dev_now += ws.bytes;
+    dev_peak = std::max(dev_peak, dev_now);
+    launch_make_keys(st, bits, d_packed, n, d_keys_a, L);
+    const int key_bits = spw * bits;
+    const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, n, 0, key_bits, true, L,
+                                        ev_pass0, ev_pass1);
+    uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
+    uint32_t *d_sorted_vals = (passes & 1) ? d_vals_b : d_vals_a;
+    uint32_t *d_other_vals = (passes & 1) ? d_vals_a : d_vals_b;
+    stats.sort_passes = passes;
+    stats.sort_pass_bytes = n * 24ull;
+
+    const uint64_t hwords = head_words_for(n);
+    uint32_t *d_head[2];
+    d_head[0] = static_cast<uint32_t *>(dmalloc(hwords * 4));
+    d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
+    unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(64 * 8));
+    const uint32_t big_cap = (uint32_t)(n / kRefGroupMax + 2);
+    uint32_t *d_big_heads = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
+    uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
+    uint32_t *d_big_count = static_cast<uint32_t *>(dmalloc(4));
+    DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+    launch_heads(st, bits, d_sorted_keys, n, d_head[0], hwords, d_remaining, L);
+    DSM_CUDA(cudaEventRecord(ev[2], st));
+
+    auto read_remaining = [&]() -> uint64_t {
+        unsigned long long h[64];
+        DSM_CUDA(cudaMemcpyAsync(h, d_remaining, sizeof h, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        uint64_t t = 0;
+        for (auto x : h) t += x;
+        return t;
+    };
+    uint64_t remaining = read_remaining();
+
+    // ---- refinement rounds ------------------------------------------------------------
+    // Suffixes that still agree on their first `depth` symbols are re-sorted by the next
+    // SPW symbols taken straight from the packed text.  (The reference re-keys with the
+    // ranks of the suffixes h positions ahead, utils.cpp:236-262; documents here are short,
+    // the text fits in HBM next to the suffix array, and extending the key from the text
+    // needs neither an inverse suffix array nor rank scatter traffic.)
+    int cur = 0;
+    uint32_t round = 0;
+    const uint32_t max_rounds = (uint32_t)(maxgap / spw + 3);
+    while (remaining > 0) {
+        if (round >= max_rounds)
+            throw CudaError{cudaErrorUnknown, "refinement did not converge (internal error)", __FILE__, __LINE__};
+        if (round < 32) stats.active[round] = remaining;
+        ++round;
+        const uint32_t depth = round * (uint32_t)spw;
+        DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hwords * 4, cudaMemcpyDeviceToDevice, st));
+        DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+        DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
+        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, d_big_heads, big_cap,
+                      d_big_count, d_remaining, L);
+        uint32_t nbig = 0;
+        DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
+        remaining = read_remaining();
+        if (nbig > 0) {
+            // groups too large for one CTA: one global (group, key) radix sort over all of them
+            if (nbig > big_cap) throw CudaError{cudaErrorUnknown, "large-group list overflow", __FILE__, __LINE__};
+            launch_big_extent(st, d_head[cur], n, d_big_heads, nbig, d_big_len, L);
+            std::vector<uint32_t> heads(nbig), lens(nbig);
+            DSM_CUDA(cudaMemcpyAsync(heads.data(), d_big_heads, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaMemcpyAsync(lens.data(), d_big_len, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> order(nbig);
+            for (uint32_t i = 0; i < nbig; ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return heads[a] < heads[b]; });
+            std::vector<uint32_t> sheads(nbig);
+            std::vector<uint64_t> offs(nbig + 1);
+            uint64_t total = 0;
+            for (uint32_t i = 0; i < nbig; ++i) {
+                sheads[i] = heads[order[i]];
+                offs[i] = total;
+                total += lens[order[i]];
+            }
+            offs[nbig] = total;
+            stats.fallback_elems += total;
+            uint64_t *d_off = static_cast<uint64_t *>(dmalloc((size_t)(nbig + 1) * 8));
+            uint32_t *d_bsa = static_cast<uint32_t *>(dmalloc(total * 4));
+            uint32_t *d_bgid = static_cast<uint32_t *>(dmalloc(total * 4));
+            uint64_t *d_bkey = static_cast<uint64_t *>(dmalloc(total * 8));
+            uint32_t *d_perm = static_cast<uint32_t *>(dmalloc(total * 4 + 16));
+            DSM_CUDA(cudaMemcpyAsync(d_big_heads, sheads.data(), (size_t)nbig * 4, cudaMemcpyHostToDevice, st));
+            DSM_CUDA(cudaMemcpyAsync(d_off, offs.data(), (size_t)(nbig + 1) * 8, cudaMemcpyHostToDevice, st));
+            launch_big_gather(st, bits, d_packed, d_sorted_vals, depth, d_big_heads, d_off, nbig, total, d_bsa, d_bkey,
+                              d_bgid, L);
+            // the key buffers of the initial sort are free by now
+            DSM_CUDA(cudaMemcpyAsync(d_keys_a, d_bkey, total * 8, cudaMemcpyDeviceToDevice, st));
+            int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, key_bits, true, L);
+            // pass 0 writes (keys_b, perm); an odd pass count leaves the result there
+            uint64_t *kfree = (p1 & 1) ? d_keys_a : d_keys_b;
+            uint32_t *pres = (p1 & 1) ? d_perm : d_other_vals;
+            uint32_t *pfree = (p1 & 1) ? d_other_vals : d_perm;
+            if (nbig > 1) {
+                int gbits = 1;
+                while ((1ull << gbits) < nbig) ++gbits;
+                launch_gather_u32_to_u64(st, d_bgid, pres, total, kfree, L);
+                uint64_t *k2a = kfree, *k2b = (kfree == d_keys_a) ? d_keys_b : d_keys_a;
+                int p2 = radix_sort_pairs(st, ws, k2a, pres, k2b, pfree, total, 0, gbits, false, L);
+                if (p2 & 1) std::swap(pres, pfree);
+            }
+            launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, d_sorted_vals,
+                               d_head[cur ^ 1], L);
+            DSM_CUDA(cudaStreamSynchronize(st));
+            dfree(d_off);
+            dfree(d_bsa);
+            dfree(d_bgid);
+            dfree(d_bkey);
+            dfree(d_perm);
+            remaining += total; // re-examined (and counted exactly) by the next round
+        }
+        cur ^= 1;
+    }
+    stats.rounds = round;
+    DSM_CUDA(cudaEventRecord(ev[3], st));
+
+    // ---- BWT ------------------------------------------------------------------------
+    d_bwt = reinterpret_cast<uint8_t *>(d_keys_a); // key buffers are free
+    launch_bwt(st, d_raw, d_sorted_vals, n, d_bwt, L);
+    DSM_CUDA(cudaEventRecord(ev[4], st));
+
+    // ---- C table, code table, wavelet tree ---------------------------------------------
+    index.C[0] = 0;
+    for (int i = 1; i < 256; ++i) index.C[i] = index.C[i - 1] + counts[i - 1]; // FMIndex.cpp:397-409
+    const uint32_t maxbits = build_codetable(counts, index.codetable);
+    if (maxbits > 31)
+        throw CudaError{cudaErrorInvalidValue, "Huffman code longer than 31 bits (the .fmi code field is 32 bits)", __FILE__, __LINE__};
+    size_t wt_bytes = 0;
+    wavelet_build_device(st, d_bwt, n, index.codetable, wt, L, &wt_bytes);
+    dev_now += wt_bytes;
+    dev_peak = std::max(dev_peak, dev_now);
+    dev_now -= wt_bytes - std::min(wt_bytes, wt.section_bytes);
+    DSM_CUDA(cudaEventRecord(ev[5], st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+
+    // ---- release what the sections do not need ---------------------------------------
+    dfree(d_map);
+    dfree(d_packed);
+    dfree(d_keys_b);
+    dfree(d_head[0]);
+    dfree(d_head[1]);
+    dfree(d_remaining);
+    dfree(d_big_heads);
+    dfree(d_big_len);
+    dfree(d_big_count);
+    dev_now -= std::min(dev_now, ws.bytes);
+    ws.release();
+    dfree(d_other_vals);
+    if (flags & DSMFM_FLAG_KEEP_SA)
+        d_sa = d_sorted_vals;
+    else
+        dfree(d_sorted_vals);
+    dfree(d_raw);
+    chunks.clear();
+    d_raw = nullptr;
+
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[5]); stats.ms_total = ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); stats.ms_pack = ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); stats.ms_sort = ms;
+    cudaEventElapsedTime(&ms, ev_pass0, ev_pass1); stats.ms_sort_pass = passes ? ms / passes : 0.f;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]); stats.ms_refine = ms;
+    cudaEventElapsedTime(&ms, ev[3], ev[4]); stats.ms_bwt = ms;
+    cudaEventElapsedTime(&ms, ev[4], ev[5]); stats.ms_wt = ms;
+    stats.device_bytes_peak = dev_peak;
+    for (auto &e : ev) cudaEventDestroy(e);
+    cudaEventDestroy(ev_pass0);
+    cudaEventDestroy(ev_pass1);
+    built = true;
+}
+
+void dsmfm_builder::fetch()
+{
+    cudaEvent_t e0, e1;
+    DSM_CUDA(cudaEventCreate(&e0));
+    DSM_CUDA(cudaEventCreate(&e1));
+    DSM_CUDA(cudaEventRecord(e0, stream));
+    wavelet_fetch(stream, wt);
+    if (flags & DSMFM_FLAG_KEEP_BWT) {
+        DSM_CUDA(cudaMallocHost(&h_bwt, index.n));
+        DSM_CUDA(cudaMemcpyAsync(h_bwt, d_bwt, index.n, cudaMemcpyDeviceToHost, stream));
+    }
+    DSM_CUDA(cudaEventRecord(e1, stream));
+    DSM_CUDA(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    stats.ms_d2h = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    index.n_nodes = (uint32_t)wt.shape.nodes.size();
+    index.nodes = wt.shape.nodes.data();
+    index.bwt = h_bwt;
+    // the device copies are no longer needed
+    dfree(d_bwt);
+    d_bwt = nullptr;
+    if (wt.d_sections) { cudaFree(wt.d_sections); wt.d_sections = nullptr; }
+    if (wt.d_ch) { cudaFree(wt.d_ch); wt.d_ch = nullptr; }
+    fetched = true;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+#define API_GUARD(b)                                              \
+    if (!(b)) return DSMFM_EINVAL;                                \
+    cudaSetDevice((b)->device)
+
+extern "C" {
+
+DSMFM_API int dsmfm_version(void) { return DSMFM_VERSION; }
+
+DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
+{
+    if (!out) return DSMFM_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                         " (this library has no CPU fallback)";
+        return DSMFM_ECUDA;
+    }
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) {
+        g_create_error = "device ordinal out of range";
+        return DSMFM_EINVAL;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100 or newer (kernels are built for sm_100a only)";
+        return DSMFM_ECUDA;
+    }
+    dsmfm_builder *b = new (std::nothrow) dsmfm_builder();
+    if (!b) return DSMFM_ENOMEM;
+    b->device = dev;
+    std::memset(&b->index, 0, sizeof b->index);
+    std::memset(&b->stats, 0, sizeof b->stats);
+    std::memset(b->counts, 0, sizeof b->counts);
+    if (opts) {
+        b->samplerate = opts->samplerate ? opts->samplerate : DSMFM_DEFAULT_SAMPLERATE;
+        b->flags = opts->flags;
+        b->expected = opts->expected_bytes;
+        b->stream = static_cast<cudaStream_t>(opts->stream);
+    }
+    try {
+        DSM_CUDA(cudaSetDevice(dev));
+        if (!b->stream) {
+            DSM_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+            b->own_stream = true;
+        }
+    } catch (const CudaError &ce) {
+        g_create_error = std::string("CUDA error: ") + cudaGetErrorString(ce.code);
+        delete b;
+        return DSMFM_ECUDA;
+    }
+    *out = b;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len)
+{
+    API_GUARD(b);
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_append: new text can not be inserted after dsmfm_finish");
+    if (!doc) return b->fail(DSMFM_EINVAL, "dsmfm_append: null document");
+    if (len == 0) return b->fail(DSMFM_EEMPTY, "dsmfm_append: can not index empty texts");
+    try {
+        if (!b->stage[0]) {
+            for (int i = 0; i < 2; ++i) {
+                DSM_CUDA(cudaMallocHost(&b->stage[i], dsmfm_builder::kStage));
+                DSM_CUDA(cudaEventCreateWithFlags(&b->stage_free[i], cudaEventDisableTiming));
+            }
+        }
+        const uint8_t *p = doc;
+        size_t left = len;
+        while (left) { // documents longer than the staging buffer are split across flushes
+            if (b->cur_used == dsmfm_builder::kStage) b->flush_stage();
+            const size_t take = std::min(left, dsmfm_builder::kStage - b->cur_used);
+            std::memcpy(b->stage[b->cur] + b->cur_used, p, take);
+            b->cur_used += take;
+            p += take;
+            left -= take;
+        }
+        if (b->cur_used == dsmfm_builder::kStage) b->flush_stage();
+        b->stage[b->cur][b->cur_used++] = 0;
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
+static int append_bulk(dsmfm_builder *b, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    if (b->finished) return b->fail(DSMFM_EINVAL, "append: new text can not be inserted after dsmfm_finish");
+    if (!src || bytes == 0) return b->fail(DSMFM_EINVAL, "append: empty batch");
+    try {
+        b->flush_stage();
+        b->push_device(src, bytes, kind);
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_append_batch(dsmfm_builder *b, const uint8_t *docs, size_t bytes)
+{
+    API_GUARD(b);
+    if (docs && bytes && docs[bytes - 1] != 0)
+        return b->fail(DSMFM_EINVAL, "dsmfm_append_batch: the batch must end with a document terminator");
+    return append_bulk(b, docs, bytes, cudaMemcpyHostToDevice);
+}
+
+DSMFM_API int dsmfm_append_batch_device(dsmfm_builder *b, const void *docs_dev, size_t bytes)
+{
+    API_GUARD(b);
+    return append_bulk(b, docs_dev, bytes, cudaMemcpyDeviceToDevice);
+}
+
+DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
+{
+    API_GUARD(b);
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_build_device: already built");
+    b->finished = true;
+    try {
+        b->build();
+    } catch (const CudaError &e) {
+        b->release_device();
+        if (e.what && std::strcmp(e.what, "EMPTY") == 0)
+            return b->fail(DSMFM_EEMPTY, "can not index empty texts (two consecutive terminators in the input)");
+        if (e.code == cudaErrorInvalidValue && e.what && std::strstr(e.what, "2^32"))
+            return b->fail(DSMFM_ELIMIT, "%s", e.what);
+        if (e.code == cudaErrorInvalidValue && e.what && std::strstr(e.what, "Huffman"))
+            return b->fail(DSMFM_ELIMIT, "%s", e.what);
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        b->release_device();
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out)
+{
+    API_GUARD(b);
+    if (!b->built) return b->fail(DSMFM_EINVAL, "dsmfm_fetch: nothing built");
+    try {
+        if (!b->fetched) b->fetch();
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    if (out) *out = b->index;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_finish(dsmfm_builder *b, dsmfm_index *out)
+{
+    int rc = dsmfm_build_device(b);
+    if (rc) return rc;
+    return dsmfm_fetch(b, out);
+}
+
+DSMFM_API int dsmfm_copy_sa(dsmfm_builder *b, uint32_t *out, uint64_t first, uint64_t count)
+{
+    API_GUARD(b);
+    if (!b->d_sa) return b->fail(DSMFM_EINVAL, "dsmfm_copy_sa: needs DSMFM_FLAG_KEEP_SA and a finished build");
+    if (!out || first > b->index.n || count > b->index.n - first) return b->fail(DSMFM_EINVAL, "dsmfm_copy_sa: range out of bounds");
+    cudaError_t e = cudaMemcpy(out, b->d_sa + first, count * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return b->fail(DSMFM_ECUDA, "dsmfm_copy_sa: %s", cudaGetErrorString(e));
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_get_stats(const dsmfm_builder *b, dsmfm_stats *out)
+{
+    if (!b || !out) return DSMFM_EINVAL;
+    *out = b->stats;
+    return DSMFM_OK;
+}
+
+DSMFM_API const char *dsmfm_last_error(const dsmfm_builder *b)
+{
+    return b ? b->err.c_str() : g_create_error.c_str();
+}
+
+DSMFM_API void dsmfm_destroy(dsmfm_builder *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    b->release_device();
+    if (b->h_bwt) cudaFreeHost(b->h_bwt);
+    for (int i = 0; i < 2; ++i) {
+        if (b->stage[i]) cudaFreeHost(b->stage[i]);
+        if (b->stage_free[i]) cudaEventDestroy(b->stage_free[i]);
+    }
+    if (b->own_stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+// ---- serialisation: FMIndex::save, FMIndex.cpp:155-217 ---------------------------------------
+
+namespace {
+struct Sink {
+    FILE *f = nullptr;
+    uint8_t *mem = nullptr;
+    uint64_t cap = 0, pos = 0;
+    bool ok = true;
+    void put(const void *p, size_t n)
+    {
+        if (!ok) return;
+        if (f) {
+            if (n && std::fwrite(p, 1, n, f) != n) ok = false;
+        } else if (mem) {
+            if (pos + n > cap) { ok = false; return; }
+            std::memcpy(mem + pos, p, n);
+        }
+        pos += n;
+    }
+};
+
+void serialize(const dsmfm_index *idx, Sink &s)
+{
+    const uint8_t version = 17; // FMIndex.cpp:51
+    const uint64_t bwt_end_pos = 0; // never computed on the builder path (FMIndex.cpp:95)
+    s.put(&version, 1);
+    s.put(&idx->n, 8);
+    s.put(&idx->samplerate, 4);
+    s.put(idx->C, sizeof idx->C);
+    s.put(&bwt_end_pos, 8);
+    for (int i = 0; i < 256; ++i) { // TCodeEntry::save, HuffWT.h:37-45
+        s.put(&idx->codetable[i].count, 8);
+        s.put(&idx->codetable[i].bits, 4);
+        s.put(&idx->codetable[i].code, 4);
+    }
+    const uint32_t b64 = 64, s256 = 256;
+    for (uint32_t i = 0; i < idx->n_nodes; ++i) { // HuffWT::save pre-order, HuffWT.cpp:73-86
+        const dsmfm_node &nd = idx->nodes[i];
+        s.put(&nd.leaf, 1);
+        s.put(&nd.ch, 1);
+        if (nd.leaf) continue;
+        s.put(&nd.nbits, 8); // BitRank::save, BitRank.cpp:134-151
+        s.put(&nd.integers, 8);
+        s.put(&b64, 4);
+        s.put(&s256, 4);
+        s.put(nd.data, nd.integers * 8);
+        s.put(nd.Rs, (nd.nbits / 256 + 1) * 8);
+        s.put(nd.Rb, nd.nbits / 64 + 1);
+    }
+    const uint8_t z8 = 0;
+    const uint32_t z32 = 0;
+    s.put(&idx->number_of_texts, 4);
+    s.put(&idx->max_text_length, 8);
+    s.put(&z8, 1);  // no names   (FMIndex.cpp:190-196)
+    s.put(&z8, 1);  // no text    (FMIndex.cpp:198-204)
+    s.put(&z8, 1);  // colorCoded (FMIndex.cpp:207)
+    s.put(&z32, 4); // rotationLength
+}
+} // namespace
+
+DSMFM_API uint64_t dsmfm_fmi_size(const dsmfm_index *idx)
+{
+    if (!idx) return 0;
+    Sink s;
+    serialize(idx, s);
+    return s.pos;
+}
+
+DSMFM_API int dsmfm_fmi_serialize(const dsmfm_index *idx, uint8_t *out, uint64_t out_cap)
+{
+    if (!idx || !out) return DSMFM_EINVAL;
+    Sink s;
+    s.mem = out;
+    s.cap = out_cap;
+    serialize(idx, s);
+    return s.ok ? DSMFM_OK : DSMFM_EINVAL;
+}
+
+DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix)
+{
+    if (!idx || !path_prefix) return DSMFM_EINVAL;
+    const std::string name = std::string(path_prefix) + ".fmi"; // TextCollection::FMINDEX_EXTENSION
+    Sink s;
+    s.f = std::fopen(name.c_str(), "wb");
+    if (!s.f) return DSMFM_EIO;
+    serialize(idx, s);
+    if (std::fflush(s.f) != 0) s.ok = false;
+    std::fclose(s.f);
+    return s.ok ? DSMFM_OK : DSMFM_EIO;
+}
+
+// ---- kernel-level test entry points ------------------------------------------------------
+
+DSMFM_API int dsmfm_dbg_radix_sort(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit)
+{
+    if (!keys || !vals || begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) return DSMFM_EINVAL;
+    if (cudaSetDevice(device < 0 ? 0 : device) != cudaSuccess) return DSMFM_ECUDA;
+    if (n == 0) return DSMFM_OK;
+    uint64_t *ka = nullptr, *kb = nullptr;
+    uint32_t *va = nullptr, *vb = nullptr;
+    RadixWorkspace ws;
+    int rc = DSMFM_OK;
+    try {
+        DSM_CUDA(cudaMalloc(&ka, n * 8));
+        DSM_CUDA(cudaMalloc(&kb, n * 8));
+        DSM_CUDA(cudaMalloc(&va, n * 4));
+        DSM_CUDA(cudaMalloc(&vb, n * 4));
+        ws.allocate(n);
+        DSM_CUDA(cudaMemcpy(ka, keys, n * 8, cudaMemcpyHostToDevice));
+        DSM_CUDA(cudaMemcpy(va, vals, n * 4, cudaMemcpyHostToDevice));
+        const int p = radix_sort_pairs(nullptr, ws, ka, va, kb, vb, n, begin_bit, end_bit, false, nullptr);
+        DSM_CUDA(cudaDeviceSynchronize());
+        DSM_CUDA(cudaMemcpy(keys, (p & 1) ? kb : ka, n * 8, cudaMemcpyDeviceToHost));
+        DSM_CUDA(cudaMemcpy(vals, (p & 1) ? vb : va, n * 4, cudaMemcpyDeviceToHost));
+    } catch (const CudaError &e) {
+        g_create_error = std::string("dsmfm_dbg_radix_sort: ") + cudaGetErrorString(e.code) + " in " + e.what;
+        rc = DSMFM_ECUDA;
+    }
+    ws.release();
+    cudaFree(ka); cudaFree(kb); cudaFree(va); cudaFree(vb);
+    return rc;
+}
+
+namespace {
+struct DbgIndex {
+    WaveletResult wt;
+    dsmfm_index index;
+};
+}
+
+DSMFM_API int dsmfm_dbg_wavelet(int device, const uint8_t *seq, uint64_t n, dsmfm_index *out, void **owner)
+{
+    if (!seq || !out || !owner || n == 0) return DSMFM_EINVAL;
+    if (cudaSetDevice(device < 0 ? 0 : device) != cudaSuccess) return DSMFM_ECUDA;
+    DbgIndex *d = new DbgIndex();
+    std::memset(&d->index, 0, sizeof d->index);
+    uint8_t *d_seq = nullptr;
+    uint64_t *d_counts = nullptr;
+    int rc = DSMFM_OK;
+    try {
+        DSM_CUDA(cudaMalloc(&d_seq, n + 64));
+        DSM_CUDA(cudaMalloc(&d_counts, 256 * 8));
+        DSM_CUDA(cudaMemcpy(d_seq, seq, n, cudaMemcpyHostToDevice));
+        DSM_CUDA(cudaMemset(d_counts, 0, 256 * 8));
+        launch_byte_hist(nullptr, d_seq, n, d_counts, nullptr);
+        uint64_t counts[256];
+        DSM_CUDA(cudaMemcpy(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost));
+        d->index.n = n;
+        d->index.samplerate = DSMFM_DEFAULT_SAMPLERATE;
+        d->index.C[0] = 0;
+        for (int i = 1; i < 256; ++i) d->index.C[i] = d->index.C[i - 1] + counts[i - 1];
+        if (build_codetable(counts, d->index.codetable) > 31)
+            throw CudaError{cudaErrorInvalidValue, "Huffman code longer than 31 bits", __FILE__, __LINE__};
+        wavelet_build_device(nullptr, d_seq, n, d->index.codetable, d->wt, nullptr, nullptr);
+        wavelet_fetch(nullptr, d->wt);
+        d->index.n_nodes = (uint32_t)d->wt.shape.nodes.size();
+        d->index.nodes = d->wt.shape.nodes.data();
+    } catch (const CudaError &e) {
+        g_create_error = std::string("dsmfm_dbg_wavelet: ") + cudaGetErrorString(e.code) + " in " + e.what;
+        rc = DSMFM_ECUDA;
+    }
+    cudaFree(d_seq);
+    cudaFree(d_counts);
+    if (rc) {
+        d->wt.release();
+        delete d;
+        return rc;
+    }
+    *out = d->index;
+    *owner = d;
+    return DSMFM_OK;
+}
+
+DSMFM_API void dsmfm_dbg_free_index(void *owner)
+{
+    DbgIndex *d = static_cast<DbgIndex *>(owner);
+    if (!d) return;
+    d->wt.release();
+    delete d;
+}
+
+} // extern "C"

@@ -1,0 +1,910 @@
+// kernels.cu -- FM-index build kernels for sm_100a: ingest, key build, group
+// heads, segmented refinement rounds, BWT emission, Huffman-shaped wavelet tree
+// and BitRank directories.  All integer / byte work, HBM-bound; no tensor cores.
+#include "kernels.cuh"
+
+namespace dsmfm {
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// small block-level helpers (256-thread CTAs unless noted)
+// ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T warp_incl_sum(T v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Exclusive block scan; `scratch` holds blockDim.x/32 + 1 entries; returns the
+// exclusive prefix of v and puts the block total in *total.  Two barriers.
+template <typename T> __device__ __forceinline__ T block_excl_sum(T v, T *scratch, T *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    T incl = warp_incl_sum(v);
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    T base = 0, tot = 0;
+    for (int w = 0; w < nw; ++w) {
+        T s = scratch[w];
+        if (w < warp) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+// ---------------------------------------------------------------------------
+// ingest
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t *__restrict__ raw, uint64_t n,
+                                                        uint64_t *__restrict__ counts)
+{
+    __shared__ uint32_t h[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t *mine = h[threadIdx.x >> 5];
+    const uint64_t nvec = n / 16;
+    const uint4 *v = reinterpret_cast<const uint4 *>(raw);
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
+        const uint4 x = __ldg(v + i);
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&mine[w[j] & 0xff], 1u);
+            atomicAdd(&mine[(w[j] >> 8) & 0xff], 1u);
+            atomicAdd(&mine[(w[j] >> 16) & 0xff], 1u);
+            atomicAdd(&mine[w[j] >> 24], 1u);
+        }
+    }
+    if (blockIdx.x == 0)
+        for (uint64_t i = nvec * 16 + threadIdx.x; i < n; i += 256) atomicAdd(&mine[raw[i]], 1u);
+    __syncthreads();
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c += h[w][threadIdx.x];
+    if (c) atomicAdd((unsigned long long *)&counts[threadIdx.x], (unsigned long long)c);
+}
+
+__global__ void __launch_bounds__(256) doc_stats_kernel(const uint8_t *__restrict__ raw, uint64_t n,
+                                                        ChunkStat *__restrict__ out)
+{
+    constexpr int PER = kStatChunk / 256; // bytes per thread
+    __shared__ long long s_last[8];
+    __shared__ long long s_first[8];
+    __shared__ unsigned long long s_max[8], s_min[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t begin = (uint64_t)blockIdx.x * kStatChunk + (uint64_t)threadIdx.x * PER;
+    long long first = -1, last = -1;
+    unsigned long long gmax = 0, gmin = ~0ull;
+    if (begin < n) {
+        const uint64_t end = begin + PER < n ? begin + PER : n;
+        for (uint64_t p = begin; p < end; ++p) {
+            if (raw[p] == 0) {
+                if (last >= 0) {
+                    const unsigned long long g = p - (uint64_t)last;
+                    gmax = g > gmax ? g : gmax;
+                    gmin = g < gmin ? g : gmin;
+                } else {
+                    first = (long long)p;
+                }
+                last = (long long)p;
+            }
+        }
+    }
+    // inclusive max-scan of `last` over the block -> previous terminator of each thread
+    long long incl = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = t > incl ? t : incl;
+    }
+    if (lane == 31) s_last[warp] = incl;
+    __syncthreads();
+    long long prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) prev = -1;
+    for (int w = 0; w < warp; ++w) prev = s_last[w] > prev ? s_last[w] : prev;
+    if (first >= 0 && prev >= 0) {
+        const unsigned long long g = (uint64_t)first - (uint64_t)prev;
+        gmax = g > gmax ? g : gmax;
+        gmin = g < gmin ? g : gmin;
+    }
+    // block reductions
+    long long bfirst = first >= 0 ? first : 0x7fffffffffffffffll;
+    long long blast = last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long f = __shfl_xor_sync(0xffffffffu, bfirst, o);
+        long long l = __shfl_xor_sync(0xffffffffu, blast, o);
+        unsigned long long a = __shfl_xor_sync(0xffffffffu, gmax, o);
+        unsigned long long b = __shfl_xor_sync(0xffffffffu, gmin, o);
+        bfirst = f < bfirst ? f : bfirst;
+        blast = l > blast ? l : blast;
+        gmax = a > gmax ? a : gmax;
+        gmin = b < gmin ? b : gmin;
+    }
+    __syncthreads(); // s_last reads above are done
+    if (lane == 0) {
+        s_first[warp] = bfirst;
+        s_last[warp] = blast;
+        s_max[warp] = gmax;
+        s_min[warp] = gmin;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) {
+            bfirst = s_first[w] < bfirst ? s_first[w] : bfirst;
+            blast = s_last[w] > blast ? s_last[w] : blast;
+            gmax = s_max[w] > gmax ? s_max[w] : gmax;
+            gmin = s_min[w] < gmin ? s_min[w] : gmin;
+        }
+        ChunkStat cs;
+        cs.first = blast >= 0 ? bfirst : -1;
+        cs.last = blast;
+        cs.maxgap = gmax;
+        cs.mingap = gmin;
+        out[blockIdx.x] = cs;
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ raw, uint64_t n,
+                                                   const uint8_t *__restrict__ code_map, uint64_t *__restrict__ packed,
+                                                   uint64_t nwords)
+{
+    using P = Pack<BITS>;
+    __shared__ uint8_t map[256];
+    map[threadIdx.x] = code_map[threadIdx.x];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x; w < nwords; w += stride) {
+        const uint64_t p0 = w * P::SPW;
+        uint64_t x = 0;
+#pragma unroll
+        for (int j = 0; j < P::SPW; ++j) {
+            const uint64_t p = p0 + j;
+            const uint64_t c = p < n ? map[raw[p]] : 0;
+            x = (x << BITS) | c;
+        }
+        packed[w] = x;
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restrict__ packed, uint64_t n,
+                                                        uint64_t *__restrict__ keys)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += stride)
+        keys[p] = text_window<BITS>(packed, p);
+}
+
+// ---------------------------------------------------------------------------
+// group heads after the initial sort
+// ---------------------------------------------------------------------------
+template <int BITS>
+__global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+                                                    uint32_t *__restrict__ head, uint64_t head_words,
+                                                    unsigned long long *__restrict__ remaining)
+{
+    __shared__ unsigned long long s_cnt[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t warps_total = (uint64_t)gridDim.x * 8;
+    unsigned long long active = 0;
+    for (uint64_t w = (uint64_t)blockIdx.x * 8 + warp; w < head_words; w += warps_total) {
+        const uint64_t i = w * 32 + lane;
+        bool h = true, act = false;
+        if (i < n) {
+            const uint64_t k = keys[i];
+            h = (i == 0) || key_terminated<BITS>(k) || keys[i - 1] != k;
+            bool hn = true;
+            if (i + 1 < n) {
+                const uint64_t kn = keys[i + 1];
+                hn = key_terminated<BITS>(kn) || kn != k;
+            }
+            act = !(h && hn);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, h);
+        const uint32_t aw = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) {
+            head[w] = word;
+            active += __popc(aw);
+        }
+    }
+    if (lane == 0) s_cnt[warp] = active;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += s_cnt[w];
+        if (t) atomicAdd(&remaining[blockIdx.x & 63], t);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// refinement round
+// ---------------------------------------------------------------------------
+// last set bit at a position <= r / first set bit at a position > r in a bit array
+__device__ __forceinline__ int prev_set_le(const uint32_t *hw, int r)
+{
+    int w = r >> 5;
+    uint32_t m = hw[w] & (0xffffffffu >> (31 - (r & 31)));
+    while (m == 0) m = hw[--w];
+    return (w << 5) + 31 - __clz(m);
+}
+__device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
+{
+    int w = r >> 5;
+    uint32_t m = (r & 31) == 31 ? 0u : (hw[w] & (0xffffffffu << ((r & 31) + 1)));
+    while (m == 0) m = hw[++w];
+    return (w << 5) + __ffs(m) - 1;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(kRefThreads)
+refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
+              uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, uint32_t *__restrict__ big_heads,
+              uint32_t big_cap, uint32_t *__restrict__ big_count, unsigned long long *__restrict__ remaining)
+{
+    constexpr int ITEMS = kRefCap / kRefThreads;
+    constexpr int HW = kRefCap / 32 + 2;            // head words held in shared memory
+    constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
+    static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
+    __shared__ uint64_t s_key[kRefCap];
+    __shared__ uint32_t s_sa[kRefCap];
+    __shared__ uint32_t s_head[HW];
+    __shared__ uint32_t s_new[HW];
+    __shared__ int s_range[2];
+    __shared__ unsigned long long s_cnt[kRefThreads / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t win = (uint64_t)blockIdx.x * kRefWindow; // first slot of this CTA's window
+    const uint64_t w0 = win >> 5;
+    for (int i = tid; i < HW; i += kRefThreads) {
+        s_head[i] = head_cur[w0 + i];
+        s_new[i] = 0;
+    }
+    __syncthreads();
+
+    // Ownership: this CTA sorts the groups whose head lies in [win, win+kRefWindow).
+    if (warp == 0) {
+        const uint32_t hw = s_head[lane];
+        const uint32_t nz = __ballot_sync(0xffffffffu, hw != 0);
+        int start = -1, end = -1;
+        if (nz) {
+            const int fl = __ffs(nz) - 1, ll = 31 - __clz(nz);
+            const uint32_t fw = __shfl_sync(0xffffffffu, hw, fl), lw = __shfl_sync(0xffffffffu, hw, ll);
+            start = fl * 32 + __ffs(fw) - 1;
+            const int hl = ll * 32 + 31 - __clz(lw); // head of the last owned group
+            // its end: first head at or after the window end
+            const uint32_t ew = s_head[WIN_WORDS + lane];
+            const uint32_t enz = __ballot_sync(0xffffffffu, ew != 0);
+            int e = -1;
+            if (enz) {
+                const int el = __ffs(enz) - 1;
+                const uint32_t x = __shfl_sync(0xffffffffu, ew, el);
+                e = kRefWindow + el * 32 + __ffs(x) - 1;
+            } else if (s_head[2 * WIN_WORDS] & 1u) {
+                e = kRefWindow + kRefGroupMax;
+            }
+            if (e >= 0 && e - hl <= kRefGroupMax) {
+                end = e;
+            } else {
+                // the last group is too large for shared memory: leave it to the global path
+                end = hl;
+                if (lane == 0) {
+                    const uint32_t slot = atomicAdd(big_count, 1u);
+                    if (slot < big_cap) big_heads[slot] = (uint32_t)(win + hl);
+                }
+            }
+        }
+        if (lane == 0) {
+            s_range[0] = start;
+            s_range[1] = end;
+        }
+    }
+    __syncthreads();
+    const int start = s_range[0], end = s_range[1];
+    if (start < 0 || end <= start) return;
+
+    // gather the next SPW symbols of every suffix that is still in a group of >= 2
+    uint64_t key[ITEMS];
+    uint32_t sav[ITEMS];
+    bool act[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int r = start + tid + k * kRefThreads;
+        act[k] = false;
+        key[k] = 0;
+        sav[k] = 0;
+        if (r < end) {
+            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+            act[k] = !(h0 && h1);
+            if (act[k]) sav[k] = sa[win + r];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (act[k]) {
+            key[k] = text_window<BITS>(packed, (uint64_t)sav[k] + depth);
+            s_key[start + tid + k * kRefThreads - start] = key[k];
+        }
+    }
+    __syncthreads();
+
+    // stable rank of every active suffix inside its group
+    int npos[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        npos[k] = -1;
+        if (act[k]) {
+            const int r = start + tid + k * kRefThreads;
+            const int gs = prev_set_le(s_head, r);
+            const int ge = next_set_gt(s_head, r);
+            const uint64_t mine = key[k];
+            int c = 0;
+            for (int j = gs; j < ge; ++j) {
+                const uint64_t o = s_key[j - start];
+                c += (o < mine) || (o == mine && j < r);
+            }
+            npos[k] = gs + c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (act[k]) {
+            s_key[npos[k] - start] = key[k];
+            s_sa[npos[k] - start] = sav[k];
+        }
+    }
+    __syncthreads();
+
+    // write back, mark the new heads, count what is still unresolved
+    unsigned long long still = 0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (act[k]) {
+            const int r = start + tid + k * kRefThreads;
+            sa[win + r] = s_sa[r - start];
+            const bool was_head = (s_head[r >> 5] >> (r & 31)) & 1u;
+            if (!was_head) {
+                const uint64_t me = s_key[r - start];
+                if (key_terminated<BITS>(me) || me != s_key[r - 1 - start]) atomicOr(&s_new[r >> 5], 1u << (r & 31));
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        if (act[k]) {
+            const int r = start + tid + k * kRefThreads;
+            const bool h0 = ((s_head[r >> 5] | s_new[r >> 5]) >> (r & 31)) & 1u;
+            const bool h1 = ((s_head[(r + 1) >> 5] | s_new[(r + 1) >> 5]) >> ((r + 1) & 31)) & 1u;
+            still += !(h0 && h1);
+        }
+    }
+    for (int i = tid; i < HW; i += kRefThreads)
+        if (s_new[i]) atomicOr(&head_next[w0 + i], s_new[i]);
+    still = warp_sum(still);
+    if (lane == 0) s_cnt[warp] = still;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kRefThreads / 32; ++w) t += s_cnt[w];
+        if (t) atomicAdd(&remaining[blockIdx.x & 63], t);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// large-group path
+// ---------------------------------------------------------------------------
+// One warp per listed group: distance from its head to the next head.
+__global__ void __launch_bounds__(256) big_extent_kernel(const uint32_t *__restrict__ head_cur, uint64_t n,
+                                                         const uint32_t *__restrict__ big_heads, uint32_t nbig,
+                                                         uint32_t *__restrict__ big_len)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (g >= nbig) return;
+    const uint64_t h = big_heads[g];
+    // first set bit at a position > h (bits >= n are set, so the scan ends)
+    uint64_t w = h >> 5;
+    uint32_t first = (h & 31) == 31 ? 0u : (head_cur[w] & (0xffffffffu << ((h & 31) + 1)));
+    uint64_t found = ~0ull;
+    if (first) {
+        found = (w << 5) + __ffs(first) - 1;
+    } else {
+        for (uint64_t base = w + 1;; base += 32) {
+            const uint32_t x = head_cur[base + lane];
+            const uint32_t nz = __ballot_sync(0xffffffffu, x != 0);
+            if (nz) {
+                const int l = __ffs(nz) - 1;
+                const uint32_t xw = __shfl_sync(0xffffffffu, x, l);
+                found = ((base + l) << 5) + __ffs(xw) - 1;
+                break;
+            }
+        }
+    }
+    if (found > n) found = n;
+    if (lane == 0) big_len[g] = (uint32_t)(found - h);
+}
+
+__device__ __forceinline__ uint32_t find_group(const uint64_t *__restrict__ off, uint32_t nbig, uint64_t j)
+{
+    // largest g with off[g] <= j  (off has nbig+1 entries, off[nbig] = total)
+    uint32_t lo = 0, hi = nbig;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+big_gather_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ sa, uint32_t depth,
+                  const uint32_t *__restrict__ big_heads, const uint64_t *__restrict__ big_off, uint32_t nbig,
+                  uint64_t total, uint32_t *__restrict__ bsa, uint64_t *__restrict__ bkey, uint32_t *__restrict__ bgid)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += stride) {
+        const uint32_t g = find_group(big_off, nbig, j);
+        const uint64_t slot = (uint64_t)big_heads[g] + (j - big_off[g]);
+        const uint32_t s = sa[slot];
+        bsa[j] = s;
+        bkey[j] = text_window<BITS>(packed, (uint64_t)s + depth);
+        bgid[j] = g;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_u32_to_u64_kernel(const uint32_t *__restrict__ src,
+                                                                const uint32_t *__restrict__ perm, uint64_t n,
+                                                                uint64_t *__restrict__ dst)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < n; j += stride) dst[j] = src[perm[j]];
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+big_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ bsa,
+                   const uint64_t *__restrict__ bkey, const uint32_t *__restrict__ bgid,
+                   const uint32_t *__restrict__ big_heads, const uint64_t *__restrict__ big_off, uint64_t total,
+                   uint32_t *__restrict__ sa, uint32_t *__restrict__ head_next)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += stride) {
+        const uint32_t idx = perm[j];
+        const uint32_t g = bgid[idx];
+        const uint64_t slot = (uint64_t)big_heads[g] + (j - big_off[g]);
+        sa[slot] = bsa[idx];
+        if (j > big_off[g]) {
+            const uint64_t me = bkey[idx], before = bkey[perm[j - 1]];
+            if (key_terminated<BITS>(me) || me != before) atomicOr(&head_next[slot >> 5], 1u << (slot & 31));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// BWT
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwt_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ sa,
+                                                  uint64_t n, uint8_t *__restrict__ bwt)
+{
+    const uint64_t nquad = n / 4;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x; q < nquad; q += stride) {
+        const uint4 s = *reinterpret_cast<const uint4 *>(sa + 4 * q);
+        const uint32_t b0 = s.x ? __ldg(raw + s.x - 1) : 0u;
+        const uint32_t b1 = s.y ? __ldg(raw + s.y - 1) : 0u;
+        const uint32_t b2 = s.z ? __ldg(raw + s.z - 1) : 0u;
+        const uint32_t b3 = s.w ? __ldg(raw + s.w - 1) : 0u;
+        *reinterpret_cast<uint32_t *>(bwt + 4 * q) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+    if (blockIdx.x == 0)
+        for (uint64_t i = nquad * 4 + threadIdx.x; i < n; i += 256) {
+            const uint32_t p = sa[i];
+            bwt[i] = p ? raw[p - 1] : 0;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// wavelet tree
+// ---------------------------------------------------------------------------
+constexpr int kWtInfoSmemNodes = 64; // node tables of up to this many internal nodes are staged in shared memory
+
+// the 32 symbols of thread t of tile `tile`
+__device__ __forceinline__ void wt_load32(const uint8_t *__restrict__ seq, uint64_t n, uint64_t p0, uint32_t (&w)[8])
+{
+    if (p0 + 32 <= n) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(seq + p0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(seq + p0 + 16));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t x = 0;
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t p = p0 + 4 * i + j;
+                if (p < n) x |= (uint32_t)seq[p] << (8 * j);
+            }
+            w[i] = x;
+        }
+    }
+}
+
+// member / branch masks of the thread's 32 symbols for node table `info`
+__device__ __forceinline__ void wt_masks(const uint8_t *info, const uint32_t (&w)[8], uint32_t valid, uint32_t &m,
+                                         uint32_t &b)
+{
+    m = 0;
+    b = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t v = info[(w[i] >> (8 * j)) & 0xff];
+            m |= (v & 1u) << (4 * i + j);
+            b |= (v >> 1) << (4 * i + j);
+        }
+    }
+    m &= valid;
+    b &= valid;
+}
+
+__device__ __forceinline__ uint32_t wt_valid_mask(uint64_t n, uint64_t p0)
+{
+    if (p0 >= n) return 0u;
+    const uint64_t left = n - p0;
+    return left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+}
+
+__global__ void __launch_bounds__(256)
+wt_count_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
+                uint64_t ntiles, uint64_t *__restrict__ tile_count)
+{
+    extern __shared__ uint8_t s_info[];
+    __shared__ uint32_t s_sum[8];
+    const bool staged = n_internal <= kWtInfoSmemNodes;
+    if (staged) {
+        for (int i = threadIdx.x; i < n_internal * 256; i += 256) s_info[i] = node_info[i];
+        __syncthreads();
+    }
+    const uint8_t *info = staged ? s_info : node_info;
+    const uint64_t tile = blockIdx.x;
+    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
+    uint32_t w[8];
+    wt_load32(seq, n, p0, w);
+    const uint32_t valid = wt_valid_mask(n, p0);
+    for (int v = 0; v < n_internal; ++v) {
+        uint32_t m, b;
+        wt_masks(info + v * 256, w, valid, m, b);
+        uint32_t c = warp_sum((uint32_t)__popc(m));
+        if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int k = 0; k < 8; ++k) t += s_sum[k];
+            tile_count[(uint64_t)v * ntiles + tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) wt_scan_kernel(uint64_t *__restrict__ tile_count, uint64_t ntiles)
+{
+    __shared__ uint64_t scratch[33];
+    uint64_t *row = tile_count + (uint64_t)blockIdx.x * ntiles;
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < ntiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < ntiles ? row[i] : 0;
+        uint64_t total;
+        const uint64_t e = block_excl_sum(v, scratch, &total);
+        if (i < ntiles) row[i] = carry + e;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
+               uint64_t ntiles, const uint64_t *__restrict__ tile_off, uint64_t *const *__restrict__ node_data,
+               uint8_t *__restrict__ node_ch)
+{
+    extern __shared__ uint8_t s_info[];
+    __shared__ uint32_t scratch[9];
+    const bool staged = n_internal <= kWtInfoSmemNodes;
+    if (staged) {
+        for (int i = threadIdx.x; i < n_internal * 256; i += 256) s_info[i] = node_info[i];
+        __syncthreads();
+    }
+    const uint8_t *info = staged ? s_info : node_info;
+    const uint64_t tile = blockIdx.x;
+    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
+    uint32_t w[8];
+    wt_load32(seq, n, p0, w);
+    const uint32_t valid = wt_valid_mask(n, p0);
+    for (int v = 0; v < n_internal; ++v) {
+        uint32_t m, b;
+        wt_masks(info + v * 256, w, valid, m, b);
+        const uint32_t c = __popc(m);
+        uint32_t total;
+        const uint32_t e = block_excl_sum(c, scratch, &total);
+        if (c) {
+            // compress the branch bits of the members (software pext)
+            uint64_t bits = 0;
+            uint32_t mm = m;
+            int out = 0;
+            while (mm) {
+                const int j = __ffs(mm) - 1;
+                bits |= (uint64_t)((b >> j) & 1u) << out;
+                ++out;
+                mm &= mm - 1;
+            }
+            const uint64_t o = tile_off[(uint64_t)v * ntiles + tile] + e; // bit offset in the node's array
+            unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]);
+            const int sh = (int)(o & 63);
+            if (bits << sh) atomicOr(d + (o >> 6), (unsigned long long)(bits << sh));
+            if (sh + (int)c > 64 && (bits >> (64 - sh))) atomicOr(d + (o >> 6) + 1, (unsigned long long)(bits >> (64 - sh)));
+            if (o == 0) { // first symbol of the node's subsequence (HuffWT.cpp:8)
+                const int j = __ffs(m) - 1;
+                node_ch[v] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+            }
+        }
+    }
+}
+
+// BitRank: popcount of every chunk of kRankChunk superblocks
+__global__ void __launch_bounds__(256) rank_chunk_sum_kernel(const uint64_t *__restrict__ data, uint64_t integers,
+                                                             uint64_t *__restrict__ chunk_sum)
+{
+    __shared__ uint64_t s[8];
+    const uint64_t w0 = (uint64_t)blockIdx.x * kRankChunk * 4;
+    uint64_t c = 0;
+    for (int i = threadIdx.x; i < kRankChunk * 4; i += 256) {
+        const uint64_t w = w0 + i;
+        if (w < integers) c += __popcll(data[w]);
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t t = 0;
+        for (int k = 0; k < 8; ++k) t += s[k];
+        chunk_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) rank_chunk_scan_kernel(uint64_t *__restrict__ chunk_sum, uint64_t nchunks)
+{
+    __shared__ uint64_t scratch[33];
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < nchunks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < nchunks ? chunk_sum[i] : 0;
+        uint64_t total;
+        const uint64_t e = block_excl_sum(v, scratch, &total);
+        if (i < nchunks) chunk_sum[i] = carry + e;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rank_write_kernel(const uint64_t *__restrict__ data, uint64_t integers, uint64_t nbits,
+                  const uint64_t *__restrict__ chunk_base, uint64_t *__restrict__ Rs, uint8_t *__restrict__ Rb)
+{
+    constexpr int SB_PER_THREAD = kRankChunk / 256; // 8
+    __shared__ uint64_t scratch[9];
+    const uint64_t nsb = nbits / 256, nb = nbits / 64;
+    const uint64_t sb0 = (uint64_t)blockIdx.x * kRankChunk + (uint64_t)threadIdx.x * SB_PER_THREAD;
+    uint32_t cnt[SB_PER_THREAD];
+    uint64_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < SB_PER_THREAD; ++q) {
+        const uint64_t j = sb0 + q;
+        uint32_t run = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint64_t k = 4 * j + t;
+            if (k <= nb) Rb[k] = (uint8_t)run;
+            if (k < integers) run += __popcll(data[k]);
+        }
+        cnt[q] = run;
+        mine += run;
+    }
+    uint64_t total;
+    uint64_t e = block_excl_sum(mine, scratch, &total) + chunk_base[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < SB_PER_THREAD; ++q) {
+        const uint64_t j = sb0 + q;
+        if (j <= nsb) Rs[j] = e;
+        e += cnt[q];
+    }
+}
+
+int grid_for(uint64_t items, int per_cta, int max_waves = 8)
+{
+    uint64_t want = div_up(items ? items : 1, (uint64_t)per_cta);
+    uint64_t cap = (uint64_t)kNumSMs * max_waves;
+    return (int)(want < cap ? want : cap);
+}
+
+#define DISPATCH_BITS(bits, CALL)                                                                     \
+    do {                                                                                              \
+        if ((bits) == 3) { CALL(3); }                                                                 \
+        else if ((bits) == 4) { CALL(4); }                                                            \
+        else if ((bits) == 8) { CALL(8); }                                                            \
+        else throw CudaError{cudaErrorInvalidValue, "unsupported bits per symbol", __FILE__, __LINE__}; \
+    } while (0)
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+void launch_byte_hist(cudaStream_t st, const uint8_t *raw, uint64_t n, uint64_t *counts, uint32_t *launches)
+{
+    byte_hist_kernel<<<grid_for(n, 256 * 64), 256, 0, st>>>(raw, n, counts);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_doc_stats(cudaStream_t st, const uint8_t *raw, uint64_t n, ChunkStat *out, uint32_t *launches)
+{
+    if (n == 0) return;
+    doc_stats_kernel<<<(unsigned)div_up(n, kStatChunk), 256, 0, st>>>(raw, n, out);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_pack(cudaStream_t st, int bits, const uint8_t *raw, uint64_t n, const uint8_t *code_map, uint64_t *packed,
+                 uint64_t nwords, uint32_t *launches)
+{
+#define CALL(B) pack_kernel<B><<<grid_for(nwords, 256), 256, 0, st>>>(raw, n, code_map, packed, nwords)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, uint32_t *launches)
+{
+#define CALL(B) make_keys_kernel<B><<<grid_for(n, 256 * 8), 256, 0, st>>>(packed, n, keys)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
+                  uint64_t head_words, unsigned long long *remaining, uint32_t *launches)
+{
+#define CALL(B) heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
+                   uint32_t *head_next, uint64_t n, uint32_t depth, uint32_t *big_heads, uint32_t big_cap,
+                   uint32_t *big_count, unsigned long long *remaining, uint32_t *launches)
+{
+    const unsigned grid = (unsigned)div_up(n, kRefWindow);
+#define CALL(B)                                                                                                  \
+    refine_kernel<B><<<grid, kRefThreads, 0, st>>>(packed, sa, head_cur, head_next, n, depth, big_heads, big_cap, \
+                                                   big_count, remaining)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads, uint32_t nbig,
+                       uint32_t *big_len, uint32_t *launches)
+{
+    big_extent_kernel<<<(unsigned)div_up(nbig, 8), 256, 0, st>>>(head_cur, n, big_heads, nbig, big_len);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_big_gather(cudaStream_t st, int bits, const uint64_t *packed, const uint32_t *sa, uint32_t depth,
+                       const uint32_t *big_heads, const uint64_t *big_off, uint32_t nbig, uint64_t total, uint32_t *bsa,
+                       uint64_t *bkey, uint32_t *bgid, uint32_t *launches)
+{
+#define CALL(B)                                                                                                    \
+    big_gather_kernel<B><<<grid_for(total, 256 * 4), 256, 0, st>>>(packed, sa, depth, big_heads, big_off, nbig, total, \
+                                                                   bsa, bkey, bgid)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_gather_u32_to_u64(cudaStream_t st, const uint32_t *src, const uint32_t *perm, uint64_t n, uint64_t *dst,
+                              uint32_t *launches)
+{
+    gather_u32_to_u64_kernel<<<grid_for(n, 256 * 4), 256, 0, st>>>(src, perm, n, dst);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const uint32_t *bsa, const uint64_t *bkey,
+                        const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
+                        uint32_t *sa, uint32_t *head_next, uint32_t *launches)
+{
+#define CALL(B)                                                                                                   \
+    big_scatter_kernel<B><<<grid_for(total, 256 * 4), 256, 0, st>>>(perm, bsa, bkey, bgid, big_heads, big_off, total, \
+                                                                    sa, head_next)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_bwt(cudaStream_t st, const uint8_t *raw, const uint32_t *sa, uint64_t n, uint8_t *bwt, uint32_t *launches)
+{
+    bwt_kernel<<<grid_for(n, 256 * 16), 256, 0, st>>>(raw, sa, n, bwt);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+static size_t wt_info_smem(int n_internal) { return n_internal <= kWtInfoSmemNodes ? (size_t)n_internal * 256 : 0; }
+
+void launch_wt_count(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                     uint64_t ntiles, uint64_t *tile_count, uint32_t *launches)
+{
+    wt_count_kernel<<<(unsigned)ntiles, 256, wt_info_smem(n_internal), st>>>(seq, n, node_info, n_internal, ntiles,
+                                                                            tile_count);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_wt_scan(cudaStream_t st, uint64_t *tile_count, int n_internal, uint64_t ntiles, uint32_t *launches)
+{
+    wt_scan_kernel<<<n_internal, 1024, 0, st>>>(tile_count, ntiles);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                    uint64_t ntiles, const uint64_t *tile_off, uint64_t *const *node_data, uint8_t *node_ch,
+                    uint32_t *launches)
+{
+    wt_fill_kernel<<<(unsigned)ntiles, 256, wt_info_smem(n_internal), st>>>(seq, n, node_info, n_internal, ntiles,
+                                                                           tile_off, node_data, node_ch);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_bitrank(cudaStream_t st, const uint64_t *data, uint64_t nbits, uint64_t *Rs, uint8_t *Rb, uint64_t *scratch,
+                    uint32_t *launches)
+{
+    const uint64_t integers = nbits / 64 + 1;
+    const uint64_t nsb = nbits / 256 + 1; // superblock entries 0..nbits/256
+    const unsigned nchunks = (unsigned)div_up(nsb, kRankChunk);
+    rank_chunk_sum_kernel<<<nchunks, 256, 0, st>>>(data, integers, scratch);
+    DSM_LAUNCH_CHECK();
+    rank_chunk_scan_kernel<<<1, 1024, 0, st>>>(scratch, nchunks);
+    DSM_LAUNCH_CHECK();
+    rank_write_kernel<<<nchunks, 256, 0, st>>>(data, integers, nbits, scratch, Rs, Rb);
+    DSM_LAUNCH_CHECK();
+    if (launches) *launches += 3;
+}
+
+} // namespace dsmfm

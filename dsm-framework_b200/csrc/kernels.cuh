@@ -1,0 +1,95 @@
+// kernels.cuh -- launch wrappers of the FM-index build kernels (sm_100a).
+// Every wrapper enqueues on `stream`, checks the launch and bumps *launches.
+#pragma once
+#include "common.cuh"
+
+namespace dsmfm {
+
+// ---- ingest -----------------------------------------------------------------
+// 256-bin histogram of the raw text (counts[0] = number of documents).
+void launch_byte_hist(cudaStream_t st, const uint8_t *raw, uint64_t n, uint64_t *counts, uint32_t *launches);
+
+// Per-chunk terminator summary used to get numberOfTexts / maxTextLength / empty
+// documents for bulk-appended text (TextCollectionBuilder.cpp:73-91).
+constexpr int kStatChunk = 16384;
+struct ChunkStat {
+    int64_t first;   // position of the first terminator in the chunk, -1 if none
+    int64_t last;    // position of the last terminator in the chunk
+    uint64_t maxgap; // largest distance between consecutive terminators inside the chunk
+    uint64_t mingap; // smallest such distance (UINT64_MAX if fewer than two)
+};
+void launch_doc_stats(cudaStream_t st, const uint8_t *raw, uint64_t n, ChunkStat *out, uint32_t *launches);
+
+// raw bytes -> dense codes packed BITS per symbol (common.cuh); `code_map` is a
+// device table of 256 bytes.  `nwords` words are written (tail zero-padded).
+void launch_pack(cudaStream_t st, int bits, const uint8_t *raw, uint64_t n, const uint8_t *code_map, uint64_t *packed,
+                 uint64_t nwords, uint32_t *launches);
+
+// ---- suffix sorting ---------------------------------------------------------
+// key[p] = the first SPW symbols of suffix p, cut at its terminator.
+void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys,
+                      uint32_t *launches);
+
+// Group heads after the initial sort: bit i set iff suffix i starts a new group
+// (key differs from its predecessor) or is already finished (key holds the
+// terminator).  Bits >= n are set.  *remaining += suffixes left in groups of >= 2.
+void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
+                  uint64_t head_words, unsigned long long *remaining, uint32_t *launches);
+
+constexpr int kRefThreads = 256;
+constexpr int kRefWindow = 1024;   // group heads owned by one CTA lie in a window of this many slots
+constexpr int kRefGroupMax = 1024; // larger groups go through the global path
+constexpr int kRefCap = kRefWindow + kRefGroupMax;
+
+inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32 + 8; }
+
+// One refinement round: every group of >= 2 suffixes that still agree on their
+// first `depth` symbols is sorted (stably) by the next SPW symbols and split.
+// head_next must hold a copy of head_cur.  Groups larger than kRefGroupMax are
+// left untouched and their head slots appended to big_heads.
+void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
+                   uint32_t *head_next, uint64_t n, uint32_t depth, uint32_t *big_heads, uint32_t big_cap,
+                   uint32_t *big_count, unsigned long long *remaining, uint32_t *launches);
+
+// Large-group path, step 1: length of each listed group (distance to the next head).
+void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,
+                       uint32_t nbig, uint32_t *big_len, uint32_t *launches);
+// step 2: gather (suffix, next key, group ordinal) of all listed groups into dense arrays
+void launch_big_gather(cudaStream_t st, int bits, const uint64_t *packed, const uint32_t *sa, uint32_t depth,
+                       const uint32_t *big_heads, const uint64_t *big_off, uint32_t nbig, uint64_t total,
+                       uint32_t *bsa, uint64_t *bkey, uint32_t *bgid, uint32_t *launches);
+// step 3 helper: k2[j] = gid[perm[j]]
+void launch_gather_u32_to_u64(cudaStream_t st, const uint32_t *src, const uint32_t *perm, uint64_t n, uint64_t *dst,
+                              uint32_t *launches);
+// step 4: write the sorted groups back and mark the new heads
+void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const uint32_t *bsa, const uint64_t *bkey,
+                        const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
+                        uint32_t *sa, uint32_t *head_next, uint32_t *launches);
+
+// ---- BWT --------------------------------------------------------------------
+// bwt[i] = raw[sa[i]-1], or 0 when suffix i is a whole document (incbwt/rlcsa.cpp:815-845).
+void launch_bwt(cudaStream_t st, const uint8_t *raw, const uint32_t *sa, uint64_t n, uint8_t *bwt,
+                uint32_t *launches);
+
+// ---- wavelet tree -------------------------------------------------------------
+constexpr int kWtTile = 8192; // symbols per CTA
+constexpr int kWtMaxNodes = 255;
+
+// node_info[v*256 + c]: 0 = symbol c not below internal node v, 1 = member with bit 0, 3 = member with bit 1
+void launch_wt_count(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                     uint64_t ntiles, uint64_t *tile_count, uint32_t *launches);
+// in-place exclusive scan of tile_count[v][0..ntiles) for every node v
+void launch_wt_scan(cudaStream_t st, uint64_t *tile_count, int n_internal, uint64_t ntiles, uint32_t *launches);
+// node_data[v] = device pointer of node v's (zeroed) bit array; node_ch[v] receives the first member symbol
+void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                    uint64_t ntiles, const uint64_t *tile_off, uint64_t *const *node_data, uint8_t *node_ch,
+                    uint32_t *launches);
+
+// BitRank directories of one bit array (BitRank.cpp:154-187): Rs[j] = ones in
+// words [0,4j), j <= nbits/256; Rb[k] = ones in words [4*(k/4), k), k <= nbits/64.
+// `scratch` holds ceil((nbits/256+1)/kRankChunk)+1 u64.
+constexpr int kRankChunk = 2048; // superblocks per CTA
+void launch_bitrank(cudaStream_t st, const uint64_t *data, uint64_t nbits, uint64_t *Rs, uint8_t *Rb,
+                    uint64_t *scratch, uint32_t *launches);
+
+} // namespace dsmfm

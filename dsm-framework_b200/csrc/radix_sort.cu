@@ -1,0 +1,295 @@
+// radix_sort.cu -- one-sweep LSD radix sort kernels (see radix_sort.cuh).
+#include "radix_sort.cuh"
+
+namespace dsmfm {
+
+namespace {
+
+constexpr uint32_t kFlagAgg = 1u << 30;    // tile's own digit count is published
+constexpr uint32_t kFlagPrefix = 2u << 30; // inclusive prefix over all tiles so far is published
+constexpr uint32_t kValueMask = (1u << 30) - 1;
+
+// Lanes of the warp holding the same digit (ballot multi-split).
+__device__ __forceinline__ uint32_t match_digit(uint32_t d)
+{
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixBits; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+}
+
+// All digit histograms of a sort in one pass over the keys.
+__global__ void __launch_bounds__(512) radix_hist_kernel(const uint64_t *__restrict__ keys, uint64_t n, int begin_bit,
+                                                         int end_bit, int npass, uint64_t *__restrict__ ghist)
+{
+    __shared__ uint32_t h[kMaxPasses][kRadix];
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = keys[i];
+#pragma unroll
+        for (int p = 0; p < kMaxPasses; ++p) {
+            if (p < npass) {
+                const int shift = begin_bit + kRadixBits * p;
+                const int bits = min(kRadixBits, end_bit - shift);
+                const uint32_t d = (uint32_t)(k >> shift) & ((1u << bits) - 1u);
+                atomicAdd(&h[p][d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
+        const uint32_t c = (&h[0][0])[i];
+        if (c) atomicAdd((unsigned long long *)&ghist[i], (unsigned long long)c);
+    }
+}
+
+// Exclusive scan of each pass's 256 counts, in place.  One CTA of 256 threads per pass.
+__global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint64_t *__restrict__ ghist)
+{
+    __shared__ uint64_t warp_sum[kRadix / 32];
+    uint64_t *h = ghist + (size_t)blockIdx.x * kRadix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t v = h[tid];
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint64_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_sum[w];
+    h[tid] = base + incl - v;
+}
+
+struct SweepSmem {
+    uint64_t keys[kSweepTile];                 // tile in sorted order
+    uint32_t vals[kSweepTile];
+    uint64_t goff[kRadix];                     // global offset of digit run minus its tile-local start
+    uint32_t cnt[kSweepThreads / 32][kRadix];  // per-warp digit counters -> per-warp digit bases
+    uint32_t excl[kRadix];                     // tile-local start of each digit run
+    uint32_t warp_sum[kSweepThreads / 32];
+    uint32_t tile;
+};
+
+// One LSD pass over one portion (<= kSweepPortion pairs) of the input.
+template <bool IOTA>
+__global__ void __launch_bounds__(kSweepThreads, 3)
+onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
+                int shift, uint32_t mask, const uint64_t *__restrict__ base_in, uint64_t *__restrict__ base_out,
+                volatile uint32_t *status, uint32_t *counter, uint32_t last_tile)
+{
+    static_assert(kSweepThreads == kRadix, "one thread per digit in the look-back");
+    constexpr int WARPS = kSweepThreads / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SweepSmem &s = *reinterpret_cast<SweepSmem *>(smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) s.tile = atomicAdd(counter, 1u);
+    for (int i = tid; i < WARPS * kRadix; i += kSweepThreads) (&s.cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s.tile;
+    const uint32_t tile_base = tile * (uint32_t)kSweepTile;
+    const uint32_t valid = min((uint32_t)kSweepTile, n - tile_base);
+    const uint32_t first = tile_base + warp * (32 * kSweepItems) + lane;
+
+    // warp-striped load: item k of lane l is element first + 32k, so the order
+    // (warp, k, lane) is the input order and the ranking below is stable
+    uint64_t key[kSweepItems];
+#pragma unroll
+    for (int k = 0; k < kSweepItems; ++k) {
+        const uint32_t idx = first + 32 * k;
+        key[k] = idx < n ? keys_in[idx] : ~0ull; // padding sorts to the very end of the tile
+    }
+
+    uint32_t lpos[kSweepItems];
+#pragma unroll
+    for (int k = 0; k < kSweepItems; ++k) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+        const uint32_t peers = match_digit(d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s.cnt[warp][d];
+            s.cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        lpos[k] = old + __popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d owns digit d: turn per-warp counts into per-warp bases, get the tile total
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t t = s.cnt[w][tid];
+        s.cnt[w][tid] = total;
+        total += t;
+    }
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s.warp_sum[warp] = incl;
+
+    // values are fetched now so that their latency overlaps the look-back
+    uint32_t val[kSweepItems];
+#pragma unroll
+    for (int k = 0; k < kSweepItems; ++k) {
+        const uint32_t idx = first + 32 * k;
+        if (IOTA)
+            val[k] = (uint32_t)(iota_base + idx);
+        else
+            val[k] = idx < n ? vals_in[idx] : 0u;
+    }
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
+    const uint32_t excl = wbase + incl - total;
+    s.excl[tid] = excl;
+
+    // decoupled look-back, one chain per digit
+    uint32_t pub = total;
+    if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
+    volatile uint32_t *mine = status + (size_t)tile * kRadix + tid;
+    uint32_t exclusive = 0;
+    if (tile == 0) {
+        *mine = kFlagPrefix | pub;
+    } else {
+        *mine = kFlagAgg | pub;
+        for (uint32_t t = tile; t-- > 0;) {
+            uint32_t w;
+            do {
+                w = status[(size_t)t * kRadix + tid];
+            } while ((w >> 30) == 0);
+            exclusive += w & kValueMask;
+            if (w & kFlagPrefix) break;
+        }
+        *mine = kFlagPrefix | (exclusive + pub);
+    }
+    const uint64_t gbase = base_in[tid] + exclusive;
+    s.goff[tid] = gbase - excl;
+    if (tile == last_tile) base_out[tid] = gbase + pub;
+    __syncthreads();
+
+    // stage the tile in sorted order
+#pragma unroll
+    for (int k = 0; k < kSweepItems; ++k) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+        const uint32_t p = lpos[k] + s.excl[d] + s.cnt[warp][d];
+        s.keys[p] = key[k];
+        s.vals[p] = val[k];
+    }
+    __syncthreads();
+
+    // every digit run goes out as one contiguous burst
+    for (uint32_t i = tid; i < valid; i += kSweepThreads) {
+        const uint64_t kk = s.keys[i];
+        const uint32_t d = (uint32_t)(kk >> shift) & mask;
+        const uint64_t o = s.goff[d] + i;
+        keys_out[o] = kk;
+        vals_out[o] = s.vals[i];
+    }
+}
+
+} // namespace
+
+void RadixWorkspace::allocate(uint64_t max_n)
+{
+    release();
+    const uint64_t portion = max_n < kSweepPortion ? max_n : kSweepPortion;
+    status_tiles = div_up(portion ? portion : 1, kSweepTile);
+    DSM_CUDA(cudaMalloc(&hist, sizeof(uint64_t) * kMaxPasses * kRadix));
+    DSM_CUDA(cudaMalloc(&carry, sizeof(uint64_t) * 2 * kRadix));
+    DSM_CUDA(cudaMalloc(&status, sizeof(uint32_t) * status_tiles * kRadix));
+    DSM_CUDA(cudaMalloc(&counter, sizeof(uint32_t)));
+    bytes = sizeof(uint64_t) * (kMaxPasses + 2) * kRadix + sizeof(uint32_t) * (status_tiles * kRadix + 1);
+}
+
+void RadixWorkspace::release()
+{
+    if (hist) cudaFree(hist);
+    if (carry) cudaFree(carry);
+    if (status) cudaFree(status);
+    if (counter) cudaFree(counter);
+    hist = carry = nullptr;
+    status = counter = nullptr;
+    status_tiles = 0;
+    bytes = 0;
+}
+
+int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b,
+                     uint32_t *vals_b, uint64_t n, int begin_bit, int end_bit, bool iota_first,
+                     uint32_t *launches, cudaEvent_t ev_begin, cudaEvent_t ev_end)
+{
+    const int npass = (int)div_up((uint64_t)(end_bit - begin_bit), kRadixBits);
+    if (n == 0 || npass <= 0) return 0;
+    if (npass > kMaxPasses) throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: too many passes", __FILE__, __LINE__};
+    if (div_up(n < kSweepPortion ? n : kSweepPortion, kSweepTile) > ws.status_tiles)
+        throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: workspace too small", __FILE__, __LINE__};
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmem)));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmem)));
+        attr_set = true;
+    }
+
+    DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * npass * kRadix, stream));
+    {
+        uint64_t want = div_up(n, 512 * 16);
+        int grid = (int)(want < (uint64_t)kNumSMs * 4 ? (want ? want : 1) : (uint64_t)kNumSMs * 4);
+        radix_hist_kernel<<<grid, 512, 0, stream>>>(keys_a, n, begin_bit, end_bit, npass, ws.hist);
+        DSM_LAUNCH_CHECK();
+        radix_scan_kernel<<<npass, kRadix, 0, stream>>>(ws.hist);
+        DSM_LAUNCH_CHECK();
+        if (launches) *launches += 2;
+    }
+    if (ev_begin) DSM_CUDA(cudaEventRecord(ev_begin, stream));
+    for (int p = 0; p < npass; ++p) {
+        const int shift = begin_bit + kRadixBits * p;
+        const int bits = (end_bit - shift) < kRadixBits ? (end_bit - shift) : kRadixBits;
+        const uint32_t mask = (1u << bits) - 1u;
+        uint64_t *src_k = (p & 1) ? keys_b : keys_a, *dst_k = (p & 1) ? keys_a : keys_b;
+        uint32_t *src_v = (p & 1) ? vals_b : vals_a, *dst_v = (p & 1) ? vals_a : vals_b;
+        const bool iota = (p == 0 && iota_first);
+        const uint64_t *base_in = ws.hist + (size_t)p * kRadix;
+        int flip = 0;
+        for (uint64_t start = 0; start < n; start += kSweepPortion) {
+            const uint64_t cnt = (n - start) < kSweepPortion ? (n - start) : kSweepPortion;
+            const uint32_t tiles = (uint32_t)div_up(cnt, kSweepTile);
+            uint64_t *base_out = ws.carry + (size_t)flip * kRadix;
+            DSM_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(uint32_t) * (size_t)tiles * kRadix, stream));
+            DSM_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream));
+            if (iota)
+                onesweep_kernel<true><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(
+                    src_k + start, nullptr, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out,
+                    ws.status, ws.counter, tiles - 1);
+            else
+                onesweep_kernel<false><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(
+                    src_k + start, src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out,
+                    ws.status, ws.counter, tiles - 1);
+            DSM_LAUNCH_CHECK();
+            if (launches) *launches += 1;
+            base_in = base_out;
+            flip ^= 1;
+        }
+    }
+    if (ev_end) DSM_CUDA(cudaEventRecord(ev_end, stream));
+    return npass;
+}
+
+} // namespace dsmfm

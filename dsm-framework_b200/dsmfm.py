@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI in include/dsmfm.h (libdsmfm.so).
+
+This is plumbing for the tests and bench.py; the product is the shared library
+and the C++ facade in host/.  There is no CPU fallback: importing works
+anywhere (so that symbol checks can run on a CPU-only box) but every call that
+computes needs a B200 and fails loudly otherwise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsmfm.so")
+
+OK, EINVAL, ECUDA, ENOMEM, EEMPTY, ELIMIT, EIO = 0, -1, -2, -3, -4, -5, -6
+FLAG_KEEP_BWT, FLAG_KEEP_SA = 1, 2
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("samplerate", C.c_uint32), ("expected_bytes", C.c_uint64),
+                ("stream", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Code(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("bits", C.c_uint32), ("code", C.c_uint32)]
+
+
+class Node(C.Structure):
+    _fields_ = [("leaf", C.c_uint8), ("ch", C.c_uint8), ("pad", C.c_uint8 * 6), ("nbits", C.c_uint64),
+                ("integers", C.c_uint64), ("data", C.POINTER(C.c_uint64)), ("Rs", C.POINTER(C.c_uint64)),
+                ("Rb", C.POINTER(C.c_uint8))]
+
+
+class Index(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("samplerate", C.c_uint32), ("number_of_texts", C.c_uint32),
+                ("max_text_length", C.c_uint64), ("C", C.c_uint64 * 256), ("codetable", Code * 256),
+                ("n_nodes", C.c_uint32), ("reserved", C.c_uint32), ("nodes", C.POINTER(Node)),
+                ("bwt", C.POINTER(C.c_uint8))]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("bases", C.c_uint64), ("bits_per_symbol", C.c_uint32), ("sigma", C.c_uint32),
+                ("rounds", C.c_uint32), ("kernel_launches", C.c_uint32), ("active", C.c_uint64 * 32),
+                ("fallback_elems", C.c_uint64), ("ms_total", C.c_float), ("ms_pack", C.c_float),
+                ("ms_sort", C.c_float), ("ms_sort_pass", C.c_float), ("ms_refine", C.c_float), ("ms_bwt", C.c_float),
+                ("ms_wt", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("sort_passes", C.c_uint32),
+                ("reserved", C.c_uint32), ("sort_pass_bytes", C.c_uint64), ("device_bytes_peak", C.c_uint64)]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+class DsmfmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("dsmfm error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libdsmfm.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libdsmfm.so is missing (%s): build it with `make -C dsm-framework_b200` or "
+                           "__graft_entry__.build(); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    B = C.c_void_p
+    L.dsmfm_version.restype = C.c_int
+    L.dsmfm_create.argtypes = [C.POINTER(Options), C.POINTER(B)]
+    L.dsmfm_append.argtypes = [B, C.c_void_p, C.c_size_t]
+    L.dsmfm_append_batch.argtypes = [B, C.c_void_p, C.c_size_t]
+    L.dsmfm_append_batch_device.argtypes = [B, C.c_void_p, C.c_size_t]
+    L.dsmfm_finish.argtypes = [B, C.POINTER(Index)]
+    L.dsmfm_build_device.argtypes = [B]
+    L.dsmfm_fetch.argtypes = [B, C.POINTER(Index)]
+    L.dsmfm_write_fmi.argtypes = [C.POINTER(Index), C.c_char_p]
+    L.dsmfm_fmi_size.argtypes = [C.POINTER(Index)]
+    L.dsmfm_fmi_size.restype = C.c_uint64
+    L.dsmfm_fmi_serialize.argtypes = [C.POINTER(Index), C.c_void_p, C.c_uint64]
+    L.dsmfm_copy_sa.argtypes = [B, C.c_void_p, C.c_uint64, C.c_uint64]
+    L.dsmfm_get_stats.argtypes = [B, C.POINTER(Stats)]
+    L.dsmfm_last_error.argtypes = [B]
+    L.dsmfm_last_error.restype = C.c_char_p
+    L.dsmfm_destroy.argtypes = [B]
+    L.dsmfm_destroy.restype = None
+    L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
+    L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]
+    L.dsmfm_dbg_free_index.restype = None
+    _lib = L
+    return L
+
+
+def _ptr(buf):
+    """(address, nbytes, keepalive) of bytes / bytearray / numpy array / torch tensor."""
+    if isinstance(buf, (bytes, bytearray)):
+        arr = (C.c_char * len(buf)).from_buffer_copy(buf) if isinstance(buf, bytes) else (C.c_char * len(buf)).from_buffer(buf)
+        return C.addressof(arr), len(buf), arr
+    if hasattr(buf, "data_ptr"):  # torch tensor (host or device)
+        return buf.data_ptr(), buf.numel() * buf.element_size(), buf
+    if hasattr(buf, "ctypes"):  # numpy
+        return buf.ctypes.data, buf.nbytes, buf
+    raise TypeError("unsupported buffer type %r" % type(buf))
+
+
+def fmi_bytes(index):
+    """Serialise a dsmfm_index into the bytes of the reference's .fmi file."""
+    L = lib()
+    size = L.dsmfm_fmi_size(C.byref(index))
+    out = bytearray(size)
+    arr = (C.c_char * size).from_buffer(out)
+    rc = L.dsmfm_fmi_serialize(C.byref(index), C.addressof(arr), size)
+    if rc != OK:
+        raise DsmfmError(rc, "dsmfm_fmi_serialize failed")
+    del arr
+    return bytes(out)
+
+
+class Builder:
+    """Mirror of the reference's TextCollectionBuilder over the C ABI."""
+
+    def __init__(self, device=-1, samplerate=0, expected_bytes=0, stream=None, flags=0):
+        self._L = lib()
+        opt = Options(device=device, samplerate=samplerate, expected_bytes=expected_bytes,
+                      stream=stream, flags=flags, reserved=0)
+        self._h = C.c_void_p()
+        rc = self._L.dsmfm_create(C.byref(opt), C.byref(self._h))
+        if rc != OK:
+            raise DsmfmError(rc, (self._L.dsmfm_last_error(None) or b"").decode())
+        self.index = None
+        self._keep = []
+
+    def _check(self, rc):
+        if rc != OK:
+            raise DsmfmError(rc, (self._L.dsmfm_last_error(self._h) or b"").decode())
+
+    def insert_text(self, doc):
+        """TextCollectionBuilder::InsertText: one document, no terminator."""
+        addr, n, keep = _ptr(doc)
+        self._check(self._L.dsmfm_append(self._h, addr, n))
+
+    def append_batch(self, docs):
+        """'\\0'-terminated documents back to back, in host memory."""
+        addr, n, keep = _ptr(docs)
+        self._keep.append(keep)
+        self._check(self._L.dsmfm_append_batch(self._h, addr, n))
+
+    def append_batch_device(self, tensor):
+        addr, n, keep = _ptr(tensor)
+        self._keep.append(keep)
+        self._check(self._L.dsmfm_append_batch_device(self._h, addr, n))
+
+    def build_device(self):
+        self._check(self._L.dsmfm_build_device(self._h))
+
+    def fetch(self):
+        idx = Index()
+        self._check(self._L.dsmfm_fetch(self._h, C.byref(idx)))
+        self.index = idx
+        return idx
+
+    def finish(self):
+        """TextCollectionBuilder::InitTextCollection."""
+        idx = Index()
+        self._check(self._L.dsmfm_finish(self._h, C.byref(idx)))
+        self.index = idx
+        self._keep = []
+        return idx
+
+    def fmi(self):
+        return fmi_bytes(self.index)
+
+    def bwt(self):
+        if not self.index or not self.index.bwt:
+            raise RuntimeError("build with FLAG_KEEP_BWT")
+        return C.string_at(self.index.bwt, self.index.n)
+
+    def suffix_array(self, first=0, count=None):
+        import numpy as np
+        if count is None:
+            count = self.index.n - first
+        out = np.empty(count, dtype=np.uint32)
+        self._check(self._L.dsmfm_copy_sa(self._h, out.ctypes.data, first, count))
+        return out
+
+    def save(self, prefix):
+        rc = self._L.dsmfm_write_fmi(C.byref(self.index), os.fsencode(prefix))
+        if rc != OK:
+            raise DsmfmError(rc, "dsmfm_write_fmi failed")
+
+    def stats(self):
+        s = Stats()
+        self._check(self._L.dsmfm_get_stats(self._h, C.byref(s)))
+        return s
+
+    def close(self):
+        if self._h:
+            self._L.dsmfm_destroy(self._h)
+            self._h = C.c_void_p()
+            self.index = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def build_fmi(docs, **kw):
+    """docs: '\\0'-terminated documents (bytes-like).  Returns the .fmi bytes."""
+    with Builder(**kw) as b:
+        if len(docs):
+            b.append_batch(docs)
+        b.finish()
+        return b.fmi()
+
+
+def radix_sort(keys, vals, begin_bit=0, end_bit=64, device=0):
+    """In-place stable sort of numpy uint64 keys / uint32 vals with the build's one-sweep kernels."""
+    L = lib()
+    rc = L.dsmfm_dbg_radix_sort(device, keys.ctypes.data, vals.ctypes.data, keys.size, begin_bit, end_bit)
+    if rc != OK:
+        raise DsmfmError(rc, (L.dsmfm_last_error(None) or b"").decode())
+
+
+def wavelet_fmi(seq, device=0):
+    """.fmi bytes of a wavelet tree built over an arbitrary byte sequence (numberOfTexts/maxTextLength = 0)."""
+    L = lib()
+    addr, n, keep = _ptr(seq)
+    idx = Index()
+    owner = C.c_void_p()
+    rc = L.dsmfm_dbg_wavelet(device, addr, n, C.byref(idx), C.byref(owner))
+    if rc != OK:
+        raise DsmfmError(rc, (L.dsmfm_last_error(None) or b"").decode())
+    try:
+        return fmi_bytes(idx)
+    finally:
+        L.dsmfm_dbg_free_index(owner)

@@ -1,0 +1,230 @@
+// builder -- drop-in replacement of the reference's `builder` command line
+// (builder.cpp:287-471): `builder [-s N] [-v] <input or -> [output]` reads a
+// FASTA file and writes `<output or input>.fmi`.  The front end reproduces the
+// reference's record handling (builder.cpp:203-262) and per-read transform
+// (builder.cpp:60-104, 183-201); the index itself is built on the GPU behind
+// TextCollectionBuilder.  There is no CPU fallback.
+#include "TextCollectionBuilder.h"
+
+#include <chrono>
+#include <cstdlib>
+#include <fstream>
+#include <getopt.h>
+#include <iostream>
+#include <sstream>
+#include <string>
+
+namespace {
+
+bool g_verbose = false;
+
+struct Clock
+{
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double seconds() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// Symbol classes of the reference's normalize() (builder.cpp:60-104): lower-case
+// acgtn are folded to upper case, ACGTN and the colour-space symbols 0123. pass,
+// everything else becomes N and is reported once per record.
+struct SymbolTable
+{
+    unsigned char map[256];
+    bool valid[256];
+    unsigned char comp[256];
+    SymbolTable()
+    {
+        for (int c = 0; c < 256; ++c) { map[c] = 'N'; valid[c] = false; comp[c] = (unsigned char)c; }
+        const char *keep = "ACGTN0123.";
+        for (const char *k = keep; *k; ++k) { map[(unsigned char)*k] = (unsigned char)*k; valid[(unsigned char)*k] = true; }
+        const char *lower = "acgtn";
+        for (const char *k = lower; *k; ++k) { map[(unsigned char)*k] = (unsigned char)(*k - 'a' + 'A'); valid[(unsigned char)*k] = true; }
+        comp['A'] = 'T'; comp['T'] = 'A'; comp['C'] = 'G'; comp['G'] = 'C'; // builder.cpp:35-55
+    }
+};
+const SymbolTable kSym;
+
+// doc = reverse(read + '-' + revcomp(read)) = complement(read) + '-' + reverse(read)   (builder.cpp:183-201)
+void make_document(std::string const &read, std::string const &name, std::string &doc)
+{
+    const size_t len = read.size();
+    std::string offending;
+    doc.resize(2 * len + 1);
+    for (size_t i = 0; i < len; ++i)
+    {
+        const unsigned char raw = (unsigned char)read[i];
+        if (!kSym.valid[raw] && offending.find((char)raw) == std::string::npos) offending += (char)raw;
+        const unsigned char c = kSym.map[raw];
+        doc[i] = (char)kSym.comp[c];
+        doc[2 * len - i] = (char)c;
+    }
+    doc[len] = '-';
+    if (!offending.empty())
+        std::cerr << "Warning: sequence " << name << " contains invalid symbol(s): " << offending << std::endl;
+}
+
+void usage(char const *name)
+{
+    std::cerr << "usage: " << name << " [options] <input> [output]" << std::endl
+              << "Check README or `" << name << " --help' for more information." << std::endl;
+}
+
+void help(char const *name)
+{
+    std::cerr << "usage: " << name << " [options] <input> [output]" << std::endl << std::endl
+              << "<input> is the input filename. "
+              << "If no output filename is given, the index is stored as <input>.fmi" << std::endl << std::endl
+              << "Options:" << std::endl
+              << " -s <int>, --sample-rate <int> Sampling rate for the index, a smaller number " << std::endl
+              << "                               yields a bigger index but can decrease search " << std::endl
+              << "                               time (default: " << TEXTCOLLECTION_DEFAULT_SAMPLERATE << ")." << std::endl
+              << " -h, --help                    Display command line options." << std::endl
+              << " -v, --verbose                 Print progress information." << std::endl;
+}
+
+int parse_int_at_least(char const *value, int min, char const *parameter, char const *name)
+{
+    std::istringstream iss(value);
+    int i;
+    char c;
+    const bool ok = (iss >> i) && !iss.get(c);
+    if (!ok || i < min)
+    {
+        std::cerr << "readaligner: argument of " << parameter << " must be "
+                  << (ok ? "" : "of type <int>, and ") << "greater than or equal to " << min << std::endl
+                  << "Check README or `" << name << " --help' for more information." << std::endl;
+        std::exit(1);
+    }
+    return i;
+}
+
+void build(std::istream &in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
+{
+    TextCollectionBuilder *tcb = new TextCollectionBuilder(samplerate, 1);
+    unsigned long bases = 0;
+    unsigned records = 0;
+    std::string seq, name = "undef", row, doc;
+
+    auto flush = [&]() {
+        bases += seq.size();
+        if (!seq.empty())
+        {
+            make_document(seq, name, doc);
+            tcb->InsertText((uchar const *)doc.c_str(), name);
+        }
+        seq.clear();
+    };
+
+    // `getline(...).good()`: a last line without '\n' sets eofbit and is dropped (builder.cpp:211)
+    while (std::getline(in, row).good())
+    {
+        if (!row.empty() && row[0] == '>')
+        {
+            // name = header without leading blanks, cut at the first blank (builder.cpp:215-216);
+            // like the reference, a header consisting only of '>' throws std::out_of_range
+            row = row.substr(row.find_first_not_of(" \t", 1));
+            row = row.substr(0, row.find_first_of(" \t"));
+            ++records;
+            if (row.empty())
+            {
+                std::ostringstream ss;
+                ss << records - 2;
+                row = ss.str();
+            }
+            if (g_verbose && records % 1000000 == 0)
+                std::cerr << "Inserting: " << row << " (" << (bases + seq.size()) / (1024 * 1024) << " MB, elapsed "
+                          << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)" << std::endl;
+            flush();
+            name = row;
+        }
+        else
+            seq.append(row);
+    }
+    flush();
+
+    std::cerr << "Warning: not thread-safe" << std::endl;
+    if (g_verbose)
+        std::cerr << "Creating new index with " << records << " sequences, total " << bases << " bytes, "
+                  << bases / 1024 << " kb (elapsed " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)"
+                  << std::endl;
+
+    TextCollection *tc = tcb->InitTextCollection(false, false, 0);
+    delete tcb;
+    tcb = 0;
+
+    if (g_verbose)
+        std::cerr << tc->buildReport() << std::endl
+                  << "Saving to file " << outputfile << std::endl
+                  << "(total wall-clock time " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)"
+                  << std::endl;
+    tc->save(outputfile);
+    delete tc;
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    std::cerr << "Warning: Reversing the string by default" << std::endl;
+    if (argc == 1)
+    {
+        usage(argv[0]);
+        return 1;
+    }
+    unsigned samplerate = 0;
+    static struct option long_options[] = {{"sample-rate", required_argument, 0, 's'},
+                                           {"help", no_argument, 0, 'h'},
+                                           {"verbose", no_argument, 0, 'v'},
+                                           {0, 0, 0, 0}};
+    int option_index = 0, c;
+    // same option string as the reference (builder.cpp:353): -c, -R and -F are accepted by getopt
+    // and then rejected, exactly as upstream
+    while ((c = getopt_long(argc, argv, "cR:s:F:hv", long_options, &option_index)) != -1)
+    {
+        switch (c)
+        {
+        case 's': samplerate = (unsigned)parse_int_at_least(optarg, 1, "-s, --sample-rate", argv[0]); break;
+        case 'h': help(argv[0]); return 0;
+        case 'v': g_verbose = true; break;
+        case '?': usage(argv[0]); return 1;
+        default: usage(argv[0]); std::abort();
+        }
+    }
+    std::cerr << "Warning: sampling is disabled!" << std::endl;
+    if (samplerate && samplerate <= 3)
+        std::cerr << "Warning: small samplerates (-s, --sample-rate) may yield infeasible index sizes" << std::endl;
+    if (argc - optind < 1)
+    {
+        std::cerr << "readaligner: no input filename given!" << std::endl;
+        usage(argv[0]);
+        return 1;
+    }
+    if (argc - optind > 2)
+        std::cerr << "Warning: too many filenames given! Ignoring all but first two." << std::endl;
+
+    const std::string inputfile = argv[optind++];
+    std::string outputfile = optind != argc ? std::string(argv[optind++]) : inputfile; // ".fmi" is added by save()
+
+    std::ifstream file;
+    std::istream *in = &std::cin;
+    if (inputfile != "-")
+    {
+        file.open(inputfile.c_str());
+        in = &file;
+    }
+    if (!in->good())
+    {
+        std::cerr << "builder: unable to read input file " << inputfile << std::endl;
+        return 1;
+    }
+
+    std::cerr << std::fixed;
+    std::cerr.precision(2);
+    Clock wall;
+    if (g_verbose) std::cerr << "Building the forward index:" << std::endl;
+    build(*in, outputfile, samplerate, wall);
+    if (g_verbose)
+        std::cerr << "Skipping reverse indexing. Save complete. (total wall-clock time " << wall.seconds() << " s, "
+                  << wall.seconds() / 3600 << " hours)" << std::endl;
+    return 0;
+}

@@ -1,0 +1,194 @@
+/*
+ * dsmfm.h -- C ABI of the B200-native FM-index construction path.
+ *
+ * This is the drop-in boundary for ONE path of HIITMetagenomics/dsm-framework:
+ * what `builder -v input.fasta` does between TextCollectionBuilder::InsertText
+ * and the bytes of the `.fmi` file.  The reference has no plugin ABI for this
+ * path -- it is a C++ class (TextCollectionBuilder.h:41-73) over incbwt -- so
+ * the entry points below are what a binding from the reference's C++ facade
+ * binds; INTEGRATION.md shows that binding.  Each entry point cites the
+ * reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Plain C, plain pointers and sizes; no CUDA, torch or C++ types.  All entry
+ * points return 0 on success or a negative DSMFM_E* code; the message is then
+ * available from dsmfm_last_error().  There is NO CPU fallback: without a
+ * usable sm_100 device dsmfm_create fails with DSMFM_ECUDA.
+ *
+ * Threading: one builder per thread, not re-entrant per handle (the reference
+ * is "not thread-safe" as well, builder.cpp:266).
+ */
+#ifndef DSMFM_H_
+#define DSMFM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSMFM_API __attribute__((visibility("default")))
+
+#define DSMFM_VERSION 1
+
+enum {
+    DSMFM_OK = 0,
+    DSMFM_EINVAL = -1,  /* bad argument / call order (e.g. append after finish) */
+    DSMFM_ECUDA = -2,   /* CUDA runtime error, or no usable device            */
+    DSMFM_ENOMEM = -3,  /* host or device allocation failed                    */
+    DSMFM_EEMPTY = -4,  /* an empty document was inserted                      */
+    DSMFM_ELIMIT = -5,  /* input exceeds a limit of this build (see message)   */
+    DSMFM_EIO = -6      /* file write error                                    */
+};
+
+/* Default SA sample rate written into the .fmi header
+ * (TEXTCOLLECTION_DEFAULT_SAMPLERATE, TextCollectionBuilder.h:30). */
+#define DSMFM_DEFAULT_SAMPLERATE 124
+
+typedef struct dsmfm_builder dsmfm_builder;
+
+typedef struct dsmfm_options {
+    int32_t device;          /* CUDA device ordinal; -1 = current device                         */
+    uint32_t samplerate;     /* 0 -> 124, as TextCollectionBuilder.cpp:37-39                      */
+    uint64_t expected_bytes; /* hint: total bytes of documents incl. terminators (0 = unknown)    */
+    void *stream;            /* cudaStream_t to run on; NULL = the builder creates its own        */
+    uint32_t flags;          /* DSMFM_FLAG_*                                                      */
+    uint32_t reserved;
+} dsmfm_options;
+
+#define DSMFM_FLAG_KEEP_BWT 1u /* keep the plain BWT in host memory after finish (dsmfm_index.bwt)   */
+#define DSMFM_FLAG_KEEP_SA 2u  /* keep the suffix array on the device for dsmfm_write_sa / debugging */
+
+/* One Huffman code-table entry: HuffWT::TCodeEntry, HuffWT.h:13-19. */
+typedef struct dsmfm_code {
+    uint64_t count;
+    uint32_t bits;
+    uint32_t code;
+} dsmfm_code;
+
+/* One wavelet-tree node in pre-order: HuffWT members (HuffWT.h:48-53) plus its
+ * BitRank (BitRank.h:19-24).  For a leaf only `leaf` and `ch` are meaningful. */
+typedef struct dsmfm_node {
+    uint8_t leaf;
+    uint8_t ch;            /* first symbol of the node's subsequence (HuffWT.cpp:8) */
+    uint8_t pad[6];
+    uint64_t nbits;        /* BitRank::n                                             */
+    uint64_t integers;     /* BitRank::integers = ceil((n+1)/64)                     */
+    const uint64_t *data;  /* [integers]                                             */
+    const uint64_t *Rs;    /* [nbits/256 + 1]                                        */
+    const uint8_t *Rb;     /* [nbits/64 + 1]                                         */
+} dsmfm_node;
+
+/* Everything FMIndex::save (FMIndex.cpp:155-217) writes, as host pointers that
+ * stay valid until dsmfm_destroy. */
+typedef struct dsmfm_index {
+    uint64_t n;              /* indexed symbols incl. terminators (FMIndex::n)           */
+    uint32_t samplerate;
+    uint32_t number_of_texts;
+    uint64_t max_text_length;
+    uint64_t C[256];         /* FMIndex.cpp:397-409                                      */
+    dsmfm_code codetable[256];
+    uint32_t n_nodes;
+    uint32_t reserved;
+    const dsmfm_node *nodes; /* pre-order, n_nodes entries                               */
+    const uint8_t *bwt;      /* [n] if DSMFM_FLAG_KEEP_BWT, else NULL                    */
+} dsmfm_index;
+
+/* Per-build measurements (device times from CUDA events on the build stream). */
+typedef struct dsmfm_stats {
+    uint64_t n;                  /* indexed symbols                                        */
+    uint64_t bases;              /* sum of document lengths excl. terminators              */
+    uint32_t bits_per_symbol;    /* 3, 4 or 8                                               */
+    uint32_t sigma;              /* distinct non-terminator symbols                        */
+    uint32_t rounds;             /* refinement rounds run after the initial sort           */
+    uint32_t kernel_launches;    /* kernels launched by the build (our own kernels only)   */
+    uint64_t active[32];         /* suffixes in non-singleton groups entering round r      */
+    uint64_t fallback_elems;     /* suffixes that went through the large-group path        */
+    float ms_total;              /* whole device build                                      */
+    float ms_pack;               /* histogram + pack                                        */
+    float ms_sort;               /* key build + LSD radix sort + head marking               */
+    float ms_sort_pass;          /* mean duration of one onesweep pass (dominant kernel)    */
+    float ms_refine;             /* all refinement rounds                                   */
+    float ms_bwt;                /* BWT emission                                            */
+    float ms_wt;                 /* wavelet tree + BitRank directories                      */
+    float ms_h2d;                /* last finish: host->device copies not overlapped         */
+    float ms_d2h;                /* last finish: device->host of the sections               */
+    uint32_t sort_passes;        /* onesweep launches in the initial sort                   */
+    uint32_t reserved;
+    uint64_t sort_pass_bytes;    /* algorithmic bytes moved by ONE onesweep pass            */
+    uint64_t device_bytes_peak;  /* peak device memory held by the builder                  */
+} dsmfm_stats;
+
+/* Replaces: TextCollectionBuilder::TextCollectionBuilder (TextCollectionBuilder.cpp:32-57). */
+DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out);
+
+/* Replaces: TextCollectionBuilder::InsertText -> RLCSABuilder::insertSequence
+ * (TextCollectionBuilder.cpp:65-98; incbwt/rlcsa_builder.cpp:36-78).
+ * `doc` holds `len` symbols from [1,255] (no terminator); it is copied.  The
+ * i-th call gets document id i-1.  len == 0 -> DSMFM_EEMPTY (the reference
+ * prints an error and exits, TextCollectionBuilder.cpp:86-91). */
+DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len);
+
+/* Bulk form of dsmfm_append: `bytes` bytes holding documents each followed by
+ * one '\0' (the layout RLCSABuilder keeps in its buffer, rlcsa_builder.cpp:54-60).
+ * The last byte must be '\0'.  Document count and longest length are taken on
+ * the device. */
+DSMFM_API int dsmfm_append_batch(dsmfm_builder *b, const uint8_t *docs, size_t bytes);
+
+/* Same, but `docs` is DEVICE memory on the builder's device (inputs already
+ * resident in HBM); copied device-to-device on the builder's stream. */
+DSMFM_API int dsmfm_append_batch_device(dsmfm_builder *b, const void *docs_dev, size_t bytes);
+
+/* Replaces: TextCollectionBuilder::InitTextCollection -> RLCSABuilder::getBWT
+ * -> FMIndex::FMIndex -> makewavelet -> HuffWT::makeHuffWT -> BitRank::BuildRank
+ * (TextCollectionBuilder.cpp:100-152; rlcsa_builder.cpp:166-179; FMIndex.cpp:92-123,
+ * 395-425; HuffWT.cpp:5-55,133-192; BitRank.cpp:89-103,154-187).
+ * Runs the whole device path and returns the finished sections in host
+ * memory.  No documents -> the reference's one-symbol "\0" index
+ * (TextCollectionBuilder.cpp:111-119).  Further appends fail. */
+DSMFM_API int dsmfm_finish(dsmfm_builder *b, dsmfm_index *out);
+
+/* The two halves of dsmfm_finish, for measuring the device path alone:
+ * dsmfm_build_device runs every kernel and leaves the sections in HBM;
+ * dsmfm_fetch copies them to the host and fills `out`. */
+DSMFM_API int dsmfm_build_device(dsmfm_builder *b);
+DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out);
+
+/* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
+ * byte-for-byte in the reference layout (version 17). */
+DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix);
+
+/* Serialise the same bytes into memory.  dsmfm_fmi_size gives the exact size. */
+DSMFM_API uint64_t dsmfm_fmi_size(const dsmfm_index *idx);
+DSMFM_API int dsmfm_fmi_serialize(const dsmfm_index *idx, uint8_t *out, uint64_t out_cap);
+
+/* Copy suffix-array entries [first, first+count) (text positions) to the host;
+ * needs DSMFM_FLAG_KEEP_SA.  For tests and the .sa writer. */
+DSMFM_API int dsmfm_copy_sa(dsmfm_builder *b, uint32_t *out, uint64_t first, uint64_t count);
+
+DSMFM_API int dsmfm_get_stats(const dsmfm_builder *b, dsmfm_stats *out);
+
+/* Message of the last failure on this handle (or of a failed dsmfm_create when b == NULL). */
+DSMFM_API const char *dsmfm_last_error(const dsmfm_builder *b);
+
+/* Replaces: TextCollectionBuilder::~TextCollectionBuilder + ~FMIndex. */
+DSMFM_API void dsmfm_destroy(dsmfm_builder *b);
+
+DSMFM_API int dsmfm_version(void);
+
+/* ---- kernel-level entry points used by the unit tests (host buffers in/out) ---- */
+
+/* Stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit) with
+ * the same onesweep kernels the build uses.  Sorts in place. */
+DSMFM_API int dsmfm_dbg_radix_sort(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit);
+
+/* Wavelet tree + BitRank directories for an arbitrary byte sequence (the
+ * HuffWT::makeHuffWT path alone); `out` pointers are valid until
+ * dsmfm_dbg_free_index. */
+DSMFM_API int dsmfm_dbg_wavelet(int device, const uint8_t *seq, uint64_t n, dsmfm_index *out, void **owner);
+DSMFM_API void dsmfm_dbg_free_index(void *owner);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMFM_H_ */

@@ -1,0 +1,50 @@
+"""Seeded small inputs shared by the golden-file generator and the parity tests."""
+import random
+
+
+def rnd_fasta(seed, nreads, maxlen, alpha="ACGT", dup=0.2, pn=0.02, genome=2000, minlen=1, lower=0.0, wrap=0):
+    rng = random.Random(seed)
+    g = "".join(rng.choice(alpha) for _ in range(genome))
+    reads, out = [], []
+    for i in range(nreads):
+        if reads and rng.random() < dup:
+            r = rng.choice(reads)
+        else:
+            ln = rng.randint(minlen, maxlen)
+            s = rng.randint(0, genome - ln)
+            r = "".join("N" if rng.random() < pn else c for c in g[s:s + ln])
+            if lower and rng.random() < lower:
+                r = r.lower()
+        reads.append(r)
+        body = r if not wrap else "\n".join(r[j:j + wrap] for j in range(0, len(r), wrap))
+        out.append(">r%d some description\n%s\n" % (i, body))
+    return "".join(out).encode()
+
+
+# name -> FASTA bytes.  Small enough for the plain-C oracle and for committing the reference's output.
+def golden_cases():
+    c = {}
+    c["empty"] = b""
+    c["single"] = b">a\nACGT\n"
+    c["no_trailing_newline"] = b">a\nACGT\n>b\nGGCA"          # last line dropped (builder.cpp:211)
+    c["multiline_and_blank"] = b">a\nAC\nGT\n>b\n\n>c\nacgtnxyz0123.\n>d \tname cut\nTTTT\n"
+    c["crlf"] = b">a\r\nACGT\r\n>b\r\nGG\r\n"                  # '\r' is an invalid symbol -> N
+    c["no_header_first"] = b"ACGT\n>b\nGGA\n"
+    c["duplicates"] = (b">x\nACGTACGTAC\n" * 7) + b">y\nACGTACGTAC\n>z\nCGTACGTACG\n"
+    c["one_base_reads"] = b"".join(b">r%d\n%s\n" % (i, b"ACGTN"[i % 5:i % 5 + 1]) for i in range(23))
+    c["poly_a"] = rnd_fasta(3, 200, 40, alpha="A", genome=100)          # huge tie groups
+    c["two_letter"] = rnd_fasta(4, 300, 50, alpha="AC", genome=100)
+    c["colour_space"] = rnd_fasta(5, 150, 35, alpha="0123.", genome=400, pn=0.0)   # 4-bit alphabet
+    c["mixed_alphabet"] = rnd_fasta(6, 150, 35, alpha="ACGT0123.", genome=400)     # sigma = 11
+    c["small_random"] = rnd_fasta(7, 50, 30)
+    c["reads100"] = rnd_fasta(8, 400, 100, minlen=100, genome=3000, lower=0.3, wrap=60)
+    return c
+
+
+# Larger seeded cases: only their SHA-256 is committed (tests/golden/manifest.json).
+def digest_cases():
+    c = {}
+    c["reads100_3k"] = rnd_fasta(9, 3000, 100, minlen=100, genome=5000)
+    c["ragged_2k"] = rnd_fasta(10, 2000, 150, genome=4000, dup=0.3)
+    c["high_coverage"] = rnd_fasta(11, 4000, 60, minlen=60, genome=600, dup=0.0, pn=0.0)
+    return c

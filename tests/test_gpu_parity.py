@@ -1,0 +1,236 @@
+"""GPU suite: the CUDA path, called through the C ABI (libdsmfm.so), against the oracle and the
+golden files of the unmodified reference.  Bit-exact everywhere (integer / byte work)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MANIFEST = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+
+
+def _golden(name, ext):
+    with open(os.path.join(GOLDEN, name + ext), "rb") as f:
+        return f.read()
+
+
+def _build(docs, **kw):
+    import dsmfm
+    return dsmfm.build_fmi(docs, **kw)
+
+
+def _assert_same_fmi(got, want):
+    assert oracle.diff_fmi(got, want) == []
+    assert got == want
+
+
+# ---- kernels in isolation -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 100_003, 3_000_000])
+@pytest.mark.parametrize("bits", [(0, 64), (0, 63), (3, 19), (0, 5)])
+def test_radix_sort_matches_stable_numpy_sort(n, bits):
+    import dsmfm
+    rng = np.random.default_rng(n * 131 + bits[1])
+    keys = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    if n > 1000:  # plant long runs of equal keys to exercise stability
+        keys[: n // 3] = keys[0]
+    vals = np.arange(n, dtype=np.uint32)
+    lo, hi = bits
+    mask = np.uint64(((1 << (hi - lo)) - 1) << lo) if hi - lo < 64 else np.uint64(2**64 - 1)
+    order = np.argsort(keys & mask, kind="stable")
+    k, v = keys.copy(), vals.copy()
+    dsmfm.radix_sort(k, v, lo, hi)
+    assert np.array_equal(v, vals[order])
+    assert np.array_equal(k, keys[order])
+
+
+def test_radix_sort_dna_like_keys():
+    """3-bit symbols, only 5 of 8 codes in use: the skewed digit histograms of the real workload."""
+    import dsmfm
+    rng = np.random.default_rng(7)
+    n = 1_500_000
+    sym = rng.choice(np.array([2, 3, 4, 6], dtype=np.uint64), size=(n, 21))
+    keys = np.zeros(n, dtype=np.uint64)
+    for j in range(21):
+        keys = (keys << np.uint64(3)) | sym[:, j]
+    vals = np.arange(n, dtype=np.uint32)
+    order = np.argsort(keys, kind="stable")
+    k, v = keys.copy(), vals.copy()
+    dsmfm.radix_sort(k, v, 0, 63)
+    assert np.array_equal(v, vals[order])
+
+
+@pytest.mark.parametrize("alpha,n", [(b"\0-ACGNT", 1), (b"\0-ACGNT", 63), (b"\0-ACGNT", 64), (b"\0-ACGNT", 8191),
+                                     (b"\0-ACGNT", 8192), (b"\0-ACGNT", 300_001), (b"A", 1000), (b"AB", 5000),
+                                     (bytes(range(256)), 70_000), (b"\0-.0123ACGNT", 50_000)])
+def test_wavelet_tree_and_bitrank_match_oracle(alpha, n):
+    import dsmfm
+    rng = np.random.default_rng(n)
+    # skewed symbol frequencies, like a BWT of reads
+    w = rng.random(len(alpha)) ** 3 + 1e-3
+    seq = np.frombuffer(alpha, dtype=np.uint8)[rng.choice(len(alpha), size=n, p=w / w.sum())]
+    got = dsmfm.wavelet_fmi(seq)
+    want = oracle.fmi_from_bwt(seq.tobytes(), 124, 0, 0)
+    _assert_same_fmi(got, want)
+
+
+# ---- the whole path against the reference's golden files -------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(MANIFEST["files"]))
+def test_build_matches_reference_golden_file(name):
+    docs, nd = oracle.fasta_to_docs(_golden(name, ".fasta"))
+    _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
+
+
+def test_samplerate_option():
+    docs, _ = oracle.fasta_to_docs(_golden("small_random", ".fasta"))
+    assert _build(docs, samplerate=32) == _golden("small_random", ".s32.fmi")
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST["digests"]))
+def test_build_matches_reference_digest(name):
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()[name])
+    got = _build(docs)
+    assert len(got) == MANIFEST["digests"][name]["fmi_bytes"]
+    assert hashlib.sha256(got).hexdigest() == MANIFEST["digests"][name]["fmi_sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST["generated"]))
+def test_build_matches_reference_on_generated_reads(name):
+    import dsmgen
+    g = MANIFEST["generated"][name]
+    got = _build(dsmgen.docs(**g["params"]))
+    assert len(got) == g["fmi_bytes"]
+    assert hashlib.sha256(got).hexdigest() == g["fmi_sha256"]
+
+
+# ---- against the oracle on seeded inputs, including the intermediate products ------------------------
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(nreads=500, maxlen=100, genome=2000)),
+    (2, dict(nreads=3000, maxlen=60, minlen=60, genome=500, dup=0.0, pn=0.0)),   # deep ties
+    (3, dict(nreads=800, maxlen=300, genome=1200, dup=0.4)),                     # long ragged reads
+    (4, dict(nreads=2500, maxlen=45, alpha="A", genome=64)),                     # groups beyond one CTA
+    (5, dict(nreads=700, maxlen=80, alpha="ACGT0123.", genome=900)),             # 4 bits per symbol
+])
+def test_suffix_array_bwt_and_index_match_oracle(seed, kw):
+    import dsmfm
+    docs, nd = oracle.fasta_to_docs(cases.rnd_fasta(seed, **kw))
+    want_bwt, want_sa = oracle.bwt(docs, want_sa=True)
+    with dsmfm.Builder(flags=dsmfm.FLAG_KEEP_BWT | dsmfm.FLAG_KEEP_SA) as b:
+        b.append_batch(docs)
+        idx = b.finish()
+        assert idx.n == len(docs) and idx.number_of_texts == nd
+        assert idx.max_text_length == oracle.doc_stats(docs)[1]
+        sa = b.suffix_array()
+        bad = np.nonzero(sa.astype(np.uint64) != want_sa)[0]
+        assert bad.size == 0, "first suffix-array mismatch at rank %d" % bad[0]
+        assert b.bwt() == want_bwt
+        _assert_same_fmi(b.fmi(), oracle.fmi_from_docs(docs))
+
+
+def test_arbitrary_byte_alphabet():
+    """TextCollectionBuilder admits any byte 1..255 (TextCollectionBuilder.h:52): 8 bits per symbol."""
+    rng = np.random.default_rng(11)
+    parts = []
+    for _ in range(300):
+        ln = int(rng.integers(1, 120))
+        parts.append(rng.integers(1, 256, size=ln, dtype=np.uint8).tobytes() + b"\0")
+    docs = b"".join(parts)
+    _assert_same_fmi(_build(docs), oracle.fmi_from_docs(docs))
+
+
+def test_insert_text_one_by_one_equals_batch():
+    import dsmfm
+    docs, nd = oracle.fasta_to_docs(_golden("reads100", ".fasta"))
+    with dsmfm.Builder() as b:
+        for d in docs.split(b"\0")[:-1]:
+            b.insert_text(d)
+        b.finish()
+        assert b.fmi() == _golden("reads100", ".fmi")
+
+
+def test_error_behaviour():
+    import dsmfm
+    with dsmfm.Builder() as b:
+        with pytest.raises(dsmfm.DsmfmError) as e:
+            b.insert_text(b"")                       # TextCollectionBuilder.cpp:86-91
+        assert e.value.code == dsmfm.EEMPTY
+    with dsmfm.Builder() as b:
+        b.append_batch(b"AC\0\0GT\0")                # empty document inside a batch
+        with pytest.raises(dsmfm.DsmfmError) as e:
+            b.finish()
+        assert e.value.code == dsmfm.EEMPTY
+    with dsmfm.Builder() as b:
+        with pytest.raises(dsmfm.DsmfmError) as e:
+            b.append_batch(b"ACGT")                  # unterminated
+        assert e.value.code == dsmfm.EINVAL
+    with dsmfm.Builder() as b:
+        b.append_batch(b"ACGT\0")
+        b.finish()
+        with pytest.raises(dsmfm.DsmfmError) as e:   # TextCollectionBuilder.cpp:67-71
+            b.insert_text(b"AC")
+        assert e.value.code == dsmfm.EINVAL
+
+
+def test_stats_are_reported():
+    import dsmfm
+    import dsmgen
+    kw = MANIFEST["generated"]["gen_20k"]["params"]
+    with dsmfm.Builder() as b:
+        b.append_batch(dsmgen.docs(**kw))
+        b.finish()
+        s = b.stats()
+        assert s.n == 20_000 * 202 and s.bases == 20_000 * 201
+        assert s.bits_per_symbol == 3 and s.sigma == 6
+        assert s.sort_passes == 8 and s.kernel_launches > 10
+        assert s.rounds >= 1 and s.active[0] > 0
+        assert s.ms_total > 0 and s.ms_sort_pass > 0
+
+
+# ---- the drop-in CLI ----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["empty", "multiline_and_blank", "no_trailing_newline", "crlf", "reads100",
+                                  "mixed_alphabet"])
+def test_builder_cli_writes_the_reference_bytes(name, tmp_path):
+    exe = os.path.join(ROOT, "dsm-framework_b200", "builder")
+    fa = tmp_path / (name + ".fasta")
+    fa.write_bytes(_golden(name, ".fasta"))
+    r = subprocess.run([exe, "-v", str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = open(str(fa) + ".fmi", "rb").read()
+    _assert_same_fmi(got, _golden(name, ".fmi"))
+    # explicit output name and stdin input (builder.cpp:396-397, 426-427)
+    r = subprocess.run([exe, "-", str(tmp_path / "out")], input=_golden(name, ".fasta"), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    assert open(str(tmp_path / "out.fmi"), "rb").read() == _golden(name, ".fmi")
+
+
+def test_builder_cli_samplerate(tmp_path):
+    exe = os.path.join(ROOT, "dsm-framework_b200", "builder")
+    fa = tmp_path / "s.fasta"
+    fa.write_bytes(_golden("small_random", ".fasta"))
+    subprocess.run([exe, "-s", "32", str(fa)], check=True, capture_output=True)
+    assert open(str(fa) + ".fmi", "rb").read() == _golden("small_random", ".s32.fmi")
+
+
+# ---- live differential runs when the compiled reference travelled with the snapshot --------------------
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not present")
+def test_toydata_shaped_sample_matches_live_reference(tmp_path):
+    """A 60k-read toydata-shaped sample through both builders (the reference needs ~8 s for it)."""
+    import dsmgen
+    kw = dict(seed=31, pool_seed=99, pool_size=16, n_genomes=10, genome_len=60_000, n_reads=60_000, read_len=100,
+              sub=0.005, pn=0.001)
+    fasta = dsmgen.fasta(**kw).tobytes()
+    want = oracle.reference_build(fasta, tmp_path)
+    _assert_same_fmi(_build(dsmgen.docs(**kw)), want)
