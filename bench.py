@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- FM-index build throughput (Mbp/s) of the B200-native `builder` path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation
+
+A step = one complete FM-index build (pack, suffix sort, BWT, HuffWT + BitRank) of one synthetic
+sample.  N=1: the 1 Gbp sample of BASELINE.json configs[2] (SURVEY 8d "C3": 10M x 100-bp reads,
+n = 2.02 G indexed symbols).  N>1 (torchrun, one rank per GPU): every rank builds the index of its
+own 1 Gbp block of reads (weak scaling, no data-path collective; the cross-GPU BWT merge of the
+north star is not built yet, so the result is one index per GPU).
+
+value   = input bases of all ranks / max-over-ranks device time, documents already resident in HBM.
+e2e     = the same through the C ABI with HOST buffers: dsmfm_append_batch from pinned host memory
+          (H2D inside the timed region) ... dsmfm_finish (sections copied back to the host).
+roofline: the dominant kernel is one LSD pass of the one-sweep radix sort (8 launches per build);
+          achieved = 24 B/pair (8+4 read, 8+4 written) x n pairs / mean pass time (CUDA events on
+          the build stream, recorded inside the library around the 8 passes of every timed step).
+cpu_baseline: the UNMODIFIED reference `builder` (oracle/_ref/builder, single-threaded as shipped)
+          on a bounded toydata-shaped sample, on this box's host cores, rank 0 at N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dsm-framework_b200"))
+
+WORKLOADS = {
+    # name -> generator parameters (dsmgen.CONFIGS) ; per-rank seed offset is added for N>1
+    "C3": "C3",
+    "C1": "C1",
+}
+CPU_SAMPLE = dict(seed=1, pool_seed=1, pool_size=10, n_genomes=10, genome_len=100_000, n_reads=100_000,
+                  read_len=100, sub=0.005, pn=0.001)  # 10 Mbp at the 10x coverage of C1
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="override the number of reads (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # median over the samples taken under load (the upper half by power draw)
+        idx = sorted(range(len(sm)), key=lambda i: power[i])[len(sm) // 2:]
+        load = sorted(sm[i] for i in idx)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def section_bytes(idx):
+    total = 0
+    for i in range(idx.n_nodes):
+        nd = idx.nodes[i]
+        if not nd.leaf:
+            total += 8 * nd.integers + 8 * (nd.nbits // 256 + 1) + (nd.nbits // 64 + 1)
+    return total
+
+
+def cpu_reference_run(threads, params, tmpdir):
+    """Times the reference's own CPU implementation on a bounded sample.  threads == 1: the stock
+    `builder` binary; threads > 1: oracle/_ref/ref_driver, which drives the same reference classes
+    with incbwt's OpenMP sort enabled (RLCSABuilder's `threads` argument)."""
+    import dsmgen
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    bases = params["n_reads"] * params["read_len"]
+    if threads <= 1:
+        path = os.path.join(tmpdir, "cpu_sample.fasta")
+        dsmgen.fasta(**params).tofile(path)
+        t0 = time.perf_counter()
+        subprocess.run([os.path.join(ref, "builder"), path], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+    else:
+        path = os.path.join(tmpdir, "cpu_sample.docs")
+        dsmgen.docs(**params).tofile(path)
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        t0 = time.perf_counter()
+        subprocess.run([os.path.join(ref, "ref_driver"), "fmi", path, os.path.join(tmpdir, "cpu_sample"),
+                        str(threads)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+        dt = time.perf_counter() - t0
+    return bases / dt / 1e6, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import tempfile
+    have = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver"))
+    if not have:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
+        return 0
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    times = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for i in range(args.warmup + args.steps):
+            mbps, dt = cpu_reference_run(threads, CPU_SAMPLE, tmp)
+            if i >= args.warmup:
+                times.append(dt)
+    bases = CPU_SAMPLE["n_reads"] * CPU_SAMPLE["read_len"]
+    total = sum(times)
+    value = bases * len(times) / total / 1e6
+    sample = ("%d x %d-bp reads (%.0f Mbp, 10x coverage, sub 0.005, N 0.001) per step; the reference classes "
+              "(RLCSABuilder -> FMIndex -> HuffWT) driven by oracle/ref_driver.cpp with incbwt's OpenMP sort on "
+              "%d threads" % (CPU_SAMPLE["n_reads"], CPU_SAMPLE["read_len"], bases / 1e6, threads))
+    line = {"impl": "reference", "metric": "fm_index_build_throughput", "value": round(value, 4), "unit": "Mbp/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1000 * total / len(times), 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "bounded sample of " + args.workload + ": " + sample},
+            "cpu_baseline": {"value": round(value, 4), "unit": "Mbp/s", "cores": threads, "kind": "reference",
+                             "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import dsmfm
+    import dsmgen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kw = dict(dsmgen.CONFIGS[WORKLOADS[args.workload]])
+    kw["seed"] += 1000 * rank  # every rank indexes its own block of reads
+    if args.reads:
+        kw["n_reads"] = args.reads
+    n_reads, L = kw["n_reads"], kw["read_len"]
+    bases = n_reads * L
+    nbytes = n_reads * (2 * L + 2)
+
+    host_docs = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dsmgen.docs(out=host_docs, **kw)
+    dev_docs = host_docs.cuda(non_blocking=False)
+    stream = torch.cuda.current_stream()
+    flags = 0
+
+    def device_step():
+        b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
+        b.append_batch_device(dev_docs)
+        b.build_device()
+        s = b.stats()
+        b.close()
+        return s
+
+    def e2e_step():
+        b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
+        b.append_batch(host_docs)
+        idx = b.finish()
+        out_bytes = section_bytes(idx)
+        s = b.stats()
+        b.close()
+        return s, out_bytes
+
+    # ---- device-resident throughput ("value") ------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stats = [device_step() for _ in range(args.steps)]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ---------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_out = [e2e_step() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    barrier()
+    t_e2e = float(t_e2e.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    s0 = stats[-1]
+    pass_ms = sum(s.ms_sort_pass for s in stats) / len(stats)
+    achieved = s0.sort_pass_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
+    profile = {}
+    try:
+        profile = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+    except Exception:
+        pass
+
+    line = {
+        "metric": "fm_index_build_throughput",
+        "value": round(world * bases * args.steps / (ms_total * 1e-3) / 1e6, 2),
+        "unit": "Mbp/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": "%s: %d x %d-bp ACGTN reads per GPU (%.2f Gbp, n = %d indexed symbols), SA + BWT + HuffWT + BitRank"
+                        % (args.workload, n_reads, L, bases / 1e9, nbytes),
+            "parallelism": "1 GPU" if world == 1 else "%d independent samples, one index per GPU (no cross-GPU BWT merge yet)" % world,
+            "cache": "inputs (%.2f GB) and sort buffers are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
+            "bits_per_symbol": s0.bits_per_symbol,
+            "refine_rounds": s0.rounds,
+            "active_fraction_per_round": [round(s0.active[r] / s0.n, 4) for r in range(min(s0.rounds, 32))],
+            "phase_ms": {"pack": round(s0.ms_pack, 2), "sort": round(s0.ms_sort, 2), "refine": round(s0.ms_refine, 2),
+                         "bwt": round(s0.ms_bwt, 2), "wavelet": round(s0.ms_wt, 2), "total": round(s0.ms_total, 2)},
+            "device_bytes_peak": s0.device_bytes_peak,
+        },
+        "clocks": clocks,
+        "e2e": {
+            "value": round(world * bases * args.steps / t_e2e / 1e6, 2),
+            "unit": "Mbp/s",
+            "h2d_bytes_per_step": nbytes,
+            "d2h_bytes_per_step": e2e_out[-1][1],
+            "ms_per_step": round(1000 * t_e2e / args.steps, 2),
+            "api": "dsmfm_create / dsmfm_append_batch (pinned host buffer) / dsmfm_finish / dsmfm_destroy",
+        },
+        "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+        "roofline": {
+            "bound": "hbm",
+            "kernel": "onesweep_kernel (one LSD radix pass over (u64 key, u32 suffix) pairs; %d passes per build)" % s0.sort_passes,
+            "achieved": round(achieved, 1),
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": round(achieved / peak, 4),
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": s0.sort_pass_bytes,
+            "ms_per_launch": round(pass_ms, 4),
+            "traffic": profile.get("onesweep_dram_bytes_per_launch"),
+        },
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        import tempfile
+        try:
+            with tempfile.TemporaryDirectory() as tmp:
+                mbps, dt = cpu_reference_run(1, CPU_SAMPLE, tmp)
+            line["cpu_baseline"] = {
+                "value": round(mbps, 4), "unit": "Mbp/s", "cores": 1, "kind": "reference",
+                "sample": "stock reference `builder` (single-threaded as shipped) on %d x %d-bp reads (%.0f Mbp, same generator "
+                          "and error model as the workload), %.1f s" % (CPU_SAMPLE["n_reads"], CPU_SAMPLE["read_len"],
+                                                                          CPU_SAMPLE["n_reads"] * CPU_SAMPLE["read_len"] / 1e6, dt)}
+        except Exception:  # the compiled reference did not travel: time the oracle port instead
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle
+            small = dict(CPU_SAMPLE, n_reads=20_000, genome_len=20_000)
+            fa = dsmgen.fasta(**small).tobytes()
+            t0 = time.perf_counter()
+            oracle.build(fa)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": round(small["n_reads"] * small["read_len"] / dt / 1e6, 4), "unit": "Mbp/s", "cores": 1,
+                "kind": "port", "sample": "oracle/dsm_oracle.c on %d x %d-bp reads, %.1f s (oracle/_ref absent)"
+                                          % (small["n_reads"], small["read_len"], dt)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
