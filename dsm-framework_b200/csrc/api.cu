@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <queue>
 #include <string>
 #include <vector>
@@ -20,6 +21,65 @@ using namespace dsmfm;
 namespace {
 
 thread_local std::string g_create_error;
+
+// ---------------------------------------------------------------------------
+// Memory: device buffers come from the device's stream-ordered pool
+// (cudaMallocAsync) whose release threshold is raised so that a second build
+// reuses the first one's memory instead of paying for 50 GB of cudaMalloc /
+// cudaFree; pinned host buffers (section copies, append staging) are cached in
+// a small process-wide pool for the same reason.  dsmfm_release_cached() gives
+// both back.
+// ---------------------------------------------------------------------------
+void *dev_alloc(size_t bytes, cudaStream_t st)
+{
+    void *p = nullptr;
+    DSM_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+    return p;
+}
+void dev_free(void *p, cudaStream_t st)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
+struct PinnedPool {
+    struct Buf { void *p; size_t bytes; bool busy; };
+    std::mutex mu;
+    std::vector<Buf> bufs;
+    void *get(size_t bytes)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        int best = -1;
+        for (size_t i = 0; i < bufs.size(); ++i)
+            if (!bufs[i].busy && bufs[i].bytes >= bytes && (best < 0 || bufs[i].bytes < bufs[best].bytes)) best = (int)i;
+        if (best >= 0 && bufs[best].bytes <= 2 * bytes + (1u << 20)) {
+            bufs[best].busy = true;
+            return bufs[best].p;
+        }
+        void *p = nullptr;
+        DSM_CUDA(cudaMallocHost(&p, bytes ? bytes : 1));
+        bufs.push_back(Buf{p, bytes, true});
+        return p;
+    }
+    void put(void *p)
+    {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &b : bufs)
+            if (b.p == p) b.busy = false;
+    }
+    void trim()
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < bufs.size();) {
+            if (!bufs[i].busy) {
+                cudaFreeHost(bufs[i].p);
+                bufs.erase(bufs.begin() + i);
+            } else
+                ++i;
+        }
+    }
+};
+PinnedPool g_pinned;
 
 // ---------------------------------------------------------------------------
 // Huffman code table -- node::makecodetable / maketable, HuffWT.cpp:133-184.
@@ -141,11 +201,11 @@ struct WaveletResult {
     uint8_t *h_sections = nullptr;
     std::vector<uint8_t> h_ch;
 
-    void release()
+    void release(cudaStream_t st = nullptr)
     {
-        if (d_sections) cudaFree(d_sections);
-        if (d_ch) cudaFree(d_ch);
-        if (h_sections) cudaFreeHost(h_sections);
+        dev_free(d_sections, st);
+        dev_free(d_ch, st);
+        g_pinned.put(h_sections);
         d_sections = d_ch = h_sections = nullptr;
     }
 };
@@ -176,8 +236,8 @@ void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, con
         max_sb = std::max<uint64_t>(max_sb, nd.nbits / 256 + 1);
     }
     r.section_bytes = off;
-    DSM_CUDA(cudaMalloc(&r.d_sections, off));
-    DSM_CUDA(cudaMalloc(&r.d_ch, (size_t)m));
+    r.d_sections = static_cast<uint8_t *>(dev_alloc(off, st));
+    r.d_ch = static_cast<uint8_t *>(dev_alloc((size_t)m, st));
     DSM_CUDA(cudaMemsetAsync(r.d_sections, 0, off, st));
     DSM_CUDA(cudaMemsetAsync(r.d_ch, 0, (size_t)m, st));
 
@@ -186,10 +246,10 @@ void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, con
     uint64_t *d_tile = nullptr, **d_ptrs = nullptr, *d_scratch = nullptr;
     const size_t tile_bytes = sizeof(uint64_t) * (size_t)m * ntiles;
     const size_t scratch_bytes = sizeof(uint64_t) * (div_up(max_sb, kRankChunk) + 1);
-    DSM_CUDA(cudaMalloc(&d_info, (size_t)m * 256));
-    DSM_CUDA(cudaMalloc(&d_tile, tile_bytes));
-    DSM_CUDA(cudaMalloc(&d_ptrs, sizeof(uint64_t *) * m));
-    DSM_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
+    d_info = static_cast<uint8_t *>(dev_alloc((size_t)m * 256, st));
+    d_tile = static_cast<uint64_t *>(dev_alloc(tile_bytes, st));
+    d_ptrs = static_cast<uint64_t **>(dev_alloc(sizeof(uint64_t *) * m, st));
+    d_scratch = static_cast<uint64_t *>(dev_alloc(scratch_bytes, st));
     if (dev_bytes) *dev_bytes = off + m + (size_t)m * 256 + tile_bytes + sizeof(uint64_t *) * m + scratch_bytes;
     std::vector<uint64_t *> ptrs(m);
     for (int v = 0; v < m; ++v) ptrs[v] = reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]);
@@ -208,20 +268,20 @@ void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, con
         }
         DSM_CUDA(cudaStreamSynchronize(st)); // ptrs / info are host vectors: keep them alive until consumed
     } catch (...) {
-        cudaFree(d_info); cudaFree(d_tile); cudaFree(d_ptrs); cudaFree(d_scratch);
+        dev_free(d_info, st); dev_free(d_tile, st); dev_free(d_ptrs, st); dev_free(d_scratch, st);
         throw;
     }
-    cudaFree(d_info);
-    cudaFree(d_tile);
-    cudaFree(d_ptrs);
-    cudaFree(d_scratch);
+    dev_free(d_info, st);
+    dev_free(d_tile, st);
+    dev_free(d_ptrs, st);
+    dev_free(d_scratch, st);
 }
 
 void wavelet_fetch(cudaStream_t st, WaveletResult &r)
 {
     const int m = r.shape.n_internal;
     if (m > 0) {
-        DSM_CUDA(cudaMallocHost(&r.h_sections, r.section_bytes));
+        r.h_sections = static_cast<uint8_t *>(g_pinned.get(r.section_bytes));
         r.h_ch.resize(m);
         DSM_CUDA(cudaMemcpyAsync(r.h_sections, r.d_sections, r.section_bytes, cudaMemcpyDeviceToHost, st));
         DSM_CUDA(cudaMemcpyAsync(r.h_ch.data(), r.d_ch, (size_t)m, cudaMemcpyDeviceToHost, st));
@@ -299,8 +359,7 @@ struct dsmfm_builder {
     std::vector<std::pair<void *, size_t>> allocs;
     void *dmalloc(size_t bytes)
     {
-        void *p = nullptr;
-        DSM_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        void *p = dev_alloc(bytes, stream);
         allocs.emplace_back(p, bytes);
         dev_now += bytes;
         dev_peak = std::max(dev_peak, dev_now);
@@ -313,7 +372,7 @@ struct dsmfm_builder {
             if (allocs[i].first != p) continue;
             dev_now -= std::min(dev_now, allocs[i].second);
             allocs.erase(allocs.begin() + i);
-            cudaFree(p);
+            dev_free(p, stream);
             return;
         }
     }
@@ -350,14 +409,14 @@ struct dsmfm_builder {
 
     void release_device()
     {
-        for (auto &a : allocs) cudaFree(a.first);
+        for (auto &a : allocs) dev_free(a.first, stream);
         allocs.clear();
         chunks.clear();
         d_raw = nullptr;
         d_sa = nullptr;
         d_bwt = nullptr;
         dev_now = 0;
-        wt.release();
+        wt.release(stream);
     }
 
     void build();
@@ -446,6 +505,18 @@ void dsmfm_builder::build()
         if (counts[c]) code_map[c] = (uint8_t)++sigma;
     const int bits = sigma <= 7 ? 3 : (sigma <= 15 ? 4 : 8);
     const int spw = 64 / bits;
+    // The initial radix sort orders suffixes by their first `first_syms` symbols only (48 key bits = 6
+    // LSD passes instead of 8); the refinement rounds extend from there.  For DNA reads 16 symbols
+    // already separate everything that is not a genuine repeat, so the two saved passes cost almost
+    // no extra refinement work.  DSMFM_FIRST_KEY_BITS overrides (multiple of 8 and of bits/symbol).
+    int first_key_bits = 48;
+    if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
+    if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
+    const int first_syms = std::max(1, first_key_bits / bits);
+    uint8_t inv_map[256];
+    std::memset(inv_map, 0, sizeof inv_map);
+    for (int c = 1; c < 256; ++c)
+        if (code_map[c]) inv_map[code_map[c]] = (uint8_t)c;
 
     index.n = n;
     index.samplerate = samplerate;
@@ -459,6 +530,8 @@ void dsmfm_builder::build()
     // ---- pack -----------------------------------------------------------------------
     const uint64_t nwords = div_up(n, spw) + 2;
     uint8_t *d_map = static_cast<uint8_t *>(dmalloc(256));
+    uint8_t *d_inv = static_cast<uint8_t *>(dmalloc(256));
+    DSM_CUDA(cudaMemcpyAsync(d_inv, inv_map, 256, cudaMemcpyHostToDevice, st));
     uint64_t *d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
     DSM_CUDA(cudaMemcpyAsync(d_map, code_map, 256, cudaMemcpyHostToDevice, st));
     launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
@@ -469,12 +542,18 @@ void dsmfm_builder::build()
     uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(n * 8));
     uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
     uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
-    RadixWorkspace ws;
-    ws.allocate(n);
-    dev_now += ws.bytes;
-    dev_peak = std::max(dev_peak, dev_now);
-    launch_make_keys(st, bits, d_packed, n, d_keys_a, L);
-    const int key_bits = spw * bits;
+    RadixWorkspace ws; // buffers owned by the builder's allocation list
+    ws.status_tiles = div_up(n < kSweepPortion ? n : kSweepPortion, kSweepTile);
+    ws.hist = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * kMaxPasses * kRadix));
+    ws.carry = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * 2 * kRadix));
+    ws.status = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t) * ws.status_tiles * kRadix));
+    ws.counter = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t)));
+    // When the key leaves room, the symbol before each suffix rides above the sorted bits and the BWT
+    // falls out of the sort; otherwise it is gathered from the text at the end.
+    const bool carry_bwt = first_syms * bits + bits <= 64;
+    launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
+    const int key_bits = first_syms * bits; // sorted bits of the first key
+    const int full_key_bits = spw * bits;   // sorted bits of a refinement key (large-group path)
     const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, n, 0, key_bits, true, L,
                                         ev_pass0, ev_pass1);
     uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
@@ -493,7 +572,10 @@ void dsmfm_builder::build()
     uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_count = static_cast<uint32_t *>(dmalloc(4));
     DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
-    launch_heads(st, bits, d_sorted_keys, n, d_head[0], hwords, d_remaining, L);
+    // the BWT lives in its own buffer while the key buffers are still needed by the large-group path
+    d_bwt = static_cast<uint8_t *>(dmalloc(n + 64));
+    launch_heads(st, bits, d_sorted_keys, n, d_head[0], hwords, d_remaining, key_bits, d_inv,
+                 carry_bwt ? d_bwt : nullptr, L);
     DSM_CUDA(cudaEventRecord(ev[2], st));
 
     auto read_remaining = [&]() -> uint64_t {
@@ -514,18 +596,31 @@ void dsmfm_builder::build()
     // needs neither an inverse suffix array nor rank scatter traffic.)
     int cur = 0;
     uint32_t round = 0;
-    const uint32_t max_rounds = (uint32_t)(maxgap / spw + 3);
+    const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
+    // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
+    const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
+    uint32_t *d_win_flag = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
+    uint32_t *d_win_list[2];
+    d_win_list[0] = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
+    d_win_list[1] = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
+    uint32_t *d_win_count = static_cast<uint32_t *>(dmalloc(4));
+    const uint32_t *win_list = nullptr;
+    uint32_t n_list = nwin;
+    int wl = 0;
     while (remaining > 0) {
         if (round >= max_rounds)
             throw CudaError{cudaErrorUnknown, "refinement did not converge (internal error)", __FILE__, __LINE__};
         if (round < 32) stats.active[round] = remaining;
         ++round;
-        const uint32_t depth = round * (uint32_t)spw;
+        const uint32_t depth = (uint32_t)first_syms + (round - 1) * (uint32_t)spw;
         DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hwords * 4, cudaMemcpyDeviceToDevice, st));
         DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
         DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
-        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, d_big_heads, big_cap,
-                      d_big_count, d_remaining, L);
+        DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
+        DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
+        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, win_list, n_list,
+                      d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
+                      carry_bwt ? d_bwt : nullptr, L);
         uint32_t nbig = 0;
         DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
         remaining = read_remaining();
@@ -561,7 +656,7 @@ void dsmfm_builder::build()
                               d_bgid, L);
             // the key buffers of the initial sort are free by now
             DSM_CUDA(cudaMemcpyAsync(d_keys_a, d_bkey, total * 8, cudaMemcpyDeviceToDevice, st));
-            int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, key_bits, true, L);
+            int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, full_key_bits, true, L);
             // pass 0 writes (keys_b, perm); an odd pass count leaves the result there
             uint64_t *kfree = (p1 & 1) ? d_keys_a : d_keys_b;
             uint32_t *pres = (p1 & 1) ? d_perm : d_other_vals;
@@ -575,8 +670,9 @@ void dsmfm_builder::build()
                 if (p2 & 1) std::swap(pres, pfree);
             }
             launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, d_sorted_vals,
-                               d_head[cur ^ 1], L);
-            DSM_CUDA(cudaStreamSynchronize(st));
+                               d_head[cur ^ 1], d_win_flag, d_win_list[wl], d_win_count, d_packed, d_inv,
+                               carry_bwt ? d_bwt : nullptr, L);
+            DSM_CUDA(cudaStreamSynchronize(st)); // sheads / offs are host vectors
             dfree(d_off);
             dfree(d_bsa);
             dfree(d_bgid);
@@ -584,14 +680,23 @@ void dsmfm_builder::build()
             dfree(d_perm);
             remaining += total; // re-examined (and counted exactly) by the next round
         }
+        DSM_CUDA(cudaMemcpyAsync(&n_list, d_win_count, 4, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        win_list = d_win_list[wl];
+        wl ^= 1;
         cur ^= 1;
+        if (remaining > 0 && n_list == 0)
+            throw CudaError{cudaErrorUnknown, "unresolved groups without an owning window (internal error)", __FILE__, __LINE__};
     }
+    dfree(d_win_flag);
+    dfree(d_win_list[0]);
+    dfree(d_win_list[1]);
+    dfree(d_win_count);
     stats.rounds = round;
     DSM_CUDA(cudaEventRecord(ev[3], st));
 
     // ---- BWT ------------------------------------------------------------------------
-    d_bwt = reinterpret_cast<uint8_t *>(d_keys_a); // key buffers are free
-    launch_bwt(st, d_raw, d_sorted_vals, n, d_bwt, L);
+    if (!carry_bwt) launch_bwt(st, bits, d_packed, d_inv, d_sorted_vals, n, d_bwt, L);
     DSM_CUDA(cudaEventRecord(ev[4], st));
 
     // ---- C table, code table, wavelet tree ---------------------------------------------
@@ -610,7 +715,9 @@ void dsmfm_builder::build()
 
     // ---- release what the sections do not need ---------------------------------------
     dfree(d_map);
+    dfree(d_inv);
     dfree(d_packed);
+    dfree(d_keys_a);
     dfree(d_keys_b);
     dfree(d_head[0]);
     dfree(d_head[1]);
@@ -618,8 +725,10 @@ void dsmfm_builder::build()
     dfree(d_big_heads);
     dfree(d_big_len);
     dfree(d_big_count);
-    dev_now -= std::min(dev_now, ws.bytes);
-    ws.release();
+    dfree(ws.hist);
+    dfree(ws.carry);
+    dfree(ws.status);
+    dfree(ws.counter);
     dfree(d_other_vals);
     if (flags & DSMFM_FLAG_KEEP_SA)
         d_sa = d_sorted_vals;
@@ -652,7 +761,7 @@ void dsmfm_builder::fetch()
     DSM_CUDA(cudaEventRecord(e0, stream));
     wavelet_fetch(stream, wt);
     if (flags & DSMFM_FLAG_KEEP_BWT) {
-        DSM_CUDA(cudaMallocHost(&h_bwt, index.n));
+        h_bwt = static_cast<uint8_t *>(g_pinned.get(index.n));
         DSM_CUDA(cudaMemcpyAsync(h_bwt, d_bwt, index.n, cudaMemcpyDeviceToHost, stream));
     }
     DSM_CUDA(cudaEventRecord(e1, stream));
@@ -668,8 +777,9 @@ void dsmfm_builder::fetch()
     // the device copies are no longer needed
     dfree(d_bwt);
     d_bwt = nullptr;
-    if (wt.d_sections) { cudaFree(wt.d_sections); wt.d_sections = nullptr; }
-    if (wt.d_ch) { cudaFree(wt.d_ch); wt.d_ch = nullptr; }
+    dev_free(wt.d_sections, stream);
+    dev_free(wt.d_ch, stream);
+    wt.d_sections = wt.d_ch = nullptr;
     fetched = true;
 }
 
@@ -720,6 +830,13 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
     }
     try {
         DSM_CUDA(cudaSetDevice(dev));
+        {
+            // keep freed device memory in the pool between builds (see dev_alloc)
+            cudaMemPool_t pool;
+            DSM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            uint64_t keep = ~0ull;
+            DSM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
         if (!b->stream) {
             DSM_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
             b->own_stream = true;
@@ -742,7 +859,7 @@ DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len)
     try {
         if (!b->stage[0]) {
             for (int i = 0; i < 2; ++i) {
-                DSM_CUDA(cudaMallocHost(&b->stage[i], dsmfm_builder::kStage));
+                b->stage[i] = static_cast<uint8_t *>(g_pinned.get(dsmfm_builder::kStage));
                 DSM_CUDA(cudaEventCreateWithFlags(&b->stage_free[i], cudaEventDisableTiming));
             }
         }
@@ -856,15 +973,32 @@ DSMFM_API const char *dsmfm_last_error(const dsmfm_builder *b)
     return b ? b->err.c_str() : g_create_error.c_str();
 }
 
+DSMFM_API int dsmfm_release_cached(int device)
+{
+    g_pinned.trim();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) return DSMFM_ECUDA;
+    for (int d = 0; d < ndev; ++d) {
+        if (device >= 0 && d != device) continue;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+            cudaSetDevice(d);
+            cudaDeviceSynchronize();
+            cudaMemPoolTrimTo(pool, 0);
+        }
+    }
+    return DSMFM_OK;
+}
+
 DSMFM_API void dsmfm_destroy(dsmfm_builder *b)
 {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     b->release_device();
-    if (b->h_bwt) cudaFreeHost(b->h_bwt);
+    g_pinned.put(b->h_bwt);
     for (int i = 0; i < 2; ++i) {
-        if (b->stage[i]) cudaFreeHost(b->stage[i]);
+        g_pinned.put(b->stage[i]);
         if (b->stage_free[i]) cudaEventDestroy(b->stage_free[i]);
     }
     if (b->own_stream) cudaStreamDestroy(b->stream);

@@ -183,13 +183,30 @@ __global__ void __launch_bounds__(256) pack_kernel(const uint8_t *__restrict__ r
     }
 }
 
+// symbol code at text position q
+template <int BITS> __device__ __forceinline__ uint32_t text_symbol(const uint64_t *__restrict__ packed, uint64_t q)
+{
+    using P = Pack<BITS>;
+    const uint64_t w = q / P::SPW;
+    const int s = (int)(q - w * P::SPW);
+    return (uint32_t)(__ldg(packed + w) >> (BITS * (P::SPW - 1 - s))) & (uint32_t)P::FIELD;
+}
+
+// key[p] = the first `first_syms` symbols of suffix p (cut at the terminator), right-aligned in the
+// low key_bits.  With carry_prev the code of the symbol BEFORE the suffix (0 at a document start) rides
+// in the bits just above: the radix sort never looks at them, so the BWT symbol of every suffix
+// arrives at its rank for free and no gather over the sorted suffix array is needed afterwards.
 template <int BITS>
 __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restrict__ packed, uint64_t n,
-                                                        uint64_t *__restrict__ keys)
+                                                        uint64_t *__restrict__ keys, int drop_bits, int key_bits,
+                                                        bool carry_prev)
 {
     const uint64_t stride = (uint64_t)gridDim.x * 256;
-    for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += stride)
-        keys[p] = text_window<BITS>(packed, p);
+    for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += stride) {
+        uint64_t k = text_window<BITS>(packed, p) >> drop_bits;
+        if (carry_prev && p) k |= (uint64_t)text_symbol<BITS>(packed, p - 1) << key_bits;
+        keys[p] = k;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -198,9 +215,14 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 template <int BITS>
 __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
-                                                    unsigned long long *__restrict__ remaining)
+                                                    unsigned long long *__restrict__ remaining, int key_bits,
+                                                    const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt)
 {
     __shared__ unsigned long long s_cnt[8];
+    __shared__ uint8_t s_inv[256];
+    if (bwt) s_inv[threadIdx.x] = inv_map[threadIdx.x];
+    __syncthreads();
+    const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t warps_total = (uint64_t)gridDim.x * 8;
     unsigned long long active = 0;
@@ -208,14 +230,17 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
         const uint64_t i = w * 32 + lane;
         bool h = true, act = false;
         if (i < n) {
-            const uint64_t k = keys[i];
-            h = (i == 0) || key_terminated<BITS>(k) || keys[i - 1] != k;
+            const uint64_t kraw = keys[i];
+            const uint64_t k = kraw & kmask;
+            h = (i == 0) || key_terminated<BITS>(k) || (keys[i - 1] & kmask) != k;
             bool hn = true;
             if (i + 1 < n) {
-                const uint64_t kn = keys[i + 1];
+                const uint64_t kn = keys[i + 1] & kmask;
                 hn = key_terminated<BITS>(kn) || kn != k;
             }
             act = !(h && hn);
+            // the symbol before suffix i rode along above the sorted bits (make_keys_kernel)
+            if (bwt) bwt[i] = s_inv[(kraw >> key_bits) & Pack<BITS>::FIELD];
         }
         const uint32_t word = __ballot_sync(0xffffffffu, h);
         const uint32_t aw = __ballot_sync(0xffffffffu, act);
@@ -244,6 +269,17 @@ __device__ __forceinline__ int prev_set_le(const uint32_t *hw, int r)
     while (m == 0) m = hw[--w];
     return (w << 5) + 31 - __clz(m);
 }
+// same over the union of two bit arrays
+__device__ __forceinline__ int prev_set_le2(const uint32_t *a, const uint32_t *b, int r)
+{
+    int w = r >> 5;
+    uint32_t m = (a[w] | b[w]) & (0xffffffffu >> (31 - (r & 31)));
+    while (m == 0) {
+        --w;
+        m = a[w] | b[w];
+    }
+    return (w << 5) + 31 - __clz(m);
+}
 __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
 {
     int w = r >> 5;
@@ -253,24 +289,28 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
 }
 
 template <int BITS>
-__global__ void __launch_bounds__(kRefThreads)
+__global__ void __launch_bounds__(kRefThreads, 6)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
-              uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, uint32_t *__restrict__ big_heads,
-              uint32_t big_cap, uint32_t *__restrict__ big_count, unsigned long long *__restrict__ remaining)
+              uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
+              uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
+              unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
+              uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint32_t nwin,
+              uint8_t *__restrict__ bwt)
 {
-    constexpr int ITEMS = kRefCap / kRefThreads;
     constexpr int HW = kRefCap / 32 + 2;            // head words held in shared memory
     constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
     static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
     __shared__ uint64_t s_key[kRefCap];
     __shared__ uint32_t s_sa[kRefCap];
+    __shared__ uint8_t s_bw[kRefCap];
     __shared__ uint32_t s_head[HW];
     __shared__ uint32_t s_new[HW];
-    __shared__ int s_range[2];
+    __shared__ int s_range[3];
     __shared__ unsigned long long s_cnt[kRefThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t win = (uint64_t)blockIdx.x * kRefWindow; // first slot of this CTA's window
+    const uint32_t wid = win_list ? win_list[blockIdx.x] : blockIdx.x; // window owned by this CTA
+    const uint64_t win = (uint64_t)wid * kRefWindow;                    // its first slot
     const uint64_t w0 = win >> 5;
     for (int i = tid; i < HW; i += kRefThreads) {
         s_head[i] = head_cur[w0 + i];
@@ -282,7 +322,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     if (warp == 0) {
         const uint32_t hw = s_head[lane];
         const uint32_t nz = __ballot_sync(0xffffffffu, hw != 0);
-        int start = -1, end = -1;
+        int start = -1, end = -1, big = 0;
         if (nz) {
             const int fl = __ffs(nz) - 1, ll = 31 - __clz(nz);
             const uint32_t fw = __shfl_sync(0xffffffffu, hw, fl), lw = __shfl_sync(0xffffffffu, hw, ll);
@@ -296,14 +336,13 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
                 const int el = __ffs(enz) - 1;
                 const uint32_t x = __shfl_sync(0xffffffffu, ew, el);
                 e = kRefWindow + el * 32 + __ffs(x) - 1;
-            } else if (s_head[2 * WIN_WORDS] & 1u) {
-                e = kRefWindow + kRefGroupMax;
             }
             if (e >= 0 && e - hl <= kRefGroupMax) {
                 end = e;
             } else {
                 // the last group is too large for shared memory: leave it to the global path
                 end = hl;
+                big = 1;
                 if (lane == 0) {
                     const uint32_t slot = atomicAdd(big_count, 1u);
                     if (slot < big_cap) big_heads[slot] = (uint32_t)(win + hl);
@@ -313,99 +352,93 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         if (lane == 0) {
             s_range[0] = start;
             s_range[1] = end;
+            s_range[2] = big;
         }
     }
     __syncthreads();
     const int start = s_range[0], end = s_range[1];
     if (start < 0 || end <= start) return;
 
-    // gather the next SPW symbols of every suffix that is still in a group of >= 2
-    uint64_t key[ITEMS];
-    uint32_t sav[ITEMS];
-    bool act[ITEMS];
+    // phase A: the next SPW symbols of every suffix that is still in a group of >= 2
+    for (int base = start + tid; base < end; base += 4 * kRefThreads) {
+        uint32_t sv[4];
+        uint8_t bv[4];
+        bool act[4];
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int r = start + tid + k * kRefThreads;
-        act[k] = false;
-        key[k] = 0;
-        sav[k] = 0;
-        if (r < end) {
-            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-            act[k] = !(h0 && h1);
-            if (act[k]) sav[k] = sa[win + r];
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (act[k]) {
-            key[k] = text_window<BITS>(packed, (uint64_t)sav[k] + depth);
-            s_key[start + tid + k * kRefThreads - start] = key[k];
-        }
-    }
-    __syncthreads();
-
-    // stable rank of every active suffix inside its group
-    int npos[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        npos[k] = -1;
-        if (act[k]) {
-            const int r = start + tid + k * kRefThreads;
-            const int gs = prev_set_le(s_head, r);
-            const int ge = next_set_gt(s_head, r);
-            const uint64_t mine = key[k];
-            int c = 0;
-            for (int j = gs; j < ge; ++j) {
-                const uint64_t o = s_key[j - start];
-                c += (o < mine) || (o == mine && j < r);
+        for (int u = 0; u < 4; ++u) {
+            const int r = base + u * kRefThreads;
+            act[u] = false;
+            if (r < end) {
+                const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+                const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+                act[u] = !(h0 && h1);
+                if (act[u]) {
+                    sv[u] = sa[win + r];
+                    if (bwt) bv[u] = bwt[win + r];
+                }
             }
-            npos[k] = gs + c;
         }
-    }
-    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (act[k]) {
-            s_key[npos[k] - start] = key[k];
-            s_sa[npos[k] - start] = sav[k];
+        for (int u = 0; u < 4; ++u) {
+            if (act[u]) {
+                const int r = base + u * kRefThreads;
+                s_sa[r - start] = sv[u];
+                if (bwt) s_bw[r - start] = bv[u];
+                s_key[r - start] = text_window<BITS>(packed, (uint64_t)sv[u] + depth);
+            }
         }
     }
     __syncthreads();
 
-    // write back, mark the new heads, count what is still unresolved
+    // phase B: stable rank inside the group; a suffix opens a new group iff no earlier member
+    // carries the same key (or its key holds the terminator, which makes it unique)
+    for (int r = start + tid; r < end; r += kRefThreads) {
+        const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+        const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+        if (h0 && h1) continue;
+        const int gs = prev_set_le(s_head, r);
+        const int ge = next_set_gt(s_head, r);
+        const uint64_t mine = s_key[r - start];
+        int lt = 0, eq = 0;
+        for (int j = gs; j < r; ++j) {
+            const uint64_t o = s_key[j - start];
+            lt += o < mine;
+            eq += o == mine;
+        }
+        for (int j = r + 1; j < ge; ++j) lt += s_key[j - start] < mine;
+        const int p = gs + lt + eq;
+        sa[win + p] = s_sa[r - start];
+        if (bwt) bwt[win + p] = s_bw[r - start]; // the BWT symbol moves with its suffix
+        if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+
+    // what is still unresolved, and which windows own it in the next round
     unsigned long long still = 0;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (act[k]) {
-            const int r = start + tid + k * kRefThreads;
-            sa[win + r] = s_sa[r - start];
-            const bool was_head = (s_head[r >> 5] >> (r & 31)) & 1u;
-            if (!was_head) {
-                const uint64_t me = s_key[r - start];
-                if (key_terminated<BITS>(me) || me != s_key[r - 1 - start]) atomicOr(&s_new[r >> 5], 1u << (r & 31));
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        if (act[k]) {
-            const int r = start + tid + k * kRefThreads;
-            const bool h0 = ((s_head[r >> 5] | s_new[r >> 5]) >> (r & 31)) & 1u;
-            const bool h1 = ((s_head[(r + 1) >> 5] | s_new[(r + 1) >> 5]) >> ((r + 1) & 31)) & 1u;
-            still += !(h0 && h1);
+    bool mine_here = s_range[2] != 0 && tid == 0, mine_next = false;
+    for (int r = start + tid; r < end; r += kRefThreads) {
+        const bool h0 = ((s_head[r >> 5] | s_new[r >> 5]) >> (r & 31)) & 1u;
+        const bool h1 = ((s_head[(r + 1) >> 5] | s_new[(r + 1) >> 5]) >> ((r + 1) & 31)) & 1u;
+        if (!(h0 && h1)) {
+            ++still;
+            // the group's head decides the owner; its head is in this window unless it lies in the overhang
+            const int gh = prev_set_le2(s_head, s_new, r);
+            if (gh >= kRefWindow) mine_next = true; else mine_here = true;
         }
     }
     for (int i = tid; i < HW; i += kRefThreads)
         if (s_new[i]) atomicOr(&head_next[w0 + i], s_new[i]);
     still = warp_sum(still);
     if (lane == 0) s_cnt[warp] = still;
-    __syncthreads();
+    const int any_here = __syncthreads_or(mine_here);
+    const int any_next = __syncthreads_or(mine_next);
     if (tid == 0) {
         unsigned long long t = 0;
         for (int w = 0; w < kRefThreads / 32; ++w) t += s_cnt[w];
-        if (t) atomicAdd(&remaining[blockIdx.x & 63], t);
+        if (t) atomicAdd(&remaining[wid & 63], t);
+        if (any_here && atomicExch(&win_flag[wid], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wid;
+        if (any_next && wid + 1 < nwin && atomicExch(&win_flag[wid + 1], 1u) == 0u)
+            win_next[atomicAdd(win_next_count, 1u)] = wid + 1;
     }
 }
 
@@ -484,14 +517,21 @@ __global__ void __launch_bounds__(256)
 big_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ bsa,
                    const uint64_t *__restrict__ bkey, const uint32_t *__restrict__ bgid,
                    const uint32_t *__restrict__ big_heads, const uint64_t *__restrict__ big_off, uint64_t total,
-                   uint32_t *__restrict__ sa, uint32_t *__restrict__ head_next)
+                   uint32_t *__restrict__ sa, uint32_t *__restrict__ head_next, uint32_t *__restrict__ win_flag,
+                   uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count,
+                   const uint64_t *__restrict__ packed, const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt)
 {
     const uint64_t stride = (uint64_t)gridDim.x * 256;
     for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += stride) {
         const uint32_t idx = perm[j];
         const uint32_t g = bgid[idx];
         const uint64_t slot = (uint64_t)big_heads[g] + (j - big_off[g]);
-        sa[slot] = bsa[idx];
+        const uint32_t pos = bsa[idx];
+        sa[slot] = pos;
+        if (bwt) bwt[slot] = pos ? inv_map[text_symbol<BITS>(packed, (uint64_t)pos - 1)] : 0;
+        // every window under a re-sorted large group is looked at again in the next round
+        const uint32_t wnd = (uint32_t)(slot / kRefWindow);
+        if (win_flag[wnd] == 0u && atomicExch(&win_flag[wnd], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wnd;
         if (j > big_off[g]) {
             const uint64_t me = bkey[idx], before = bkey[perm[j - 1]];
             if (key_terminated<BITS>(me) || me != before) atomicOr(&head_next[slot >> 5], 1u << (slot & 31));
@@ -502,23 +542,38 @@ big_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict
 // ---------------------------------------------------------------------------
 // BWT
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bwt_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ sa,
-                                                  uint64_t n, uint8_t *__restrict__ bwt)
+// bwt[i] = byte of the symbol before suffix i (0 for a whole document).  The symbol is gathered from the
+// packed text (3/8 of the raw text's footprint) and mapped back to its byte through `inv_map`.
+template <int BITS>
+__global__ void __launch_bounds__(256) bwt_kernel(const uint64_t *__restrict__ packed,
+                                                  const uint8_t *__restrict__ inv_map,
+                                                  const uint32_t *__restrict__ sa, uint64_t n,
+                                                  uint8_t *__restrict__ bwt)
 {
-    const uint64_t nquad = n / 4;
+    __shared__ uint8_t s_inv[256];
+    s_inv[threadIdx.x] = inv_map[threadIdx.x];
+    __syncthreads();
+    const uint64_t noct = n / 8;
     const uint64_t stride = (uint64_t)gridDim.x * 256;
-    for (uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x; q < nquad; q += stride) {
-        const uint4 s = *reinterpret_cast<const uint4 *>(sa + 4 * q);
-        const uint32_t b0 = s.x ? __ldg(raw + s.x - 1) : 0u;
-        const uint32_t b1 = s.y ? __ldg(raw + s.y - 1) : 0u;
-        const uint32_t b2 = s.z ? __ldg(raw + s.z - 1) : 0u;
-        const uint32_t b3 = s.w ? __ldg(raw + s.w - 1) : 0u;
-        *reinterpret_cast<uint32_t *>(bwt + 4 * q) = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    for (uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x; q < noct; q += stride) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(sa + 8 * q);
+        const uint4 b = *reinterpret_cast<const uint4 *>(sa + 8 * q + 4);
+        const uint32_t p[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = p[j] ? text_symbol<BITS>(packed, (uint64_t)p[j] - 1) : 0u;
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lo |= (uint32_t)s_inv[c[j]] << (8 * j);
+            hi |= (uint32_t)s_inv[c[4 + j]] << (8 * j);
+        }
+        *reinterpret_cast<uint2 *>(bwt + 8 * q) = make_uint2(lo, hi);
     }
     if (blockIdx.x == 0)
-        for (uint64_t i = nquad * 4 + threadIdx.x; i < n; i += 256) {
+        for (uint64_t i = noct * 8 + threadIdx.x; i < n; i += 256) {
             const uint32_t p = sa[i];
-            bwt[i] = p ? raw[p - 1] : 0;
+            bwt[i] = p ? s_inv[text_symbol<BITS>(packed, (uint64_t)p - 1)] : 0;
         }
 }
 
@@ -782,9 +837,13 @@ void launch_pack(cudaStream_t st, int bits, const uint8_t *raw, uint64_t n, cons
     if (launches) ++*launches;
 }
 
-void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, uint32_t *launches)
+void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
+                      bool carry_prev, uint32_t *launches)
 {
-#define CALL(B) make_keys_kernel<B><<<grid_for(n, 256 * 8), 256, 0, st>>>(packed, n, keys)
+    const int drop_bits = (64 / bits - first_syms) * bits;
+    const int key_bits = first_syms * bits;
+#define CALL(B) \
+    make_keys_kernel<B><<<grid_for(n, 256 * 8), 256, 0, st>>>(packed, n, keys, drop_bits, key_bits, carry_prev)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -792,9 +851,12 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
 }
 
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
-                  uint64_t head_words, unsigned long long *remaining, uint32_t *launches)
+                  uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
+                  uint8_t *bwt, uint32_t *launches)
 {
-#define CALL(B) heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining)
+#define CALL(B)                                                                                                 \
+    heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
+                                                                  key_bits, inv_map, bwt)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -802,13 +864,17 @@ void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64
 }
 
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
-                   uint32_t *head_next, uint64_t n, uint32_t depth, uint32_t *big_heads, uint32_t big_cap,
-                   uint32_t *big_count, unsigned long long *remaining, uint32_t *launches)
+                   uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
+                   uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
+                   uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, uint32_t *launches)
 {
-    const unsigned grid = (unsigned)div_up(n, kRefWindow);
-#define CALL(B)                                                                                                  \
-    refine_kernel<B><<<grid, kRefThreads, 0, st>>>(packed, sa, head_cur, head_next, n, depth, big_heads, big_cap, \
-                                                   big_count, remaining)
+    const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
+    const unsigned grid = win_list ? n_list : nwin;
+    if (grid == 0) return;
+#define CALL(B)                                                                                                   \
+    refine_kernel<B><<<grid, kRefThreads, 0, st>>>(packed, sa, head_cur, head_next, n, depth, win_list, big_heads, \
+                                                   big_cap, big_count, remaining, win_flag, win_next,              \
+                                                   win_next_count, nwin, bwt)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -846,20 +912,26 @@ void launch_gather_u32_to_u64(cudaStream_t st, const uint32_t *src, const uint32
 
 void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const uint32_t *bsa, const uint64_t *bkey,
                         const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
-                        uint32_t *sa, uint32_t *head_next, uint32_t *launches)
+                        uint32_t *sa, uint32_t *head_next, uint32_t *win_flag, uint32_t *win_next,
+                        uint32_t *win_next_count, const uint64_t *packed, const uint8_t *inv_map, uint8_t *bwt,
+                        uint32_t *launches)
 {
 #define CALL(B)                                                                                                   \
     big_scatter_kernel<B><<<grid_for(total, 256 * 4), 256, 0, st>>>(perm, bsa, bkey, bgid, big_heads, big_off, total, \
-                                                                    sa, head_next)
+                                                                    sa, head_next, win_flag, win_next, win_next_count,      \
+                                                                    packed, inv_map, bwt)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }
 
-void launch_bwt(cudaStream_t st, const uint8_t *raw, const uint32_t *sa, uint64_t n, uint8_t *bwt, uint32_t *launches)
+void launch_bwt(cudaStream_t st, int bits, const uint64_t *packed, const uint8_t *inv_map, const uint32_t *sa,
+                uint64_t n, uint8_t *bwt, uint32_t *launches)
 {
-    bwt_kernel<<<grid_for(n, 256 * 16), 256, 0, st>>>(raw, sa, n, bwt);
+#define CALL(B) bwt_kernel<B><<<grid_for(n, 256 * 16), 256, 0, st>>>(packed, inv_map, sa, n, bwt)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

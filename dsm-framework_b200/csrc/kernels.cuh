@@ -26,15 +26,19 @@ void launch_pack(cudaStream_t st, int bits, const uint8_t *raw, uint64_t n, cons
                  uint64_t nwords, uint32_t *launches);
 
 // ---- suffix sorting ---------------------------------------------------------
-// key[p] = the first SPW symbols of suffix p, cut at its terminator.
-void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys,
-                      uint32_t *launches);
+// key[p] = the first `first_syms` (<= SPW) symbols of suffix p, cut at its terminator, right-aligned.
+// With carry_prev the code of the symbol before the suffix rides in the BITS bits above the key.
+void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
+                      bool carry_prev, uint32_t *launches);
 
 // Group heads after the initial sort: bit i set iff suffix i starts a new group
 // (key differs from its predecessor) or is already finished (key holds the
 // terminator).  Bits >= n are set.  *remaining += suffixes left in groups of >= 2.
+// Only the low key_bits of a key are compared.  If bwt != nullptr, bwt[i] = inv_map[code carried above
+// the key bits] is written for every rank i.
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
-                  uint64_t head_words, unsigned long long *remaining, uint32_t *launches);
+                  uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
+                  uint8_t *bwt, uint32_t *launches);
 
 constexpr int kRefThreads = 256;
 constexpr int kRefWindow = 1024;   // group heads owned by one CTA lie in a window of this many slots
@@ -46,10 +50,15 @@ inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32
 // One refinement round: every group of >= 2 suffixes that still agree on their
 // first `depth` symbols is sorted (stably) by the next SPW symbols and split.
 // head_next must hold a copy of head_cur.  Groups larger than kRefGroupMax are
-// left untouched and their head slots appended to big_heads.
+// left untouched and their head slots appended to big_heads.  win_list (n_list
+// entries; nullptr = every window) names the windows to visit; windows that
+// still own unresolved groups afterwards are appended to win_next (deduplicated
+// through the zeroed win_flag array, one u32 per window).  If bwt != nullptr the BWT bytes
+// (one per rank) are permuted together with the suffix array.
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
-                   uint32_t *head_next, uint64_t n, uint32_t depth, uint32_t *big_heads, uint32_t big_cap,
-                   uint32_t *big_count, unsigned long long *remaining, uint32_t *launches);
+                   uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
+                   uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
+                   uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, uint32_t *launches);
 
 // Large-group path, step 1: length of each listed group (distance to the next head).
 void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,
@@ -64,12 +73,15 @@ void launch_gather_u32_to_u64(cudaStream_t st, const uint32_t *src, const uint32
 // step 4: write the sorted groups back and mark the new heads
 void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const uint32_t *bsa, const uint64_t *bkey,
                         const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
-                        uint32_t *sa, uint32_t *head_next, uint32_t *launches);
+                        uint32_t *sa, uint32_t *head_next, uint32_t *win_flag, uint32_t *win_next,
+                        uint32_t *win_next_count, const uint64_t *packed, const uint8_t *inv_map, uint8_t *bwt,
+                        uint32_t *launches);
 
 // ---- BWT --------------------------------------------------------------------
-// bwt[i] = raw[sa[i]-1], or 0 when suffix i is a whole document (incbwt/rlcsa.cpp:815-845).
-void launch_bwt(cudaStream_t st, const uint8_t *raw, const uint32_t *sa, uint64_t n, uint8_t *bwt,
-                uint32_t *launches);
+// bwt[i] = byte of text[sa[i]-1], or 0 when suffix i is a whole document (incbwt/rlcsa.cpp:815-845);
+// gathered from the packed text, inv_map[code] gives the byte back.
+void launch_bwt(cudaStream_t st, int bits, const uint64_t *packed, const uint8_t *inv_map, const uint32_t *sa,
+                uint64_t n, uint8_t *bwt, uint32_t *launches);
 
 // ---- wavelet tree -------------------------------------------------------------
 constexpr int kWtTile = 8192; // symbols per CTA

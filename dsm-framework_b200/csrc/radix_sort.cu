@@ -1,6 +1,8 @@
 // radix_sort.cu -- one-sweep LSD radix sort kernels (see radix_sort.cuh).
 #include "radix_sort.cuh"
 
+#include <cstdlib>
+
 namespace dsmfm {
 
 namespace {
@@ -73,15 +75,21 @@ struct SweepSmem {
     uint64_t keys[kSweepTile];                 // tile in sorted order
     uint32_t vals[kSweepTile];
     uint64_t goff[kRadix];                     // global offset of digit run minus its tile-local start
-    uint32_t cnt[kSweepThreads / 32][kRadix];  // per-warp digit counters -> per-warp digit bases
+    uint16_t cnt[kSweepThreads / 32][kRadix];  // per-warp digit counters -> per-warp digit bases (<= tile size)
     uint32_t excl[kRadix];                     // tile-local start of each digit run
     uint32_t warp_sum[kSweepThreads / 32];
     uint32_t tile;
 };
 
 // One LSD pass over one portion (<= kSweepPortion pairs) of the input.
-template <bool IOTA>
-__global__ void __launch_bounds__(kSweepThreads, 3)
+//
+// Phases of a CTA (tile of 4096 pairs): load keys -> rank inside the tile (per-warp digit counters)
+// -> publish the tile's digit counts -> stage keys in sorted order in shared memory -> fetch values
+// while the look-back over the preceding tiles resolves the global offsets -> stage values -> write
+// both out, one contiguous burst per digit.  Key registers die before the values are fetched, which
+// keeps the kernel at 64 registers and 4 CTAs (32 warps) per SM.
+template <bool IOTA, bool HW_MATCH>
+__global__ void __launch_bounds__(kSweepThreads, 4)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
                 int shift, uint32_t mask, const uint64_t *__restrict__ base_in, uint64_t *__restrict__ base_out,
@@ -94,7 +102,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s.tile = atomicAdd(counter, 1u);
-    for (int i = tid; i < WARPS * kRadix; i += kSweepThreads) (&s.cnt[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * kRadix / 2; i += kSweepThreads) reinterpret_cast<uint32_t *>(&s.cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint32_t tile_base = tile * (uint32_t)kSweepTile;
@@ -110,19 +118,19 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         key[k] = idx < n ? keys_in[idx] : ~0ull; // padding sorts to the very end of the tile
     }
 
-    uint32_t lpos[kSweepItems];
+    uint16_t lpos[kSweepItems];
 #pragma unroll
     for (int k = 0; k < kSweepItems; ++k) {
         const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-        const uint32_t peers = match_digit(d);
+        const uint32_t peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit(d);
         const int leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (lane == leader) {
             old = s.cnt[warp][d];
-            s.cnt[warp][d] = old + __popc(peers);
+            s.cnt[warp][d] = (uint16_t)(old + __popc(peers));
         }
         old = __shfl_sync(0xffffffffu, old, leader);
-        lpos[k] = old + __popc(peers & lanemask_lt());
+        lpos[k] = (uint16_t)(old + __popc(peers & lanemask_lt()));
         __syncwarp();
     }
     __syncthreads();
@@ -132,9 +140,15 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
         const uint32_t t = s.cnt[w][tid];
-        s.cnt[w][tid] = total;
+        s.cnt[w][tid] = (uint16_t)total;
         total += t;
     }
+    // publish the tile's count of digit d as early as possible: later tiles are waiting for it
+    uint32_t pub = total;
+    if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
+    volatile uint32_t *mine = status + (size_t)tile * kRadix + tid;
+    if (tile != 0) *mine = kFlagAgg | pub;
+
     uint32_t incl = total;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -142,6 +156,21 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         if (lane >= o) incl += t;
     }
     if (lane == 31) s.warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
+    const uint32_t excl = wbase + incl - total;
+    s.excl[tid] = excl;
+    __syncthreads();
+
+    // stage the keys in sorted order; afterwards only their tile-local positions stay in registers
+#pragma unroll
+    for (int k = 0; k < kSweepItems; ++k) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+        const uint32_t p = lpos[k] + s.excl[d] + s.cnt[warp][d];
+        s.keys[p] = key[k];
+        lpos[k] = (uint16_t)p;
+    }
 
     // values are fetched now so that their latency overlaps the look-back
     uint32_t val[kSweepItems];
@@ -153,44 +182,39 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         else
             val[k] = idx < n ? vals_in[idx] : 0u;
     }
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
-    const uint32_t excl = wbase + incl - total;
-    s.excl[tid] = excl;
 
-    // decoupled look-back, one chain per digit
-    uint32_t pub = total;
-    if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
-    volatile uint32_t *mine = status + (size_t)tile * kRadix + tid;
+    // decoupled look-back, one chain per digit, four predecessors in flight at a time
     uint32_t exclusive = 0;
     if (tile == 0) {
         *mine = kFlagPrefix | pub;
     } else {
-        *mine = kFlagAgg | pub;
-        for (uint32_t t = tile; t-- > 0;) {
-            uint32_t w;
-            do {
-                w = status[(size_t)t * kRadix + tid];
-            } while ((w >> 30) == 0);
-            exclusive += w & kValueMask;
-            if (w & kFlagPrefix) break;
+        uint32_t t = tile; // next predecessor to read is t-1
+        bool done = false;
+        while (!done) {
+            const uint32_t cnt = t < 4u ? t : 4u;
+            uint32_t w[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < cnt) w[j] = status[(size_t)(t - 1 - j) * kRadix + tid];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                if (j < cnt && !done) {
+                    uint32_t x = w[j];
+                    while ((x >> 30) == 0) x = status[(size_t)(t - 1 - j) * kRadix + tid];
+                    exclusive += x & kValueMask;
+                    if (x & kFlagPrefix) done = true;
+                }
+            }
+            t -= cnt;
         }
         *mine = kFlagPrefix | (exclusive + pub);
     }
     const uint64_t gbase = base_in[tid] + exclusive;
     s.goff[tid] = gbase - excl;
     if (tile == last_tile) base_out[tid] = gbase + pub;
-    __syncthreads();
 
-    // stage the tile in sorted order
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-        const uint32_t p = lpos[k] + s.excl[d] + s.cnt[warp][d];
-        s.keys[p] = key[k];
-        s.vals[p] = val[k];
-    }
+    for (int k = 0; k < kSweepItems; ++k) s.vals[lpos[k]] = val[k];
     __syncthreads();
 
     // every digit run goes out as one contiguous burst
@@ -240,11 +264,18 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: workspace too small", __FILE__, __LINE__};
 
     static bool attr_set = false;
+    static bool hw_match = false;
     if (!attr_set) {
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SweepSmem)));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SweepSmem)));
+        const int sm = (int)sizeof(SweepSmem);
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        if (const char *e = getenv("DSMFM_SWEEP_MATCH")) hw_match = atoi(e) != 0; // experiment: match.any vs ballots
         attr_set = true;
     }
 
@@ -274,14 +305,16 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
             uint64_t *base_out = ws.carry + (size_t)flip * kRadix;
             DSM_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(uint32_t) * (size_t)tiles * kRadix, stream));
             DSM_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream));
-            if (iota)
-                onesweep_kernel<true><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(
-                    src_k + start, nullptr, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out,
-                    ws.status, ws.counter, tiles - 1);
-            else
-                onesweep_kernel<false><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(
-                    src_k + start, src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out,
-                    ws.status, ws.counter, tiles - 1);
+#define SWEEP(I, M)                                                                                              \
+    onesweep_kernel<I, M><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(                                  \
+        src_k + start, (I) ? nullptr : src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, \
+        base_out, ws.status, ws.counter, tiles - 1)
+            if (iota) {
+                if (hw_match) SWEEP(true, true); else SWEEP(true, false);
+            } else {
+                if (hw_match) SWEEP(false, true); else SWEEP(false, false);
+            }
+#undef SWEEP
             DSM_LAUNCH_CHECK();
             if (launches) *launches += 1;
             base_in = base_out;

@@ -176,6 +176,11 @@ DSMFM_API void dsmfm_destroy(dsmfm_builder *b);
 
 DSMFM_API int dsmfm_version(void);
 
+/* Device and pinned host memory are cached between builds (a second build of the
+ * same size allocates nothing).  This returns the cached memory of `device`
+ * (-1 = all devices) to the system. */
+DSMFM_API int dsmfm_release_cached(int device);
+
 /* ---- kernel-level entry points used by the unit tests (host buffers in/out) ---- */
 
 /* Stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit) with
