@@ -606,6 +606,10 @@ void dsmfm_builder::build()
     uint32_t *d_win_count = static_cast<uint32_t *>(dmalloc(4));
     const uint32_t *win_list = nullptr;
     uint32_t n_list = nwin;
+    // multi-step: one launch resolves every group that fits a CTA (DSMFM_REFINE_SINGLE_STEP=1 keeps
+    // the one-depth-per-launch schedule, used by the tests to exercise the worklist path)
+    bool multi_step = true;
+    if (const char *e = std::getenv("DSMFM_REFINE_SINGLE_STEP")) multi_step = std::atoi(e) == 0;
     int wl = 0;
     while (remaining > 0) {
         if (round >= max_rounds)
@@ -620,7 +624,7 @@ void dsmfm_builder::build()
         DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
         launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, win_list, n_list,
                       d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                      carry_bwt ? d_bwt : nullptr, L);
+                      carry_bwt ? d_bwt : nullptr, multi_step, L);
         uint32_t nbig = 0;
         DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
         remaining = read_remaining();

@@ -288,23 +288,30 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
     return (w << 5) + __ffs(m) - 1;
 }
 
+// One CTA owns the groups whose head lies in its window of kRefWindow slots and keeps refining
+// them in shared memory -- key = the next SPW symbols, stable rank inside the group, split -- until
+// they are all resolved (multi == true) or for a single step (multi == false).  The suffix array
+// (and the BWT bytes that travel with it) are read and written once per launch; only the text is
+// touched again in every step.
 template <int BITS>
-__global__ void __launch_bounds__(kRefThreads, 6)
+__global__ void __launch_bounds__(kRefThreads, 5)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
               uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
               uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
               unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
               uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint32_t nwin,
-              uint8_t *__restrict__ bwt)
+              uint8_t *__restrict__ bwt, int max_steps)
 {
     constexpr int HW = kRefCap / 32 + 2;            // head words held in shared memory
     constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
     static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
     __shared__ uint64_t s_key[kRefCap];
-    __shared__ uint32_t s_sa[kRefCap];
-    __shared__ uint8_t s_bw[kRefCap];
-    __shared__ uint32_t s_head[HW];
-    __shared__ uint32_t s_new[HW];
+    __shared__ uint32_t s_sa[2][kRefCap];
+    __shared__ uint8_t s_bw[2][kRefCap];
+    __shared__ uint32_t s_head[HW];   // current group heads
+    __shared__ uint32_t s_new[HW];    // heads found in the current step
+    __shared__ uint32_t s_acc[HW];    // all heads found by this CTA
+    __shared__ uint32_t s_touch[HW];  // slots that were in a group of >= 2 at entry
     __shared__ int s_range[3];
     __shared__ unsigned long long s_cnt[kRefThreads / 32];
 
@@ -315,6 +322,8 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     for (int i = tid; i < HW; i += kRefThreads) {
         s_head[i] = head_cur[w0 + i];
         s_new[i] = 0;
+        s_acc[i] = 0;
+        s_touch[i] = 0;
     }
     __syncthreads();
 
@@ -359,7 +368,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     const int start = s_range[0], end = s_range[1];
     if (start < 0 || end <= start) return;
 
-    // phase A: the next SPW symbols of every suffix that is still in a group of >= 2
+    // load the suffixes (and their BWT bytes) that sit in groups of >= 2
     for (int base = start + tid; base < end; base += 4 * kRefThreads) {
         uint32_t sv[4];
         uint8_t bv[4];
@@ -368,6 +377,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         for (int u = 0; u < 4; ++u) {
             const int r = base + u * kRefThreads;
             act[u] = false;
+            bv[u] = 0;
             if (r < end) {
                 const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
                 const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
@@ -382,52 +392,91 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         for (int u = 0; u < 4; ++u) {
             if (act[u]) {
                 const int r = base + u * kRefThreads;
-                s_sa[r - start] = sv[u];
-                if (bwt) s_bw[r - start] = bv[u];
-                s_key[r - start] = text_window<BITS>(packed, (uint64_t)sv[u] + depth);
+                s_sa[0][r - start] = sv[u];
+                s_bw[0][r - start] = bv[u];
+                atomicOr(&s_touch[r >> 5], 1u << (r & 31));
             }
         }
     }
     __syncthreads();
 
-    // phase B: stable rank inside the group; a suffix opens a new group iff no earlier member
-    // carries the same key (or its key holds the terminator, which makes it unique)
-    for (int r = start + tid; r < end; r += kRefThreads) {
-        const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-        const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-        if (h0 && h1) continue;
-        const int gs = prev_set_le(s_head, r);
-        const int ge = next_set_gt(s_head, r);
-        const uint64_t mine = s_key[r - start];
-        int lt = 0, eq = 0;
-        for (int j = gs; j < r; ++j) {
-            const uint64_t o = s_key[j - start];
-            lt += o < mine;
-            eq += o == mine;
+    int c = 0;
+    uint32_t d = depth;
+    for (int step = 0; step < max_steps; ++step) {
+        // keys: the next SPW symbols of every suffix still in a group of >= 2
+        for (int r = start + tid; r < end; r += kRefThreads) {
+            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+            if (!(h0 && h1)) s_key[r - start] = text_window<BITS>(packed, (uint64_t)s_sa[c][r - start] + d);
         }
-        for (int j = r + 1; j < ge; ++j) lt += s_key[j - start] < mine;
-        const int p = gs + lt + eq;
-        sa[win + p] = s_sa[r - start];
-        if (bwt) bwt[win + p] = s_bw[r - start]; // the BWT symbol moves with its suffix
-        if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+        __syncthreads();
+        // stable rank inside the group; a suffix opens a new group iff no earlier member carries
+        // the same key (or its key holds the terminator, which makes it unique)
+        for (int r = start + tid; r < end; r += kRefThreads) {
+            if (!((s_touch[r >> 5] >> (r & 31)) & 1u)) continue;
+            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+            int p = r;
+            if (!(h0 && h1)) {
+                const int gs = prev_set_le(s_head, r);
+                const int ge = next_set_gt(s_head, r);
+                const uint64_t mine = s_key[r - start];
+                int lt = 0, eq = 0;
+                for (int j = gs; j < r; ++j) {
+                    const uint64_t o = s_key[j - start];
+                    lt += o < mine;
+                    eq += o == mine;
+                }
+                for (int j = r + 1; j < ge; ++j) lt += s_key[j - start] < mine;
+                p = gs + lt + eq;
+                if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+            }
+            s_sa[c ^ 1][p - start] = s_sa[c][r - start];
+            s_bw[c ^ 1][p - start] = s_bw[c][r - start]; // the BWT symbol moves with its suffix
+        }
+        __syncthreads();
+        for (int i = tid; i < HW; i += kRefThreads) {
+            const uint32_t nw = s_new[i];
+            if (nw) {
+                s_head[i] |= nw;
+                s_acc[i] |= nw;
+                s_new[i] = 0;
+            }
+        }
+        c ^= 1;
+        d += Pack<BITS>::SPW;
+        __syncthreads();
+        bool more = false;
+        for (int r = start + tid; r < end; r += kRefThreads) {
+            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+            more |= !(h0 && h1);
+        }
+        if (!__syncthreads_or(more)) break;
     }
-    __syncthreads();
 
-    // what is still unresolved, and which windows own it in the next round
-    unsigned long long still = 0;
-    bool mine_here = s_range[2] != 0 && tid == 0, mine_next = false;
+    // write back what was touched, publish the new heads
     for (int r = start + tid; r < end; r += kRefThreads) {
-        const bool h0 = ((s_head[r >> 5] | s_new[r >> 5]) >> (r & 31)) & 1u;
-        const bool h1 = ((s_head[(r + 1) >> 5] | s_new[(r + 1) >> 5]) >> ((r + 1) & 31)) & 1u;
-        if (!(h0 && h1)) {
-            ++still;
-            // the group's head decides the owner; its head is in this window unless it lies in the overhang
-            const int gh = prev_set_le2(s_head, s_new, r);
-            if (gh >= kRefWindow) mine_next = true; else mine_here = true;
+        if ((s_touch[r >> 5] >> (r & 31)) & 1u) {
+            sa[win + r] = s_sa[c][r - start];
+            if (bwt) bwt[win + r] = s_bw[c][r - start];
         }
     }
     for (int i = tid; i < HW; i += kRefThreads)
-        if (s_new[i]) atomicOr(&head_next[w0 + i], s_new[i]);
+        if (s_acc[i]) atomicOr(&head_next[w0 + i], s_acc[i]);
+
+    // what is still unresolved (single-step mode), and which windows own it in the next launch
+    unsigned long long still = 0;
+    bool mine_here = s_range[2] != 0 && tid == 0, mine_next = false;
+    for (int r = start + tid; r < end; r += kRefThreads) {
+        const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
+        const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+        if (!(h0 && h1)) {
+            ++still;
+            // the group's head decides the owner: this window, or the next one if it lies in the overhang
+            if (prev_set_le(s_head, r) >= kRefWindow) mine_next = true; else mine_here = true;
+        }
+    }
     still = warp_sum(still);
     if (lane == 0) s_cnt[warp] = still;
     const int any_here = __syncthreads_or(mine_here);
@@ -866,15 +915,17 @@ void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
-                   uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, uint32_t *launches)
+                   uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
+                   uint32_t *launches)
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
+    const int max_steps = multi_step ? (1 << 30) : 1;
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
 #define CALL(B)                                                                                                   \
     refine_kernel<B><<<grid, kRefThreads, 0, st>>>(packed, sa, head_cur, head_next, n, depth, win_list, big_heads, \
                                                    big_cap, big_count, remaining, win_flag, win_next,              \
-                                                   win_next_count, nwin, bwt)
+                                                   win_next_count, nwin, bwt, max_steps)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();

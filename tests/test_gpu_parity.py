@@ -148,6 +148,16 @@ def test_first_key_width_does_not_change_the_result(first_key_bits, monkeypatch)
         _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
 
 
+def test_single_step_refinement_schedule(monkeypatch):
+    """One depth per launch with the window worklist (the schedule multi-step launches replace)."""
+    monkeypatch.setenv("DSMFM_REFINE_SINGLE_STEP", "1")
+    for name in ["reads100", "poly_a", "two_letter", "mixed_alphabet"]:
+        docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+        _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()["high_coverage"])
+    assert hashlib.sha256(_build(docs)).hexdigest() == MANIFEST["digests"]["high_coverage"]["fmi_sha256"]
+
+
 def test_arbitrary_byte_alphabet():
     """TextCollectionBuilder admits any byte 1..255 (TextCollectionBuilder.h:52): 8 bits per symbol."""
     rng = np.random.default_rng(11)
