@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -241,7 +241,11 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    stats = [device_step() for _ in range(args.steps)]
+    stats, step_wall = [], []
+    for _ in range(args.steps):
+        t_s = time.perf_counter()
+        stats.append(device_step())
+        step_wall.append(round(1000 * (time.perf_counter() - t_s), 1))
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -308,6 +312,8 @@ def main():
             "phase_ms": {"pack": round(s0.ms_pack, 2), "sort": round(s0.ms_sort, 2), "refine": round(s0.ms_refine, 2),
                          "bwt": round(s0.ms_bwt, 2), "wavelet": round(s0.ms_wt, 2), "total": round(s0.ms_total, 2)},
             "device_bytes_peak": s0.device_bytes_peak,
+            "step_wall_ms": step_wall,
+            "step_device_ms": [round(s.ms_total, 1) for s in stats],
         },
         "clocks": clocks,
         "e2e": {

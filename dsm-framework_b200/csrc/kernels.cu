@@ -290,11 +290,12 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
 
 // One CTA owns the groups whose head lies in its window of kRefWindow slots and keeps refining
 // them in shared memory -- key = the next SPW symbols, stable rank inside the group, split -- until
-// they are all resolved (multi == true) or for a single step (multi == false).  The suffix array
-// (and the BWT bytes that travel with it) are read and written once per launch; only the text is
-// touched again in every step.
+// they are all resolved (multi-step) or for a single step.  The suffix array (and the BWT bytes
+// that travel with it) are read once; a suffix is written back the moment it becomes a singleton;
+// only the text is touched again in every step.  All per-step loops run over a compact list of the
+// still-unresolved slots, so a step costs what is left, not what the window holds.
 template <int BITS>
-__global__ void __launch_bounds__(kRefThreads, 5)
+__global__ void __launch_bounds__(kRefThreads, 4)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
               uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
               uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
@@ -305,15 +306,16 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     constexpr int HW = kRefCap / 32 + 2;            // head words held in shared memory
     constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
     static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
+    static_assert(kRefCap <= 65536, "slot lists are 16-bit");
     __shared__ uint64_t s_key[kRefCap];
     __shared__ uint32_t s_sa[2][kRefCap];
     __shared__ uint8_t s_bw[2][kRefCap];
-    __shared__ uint32_t s_head[HW];   // current group heads
-    __shared__ uint32_t s_new[HW];    // heads found in the current step
-    __shared__ uint32_t s_acc[HW];    // all heads found by this CTA
-    __shared__ uint32_t s_touch[HW];  // slots that were in a group of >= 2 at entry
+    __shared__ uint16_t s_list[2][kRefCap]; // unresolved slots (relative to the window), current / next step
+    __shared__ uint32_t s_head[HW];         // current group heads
+    __shared__ uint32_t s_new[HW];          // heads found in the current step
+    __shared__ uint32_t s_acc[HW];          // all heads found by this CTA
+    __shared__ int s_n[2];
     __shared__ int s_range[3];
-    __shared__ unsigned long long s_cnt[kRefThreads / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t wid = win_list ? win_list[blockIdx.x] : blockIdx.x; // window owned by this CTA
@@ -323,8 +325,8 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         s_head[i] = head_cur[w0 + i];
         s_new[i] = 0;
         s_acc[i] = 0;
-        s_touch[i] = 0;
     }
+    if (tid < 2) s_n[tid] = 0;
     __syncthreads();
 
     // Ownership: this CTA sorts the groups whose head lies in [win, win+kRefWindow).
@@ -368,8 +370,20 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     const int start = s_range[0], end = s_range[1];
     if (start < 0 || end <= start) return;
 
+    // Appends `slot` to list `which` for the lanes with `take` set (whole warp must call).
+    auto append = [&](int which, bool take, int slot) {
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        if (m == 0) return;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n[which], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) s_list[which][base + __popc(m & lanemask_lt())] = (uint16_t)slot;
+    };
+    auto is_head = [&](int r) -> bool { return (s_head[r >> 5] >> (r & 31)) & 1u; };
+
     // load the suffixes (and their BWT bytes) that sit in groups of >= 2
-    for (int base = start + tid; base < end; base += 4 * kRefThreads) {
+    for (int b0 = start + (tid & ~31); b0 < end; b0 += 4 * kRefThreads) { // b0 is warp-uniform (append ballots)
+        const int base = b0 + lane;
         uint32_t sv[4];
         uint8_t bv[4];
         bool act[4];
@@ -378,10 +392,9 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             const int r = base + u * kRefThreads;
             act[u] = false;
             bv[u] = 0;
+            sv[u] = 0;
             if (r < end) {
-                const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-                const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-                act[u] = !(h0 && h1);
+                act[u] = !(is_head(r) && is_head(r + 1));
                 if (act[u]) {
                     sv[u] = sa[win + r];
                     if (bwt) bv[u] = bwt[win + r];
@@ -390,49 +403,46 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+            const int r = base + u * kRefThreads;
             if (act[u]) {
-                const int r = base + u * kRefThreads;
-                s_sa[0][r - start] = sv[u];
-                s_bw[0][r - start] = bv[u];
-                atomicOr(&s_touch[r >> 5], 1u << (r & 31));
+                s_sa[0][r] = sv[u];
+                s_bw[0][r] = bv[u];
             }
+            append(0, act[u], r);
         }
     }
     __syncthreads();
 
-    int c = 0;
+    int c = 0, lc = 0;
     uint32_t d = depth;
     for (int step = 0; step < max_steps; ++step) {
-        // keys: the next SPW symbols of every suffix still in a group of >= 2
-        for (int r = start + tid; r < end; r += kRefThreads) {
-            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-            if (!(h0 && h1)) s_key[r - start] = text_window<BITS>(packed, (uint64_t)s_sa[c][r - start] + d);
+        const int cnt = s_n[lc];
+        if (cnt == 0) break;
+        // keys: the next SPW symbols of every unresolved suffix
+        for (int i = tid; i < cnt; i += kRefThreads) {
+            const int r = s_list[lc][i];
+            s_key[r] = text_window<BITS>(packed, (uint64_t)s_sa[c][r] + d);
         }
         __syncthreads();
         // stable rank inside the group; a suffix opens a new group iff no earlier member carries
         // the same key (or its key holds the terminator, which makes it unique)
-        for (int r = start + tid; r < end; r += kRefThreads) {
-            if (!((s_touch[r >> 5] >> (r & 31)) & 1u)) continue;
-            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-            int p = r;
-            if (!(h0 && h1)) {
-                const int gs = prev_set_le(s_head, r);
-                const int ge = next_set_gt(s_head, r);
-                const uint64_t mine = s_key[r - start];
-                int lt = 0, eq = 0;
-                for (int j = gs; j < r; ++j) {
-                    const uint64_t o = s_key[j - start];
-                    lt += o < mine;
-                    eq += o == mine;
-                }
-                for (int j = r + 1; j < ge; ++j) lt += s_key[j - start] < mine;
-                p = gs + lt + eq;
-                if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+        for (int i = tid; i < cnt; i += kRefThreads) {
+            const int r = s_list[lc][i];
+            const int gs = prev_set_le(s_head, r);
+            const int ge = next_set_gt(s_head, r);
+            const uint64_t mine = s_key[r];
+            int lt = 0, eq = 0;
+            for (int j = gs; j < r; ++j) {
+                const uint64_t o = s_key[j];
+                lt += o < mine;
+                eq += o == mine;
             }
-            s_sa[c ^ 1][p - start] = s_sa[c][r - start];
-            s_bw[c ^ 1][p - start] = s_bw[c][r - start]; // the BWT symbol moves with its suffix
+            for (int j = r + 1; j < ge; ++j) lt += s_key[j] < mine;
+            const int p = gs + lt + eq;
+            if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+            s_sa[c ^ 1][p] = s_sa[c][r];
+            s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+            s_list[lc][i] = (uint16_t)p;  // where this suffix went
         }
         __syncthreads();
         for (int i = tid; i < HW; i += kRefThreads) {
@@ -443,48 +453,44 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
                 s_new[i] = 0;
             }
         }
+        if (tid == 0) s_n[lc ^ 1] = 0;
+        __syncthreads();
+        // resolved suffixes go home now; the rest form the next step's list
+        for (int i = tid; (i & ~31) < cnt; i += kRefThreads) {
+            bool again = false;
+            int p = 0;
+            if (i < cnt) {
+                p = s_list[lc][i];
+                again = !(is_head(p) && is_head(p + 1));
+                if (!again) {
+                    sa[win + p] = s_sa[c ^ 1][p];
+                    if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
+                }
+            }
+            append(lc ^ 1, again, p);
+        }
         c ^= 1;
+        lc ^= 1;
         d += Pack<BITS>::SPW;
         __syncthreads();
-        bool more = false;
-        for (int r = start + tid; r < end; r += kRefThreads) {
-            const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-            const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-            more |= !(h0 && h1);
-        }
-        if (!__syncthreads_or(more)) break;
     }
 
-    // write back what was touched, publish the new heads
-    for (int r = start + tid; r < end; r += kRefThreads) {
-        if ((s_touch[r >> 5] >> (r & 31)) & 1u) {
-            sa[win + r] = s_sa[c][r - start];
-            if (bwt) bwt[win + r] = s_bw[c][r - start];
-        }
+    // single-step mode: unresolved suffixes are written back in their new order and handed to the next launch
+    const int left = s_n[lc];
+    bool mine_here = s_range[2] != 0 && tid == 0, mine_next = false;
+    for (int i = tid; i < left; i += kRefThreads) {
+        const int p = s_list[lc][i];
+        sa[win + p] = s_sa[c][p];
+        if (bwt) bwt[win + p] = s_bw[c][p];
+        // the group's head decides the owner: this window, or the next one if it lies in the overhang
+        if (prev_set_le(s_head, p) >= kRefWindow) mine_next = true; else mine_here = true;
     }
     for (int i = tid; i < HW; i += kRefThreads)
         if (s_acc[i]) atomicOr(&head_next[w0 + i], s_acc[i]);
-
-    // what is still unresolved (single-step mode), and which windows own it in the next launch
-    unsigned long long still = 0;
-    bool mine_here = s_range[2] != 0 && tid == 0, mine_next = false;
-    for (int r = start + tid; r < end; r += kRefThreads) {
-        const bool h0 = (s_head[r >> 5] >> (r & 31)) & 1u;
-        const bool h1 = (s_head[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-        if (!(h0 && h1)) {
-            ++still;
-            // the group's head decides the owner: this window, or the next one if it lies in the overhang
-            if (prev_set_le(s_head, r) >= kRefWindow) mine_next = true; else mine_here = true;
-        }
-    }
-    still = warp_sum(still);
-    if (lane == 0) s_cnt[warp] = still;
     const int any_here = __syncthreads_or(mine_here);
     const int any_next = __syncthreads_or(mine_next);
     if (tid == 0) {
-        unsigned long long t = 0;
-        for (int w = 0; w < kRefThreads / 32; ++w) t += s_cnt[w];
-        if (t) atomicAdd(&remaining[wid & 63], t);
+        if (left) atomicAdd(&remaining[wid & 63], (unsigned long long)left);
         if (any_here && atomicExch(&win_flag[wid], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wid;
         if (any_next && wid + 1 < nwin && atomicExch(&win_flag[wid + 1], 1u) == 0u)
             win_next[atomicAdd(win_next_count, 1u)] = wid + 1;
