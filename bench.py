@@ -314,6 +314,8 @@ def main():
             "device_bytes_peak": s0.device_bytes_peak,
             "step_wall_ms": step_wall,
             "step_device_ms": [round(s.ms_total, 1) for s in stats],
+            "step_build_wall_ms": [round(s.ms_wall_build, 1) for s in stats],
+            "step_alloc_wall_ms": [round(s.ms_wall_alloc, 1) for s in stats],
         },
         "clocks": clocks,
         "e2e": {

@@ -8,6 +8,7 @@
 #include "radix_sort.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -30,10 +31,19 @@ thread_local std::string g_create_error;
 // a small process-wide pool for the same reason.  dsmfm_release_cached() gives
 // both back.
 // ---------------------------------------------------------------------------
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+thread_local double g_alloc_ms = 0.0;
+
 void *dev_alloc(size_t bytes, cudaStream_t st)
 {
     void *p = nullptr;
+    const double t0 = now_ms();
     DSM_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+    g_alloc_ms += now_ms() - t0;
     return p;
 }
 void dev_free(void *p, cudaStream_t st)
@@ -528,7 +538,7 @@ void dsmfm_builder::build()
     stats.sigma = sigma;
 
     // ---- pack -----------------------------------------------------------------------
-    const uint64_t nwords = div_up(n, spw) + 2;
+    const uint64_t nwords = div_up(n, spw) + 4; // zero words behind the text: windows read up to 2 words ahead
     uint8_t *d_map = static_cast<uint8_t *>(dmalloc(256));
     uint8_t *d_inv = static_cast<uint8_t *>(dmalloc(256));
     DSM_CUDA(cudaMemcpyAsync(d_inv, inv_map, 256, cudaMemcpyHostToDevice, st));
@@ -596,6 +606,7 @@ void dsmfm_builder::build()
     // needs neither an inverse suffix array nor rank scatter traffic.)
     int cur = 0;
     uint32_t round = 0;
+    uint32_t depth_next = (uint32_t)first_syms; // symbols every unresolved group is known to agree on
     const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
     // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
@@ -610,13 +621,15 @@ void dsmfm_builder::build()
     // the one-depth-per-launch schedule, used by the tests to exercise the worklist path)
     bool multi_step = true;
     if (const char *e = std::getenv("DSMFM_REFINE_SINGLE_STEP")) multi_step = std::atoi(e) == 0;
+    int key_words = 1; // symbols compared per step = key_words * SPW (DSMFM_REFINE_KEY_WORDS=2: 128-bit keys)
+    if (const char *e = std::getenv("DSMFM_REFINE_KEY_WORDS")) key_words = std::atoi(e) == 2 ? 2 : 1;
     int wl = 0;
     while (remaining > 0) {
         if (round >= max_rounds)
             throw CudaError{cudaErrorUnknown, "refinement did not converge (internal error)", __FILE__, __LINE__};
         if (round < 32) stats.active[round] = remaining;
         ++round;
-        const uint32_t depth = (uint32_t)first_syms + (round - 1) * (uint32_t)spw;
+        const uint32_t depth = depth_next;
         DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hwords * 4, cudaMemcpyDeviceToDevice, st));
         DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
         DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
@@ -624,7 +637,7 @@ void dsmfm_builder::build()
         DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
         launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, win_list, n_list,
                       d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                      carry_bwt ? d_bwt : nullptr, multi_step, L);
+                      carry_bwt ? d_bwt : nullptr, multi_step, key_words, L);
         uint32_t nbig = 0;
         DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
         remaining = read_remaining();
@@ -684,6 +697,9 @@ void dsmfm_builder::build()
             dfree(d_perm);
             remaining += total; // re-examined (and counted exactly) by the next round
         }
+        // a CTA step consumes key_words*SPW symbols, the large-group path SPW; starting the next launch at the
+        // smaller of the two is always safe (already-equal symbols just compare equal again)
+        depth_next = depth + ((multi_step || nbig > 0) ? (uint32_t)spw : (uint32_t)(key_words * spw));
         DSM_CUDA(cudaMemcpyAsync(&n_list, d_win_count, 4, cudaMemcpyDeviceToHost, st));
         DSM_CUDA(cudaStreamSynchronize(st));
         win_list = d_win_list[wl];
@@ -917,8 +933,12 @@ DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
     API_GUARD(b);
     if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_build_device: already built");
     b->finished = true;
+    const double t0 = now_ms();
+    g_alloc_ms = 0.0;
     try {
         b->build();
+        b->stats.ms_wall_build = (float)(now_ms() - t0);
+        b->stats.ms_wall_alloc = (float)g_alloc_ms;
     } catch (const CudaError &e) {
         b->release_device();
         if (e.what && std::strcmp(e.what, "EMPTY") == 0)
@@ -940,7 +960,9 @@ DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out)
     API_GUARD(b);
     if (!b->built) return b->fail(DSMFM_EINVAL, "dsmfm_fetch: nothing built");
     try {
+        const double t0 = now_ms();
         if (!b->fetched) b->fetch();
+        b->stats.ms_wall_fetch = (float)(now_ms() - t0);
     } catch (const CudaError &e) {
         return b->fail_cuda(e);
     }

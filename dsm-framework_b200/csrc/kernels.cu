@@ -269,17 +269,6 @@ __device__ __forceinline__ int prev_set_le(const uint32_t *hw, int r)
     while (m == 0) m = hw[--w];
     return (w << 5) + 31 - __clz(m);
 }
-// same over the union of two bit arrays
-__device__ __forceinline__ int prev_set_le2(const uint32_t *a, const uint32_t *b, int r)
-{
-    int w = r >> 5;
-    uint32_t m = (a[w] | b[w]) & (0xffffffffu >> (31 - (r & 31)));
-    while (m == 0) {
-        --w;
-        m = a[w] | b[w];
-    }
-    return (w << 5) + 31 - __clz(m);
-}
 __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
 {
     int w = r >> 5;
@@ -288,14 +277,27 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
     return (w << 5) + __ffs(m) - 1;
 }
 
+template <int KW> struct RefSmem {
+    uint64_t khi[kRefCap];              // key = the next KW*SPW symbols (hi [, lo])
+    uint64_t klo[KW == 2 ? kRefCap : 1];
+    uint32_t sa[2][kRefCap];    // suffixes, double buffered across a step
+    uint16_t list[2][kRefCap];  // unresolved slots (relative to the window), current / next step
+    uint8_t bw[2][kRefCap];     // BWT bytes travelling with the suffixes
+    uint32_t head[kRefCap / 32 + 2]; // current group heads
+    uint32_t newh[kRefCap / 32 + 2]; // heads found in the current step
+    uint32_t acc[kRefCap / 32 + 2];  // all heads found by this CTA
+    int n[2];
+    int range[3];
+};
+
 // One CTA owns the groups whose head lies in its window of kRefWindow slots and keeps refining
 // them in shared memory -- key = the next SPW symbols, stable rank inside the group, split -- until
 // they are all resolved (multi-step) or for a single step.  The suffix array (and the BWT bytes
 // that travel with it) are read once; a suffix is written back the moment it becomes a singleton;
 // only the text is touched again in every step.  All per-step loops run over a compact list of the
 // still-unresolved slots, so a step costs what is left, not what the window holds.
-template <int BITS>
-__global__ void __launch_bounds__(kRefThreads, 4)
+template <int BITS, int KW>
+__global__ void __launch_bounds__(kRefThreads, KW == 2 ? 3 : 4)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
               uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
               uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
@@ -307,15 +309,14 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
     static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
     static_assert(kRefCap <= 65536, "slot lists are 16-bit");
-    __shared__ uint64_t s_key[kRefCap];
-    __shared__ uint32_t s_sa[2][kRefCap];
-    __shared__ uint8_t s_bw[2][kRefCap];
-    __shared__ uint16_t s_list[2][kRefCap]; // unresolved slots (relative to the window), current / next step
-    __shared__ uint32_t s_head[HW];         // current group heads
-    __shared__ uint32_t s_new[HW];          // heads found in the current step
-    __shared__ uint32_t s_acc[HW];          // all heads found by this CTA
-    __shared__ int s_n[2];
-    __shared__ int s_range[3];
+    extern __shared__ __align__(16) unsigned char ref_smem_raw[];
+    RefSmem<KW> &S = *reinterpret_cast<RefSmem<KW> *>(ref_smem_raw);
+    uint64_t *s_khi = S.khi, *s_klo = S.klo;
+    uint32_t(*s_sa)[kRefCap] = S.sa;
+    uint8_t(*s_bw)[kRefCap] = S.bw;
+    uint16_t(*s_list)[kRefCap] = S.list;
+    uint32_t *s_head = S.head, *s_new = S.newh, *s_acc = S.acc;
+    int *s_n = S.n, *s_range = S.range;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t wid = win_list ? win_list[blockIdx.x] : blockIdx.x; // window owned by this CTA
@@ -418,10 +419,17 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     for (int step = 0; step < max_steps; ++step) {
         const int cnt = s_n[lc];
         if (cnt == 0) break;
-        // keys: the next SPW symbols of every unresolved suffix
+        // keys: the next 2*SPW symbols of every unresolved suffix (one random access buys both words)
         for (int i = tid; i < cnt; i += kRefThreads) {
             const int r = s_list[lc][i];
-            s_key[r] = text_window<BITS>(packed, (uint64_t)s_sa[c][r] + d);
+            if (KW == 2) {
+                uint64_t hi, lo;
+                text_window2<BITS>(packed, (uint64_t)s_sa[c][r] + d, hi, lo);
+                s_khi[r] = hi;
+                s_klo[r] = lo;
+            } else {
+                s_khi[r] = text_window<BITS>(packed, (uint64_t)s_sa[c][r] + d);
+            }
         }
         __syncthreads();
         // stable rank inside the group; a suffix opens a new group iff no earlier member carries
@@ -430,16 +438,33 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             const int r = s_list[lc][i];
             const int gs = prev_set_le(s_head, r);
             const int ge = next_set_gt(s_head, r);
-            const uint64_t mine = s_key[r];
+            const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
             int lt = 0, eq = 0;
-            for (int j = gs; j < r; ++j) {
-                const uint64_t o = s_key[j];
-                lt += o < mine;
-                eq += o == mine;
+            if (KW == 2) {
+                for (int j = gs; j < r; ++j) {
+                    const uint64_t oh = s_khi[j];
+                    if (oh < mh) {
+                        ++lt;
+                    } else if (oh == mh) {
+                        const uint64_t ol = s_klo[j];
+                        lt += ol < ml;
+                        eq += ol == ml;
+                    }
+                }
+                for (int j = r + 1; j < ge; ++j) {
+                    const uint64_t oh = s_khi[j];
+                    lt += (oh < mh) || (oh == mh && s_klo[j] < ml);
+                }
+            } else {
+                for (int j = gs; j < r; ++j) {
+                    const uint64_t o = s_khi[j];
+                    lt += o < mh;
+                    eq += o == mh;
+                }
+                for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
             }
-            for (int j = r + 1; j < ge; ++j) lt += s_key[j] < mine;
             const int p = gs + lt + eq;
-            if (p != gs && (eq == 0 || key_terminated<BITS>(mine))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+            if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
             s_sa[c ^ 1][p] = s_sa[c][r];
             s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
             s_list[lc][i] = (uint16_t)p;  // where this suffix went
@@ -471,7 +496,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         }
         c ^= 1;
         lc ^= 1;
-        d += Pack<BITS>::SPW;
+        d += KW * Pack<BITS>::SPW;
         __syncthreads();
     }
 
@@ -922,16 +947,31 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   uint32_t *launches)
+                   int key_words, uint32_t *launches)
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
     const int max_steps = multi_step ? (1 << 30) : 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+#define SET(B, K) \
+    DSM_CUDA(cudaFuncSetAttribute(refine_kernel<B, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefSmem<K>)))
+        SET(3, 1); SET(4, 1); SET(8, 1); SET(3, 2); SET(4, 2); SET(8, 2);
+#undef SET
+        attr_set = true;
+    }
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
-#define CALL(B)                                                                                                   \
-    refine_kernel<B><<<grid, kRefThreads, 0, st>>>(packed, sa, head_cur, head_next, n, depth, win_list, big_heads, \
-                                                   big_cap, big_count, remaining, win_flag, win_next,              \
-                                                   win_next_count, nwin, bwt, max_steps)
+#define CALL(B)                                                                                                     \
+    do {                                                                                                            \
+        if (key_words == 2)                                                                                         \
+            refine_kernel<B, 2><<<grid, kRefThreads, sizeof(RefSmem<2>), st>>>(                                     \
+                packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining,     \
+                win_flag, win_next, win_next_count, nwin, bwt, max_steps);                                          \
+        else                                                                                                        \
+            refine_kernel<B, 1><<<grid, kRefThreads, sizeof(RefSmem<1>), st>>>(                                     \
+                packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining,     \
+                win_flag, win_next, win_next_count, nwin, bwt, max_steps);                                          \
+    } while (0)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();

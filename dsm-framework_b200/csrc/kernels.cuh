@@ -56,12 +56,13 @@ inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32
 // through the zeroed win_flag array, one u32 per window).  If bwt != nullptr the BWT bytes
 // (one per rank) are permuted together with the suffix array.  With multi_step a CTA keeps
 // extending the keys (depth += SPW) until every group it owns is resolved, so that one launch
-// finishes everything except the groups that do not fit a CTA.
+// finishes everything except the groups that do not fit a CTA.  key_words = 1 or 2: a step compares
+// SPW or 2*SPW symbols (64- or 128-bit keys).
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   uint32_t *launches);
+                   int key_words, uint32_t *launches);
 
 // Large-group path, step 1: length of each listed group (distance to the next head).
 void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,

@@ -117,6 +117,10 @@ typedef struct dsmfm_stats {
     uint32_t reserved;
     uint64_t sort_pass_bytes;    /* algorithmic bytes moved by ONE onesweep pass            */
     uint64_t device_bytes_peak;  /* peak device memory held by the builder                  */
+    float ms_wall_build;         /* host wall time of dsmfm_build_device                    */
+    float ms_wall_fetch;         /* host wall time of dsmfm_fetch                           */
+    float ms_wall_alloc;         /* of which: device allocation calls                       */
+    float reserved2;
 } dsmfm_stats;
 
 /* Replaces: TextCollectionBuilder::TextCollectionBuilder (TextCollectionBuilder.cpp:32-57). */

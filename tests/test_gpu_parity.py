@@ -148,14 +148,25 @@ def test_first_key_width_does_not_change_the_result(first_key_bits, monkeypatch)
         _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
 
 
-def test_single_step_refinement_schedule(monkeypatch):
+@pytest.mark.parametrize("key_words", ["1", "2"])
+def test_single_step_refinement_schedule(monkeypatch, key_words):
     """One depth per launch with the window worklist (the schedule multi-step launches replace)."""
     monkeypatch.setenv("DSMFM_REFINE_SINGLE_STEP", "1")
+    monkeypatch.setenv("DSMFM_REFINE_KEY_WORDS", key_words)
     for name in ["reads100", "poly_a", "two_letter", "mixed_alphabet"]:
         docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
         _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
     docs, _ = oracle.fasta_to_docs(cases.digest_cases()["high_coverage"])
     assert hashlib.sha256(_build(docs)).hexdigest() == MANIFEST["digests"]["high_coverage"]["fmi_sha256"]
+
+
+def test_128_bit_refinement_keys(monkeypatch):
+    monkeypatch.setenv("DSMFM_REFINE_KEY_WORDS", "2")
+    for name in ["reads100", "poly_a", "colour_space", "duplicates"]:
+        docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+        _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()["reads100_3k"])
+    assert hashlib.sha256(_build(docs)).hexdigest() == MANIFEST["digests"]["reads100_3k"]["fmi_sha256"]
 
 
 def test_arbitrary_byte_alphabet():
