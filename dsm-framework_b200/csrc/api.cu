@@ -320,6 +320,9 @@ struct dsmfm_builder {
     uint32_t samplerate = DSMFM_DEFAULT_SAMPLERATE;
     uint32_t flags = 0;
     uint64_t expected = 0;
+    uint32_t shard_index = 0, shard_count = 1;
+    uint64_t shard_rank_begin = 0, shard_m = 0;
+    bool assembled = false;
     std::string err;
 
     // host staging for dsmfm_append (pinned, double buffered)
@@ -459,6 +462,18 @@ void dsmfm_builder::build()
         throw CudaError{cudaErrorInvalidValue, "more than 2^32 symbols on one device (shard the collection)", __FILE__, __LINE__};
     }
 
+    // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the
+    // default 64-byte L2 fetch granularity every miss drags in a second, unused sector.
+    size_t old_gran = 0;
+    cudaDeviceGetLimit(&old_gran, cudaLimitMaxL2FetchGranularity);
+    size_t want_gran = 32;
+    if (const char *e = std::getenv("DSMFM_L2_FETCH")) want_gran = (size_t)std::atoi(e);
+    if (want_gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want_gran);
+    struct RestoreGran {
+        size_t v;
+        ~RestoreGran() { if (v) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v); }
+    } restore_gran{old_gran};
+
     DSM_CUDA(cudaEventRecord(ev[0], st));
     // contiguous text
     if (chunks.size() == 1) {
@@ -522,7 +537,8 @@ void dsmfm_builder::build()
     int first_key_bits = 48;
     if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
     if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
-    const int first_syms = std::max(1, first_key_bits / bits);
+    int first_syms = std::max(1, first_key_bits / bits);
+    if (shard_count > 1 && first_syms * bits == 64) --first_syms; // key ranges need an exclusive upper bound
     uint8_t inv_map[256];
     std::memset(inv_map, 0, sizeof inv_map);
     for (int c = 1; c < 256; ++c)
@@ -547,13 +563,53 @@ void dsmfm_builder::build()
     launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
     DSM_CUDA(cudaEventRecord(ev[1], st));
 
+    // ---- which suffixes this builder sorts ------------------------------------------------
+    // Unsharded: all n.  Sharded: the ones whose first key lies in this shard's key range; the ranges
+    // are cut from a 4096-bin histogram of the top key bits, which every shard computes identically
+    // from the (replicated) text, so no communication is needed to agree on them.
+    const bool sharded = shard_count > 1;
+    const int key_bits = first_syms * bits; // sorted bits of the first key
+    uint64_t m = n, key_lo = 0, key_hi = 0;
+    if (sharded) {
+        const int top_bits = key_bits < 12 ? key_bits : 12;
+        const int nbins = 1 << top_bits;
+        unsigned long long *d_top = static_cast<unsigned long long *>(dmalloc(4096 * 8));
+        DSM_CUDA(cudaMemsetAsync(d_top, 0, 4096 * 8, st));
+        launch_key_top_hist(st, bits, d_packed, n, first_syms, top_bits, d_top, L);
+        std::vector<unsigned long long> top(4096);
+        DSM_CUDA(cudaMemcpyAsync(top.data(), d_top, 4096 * 8, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        dfree(d_top);
+        // shard s takes the bins whose running count first reaches s*n/G ... (s+1)*n/G
+        std::vector<int> cut(shard_count + 1, nbins);
+        cut[0] = 0;
+        uint64_t run = 0;
+        uint32_t next = 1;
+        for (int bin = 0; bin < nbins && next < shard_count; ++bin) {
+            run += top[bin];
+            while (next < shard_count && run >= (n / shard_count) * next + (n % shard_count) * next / shard_count) {
+                cut[next++] = bin + 1;
+            }
+        }
+        const int b_lo = cut[shard_index], b_hi = cut[shard_index + 1];
+        uint64_t before = 0;
+        m = 0;
+        for (int bin = 0; bin < b_lo; ++bin) before += top[bin];
+        for (int bin = b_lo; bin < b_hi; ++bin) m += top[bin];
+        shard_rank_begin = before;
+        key_lo = (uint64_t)b_lo << (key_bits - top_bits);
+        key_hi = b_hi >= nbins ? (key_bits >= 64 ? ~0ull : (1ull << key_bits)) : ((uint64_t)b_hi << (key_bits - top_bits));
+    }
+    shard_m = m;
+    const uint64_t ma = m ? m : 1; // allocation sizes for an empty shard
+
     // ---- initial sort by the first SPW symbols ---------------------------------------
-    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(n * 8));
-    uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(n * 8));
-    uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
-    uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(n * 4 + 16));
+    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(ma * 8));
+    uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(ma * 8));
+    uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(ma * 4 + 16));
+    uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(ma * 4 + 16));
     RadixWorkspace ws; // buffers owned by the builder's allocation list
-    ws.status_tiles = div_up(n < kSweepPortion ? n : kSweepPortion, kSweepTile);
+    ws.status_tiles = div_up(ma < kSweepPortion ? ma : kSweepPortion, kSweepTile);
     ws.hist = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * kMaxPasses * kRadix));
     ws.carry = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * 2 * kRadix));
     ws.status = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t) * ws.status_tiles * kRadix));
@@ -561,30 +617,38 @@ void dsmfm_builder::build()
     // When the key leaves room, the symbol before each suffix rides above the sorted bits and the BWT
     // falls out of the sort; otherwise it is gathered from the text at the end.
     const bool carry_bwt = first_syms * bits + bits <= 64;
-    launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
-    const int key_bits = first_syms * bits; // sorted bits of the first key
     const int full_key_bits = spw * bits;   // sorted bits of a refinement key (large-group path)
-    const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, n, 0, key_bits, true, L,
+    if (!sharded) {
+        launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
+    } else if (m) {
+        const uint64_t ntile = select_tiles(n);
+        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
+        launch_select_count(st, bits, d_packed, n, first_syms, key_lo, key_hi, d_tile, L);
+        launch_wt_scan(st, d_tile, 1, ntile, L);
+        launch_select_write(st, bits, d_packed, n, first_syms, carry_bwt, key_lo, key_hi, d_tile, d_keys_a, d_vals_a, L);
+        dfree(d_tile);
+    }
+    const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
                                         ev_pass0, ev_pass1);
     uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
     uint32_t *d_sorted_vals = (passes & 1) ? d_vals_b : d_vals_a;
     uint32_t *d_other_vals = (passes & 1) ? d_vals_a : d_vals_b;
     stats.sort_passes = passes;
-    stats.sort_pass_bytes = n * 24ull;
+    stats.sort_pass_bytes = m * 24ull;
 
-    const uint64_t hwords = head_words_for(n);
+    const uint64_t hwords = head_words_for(m);
     uint32_t *d_head[2];
     d_head[0] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(64 * 8));
-    const uint32_t big_cap = (uint32_t)(n / kRefGroupMax + 2);
+    const uint32_t big_cap = (uint32_t)(m / kRefGroupMax + 2);
     uint32_t *d_big_heads = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_count = static_cast<uint32_t *>(dmalloc(4));
     DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
     // the BWT lives in its own buffer while the key buffers are still needed by the large-group path
-    d_bwt = static_cast<uint8_t *>(dmalloc(n + 64));
-    launch_heads(st, bits, d_sorted_keys, n, d_head[0], hwords, d_remaining, key_bits, d_inv,
+    d_bwt = static_cast<uint8_t *>(dmalloc(ma + 64));
+    launch_heads(st, bits, d_sorted_keys, m, d_head[0], hwords, d_remaining, key_bits, d_inv,
                  carry_bwt ? d_bwt : nullptr, L);
     DSM_CUDA(cudaEventRecord(ev[2], st));
 
@@ -609,7 +673,7 @@ void dsmfm_builder::build()
     uint32_t depth_next = (uint32_t)first_syms; // symbols every unresolved group is known to agree on
     const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
     // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
-    const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
+    const uint32_t nwin = (uint32_t)div_up(ma, kRefWindow);
     uint32_t *d_win_flag = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
     uint32_t *d_win_list[2];
     d_win_list[0] = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
@@ -635,7 +699,7 @@ void dsmfm_builder::build()
         DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
         DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
         DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
-        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], n, depth, win_list, n_list,
+        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
                       d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
                       carry_bwt ? d_bwt : nullptr, multi_step, key_words, L);
         uint32_t nbig = 0;
@@ -644,7 +708,7 @@ void dsmfm_builder::build()
         if (nbig > 0) {
             // groups too large for one CTA: one global (group, key) radix sort over all of them
             if (nbig > big_cap) throw CudaError{cudaErrorUnknown, "large-group list overflow", __FILE__, __LINE__};
-            launch_big_extent(st, d_head[cur], n, d_big_heads, nbig, d_big_len, L);
+            launch_big_extent(st, d_head[cur], m, d_big_heads, nbig, d_big_len, L);
             std::vector<uint32_t> heads(nbig), lens(nbig);
             DSM_CUDA(cudaMemcpyAsync(heads.data(), d_big_heads, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
             DSM_CUDA(cudaMemcpyAsync(lens.data(), d_big_len, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
@@ -716,7 +780,7 @@ void dsmfm_builder::build()
     DSM_CUDA(cudaEventRecord(ev[3], st));
 
     // ---- BWT ------------------------------------------------------------------------
-    if (!carry_bwt) launch_bwt(st, bits, d_packed, d_inv, d_sorted_vals, n, d_bwt, L);
+    if (!carry_bwt && m) launch_bwt(st, bits, d_packed, d_inv, d_sorted_vals, m, d_bwt, L);
     DSM_CUDA(cudaEventRecord(ev[4], st));
 
     // ---- C table, code table, wavelet tree ---------------------------------------------
@@ -725,11 +789,13 @@ void dsmfm_builder::build()
     const uint32_t maxbits = build_codetable(counts, index.codetable);
     if (maxbits > 31)
         throw CudaError{cudaErrorInvalidValue, "Huffman code longer than 31 bits (the .fmi code field is 32 bits)", __FILE__, __LINE__};
-    size_t wt_bytes = 0;
-    wavelet_build_device(st, d_bwt, n, index.codetable, wt, L, &wt_bytes);
-    dev_now += wt_bytes;
-    dev_peak = std::max(dev_peak, dev_now);
-    dev_now -= wt_bytes - std::min(wt_bytes, wt.section_bytes);
+    if (!sharded) {
+        size_t wt_bytes = 0;
+        wavelet_build_device(st, d_bwt, n, index.codetable, wt, L, &wt_bytes);
+        dev_now += wt_bytes;
+        dev_peak = std::max(dev_peak, dev_now);
+        dev_now -= wt_bytes - std::min(wt_bytes, wt.section_bytes);
+    }
     DSM_CUDA(cudaEventRecord(ev[5], st));
     DSM_CUDA(cudaStreamSynchronize(st));
 
@@ -780,7 +846,7 @@ void dsmfm_builder::fetch()
     DSM_CUDA(cudaEventCreate(&e1));
     DSM_CUDA(cudaEventRecord(e0, stream));
     wavelet_fetch(stream, wt);
-    if (flags & DSMFM_FLAG_KEEP_BWT) {
+    if ((flags & DSMFM_FLAG_KEEP_BWT) && shard_count <= 1) {
         h_bwt = static_cast<uint8_t *>(g_pinned.get(index.n));
         DSM_CUDA(cudaMemcpyAsync(h_bwt, d_bwt, index.n, cudaMemcpyDeviceToHost, stream));
     }
@@ -847,6 +913,13 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
         b->flags = opts->flags;
         b->expected = opts->expected_bytes;
         b->stream = static_cast<cudaStream_t>(opts->stream);
+        b->shard_count = opts->shard_count ? opts->shard_count : 1;
+        b->shard_index = opts->shard_index;
+        if (b->shard_index >= b->shard_count) {
+            g_create_error = "shard_index out of range";
+            delete b;
+            return DSMFM_EINVAL;
+        }
     }
     try {
         DSM_CUDA(cudaSetDevice(dev));
@@ -955,10 +1028,52 @@ DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
     return DSMFM_OK;
 }
 
+DSMFM_API int dsmfm_shard_info(dsmfm_builder *b, dsmfm_shard *out)
+{
+    API_GUARD(b);
+    if (!out) return DSMFM_EINVAL;
+    if (!b->built) return b->fail(DSMFM_EINVAL, "dsmfm_shard_info: nothing built");
+    out->n_total = b->index.n;
+    out->rank_begin = b->shard_rank_begin;
+    out->count = b->shard_m;
+    out->bwt_dev = b->d_bwt;
+    out->sa_dev = b->d_sa;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_assemble(dsmfm_builder *b, const void *bwt_dev, uint64_t n_total)
+{
+    API_GUARD(b);
+    if (!b->built || b->shard_count <= 1) return b->fail(DSMFM_EINVAL, "dsmfm_assemble: needs a built sharded builder");
+    if (b->assembled) return b->fail(DSMFM_EINVAL, "dsmfm_assemble: already assembled");
+    if (!bwt_dev || n_total != b->index.n) return b->fail(DSMFM_EINVAL, "dsmfm_assemble: BWT size does not match the collection");
+    try {
+        cudaEvent_t e0, e1;
+        DSM_CUDA(cudaEventCreate(&e0));
+        DSM_CUDA(cudaEventCreate(&e1));
+        DSM_CUDA(cudaEventRecord(e0, b->stream));
+        wavelet_build_device(b->stream, static_cast<const uint8_t *>(bwt_dev), n_total, b->index.codetable, b->wt,
+                             &b->stats.kernel_launches, nullptr);
+        DSM_CUDA(cudaEventRecord(e1, b->stream));
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        b->stats.ms_wt = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    b->assembled = true;
+    return DSMFM_OK;
+}
+
 DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out)
 {
     API_GUARD(b);
     if (!b->built) return b->fail(DSMFM_EINVAL, "dsmfm_fetch: nothing built");
+    if (b->shard_count > 1 && !b->assembled)
+        return b->fail(DSMFM_EINVAL, "dsmfm_fetch: a sharded builder holds a slice only; call dsmfm_assemble on one of them");
     try {
         const double t0 = now_ms();
         if (!b->fetched) b->fetch();

@@ -210,6 +210,95 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 }
 
 // ---------------------------------------------------------------------------
+// key-range sharding (multi-GPU): every GPU holds the whole packed text and sorts the suffixes
+// whose first key falls into its range
+// ---------------------------------------------------------------------------
+constexpr int kSelTile = 4096; // text positions per CTA (256 threads x 16 consecutive positions)
+
+template <int BITS>
+__device__ __forceinline__ uint64_t first_key(const uint64_t *__restrict__ packed, uint64_t p, int drop_bits)
+{
+    return text_window<BITS>(packed, p) >> drop_bits;
+}
+
+// histogram of the top `top_bits` (<= 12) bits of the first key of every suffix
+template <int BITS>
+__global__ void __launch_bounds__(256)
+key_top_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bits, int top_shift,
+                    unsigned long long *__restrict__ hist)
+{
+    __shared__ uint32_t h[4096];
+    for (int i = threadIdx.x; i < 4096; i += 256) h[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += stride)
+        atomicAdd(&h[(uint32_t)(first_key<BITS>(packed, p, drop_bits) >> top_shift)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256)
+        if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
+}
+
+// number of suffixes of each tile whose first key lies in [key_lo, key_hi)
+template <int BITS>
+__global__ void __launch_bounds__(256)
+select_count_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bits, uint64_t key_lo, uint64_t key_hi,
+                    uint64_t *__restrict__ tile_count)
+{
+    __shared__ uint32_t s_sum[8];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * 16;
+    uint32_t c = 0;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        const uint64_t p = p0 + j;
+        if (p < n) {
+            const uint64_t k = first_key<BITS>(packed, p, drop_bits);
+            c += (k >= key_lo && k < key_hi);
+        }
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s_sum[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// writes (key [| previous symbol above the key bits], position) of the selected suffixes in text order
+template <int BITS>
+__global__ void __launch_bounds__(256)
+select_write_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bits, int key_bits, bool carry_prev,
+                    uint64_t key_lo, uint64_t key_hi, const uint64_t *__restrict__ tile_off,
+                    uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    __shared__ uint32_t scratch[9];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * 16;
+    uint32_t sel = 0;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        const uint64_t p = p0 + j;
+        if (p < n) {
+            const uint64_t k = first_key<BITS>(packed, p, drop_bits);
+            if (k >= key_lo && k < key_hi) sel |= 1u << j;
+        }
+    }
+    uint32_t total;
+    const uint32_t e = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
+    uint64_t o = tile_off[blockIdx.x] + e;
+    while (sel) {
+        const int j = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const uint64_t p = p0 + j;
+        uint64_t k = first_key<BITS>(packed, p, drop_bits);
+        if (carry_prev && p) k |= (uint64_t)text_symbol<BITS>(packed, p - 1) << key_bits;
+        keys[o] = k;
+        vals[o] = (uint32_t)p;
+        ++o;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // group heads after the initial sort
 // ---------------------------------------------------------------------------
 template <int BITS>
@@ -280,22 +369,23 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
 template <int KW> struct RefSmem {
     uint64_t khi[kRefCap];              // key = the next KW*SPW symbols (hi [, lo])
     uint64_t klo[KW == 2 ? kRefCap : 1];
-    uint32_t sa[2][kRefCap];    // suffixes, double buffered across a step
-    uint16_t list[2][kRefCap];  // unresolved slots (relative to the window), current / next step
-    uint8_t bw[2][kRefCap];     // BWT bytes travelling with the suffixes
-    uint32_t head[kRefCap / 32 + 2]; // current group heads
-    uint32_t newh[kRefCap / 32 + 2]; // heads found in the current step
-    uint32_t acc[kRefCap / 32 + 2];  // all heads found by this CTA
+    uint32_t sa[2][kRefCap];            // suffixes, double buffered across a step
+    uint16_t list[2][kRefCap];          // unresolved slots (relative to the window), current / next step
+    uint8_t bw[2][kRefCap];             // BWT bytes travelling with the suffixes
+    uint32_t head_a[kRefCap / 32 + 2];  // group heads the ranking phase reads
+    uint32_t head_b[kRefCap / 32 + 2];  // = head_a plus the heads found in the current step
     int n[2];
     int range[3];
 };
 
 // One CTA owns the groups whose head lies in its window of kRefWindow slots and keeps refining
-// them in shared memory -- key = the next SPW symbols, stable rank inside the group, split -- until
-// they are all resolved (multi-step) or for a single step.  The suffix array (and the BWT bytes
-// that travel with it) are read once; a suffix is written back the moment it becomes a singleton;
-// only the text is touched again in every step.  All per-step loops run over a compact list of the
-// still-unresolved slots, so a step costs what is left, not what the window holds.
+// them in shared memory -- key = the next KW*SPW symbols, stable rank inside the group, split --
+// until they are all resolved (multi-step) or for a single step.  The suffix array (and the BWT
+// bytes that travel with it) are read once; a suffix is written back the moment it becomes a
+// singleton; only the text is touched again in every step.  A step is two phases and two barriers:
+//   rank:     every unresolved suffix finds its stable rank inside its group (all pairs), moves to
+//             the other buffer and marks the new group heads;
+//   classify: resolved suffixes go home; the others fetch their next key and join the next list.
 template <int BITS, int KW>
 __global__ void __launch_bounds__(kRefThreads, KW == 2 ? 3 : 4)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
@@ -315,7 +405,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     uint32_t(*s_sa)[kRefCap] = S.sa;
     uint8_t(*s_bw)[kRefCap] = S.bw;
     uint16_t(*s_list)[kRefCap] = S.list;
-    uint32_t *s_head = S.head, *s_new = S.newh, *s_acc = S.acc;
+    uint32_t *s_ha = S.head_a, *s_hb = S.head_b;
     int *s_n = S.n, *s_range = S.range;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -323,16 +413,16 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     const uint64_t win = (uint64_t)wid * kRefWindow;                    // its first slot
     const uint64_t w0 = win >> 5;
     for (int i = tid; i < HW; i += kRefThreads) {
-        s_head[i] = head_cur[w0 + i];
-        s_new[i] = 0;
-        s_acc[i] = 0;
+        const uint32_t h = head_cur[w0 + i];
+        s_ha[i] = h;
+        s_hb[i] = h;
     }
     if (tid < 2) s_n[tid] = 0;
     __syncthreads();
 
     // Ownership: this CTA sorts the groups whose head lies in [win, win+kRefWindow).
     if (warp == 0) {
-        const uint32_t hw = s_head[lane];
+        const uint32_t hw = s_ha[lane];
         const uint32_t nz = __ballot_sync(0xffffffffu, hw != 0);
         int start = -1, end = -1, big = 0;
         if (nz) {
@@ -341,7 +431,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             start = fl * 32 + __ffs(fw) - 1;
             const int hl = ll * 32 + 31 - __clz(lw); // head of the last owned group
             // its end: first head at or after the window end
-            const uint32_t ew = s_head[WIN_WORDS + lane];
+            const uint32_t ew = s_ha[WIN_WORDS + lane];
             const uint32_t enz = __ballot_sync(0xffffffffu, ew != 0);
             int e = -1;
             if (enz) {
@@ -380,9 +470,19 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         base = __shfl_sync(0xffffffffu, base, 0);
         if (take) s_list[which][base + __popc(m & lanemask_lt())] = (uint16_t)slot;
     };
-    auto is_head = [&](int r) -> bool { return (s_head[r >> 5] >> (r & 31)) & 1u; };
+    auto fetch_key = [&](int slot, uint32_t pos, uint32_t dd) {
+        if (KW == 2) {
+            uint64_t hi, lo;
+            text_window2<BITS>(packed, (uint64_t)pos + dd, hi, lo);
+            s_khi[slot] = hi;
+            s_klo[slot] = lo;
+        } else {
+            s_khi[slot] = text_window<BITS>(packed, (uint64_t)pos + dd);
+        }
+    };
 
-    // load the suffixes (and their BWT bytes) that sit in groups of >= 2
+    // load the suffixes (and their BWT bytes) that sit in groups of >= 2, and their first keys
+    uint32_t d = depth;
     for (int b0 = start + (tid & ~31); b0 < end; b0 += 4 * kRefThreads) { // b0 is warp-uniform (append ballots)
         const int base = b0 + lane;
         uint32_t sv[4];
@@ -395,7 +495,9 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             bv[u] = 0;
             sv[u] = 0;
             if (r < end) {
-                act[u] = !(is_head(r) && is_head(r + 1));
+                const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
+                const bool h1 = (s_ha[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+                act[u] = !(h0 && h1);
                 if (act[u]) {
                     sv[u] = sa[win + r];
                     if (bwt) bv[u] = bwt[win + r];
@@ -408,6 +510,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             if (act[u]) {
                 s_sa[0][r] = sv[u];
                 s_bw[0][r] = bv[u];
+                fetch_key(r, sv[u], d);
             }
             append(0, act[u], r);
         }
@@ -415,29 +518,16 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     __syncthreads();
 
     int c = 0, lc = 0;
-    uint32_t d = depth;
     for (int step = 0; step < max_steps; ++step) {
         const int cnt = s_n[lc];
         if (cnt == 0) break;
-        // keys: the next 2*SPW symbols of every unresolved suffix (one random access buys both words)
+        if (tid == 0) s_n[lc ^ 1] = 0;
+        // rank: stable position inside the group; a suffix opens a new group iff no earlier member
+        // carries the same key (or its key holds the terminator, which makes it unique)
         for (int i = tid; i < cnt; i += kRefThreads) {
             const int r = s_list[lc][i];
-            if (KW == 2) {
-                uint64_t hi, lo;
-                text_window2<BITS>(packed, (uint64_t)s_sa[c][r] + d, hi, lo);
-                s_khi[r] = hi;
-                s_klo[r] = lo;
-            } else {
-                s_khi[r] = text_window<BITS>(packed, (uint64_t)s_sa[c][r] + d);
-            }
-        }
-        __syncthreads();
-        // stable rank inside the group; a suffix opens a new group iff no earlier member carries
-        // the same key (or its key holds the terminator, which makes it unique)
-        for (int i = tid; i < cnt; i += kRefThreads) {
-            const int r = s_list[lc][i];
-            const int gs = prev_set_le(s_head, r);
-            const int ge = next_set_gt(s_head, r);
+            const int gs = prev_set_le(s_ha, r);
+            const int ge = next_set_gt(s_ha, r);
             const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
             int lt = 0, eq = 0;
             if (KW == 2) {
@@ -464,39 +554,36 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
                 for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
             }
             const int p = gs + lt + eq;
-            if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_new[p >> 5], 1u << (p & 31));
+            if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
             s_sa[c ^ 1][p] = s_sa[c][r];
             s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
             s_list[lc][i] = (uint16_t)p;  // where this suffix went
         }
         __syncthreads();
-        for (int i = tid; i < HW; i += kRefThreads) {
-            const uint32_t nw = s_new[i];
-            if (nw) {
-                s_head[i] |= nw;
-                s_acc[i] |= nw;
-                s_new[i] = 0;
-            }
-        }
-        if (tid == 0) s_n[lc ^ 1] = 0;
-        __syncthreads();
-        // resolved suffixes go home now; the rest form the next step's list
+        // classify: resolved suffixes go home now; the rest fetch the next key and form the next list
+        d += KW * Pack<BITS>::SPW;
+        const bool more_steps = step + 1 < max_steps;
         for (int i = tid; (i & ~31) < cnt; i += kRefThreads) {
             bool again = false;
             int p = 0;
             if (i < cnt) {
                 p = s_list[lc][i];
-                again = !(is_head(p) && is_head(p + 1));
+                const bool h0 = (s_hb[p >> 5] >> (p & 31)) & 1u;
+                const bool h1 = (s_hb[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u;
+                again = !(h0 && h1);
+                const uint32_t pos = s_sa[c ^ 1][p];
                 if (!again) {
-                    sa[win + p] = s_sa[c ^ 1][p];
+                    sa[win + p] = pos;
                     if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
+                } else if (more_steps) {
+                    fetch_key(p, pos, d);
                 }
             }
             append(lc ^ 1, again, p);
         }
+        for (int i = tid; i < HW; i += kRefThreads) s_ha[i] = s_hb[i]; // not read in this phase
         c ^= 1;
         lc ^= 1;
-        d += KW * Pack<BITS>::SPW;
         __syncthreads();
     }
 
@@ -508,10 +595,12 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         sa[win + p] = s_sa[c][p];
         if (bwt) bwt[win + p] = s_bw[c][p];
         // the group's head decides the owner: this window, or the next one if it lies in the overhang
-        if (prev_set_le(s_head, p) >= kRefWindow) mine_next = true; else mine_here = true;
+        if (prev_set_le(s_hb, p) >= kRefWindow) mine_next = true; else mine_here = true;
     }
-    for (int i = tid; i < HW; i += kRefThreads)
-        if (s_acc[i]) atomicOr(&head_next[w0 + i], s_acc[i]);
+    for (int i = tid; i < HW; i += kRefThreads) {
+        const uint32_t fresh = s_hb[i] & ~head_cur[w0 + i];
+        if (fresh) atomicOr(&head_next[w0 + i], fresh);
+    }
     const int any_here = __syncthreads_or(mine_here);
     const int any_next = __syncthreads_or(mine_next);
     if (tid == 0) {
@@ -924,6 +1013,47 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
     const int key_bits = first_syms * bits;
 #define CALL(B) \
     make_keys_kernel<B><<<grid_for(n, 256 * 8), 256, 0, st>>>(packed, n, keys, drop_bits, key_bits, carry_prev)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         unsigned long long *hist, uint32_t *launches)
+{
+    const int drop_bits = (64 / bits - first_syms) * bits;
+    const int top_shift = first_syms * bits - top_bits;
+#define CALL(B) key_top_hist_kernel<B><<<grid_for(n, 256 * 16), 256, 0, st>>>(packed, n, drop_bits, top_shift, hist)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+uint64_t select_tiles(uint64_t n) { return div_up(n, kSelTile); }
+
+void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, uint64_t key_lo,
+                         uint64_t key_hi, uint64_t *tile_count, uint32_t *launches)
+{
+    const int drop_bits = (64 / bits - first_syms) * bits;
+#define CALL(B) \
+    select_count_kernel<B><<<(unsigned)select_tiles(n), 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_count)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
+                         uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
+                         uint32_t *launches)
+{
+    const int drop_bits = (64 / bits - first_syms) * bits;
+    const int key_bits = first_syms * bits;
+#define CALL(B)                                                                                                   \
+    select_write_kernel<B><<<(unsigned)select_tiles(n), 256, 0, st>>>(packed, n, drop_bits, key_bits, carry_prev, \
+                                                                      key_lo, key_hi, tile_off, keys, vals)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();

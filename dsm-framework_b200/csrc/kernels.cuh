@@ -34,6 +34,19 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
 // Group heads after the initial sort: bit i set iff suffix i starts a new group
 // (key differs from its predecessor) or is already finished (key holds the
 // terminator).  Bits >= n are set.  *remaining += suffixes left in groups of >= 2.
+// ---- key-range sharding (multi-GPU) -------------------------------------------
+// hist[4096]: counts of the top `top_bits` (<= 12) bits of every suffix's first key
+void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         unsigned long long *hist, uint32_t *launches);
+// per-tile counts (select_tiles(n) entries) of the suffixes whose first key lies in [key_lo, key_hi)
+uint64_t select_tiles(uint64_t n);
+void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, uint64_t key_lo,
+                         uint64_t key_hi, uint64_t *tile_count, uint32_t *launches);
+// (key, position) pairs of those suffixes, in text order; tile_off = exclusive scan of the counts
+void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
+                         uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
+                         uint32_t *launches);
+
 // Only the low key_bits of a key are compared.  If bwt != nullptr, bwt[i] = inv_map[code carried above
 // the key bits] is written for every rank i.
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,

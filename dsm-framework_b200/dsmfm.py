@@ -17,7 +17,13 @@ FLAG_KEEP_BWT, FLAG_KEEP_SA = 1, 2
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("samplerate", C.c_uint32), ("expected_bytes", C.c_uint64),
-                ("stream", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("stream", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
+
+
+class Shard(C.Structure):
+    _fields_ = [("n_total", C.c_uint64), ("rank_begin", C.c_uint64), ("count", C.c_uint64),
+                ("bwt_dev", C.c_void_p), ("sa_dev", C.c_void_p)]
 
 
 class Code(C.Structure):
@@ -93,6 +99,8 @@ def lib():
     L.dsmfm_destroy.argtypes = [B]
     L.dsmfm_destroy.restype = None
     L.dsmfm_release_cached.argtypes = [C.c_int]
+    L.dsmfm_shard_info.argtypes = [B, C.POINTER(Shard)]
+    L.dsmfm_assemble.argtypes = [B, C.c_void_p, C.c_uint64]
     L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
     L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]
@@ -129,10 +137,10 @@ def fmi_bytes(index):
 class Builder:
     """Mirror of the reference's TextCollectionBuilder over the C ABI."""
 
-    def __init__(self, device=-1, samplerate=0, expected_bytes=0, stream=None, flags=0):
+    def __init__(self, device=-1, samplerate=0, expected_bytes=0, stream=None, flags=0, shard_index=0, shard_count=1):
         self._L = lib()
         opt = Options(device=device, samplerate=samplerate, expected_bytes=expected_bytes,
-                      stream=stream, flags=flags, reserved=0)
+                      stream=stream, flags=flags, reserved=0, shard_index=shard_index, shard_count=shard_count)
         self._h = C.c_void_p()
         rc = self._L.dsmfm_create(C.byref(opt), C.byref(self._h))
         if rc != OK:
@@ -162,6 +170,17 @@ class Builder:
 
     def build_device(self):
         self._check(self._L.dsmfm_build_device(self._h))
+
+    def shard_info(self):
+        sh = Shard()
+        self._check(self._L.dsmfm_shard_info(self._h, C.byref(sh)))
+        return sh
+
+    def assemble(self, bwt_dev, n_total):
+        """bwt_dev: device address (int) or torch CUDA tensor holding the concatenated BWT."""
+        addr = bwt_dev.data_ptr() if hasattr(bwt_dev, "data_ptr") else int(bwt_dev)
+        self._keep.append(bwt_dev)
+        self._check(self._L.dsmfm_assemble(self._h, addr, n_total))
 
     def fetch(self):
         idx = Index()

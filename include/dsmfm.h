@@ -54,6 +54,12 @@ typedef struct dsmfm_options {
     void *stream;            /* cudaStream_t to run on; NULL = the builder creates its own        */
     uint32_t flags;          /* DSMFM_FLAG_*                                                      */
     uint32_t reserved;
+    /* Key-range sharding of ONE collection over several GPUs (one builder per GPU, every builder is
+     * given the WHOLE collection): builder `shard_index` of `shard_count` sorts the suffixes whose
+     * first key falls into its range and produces the matching contiguous slice of the global suffix
+     * array / BWT (dsmfm_shard_info).  shard_count 0 or 1 = the whole index on this GPU. */
+    uint32_t shard_index;
+    uint32_t shard_count;
 } dsmfm_options;
 
 #define DSMFM_FLAG_KEEP_BWT 1u /* keep the plain BWT in host memory after finish (dsmfm_index.bwt)   */
@@ -157,6 +163,22 @@ DSMFM_API int dsmfm_finish(dsmfm_builder *b, dsmfm_index *out);
  * dsmfm_fetch copies them to the host and fills `out`. */
 DSMFM_API int dsmfm_build_device(dsmfm_builder *b);
 DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out);
+
+/* ---- one collection over several GPUs (no counterpart in the single-process reference) ----
+ * After dsmfm_build_device on a sharded builder: the slice of the global suffix order it owns. */
+typedef struct dsmfm_shard {
+    uint64_t n_total;     /* symbols of the whole collection                                  */
+    uint64_t rank_begin;  /* global rank of the first suffix of this slice                    */
+    uint64_t count;       /* suffixes in this slice                                           */
+    const void *bwt_dev;  /* DEVICE pointer: BWT bytes of the slice [count]                   */
+    const void *sa_dev;   /* DEVICE pointer: text positions (u32) [count], needs KEEP_SA      */
+} dsmfm_shard;
+DSMFM_API int dsmfm_shard_info(dsmfm_builder *b, dsmfm_shard *out);
+
+/* On the assembling GPU: build C[], the code table, the wavelet tree and the BitRank directories
+ * from the concatenated BWT (`bwt_dev`, device memory, n_total bytes, slices in shard order).
+ * dsmfm_fetch then returns the index of the whole collection. */
+DSMFM_API int dsmfm_assemble(dsmfm_builder *b, const void *bwt_dev, uint64_t n_total);
 
 /* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
  * byte-for-byte in the reference layout (version 17). */
