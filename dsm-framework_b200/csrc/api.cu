@@ -320,7 +320,7 @@ struct dsmfm_builder {
     uint32_t samplerate = DSMFM_DEFAULT_SAMPLERATE;
     uint32_t flags = 0;
     uint64_t expected = 0;
-    uint32_t shard_index = 0, shard_count = 1;
+    uint32_t shard_index = 0, shard_count = 1, shard_span = 1;
     uint64_t shard_rank_begin = 0, shard_m = 0;
     bool assembled = false;
     std::string err;
@@ -342,7 +342,9 @@ struct dsmfm_builder {
     // device state of the build
     uint8_t *d_raw = nullptr;
     bool raw_is_chunk = false;
-    uint32_t *d_sa = nullptr;      // one of the value buffers of the sort (DSMFM_FLAG_KEEP_SA)
+    uint32_t *d_sa = nullptr;      // suffix array of the slice, low position bits (DSMFM_FLAG_KEEP_SA)
+    uint8_t *d_sa_hi = nullptr;    // wide builds: position = d_sa_hi << pos_lo_bits | d_sa
+    int pos_lo_bits = 32;
     uint8_t *d_bwt = nullptr;      // lives in the first key buffer of the sort
     WaveletResult wt;
     uint8_t *h_bwt = nullptr;
@@ -427,6 +429,7 @@ struct dsmfm_builder {
         chunks.clear();
         d_raw = nullptr;
         d_sa = nullptr;
+        d_sa_hi = nullptr;
         d_bwt = nullptr;
         dev_now = 0;
         wt.release(stream);
@@ -457,9 +460,6 @@ void dsmfm_builder::build()
         push_device(&z, 1, cudaMemcpyHostToDevice);
         DSM_CUDA(cudaStreamSynchronize(st));
         empty_collection = true;
-    }
-    if (n >= (1ull << 32) - kRefCap - 64) {
-        throw CudaError{cudaErrorInvalidValue, "more than 2^32 symbols on one device (shard the collection)", __FILE__, __LINE__};
     }
 
     // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the
@@ -538,7 +538,25 @@ void dsmfm_builder::build()
     if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
     if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
     int first_syms = std::max(1, first_key_bits / bits);
-    if (shard_count > 1 && first_syms * bits == 64) --first_syms; // key ranges need an exclusive upper bound
+    // Text positions: the u32 value of the sort holds the low `lo_bits` bits (32; fewer only in tests, which
+    // thereby exercise the wide path on small inputs), anything above rides in the key's spare top bits.
+    const bool sharded = shard_count > 1;
+    int lo_bits = 32;
+    if (const char *e = std::getenv("DSMFM_POS_LO_BITS")) lo_bits = std::min(32, std::max(4, std::atoi(e)));
+    if (!sharded) lo_bits = 32;
+    int hi_bits = 0;
+    while (lo_bits + hi_bits < 64 && ((n - 1) >> (lo_bits + hi_bits))) ++hi_bits;
+    const bool wide = hi_bits > 0;
+    if (wide && !sharded)
+        throw CudaError{cudaErrorInvalidValue, "more than 2^32 symbols in one unsharded build (set shard_count / shard_span)", __FILE__, __LINE__};
+    if (hi_bits > 8)
+        throw CudaError{cudaErrorInvalidValue, "more than 2^32 * 256 symbols", __FILE__, __LINE__};
+    // sharded builds always carry the BWT symbol (and the high position bits) above the sorted key bits
+    if (sharded)
+        while (first_syms > 1 && first_syms * bits + bits + hi_bits > 64) --first_syms;
+    const bool carry_bwt = first_syms * bits + bits + hi_bits <= 64;
+    if (sharded && !carry_bwt)
+        throw CudaError{cudaErrorInvalidValue, "no room in the key for the carried fields", __FILE__, __LINE__};
     uint8_t inv_map[256];
     std::memset(inv_map, 0, sizeof inv_map);
     for (int c = 1; c < 256; ++c)
@@ -564,13 +582,19 @@ void dsmfm_builder::build()
     DSM_CUDA(cudaEventRecord(ev[1], st));
 
     // ---- which suffixes this builder sorts ------------------------------------------------
-    // Unsharded: all n.  Sharded: the ones whose first key lies in this shard's key range; the ranges
-    // are cut from a 4096-bin histogram of the top key bits, which every shard computes identically
-    // from the (replicated) text, so no communication is needed to agree on them.
-    const bool sharded = shard_count > 1;
+    // Unsharded: all n, in one go.  Sharded: the collection is cut into `shard_count` key ranges of
+    // about equal population (from a 4096-bin histogram of the top key bits, which every builder
+    // computes identically from the replicated text, so no communication is needed to agree on them);
+    // this builder sorts ranges [shard_index, shard_index + shard_span) one after the other, which
+    // yields one contiguous slice of the global suffix order and bounds the sort buffers by the
+    // largest single range.
+    struct Range { uint64_t key_lo, key_hi, count, rank_begin; };
+    std::vector<Range> ranges;
     const int key_bits = first_syms * bits; // sorted bits of the first key
-    uint64_t m = n, key_lo = 0, key_hi = 0;
-    if (sharded) {
+    const int hi_shift = wide ? key_bits + bits : 0;
+    if (!sharded) {
+        ranges.push_back(Range{0, 0, n, 0});
+    } else {
         const int top_bits = key_bits < 12 ? key_bits : 12;
         const int nbins = 1 << top_bits;
         unsigned long long *d_top = static_cast<unsigned long long *>(dmalloc(4096 * 8));
@@ -580,207 +604,260 @@ void dsmfm_builder::build()
         DSM_CUDA(cudaMemcpyAsync(top.data(), d_top, 4096 * 8, cudaMemcpyDeviceToHost, st));
         DSM_CUDA(cudaStreamSynchronize(st));
         dfree(d_top);
-        // shard s takes the bins whose running count first reaches s*n/G ... (s+1)*n/G
+        // range s takes the bins whose running count first reaches s*n/G ... (s+1)*n/G
         std::vector<int> cut(shard_count + 1, nbins);
         cut[0] = 0;
         uint64_t run = 0;
         uint32_t next = 1;
         for (int bin = 0; bin < nbins && next < shard_count; ++bin) {
             run += top[bin];
-            while (next < shard_count && run >= (n / shard_count) * next + (n % shard_count) * next / shard_count) {
+            while (next < shard_count &&
+                   run >= (n / shard_count) * next + (n % shard_count) * next / shard_count) {
                 cut[next++] = bin + 1;
             }
         }
-        const int b_lo = cut[shard_index], b_hi = cut[shard_index + 1];
-        uint64_t before = 0;
-        m = 0;
-        for (int bin = 0; bin < b_lo; ++bin) before += top[bin];
-        for (int bin = b_lo; bin < b_hi; ++bin) m += top[bin];
-        shard_rank_begin = before;
-        key_lo = (uint64_t)b_lo << (key_bits - top_bits);
-        key_hi = b_hi >= nbins ? (key_bits >= 64 ? ~0ull : (1ull << key_bits)) : ((uint64_t)b_hi << (key_bits - top_bits));
+        std::vector<uint64_t> before(nbins + 1, 0);
+        for (int bin = 0; bin < nbins; ++bin) before[bin + 1] = before[bin] + top[bin];
+        for (uint32_t v = shard_index; v < shard_index + shard_span; ++v) {
+            const int b_lo = cut[v], b_hi = cut[v + 1];
+            Range r;
+            r.rank_begin = before[b_lo];
+            r.count = before[b_hi] - before[b_lo];
+            r.key_lo = (uint64_t)b_lo << (key_bits - top_bits);
+            r.key_hi = b_hi >= nbins ? (1ull << key_bits) : ((uint64_t)b_hi << (key_bits - top_bits));
+            if (v == shard_index) shard_rank_begin = r.rank_begin;
+            if (r.count) ranges.push_back(r);
+        }
     }
-    shard_m = m;
-    const uint64_t ma = m ? m : 1; // allocation sizes for an empty shard
+    uint64_t m_total = 0, m_max = 1;
+    for (const Range &r : ranges) {
+        m_total += r.count;
+        m_max = std::max(m_max, r.count);
+    }
+    shard_m = m_total;
+    if (m_max >= (1ull << 32) - kRefCap - 64)
+        throw CudaError{cudaErrorInvalidValue,
+                        "more than 2^32 suffixes in one sort range (use more shards: shard_count / shard_span)", __FILE__, __LINE__};
 
-    // ---- initial sort by the first SPW symbols ---------------------------------------
-    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(ma * 8));
-    uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(ma * 8));
-    uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(ma * 4 + 16));
-    uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(ma * 4 + 16));
+    // ---- buffers of one range (sized for the largest) -------------------------------------
+    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(m_max * 8));
+    uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(m_max * 8));
+    uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
+    uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
     RadixWorkspace ws; // buffers owned by the builder's allocation list
-    ws.status_tiles = div_up(ma < kSweepPortion ? ma : kSweepPortion, kSweepTile);
+    ws.status_tiles = div_up(m_max < kSweepPortion ? m_max : kSweepPortion, kSweepTile);
     ws.hist = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * kMaxPasses * kRadix));
     ws.carry = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * 2 * kRadix));
     ws.status = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t) * ws.status_tiles * kRadix));
     ws.counter = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t)));
-    // When the key leaves room, the symbol before each suffix rides above the sorted bits and the BWT
-    // falls out of the sort; otherwise it is gathered from the text at the end.
-    const bool carry_bwt = first_syms * bits + bits <= 64;
-    const int full_key_bits = spw * bits;   // sorted bits of a refinement key (large-group path)
-    if (!sharded) {
-        launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
-    } else if (m) {
-        const uint64_t ntile = select_tiles(n);
-        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
-        launch_select_count(st, bits, d_packed, n, first_syms, key_lo, key_hi, d_tile, L);
-        launch_wt_scan(st, d_tile, 1, ntile, L);
-        launch_select_write(st, bits, d_packed, n, first_syms, carry_bwt, key_lo, key_hi, d_tile, d_keys_a, d_vals_a, L);
-        dfree(d_tile);
-    }
-    const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
-                                        ev_pass0, ev_pass1);
-    uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
-    uint32_t *d_sorted_vals = (passes & 1) ? d_vals_b : d_vals_a;
-    uint32_t *d_other_vals = (passes & 1) ? d_vals_a : d_vals_b;
-    stats.sort_passes = passes;
-    stats.sort_pass_bytes = m * 24ull;
-
-    const uint64_t hwords = head_words_for(m);
+    const int full_key_bits = spw * bits; // sorted bits of a refinement key (large-group path)
+    const uint64_t hwords = head_words_for(m_max);
     uint32_t *d_head[2];
     d_head[0] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(64 * 8));
-    const uint32_t big_cap = (uint32_t)(m / kRefGroupMax + 2);
+    const uint32_t big_cap = (uint32_t)(m_max / kRefGroupMax + 2);
     uint32_t *d_big_heads = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_count = static_cast<uint32_t *>(dmalloc(4));
-    DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
-    // the BWT lives in its own buffer while the key buffers are still needed by the large-group path
-    d_bwt = static_cast<uint8_t *>(dmalloc(ma + 64));
-    launch_heads(st, bits, d_sorted_keys, m, d_head[0], hwords, d_remaining, key_bits, d_inv,
-                 carry_bwt ? d_bwt : nullptr, L);
-    DSM_CUDA(cudaEventRecord(ev[2], st));
-
-    auto read_remaining = [&]() -> uint64_t {
-        unsigned long long h[64];
-        DSM_CUDA(cudaMemcpyAsync(h, d_remaining, sizeof h, cudaMemcpyDeviceToHost, st));
-        DSM_CUDA(cudaStreamSynchronize(st));
-        uint64_t t = 0;
-        for (auto x : h) t += x;
-        return t;
-    };
-    uint64_t remaining = read_remaining();
-
-    // ---- refinement rounds ------------------------------------------------------------
-    // Suffixes that still agree on their first `depth` symbols are re-sorted by the next
-    // SPW symbols taken straight from the packed text.  (The reference re-keys with the
-    // ranks of the suffixes h positions ahead, utils.cpp:236-262; documents here are short,
-    // the text fits in HBM next to the suffix array, and extending the key from the text
-    // needs neither an inverse suffix array nor rank scatter traffic.)
-    int cur = 0;
-    uint32_t round = 0;
-    uint32_t depth_next = (uint32_t)first_syms; // symbols every unresolved group is known to agree on
-    const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
-    // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
-    const uint32_t nwin = (uint32_t)div_up(ma, kRefWindow);
-    uint32_t *d_win_flag = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
+    const uint32_t nwin_max = (uint32_t)div_up(m_max, kRefWindow);
+    uint32_t *d_win_flag = static_cast<uint32_t *>(dmalloc((size_t)nwin_max * 4));
     uint32_t *d_win_list[2];
-    d_win_list[0] = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
-    d_win_list[1] = static_cast<uint32_t *>(dmalloc((size_t)nwin * 4));
+    d_win_list[0] = static_cast<uint32_t *>(dmalloc((size_t)nwin_max * 4));
+    d_win_list[1] = static_cast<uint32_t *>(dmalloc((size_t)nwin_max * 4));
     uint32_t *d_win_count = static_cast<uint32_t *>(dmalloc(4));
-    const uint32_t *win_list = nullptr;
-    uint32_t n_list = nwin;
+    // results of the whole slice: the BWT (its own buffer: the key buffers are still needed by the
+    // large-group path), optionally the suffix array
+    d_bwt = static_cast<uint8_t *>(dmalloc(m_total + 64));
+    const bool keep_sa = (flags & DSMFM_FLAG_KEEP_SA) != 0;
+    uint32_t *d_sa_all = nullptr;
+    uint8_t *d_hi_buf = nullptr; // wide: high parts of the positions (whole slice if kept, else one range)
+    if (sharded && keep_sa) d_sa_all = static_cast<uint32_t *>(dmalloc(m_total * 4 + 16));
+    if (wide) d_hi_buf = static_cast<uint8_t *>(dmalloc((keep_sa ? m_total : m_max) + 16));
+
     // multi-step: one launch resolves every group that fits a CTA (DSMFM_REFINE_SINGLE_STEP=1 keeps
     // the one-depth-per-launch schedule, used by the tests to exercise the worklist path)
     bool multi_step = true;
     if (const char *e = std::getenv("DSMFM_REFINE_SINGLE_STEP")) multi_step = std::atoi(e) == 0;
     int key_words = 1; // symbols compared per step = key_words * SPW (DSMFM_REFINE_KEY_WORDS=2: 128-bit keys)
     if (const char *e = std::getenv("DSMFM_REFINE_KEY_WORDS")) key_words = std::atoi(e) == 2 ? 2 : 1;
-    int wl = 0;
-    while (remaining > 0) {
-        if (round >= max_rounds)
-            throw CudaError{cudaErrorUnknown, "refinement did not converge (internal error)", __FILE__, __LINE__};
-        if (round < 32) stats.active[round] = remaining;
-        ++round;
-        const uint32_t depth = depth_next;
-        DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hwords * 4, cudaMemcpyDeviceToDevice, st));
-        DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
-        DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
-        DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
-        DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
-        launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
-                      d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                      carry_bwt ? d_bwt : nullptr, multi_step, key_words, L);
-        uint32_t nbig = 0;
-        DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
-        remaining = read_remaining();
-        if (nbig > 0) {
-            // groups too large for one CTA: one global (group, key) radix sort over all of them
-            if (nbig > big_cap) throw CudaError{cudaErrorUnknown, "large-group list overflow", __FILE__, __LINE__};
-            launch_big_extent(st, d_head[cur], m, d_big_heads, nbig, d_big_len, L);
-            std::vector<uint32_t> heads(nbig), lens(nbig);
-            DSM_CUDA(cudaMemcpyAsync(heads.data(), d_big_heads, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
-            DSM_CUDA(cudaMemcpyAsync(lens.data(), d_big_len, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
-            DSM_CUDA(cudaStreamSynchronize(st));
-            std::vector<uint32_t> order(nbig);
-            for (uint32_t i = 0; i < nbig; ++i) order[i] = i;
-            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return heads[a] < heads[b]; });
-            std::vector<uint32_t> sheads(nbig);
-            std::vector<uint64_t> offs(nbig + 1);
-            uint64_t total = 0;
-            for (uint32_t i = 0; i < nbig; ++i) {
-                sheads[i] = heads[order[i]];
-                offs[i] = total;
-                total += lens[order[i]];
-            }
-            offs[nbig] = total;
-            stats.fallback_elems += total;
-            uint64_t *d_off = static_cast<uint64_t *>(dmalloc((size_t)(nbig + 1) * 8));
-            uint32_t *d_bsa = static_cast<uint32_t *>(dmalloc(total * 4));
-            uint32_t *d_bgid = static_cast<uint32_t *>(dmalloc(total * 4));
-            uint64_t *d_bkey = static_cast<uint64_t *>(dmalloc(total * 8));
-            uint32_t *d_perm = static_cast<uint32_t *>(dmalloc(total * 4 + 16));
-            DSM_CUDA(cudaMemcpyAsync(d_big_heads, sheads.data(), (size_t)nbig * 4, cudaMemcpyHostToDevice, st));
-            DSM_CUDA(cudaMemcpyAsync(d_off, offs.data(), (size_t)(nbig + 1) * 8, cudaMemcpyHostToDevice, st));
-            launch_big_gather(st, bits, d_packed, d_sorted_vals, depth, d_big_heads, d_off, nbig, total, d_bsa, d_bkey,
-                              d_bgid, L);
-            // the key buffers of the initial sort are free by now
-            DSM_CUDA(cudaMemcpyAsync(d_keys_a, d_bkey, total * 8, cudaMemcpyDeviceToDevice, st));
-            int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, full_key_bits, true, L);
-            // pass 0 writes (keys_b, perm); an odd pass count leaves the result there
-            uint64_t *kfree = (p1 & 1) ? d_keys_a : d_keys_b;
-            uint32_t *pres = (p1 & 1) ? d_perm : d_other_vals;
-            uint32_t *pfree = (p1 & 1) ? d_other_vals : d_perm;
-            if (nbig > 1) {
-                int gbits = 1;
-                while ((1ull << gbits) < nbig) ++gbits;
-                launch_gather_u32_to_u64(st, d_bgid, pres, total, kfree, L);
-                uint64_t *k2a = kfree, *k2b = (kfree == d_keys_a) ? d_keys_b : d_keys_a;
-                int p2 = radix_sort_pairs(st, ws, k2a, pres, k2b, pfree, total, 0, gbits, false, L);
-                if (p2 & 1) std::swap(pres, pfree);
-            }
-            launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, d_sorted_vals,
-                               d_head[cur ^ 1], d_win_flag, d_win_list[wl], d_win_count, d_packed, d_inv,
-                               carry_bwt ? d_bwt : nullptr, L);
-            DSM_CUDA(cudaStreamSynchronize(st)); // sheads / offs are host vectors
-            dfree(d_off);
-            dfree(d_bsa);
-            dfree(d_bgid);
-            dfree(d_bkey);
-            dfree(d_perm);
-            remaining += total; // re-examined (and counted exactly) by the next round
+
+    cudaEvent_t evr[3];
+    for (auto &e : evr) DSM_CUDA(cudaEventCreate(&e));
+    float ms_sort = 0.f, ms_refine = 0.f, ms_passes = 0.f;
+    uint64_t pass_launch_bytes = 0;
+    uint32_t pass_launches = 0, rounds_max = 0;
+    uint32_t *d_last_sorted_vals = nullptr, *d_last_other_vals = nullptr;
+
+    uint64_t off = 0; // slot of the range's first suffix inside this builder's slice
+    for (const Range &rg : ranges) {
+        const uint64_t m = rg.count;
+        uint8_t *bwt_out = d_bwt + off;
+        uint8_t *hi_out = wide ? d_hi_buf + (keep_sa ? off : 0) : nullptr;
+        DSM_CUDA(cudaEventRecord(evr[0], st));
+
+        // ---- initial sort by the first `first_syms` symbols -------------------------------
+        // When the key leaves room, the symbol before each suffix rides above the sorted bits and the
+        // BWT falls out of the sort; otherwise it is gathered from the text at the end.
+        if (!sharded) {
+            launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
+        } else {
+            const uint64_t ntile = select_tiles(n);
+            uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
+            launch_select_count(st, bits, d_packed, n, first_syms, rg.key_lo, rg.key_hi, d_tile, L);
+            launch_wt_scan(st, d_tile, 1, ntile, L);
+            launch_select_write(st, bits, d_packed, n, first_syms, carry_bwt, rg.key_lo, rg.key_hi, d_tile, d_keys_a,
+                                d_vals_a, lo_bits, hi_shift, L);
+            dfree(d_tile);
         }
-        // a CTA step consumes key_words*SPW symbols, the large-group path SPW; starting the next launch at the
-        // smaller of the two is always safe (already-equal symbols just compare equal again)
-        depth_next = depth + ((multi_step || nbig > 0) ? (uint32_t)spw : (uint32_t)(key_words * spw));
-        DSM_CUDA(cudaMemcpyAsync(&n_list, d_win_count, 4, cudaMemcpyDeviceToHost, st));
+        const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
+                                            ev_pass0, ev_pass1);
+        uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
+        uint32_t *d_sorted_vals = (passes & 1) ? d_vals_b : d_vals_a;
+        uint32_t *d_other_vals = (passes & 1) ? d_vals_a : d_vals_b;
+        d_last_sorted_vals = d_sorted_vals;
+        d_last_other_vals = d_other_vals;
+        stats.sort_passes = passes;
+        pass_launches += (uint32_t)passes;
+        pass_launch_bytes += (uint64_t)passes * m * 24ull;
+
+        DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+        const uint64_t hw = head_words_for(m);
+        launch_heads(st, bits, d_sorted_keys, m, d_head[0], hw, d_remaining, key_bits, d_inv,
+                     carry_bwt ? bwt_out : nullptr, hi_out, hi_shift, L);
+        DSM_CUDA(cudaEventRecord(evr[1], st));
+
+        auto read_remaining = [&]() -> uint64_t {
+            unsigned long long h[64];
+            DSM_CUDA(cudaMemcpyAsync(h, d_remaining, sizeof h, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            uint64_t t = 0;
+            for (auto x : h) t += x;
+            return t;
+        };
+        uint64_t remaining = read_remaining();
+
+        // ---- refinement rounds ------------------------------------------------------------
+        // Suffixes that still agree on their first `depth` symbols are re-sorted by the next
+        // SPW symbols taken straight from the packed text.  (The reference re-keys with the
+        // ranks of the suffixes h positions ahead, utils.cpp:236-262; documents here are short,
+        // the text fits in HBM next to the suffix array, and extending the key from the text
+        // needs neither an inverse suffix array nor rank scatter traffic.)
+        int cur = 0;
+        uint32_t round = 0;
+        uint32_t depth_next = (uint32_t)first_syms; // symbols every unresolved group is known to agree on
+        const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
+        // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
+        const uint32_t nwin = (uint32_t)div_up(m, kRefWindow);
+        const uint32_t *win_list = nullptr;
+        uint32_t n_list = nwin;
+        int wl = 0;
+        while (remaining > 0) {
+            if (round >= max_rounds)
+                throw CudaError{cudaErrorUnknown, "refinement did not converge (internal error)", __FILE__, __LINE__};
+            if (round < 32) stats.active[round] += remaining;
+            ++round;
+            const uint32_t depth = depth_next;
+            DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hw * 4, cudaMemcpyDeviceToDevice, st));
+            DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+            DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
+            DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
+            DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
+            launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
+                          d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
+                          carry_bwt ? bwt_out : nullptr, multi_step, key_words, hi_out, lo_bits, L);
+            uint32_t nbig = 0;
+            DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
+            remaining = read_remaining();
+            if (nbig > 0) {
+                // groups too large for one CTA: one global (group, key) radix sort over all of them
+                if (nbig > big_cap) throw CudaError{cudaErrorUnknown, "large-group list overflow", __FILE__, __LINE__};
+                launch_big_extent(st, d_head[cur], m, d_big_heads, nbig, d_big_len, L);
+                std::vector<uint32_t> heads(nbig), lens(nbig);
+                DSM_CUDA(cudaMemcpyAsync(heads.data(), d_big_heads, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+                DSM_CUDA(cudaMemcpyAsync(lens.data(), d_big_len, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
+                DSM_CUDA(cudaStreamSynchronize(st));
+                std::vector<uint32_t> order(nbig);
+                for (uint32_t i = 0; i < nbig; ++i) order[i] = i;
+                std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return heads[a] < heads[b]; });
+                std::vector<uint32_t> sheads(nbig);
+                std::vector<uint64_t> offs(nbig + 1);
+                uint64_t total = 0;
+                for (uint32_t i = 0; i < nbig; ++i) {
+                    sheads[i] = heads[order[i]];
+                    offs[i] = total;
+                    total += lens[order[i]];
+                }
+                offs[nbig] = total;
+                stats.fallback_elems += total;
+                uint64_t *d_off = static_cast<uint64_t *>(dmalloc((size_t)(nbig + 1) * 8));
+                uint32_t *d_bsa = static_cast<uint32_t *>(dmalloc(total * 4));
+                uint32_t *d_bgid = static_cast<uint32_t *>(dmalloc(total * 4));
+                uint64_t *d_bkey = static_cast<uint64_t *>(dmalloc(total * 8));
+                uint32_t *d_perm = static_cast<uint32_t *>(dmalloc(total * 4 + 16));
+                uint8_t *d_bhi = wide ? static_cast<uint8_t *>(dmalloc(total + 16)) : nullptr;
+                DSM_CUDA(cudaMemcpyAsync(d_big_heads, sheads.data(), (size_t)nbig * 4, cudaMemcpyHostToDevice, st));
+                DSM_CUDA(cudaMemcpyAsync(d_off, offs.data(), (size_t)(nbig + 1) * 8, cudaMemcpyHostToDevice, st));
+                launch_big_gather(st, bits, d_packed, d_sorted_vals, depth, d_big_heads, d_off, nbig, total, d_bsa,
+                                  d_bkey, d_bgid, hi_out, d_bhi, lo_bits, L);
+                // the key buffers of the initial sort are free by now
+                DSM_CUDA(cudaMemcpyAsync(d_keys_a, d_bkey, total * 8, cudaMemcpyDeviceToDevice, st));
+                int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, full_key_bits, true, L);
+                // pass 0 writes (keys_b, perm); an odd pass count leaves the result there
+                uint64_t *kfree = (p1 & 1) ? d_keys_a : d_keys_b;
+                uint32_t *pres = (p1 & 1) ? d_perm : d_other_vals;
+                uint32_t *pfree = (p1 & 1) ? d_other_vals : d_perm;
+                if (nbig > 1) {
+                    int gbits = 1;
+                    while ((1ull << gbits) < nbig) ++gbits;
+                    launch_gather_u32_to_u64(st, d_bgid, pres, total, kfree, L);
+                    uint64_t *k2a = kfree, *k2b = (kfree == d_keys_a) ? d_keys_b : d_keys_a;
+                    int p2 = radix_sort_pairs(st, ws, k2a, pres, k2b, pfree, total, 0, gbits, false, L);
+                    if (p2 & 1) std::swap(pres, pfree);
+                }
+                launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, d_sorted_vals,
+                                   d_head[cur ^ 1], d_win_flag, d_win_list[wl], d_win_count, d_packed, d_inv,
+                                   carry_bwt ? bwt_out : nullptr, d_bhi, hi_out, lo_bits, L);
+                DSM_CUDA(cudaStreamSynchronize(st)); // sheads / offs are host vectors
+                dfree(d_off);
+                dfree(d_bsa);
+                dfree(d_bgid);
+                dfree(d_bkey);
+                dfree(d_perm);
+                dfree(d_bhi);
+                remaining += total; // re-examined (and counted exactly) by the next round
+            }
+            // a CTA step consumes key_words*SPW symbols, the large-group path SPW; starting the next launch at the
+            // smaller of the two is always safe (already-equal symbols just compare equal again)
+            depth_next = depth + ((multi_step || nbig > 0) ? (uint32_t)spw : (uint32_t)(key_words * spw));
+            DSM_CUDA(cudaMemcpyAsync(&n_list, d_win_count, 4, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            win_list = d_win_list[wl];
+            wl ^= 1;
+            cur ^= 1;
+            if (remaining > 0 && n_list == 0)
+                throw CudaError{cudaErrorUnknown, "unresolved groups without an owning window (internal error)", __FILE__, __LINE__};
+        }
+        rounds_max = std::max(rounds_max, round);
+        // ---- BWT when it could not ride along (64-bit first keys, unsharded only) -----------
+        if (!carry_bwt) launch_bwt(st, bits, d_packed, d_inv, d_sorted_vals, m, bwt_out, L);
+        if (d_sa_all) DSM_CUDA(cudaMemcpyAsync(d_sa_all + off, d_sorted_vals, m * 4, cudaMemcpyDeviceToDevice, st));
+        DSM_CUDA(cudaEventRecord(evr[2], st));
         DSM_CUDA(cudaStreamSynchronize(st));
-        win_list = d_win_list[wl];
-        wl ^= 1;
-        cur ^= 1;
-        if (remaining > 0 && n_list == 0)
-            throw CudaError{cudaErrorUnknown, "unresolved groups without an owning window (internal error)", __FILE__, __LINE__};
+        float ms;
+        cudaEventElapsedTime(&ms, evr[0], evr[1]); ms_sort += ms;
+        cudaEventElapsedTime(&ms, evr[1], evr[2]); ms_refine += ms;
+        if (passes) { cudaEventElapsedTime(&ms, ev_pass0, ev_pass1); ms_passes += ms; }
+        off += m;
     }
+    for (auto &e : evr) cudaEventDestroy(e);
     dfree(d_win_flag);
     dfree(d_win_list[0]);
     dfree(d_win_list[1]);
     dfree(d_win_count);
-    stats.rounds = round;
+    stats.rounds = rounds_max;
+    stats.sort_pass_bytes = pass_launches ? pass_launch_bytes / pass_launches : 0;
     DSM_CUDA(cudaEventRecord(ev[3], st));
-
-    // ---- BWT ------------------------------------------------------------------------
-    if (!carry_bwt && m) launch_bwt(st, bits, d_packed, d_inv, d_sorted_vals, m, d_bwt, L);
     DSM_CUDA(cudaEventRecord(ev[4], st));
 
     // ---- C table, code table, wavelet tree ---------------------------------------------
@@ -815,11 +892,17 @@ void dsmfm_builder::build()
     dfree(ws.carry);
     dfree(ws.status);
     dfree(ws.counter);
-    dfree(d_other_vals);
-    if (flags & DSMFM_FLAG_KEEP_SA)
-        d_sa = d_sorted_vals;
-    else
-        dfree(d_sorted_vals);
+    dfree(d_last_other_vals);
+    if (sharded) {
+        dfree(d_last_sorted_vals);
+        d_sa = d_sa_all;
+        if (keep_sa) d_sa_hi = d_hi_buf; else dfree(d_hi_buf);
+    } else if (keep_sa) {
+        d_sa = d_last_sorted_vals;
+    } else {
+        dfree(d_last_sorted_vals);
+    }
+    pos_lo_bits = lo_bits;
     dfree(d_raw);
     chunks.clear();
     d_raw = nullptr;
@@ -827,10 +910,10 @@ void dsmfm_builder::build()
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[5]); stats.ms_total = ms;
     cudaEventElapsedTime(&ms, ev[0], ev[1]); stats.ms_pack = ms;
-    cudaEventElapsedTime(&ms, ev[1], ev[2]); stats.ms_sort = ms;
-    cudaEventElapsedTime(&ms, ev_pass0, ev_pass1); stats.ms_sort_pass = passes ? ms / passes : 0.f;
-    cudaEventElapsedTime(&ms, ev[2], ev[3]); stats.ms_refine = ms;
-    cudaEventElapsedTime(&ms, ev[3], ev[4]); stats.ms_bwt = ms;
+    stats.ms_sort = ms_sort;
+    stats.ms_sort_pass = pass_launches ? ms_passes / pass_launches : 0.f;
+    stats.ms_refine = ms_refine;
+    stats.ms_bwt = 0.f; // the BWT rides through the sort (or is gathered inside the range loop)
     cudaEventElapsedTime(&ms, ev[4], ev[5]); stats.ms_wt = ms;
     stats.device_bytes_peak = dev_peak;
     for (auto &e : ev) cudaEventDestroy(e);
@@ -915,8 +998,9 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
         b->stream = static_cast<cudaStream_t>(opts->stream);
         b->shard_count = opts->shard_count ? opts->shard_count : 1;
         b->shard_index = opts->shard_index;
-        if (b->shard_index >= b->shard_count) {
-            g_create_error = "shard_index out of range";
+        b->shard_span = opts->shard_span ? opts->shard_span : 1;
+        if (b->shard_index >= b->shard_count || b->shard_span > b->shard_count - b->shard_index) {
+            g_create_error = "shard_index / shard_span out of range";
             delete b;
             return DSMFM_EINVAL;
         }
@@ -1037,7 +1121,25 @@ DSMFM_API int dsmfm_shard_info(dsmfm_builder *b, dsmfm_shard *out)
     out->rank_begin = b->shard_rank_begin;
     out->count = b->shard_m;
     out->bwt_dev = b->d_bwt;
-    out->sa_dev = b->d_sa;
+    out->sa_dev = nullptr;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_shard_export(dsmfm_builder *b, void *bwt_dst_dev, void *sa_dst_dev)
+{
+    API_GUARD(b);
+    if (!b->built || !b->d_bwt) return b->fail(DSMFM_EINVAL, "dsmfm_shard_export: nothing built (or already fetched)");
+    if (sa_dst_dev && !b->d_sa) return b->fail(DSMFM_EINVAL, "dsmfm_shard_export: the suffix array needs DSMFM_FLAG_KEEP_SA");
+    const uint64_t m = b->shard_count > 1 ? b->shard_m : b->index.n;
+    try {
+        if (bwt_dst_dev && m) DSM_CUDA(cudaMemcpyAsync(bwt_dst_dev, b->d_bwt, m, cudaMemcpyDeviceToDevice, b->stream));
+        if (sa_dst_dev)
+            launch_widen_sa(b->stream, b->d_sa, b->d_sa_hi, b->pos_lo_bits, m, static_cast<uint64_t *>(sa_dst_dev),
+                            &b->stats.kernel_launches);
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
     return DSMFM_OK;
 }
 
@@ -1096,6 +1198,7 @@ DSMFM_API int dsmfm_copy_sa(dsmfm_builder *b, uint32_t *out, uint64_t first, uin
 {
     API_GUARD(b);
     if (!b->d_sa) return b->fail(DSMFM_EINVAL, "dsmfm_copy_sa: needs DSMFM_FLAG_KEEP_SA and a finished build");
+    if (b->shard_count > 1) return b->fail(DSMFM_EINVAL, "dsmfm_copy_sa: sharded builders export their slice with dsmfm_shard_export");
     if (!out || first > b->index.n || count > b->index.n - first) return b->fail(DSMFM_EINVAL, "dsmfm_copy_sa: range out of bounds");
     cudaError_t e = cudaMemcpy(out, b->d_sa + first, count * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return b->fail(DSMFM_ECUDA, "dsmfm_copy_sa: %s", cudaGetErrorString(e));

@@ -270,8 +270,9 @@ template <int BITS>
 __global__ void __launch_bounds__(256)
 select_write_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bits, int key_bits, bool carry_prev,
                     uint64_t key_lo, uint64_t key_hi, const uint64_t *__restrict__ tile_off,
-                    uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                    uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int lo_bits, int hi_shift)
 {
+    const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
     __shared__ uint32_t scratch[9];
     const uint64_t p0 = (uint64_t)blockIdx.x * kSelTile + (uint64_t)threadIdx.x * 16;
     uint32_t sel = 0;
@@ -292,8 +293,10 @@ select_write_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bi
         const uint64_t p = p0 + j;
         uint64_t k = first_key<BITS>(packed, p, drop_bits);
         if (carry_prev && p) k |= (uint64_t)text_symbol<BITS>(packed, p - 1) << key_bits;
+        // positions beyond lo_bits bits: the high part rides in the key's spare top bits (never sorted on)
+        if (hi_shift) k |= (p >> lo_bits) << hi_shift;
         keys[o] = k;
-        vals[o] = (uint32_t)p;
+        vals[o] = (uint32_t)(p & lo_mask);
         ++o;
     }
 }
@@ -305,7 +308,8 @@ template <int BITS>
 __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
                                                     unsigned long long *__restrict__ remaining, int key_bits,
-                                                    const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt)
+                                                    const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt,
+                                                    uint8_t *__restrict__ pos_hi, int hi_shift)
 {
     __shared__ unsigned long long s_cnt[8];
     __shared__ uint8_t s_inv[256];
@@ -330,6 +334,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
             act = !(h && hn);
             // the symbol before suffix i rode along above the sorted bits (make_keys_kernel)
             if (bwt) bwt[i] = s_inv[(kraw >> key_bits) & Pack<BITS>::FIELD];
+            if (pos_hi) pos_hi[i] = (uint8_t)(kraw >> hi_shift); // high part of the text position (wide builds)
         }
         const uint32_t word = __ballot_sync(0xffffffffu, h);
         const uint32_t aw = __ballot_sync(0xffffffffu, act);
@@ -366,12 +371,13 @@ __device__ __forceinline__ int next_set_gt(const uint32_t *hw, int r)
     return (w << 5) + __ffs(m) - 1;
 }
 
-template <int KW> struct RefSmem {
+template <int KW, bool WIDE> struct RefSmem {
     uint64_t khi[kRefCap];              // key = the next KW*SPW symbols (hi [, lo])
     uint64_t klo[KW == 2 ? kRefCap : 1];
     uint32_t sa[2][kRefCap];            // suffixes, double buffered across a step
     uint16_t list[2][kRefCap];          // unresolved slots (relative to the window), current / next step
     uint8_t bw[2][kRefCap];             // BWT bytes travelling with the suffixes
+    uint8_t hi[2][WIDE ? kRefCap : 1];  // wide builds: text position = hi << lo_bits | sa
     uint32_t head_a[kRefCap / 32 + 2];  // group heads the ranking phase reads
     uint32_t head_b[kRefCap / 32 + 2];  // = head_a plus the heads found in the current step
     int n[2];
@@ -386,24 +392,25 @@ template <int KW> struct RefSmem {
 //   rank:     every unresolved suffix finds its stable rank inside its group (all pairs), moves to
 //             the other buffer and marks the new group heads;
 //   classify: resolved suffixes go home; the others fetch their next key and join the next list.
-template <int BITS, int KW>
+template <int BITS, int KW, bool WIDE>
 __global__ void __launch_bounds__(kRefThreads, KW == 2 ? 3 : 4)
 refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
               uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
               uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
               unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
               uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint32_t nwin,
-              uint8_t *__restrict__ bwt, int max_steps)
+              uint8_t *__restrict__ bwt, int max_steps, uint8_t *__restrict__ sa_hi, int lo_bits)
 {
     constexpr int HW = kRefCap / 32 + 2;            // head words held in shared memory
     constexpr int WIN_WORDS = kRefWindow / 32;      // 32: one warp scans the window
     static_assert(WIN_WORDS == 32 && kRefGroupMax / 32 == 32, "window and group limit are one warp of words each");
     static_assert(kRefCap <= 65536, "slot lists are 16-bit");
     extern __shared__ __align__(16) unsigned char ref_smem_raw[];
-    RefSmem<KW> &S = *reinterpret_cast<RefSmem<KW> *>(ref_smem_raw);
+    RefSmem<KW, WIDE> &S = *reinterpret_cast<RefSmem<KW, WIDE> *>(ref_smem_raw);
     uint64_t *s_khi = S.khi, *s_klo = S.klo;
     uint32_t(*s_sa)[kRefCap] = S.sa;
     uint8_t(*s_bw)[kRefCap] = S.bw;
+    uint8_t(*s_hi)[WIDE ? kRefCap : 1] = S.hi;
     uint16_t(*s_list)[kRefCap] = S.list;
     uint32_t *s_ha = S.head_a, *s_hb = S.head_b;
     int *s_n = S.n, *s_range = S.range;
@@ -470,14 +477,14 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         base = __shfl_sync(0xffffffffu, base, 0);
         if (take) s_list[which][base + __popc(m & lanemask_lt())] = (uint16_t)slot;
     };
-    auto fetch_key = [&](int slot, uint32_t pos, uint32_t dd) {
+    auto fetch_key = [&](int slot, uint64_t pos, uint32_t dd) {
         if (KW == 2) {
             uint64_t hi, lo;
-            text_window2<BITS>(packed, (uint64_t)pos + dd, hi, lo);
+            text_window2<BITS>(packed, pos + dd, hi, lo);
             s_khi[slot] = hi;
             s_klo[slot] = lo;
         } else {
-            s_khi[slot] = text_window<BITS>(packed, (uint64_t)pos + dd);
+            s_khi[slot] = text_window<BITS>(packed, pos + dd);
         }
     };
 
@@ -486,13 +493,14 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     for (int b0 = start + (tid & ~31); b0 < end; b0 += 4 * kRefThreads) { // b0 is warp-uniform (append ballots)
         const int base = b0 + lane;
         uint32_t sv[4];
-        uint8_t bv[4];
+        uint8_t bv[4], hv[4];
         bool act[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = base + u * kRefThreads;
             act[u] = false;
             bv[u] = 0;
+            hv[u] = 0;
             sv[u] = 0;
             if (r < end) {
                 const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
@@ -501,6 +509,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
                 if (act[u]) {
                     sv[u] = sa[win + r];
                     if (bwt) bv[u] = bwt[win + r];
+                    if (WIDE) hv[u] = sa_hi[win + r];
                 }
             }
         }
@@ -510,7 +519,8 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             if (act[u]) {
                 s_sa[0][r] = sv[u];
                 s_bw[0][r] = bv[u];
-                fetch_key(r, sv[u], d);
+                if (WIDE) s_hi[0][r] = hv[u];
+                fetch_key(r, WIDE ? (((uint64_t)hv[u] << lo_bits) | sv[u]) : (uint64_t)sv[u], d);
             }
             append(0, act[u], r);
         }
@@ -557,6 +567,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
             if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
             s_sa[c ^ 1][p] = s_sa[c][r];
             s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+            if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
             s_list[lc][i] = (uint16_t)p;  // where this suffix went
         }
         __syncthreads();
@@ -575,8 +586,9 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
                 if (!again) {
                     sa[win + p] = pos;
                     if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
+                    if (WIDE) sa_hi[win + p] = s_hi[c ^ 1][p];
                 } else if (more_steps) {
-                    fetch_key(p, pos, d);
+                    fetch_key(p, WIDE ? (((uint64_t)s_hi[c ^ 1][p] << lo_bits) | pos) : (uint64_t)pos, d);
                 }
             }
             append(lc ^ 1, again, p);
@@ -594,6 +606,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
         const int p = s_list[lc][i];
         sa[win + p] = s_sa[c][p];
         if (bwt) bwt[win + p] = s_bw[c][p];
+        if (WIDE) sa_hi[win + p] = s_hi[c][p];
         // the group's head decides the owner: this window, or the next one if it lies in the overhang
         if (prev_set_le(s_hb, p) >= kRefWindow) mine_next = true; else mine_here = true;
     }
@@ -660,15 +673,22 @@ template <int BITS>
 __global__ void __launch_bounds__(256)
 big_gather_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ sa, uint32_t depth,
                   const uint32_t *__restrict__ big_heads, const uint64_t *__restrict__ big_off, uint32_t nbig,
-                  uint64_t total, uint32_t *__restrict__ bsa, uint64_t *__restrict__ bkey, uint32_t *__restrict__ bgid)
+                  uint64_t total, uint32_t *__restrict__ bsa, uint64_t *__restrict__ bkey, uint32_t *__restrict__ bgid,
+                  const uint8_t *__restrict__ sa_hi, uint8_t *__restrict__ bhi, int lo_bits)
 {
     const uint64_t stride = (uint64_t)gridDim.x * 256;
     for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += stride) {
         const uint32_t g = find_group(big_off, nbig, j);
         const uint64_t slot = (uint64_t)big_heads[g] + (j - big_off[g]);
         const uint32_t s = sa[slot];
+        uint64_t pos = s;
+        if (sa_hi) {
+            const uint8_t h = sa_hi[slot];
+            bhi[j] = h;
+            pos |= (uint64_t)h << lo_bits;
+        }
         bsa[j] = s;
-        bkey[j] = text_window<BITS>(packed, (uint64_t)s + depth);
+        bkey[j] = text_window<BITS>(packed, pos + depth);
         bgid[j] = g;
     }
 }
@@ -688,16 +708,23 @@ big_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict
                    const uint32_t *__restrict__ big_heads, const uint64_t *__restrict__ big_off, uint64_t total,
                    uint32_t *__restrict__ sa, uint32_t *__restrict__ head_next, uint32_t *__restrict__ win_flag,
                    uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count,
-                   const uint64_t *__restrict__ packed, const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt)
+                   const uint64_t *__restrict__ packed, const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt,
+                   const uint8_t *__restrict__ bhi, uint8_t *__restrict__ sa_hi, int lo_bits)
 {
     const uint64_t stride = (uint64_t)gridDim.x * 256;
     for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < total; j += stride) {
         const uint32_t idx = perm[j];
         const uint32_t g = bgid[idx];
         const uint64_t slot = (uint64_t)big_heads[g] + (j - big_off[g]);
-        const uint32_t pos = bsa[idx];
-        sa[slot] = pos;
-        if (bwt) bwt[slot] = pos ? inv_map[text_symbol<BITS>(packed, (uint64_t)pos - 1)] : 0;
+        const uint32_t plo = bsa[idx];
+        uint64_t pos = plo;
+        if (sa_hi) {
+            const uint8_t h = bhi[idx];
+            sa_hi[slot] = h;
+            pos |= (uint64_t)h << lo_bits;
+        }
+        sa[slot] = plo;
+        if (bwt) bwt[slot] = pos ? inv_map[text_symbol<BITS>(packed, pos - 1)] : 0;
         // every window under a re-sorted large group is looked at again in the next round
         const uint32_t wnd = (uint32_t)(slot / kRefWindow);
         if (win_flag[wnd] == 0u && atomicExch(&win_flag[wnd], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wnd;
@@ -706,6 +733,15 @@ big_scatter_kernel(const uint32_t *__restrict__ perm, const uint32_t *__restrict
             if (key_terminated<BITS>(me) || me != before) atomicOr(&head_next[slot >> 5], 1u << (slot & 31));
         }
     }
+}
+
+// text positions as u64: hi << lo_bits | lo  (export of a slice of a wide build)
+__global__ void __launch_bounds__(256) widen_sa_kernel(const uint32_t *__restrict__ lo, const uint8_t *__restrict__ hi,
+                                                       int lo_bits, uint64_t n, uint64_t *__restrict__ out)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
+        out[i] = (hi ? ((uint64_t)hi[i] << lo_bits) : 0ull) | lo[i];
 }
 
 // ---------------------------------------------------------------------------
@@ -1047,13 +1083,13 @@ void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint
 
 void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
                          uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
-                         uint32_t *launches)
+                         int lo_bits, int hi_shift, uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
     const int key_bits = first_syms * bits;
 #define CALL(B)                                                                                                   \
     select_write_kernel<B><<<(unsigned)select_tiles(n), 256, 0, st>>>(packed, n, drop_bits, key_bits, carry_prev, \
-                                                                      key_lo, key_hi, tile_off, keys, vals)
+                                                                      key_lo, key_hi, tile_off, keys, vals, lo_bits, hi_shift)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -1062,11 +1098,11 @@ void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint
 
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
                   uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
-                  uint8_t *bwt, uint32_t *launches)
+                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *launches)
 {
 #define CALL(B)                                                                                                 \
     heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
-                                                                  key_bits, inv_map, bwt)
+                                                                  key_bits, inv_map, bwt, pos_hi, hi_shift)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -1077,33 +1113,38 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   int key_words, uint32_t *launches)
+                   int key_words, uint8_t *sa_hi, int lo_bits, uint32_t *launches)
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
     const int max_steps = multi_step ? (1 << 30) : 1;
     static bool attr_set = false;
     if (!attr_set) {
-#define SET(B, K) \
-    DSM_CUDA(cudaFuncSetAttribute(refine_kernel<B, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefSmem<K>)))
+#define SET(B, K)                                                                                             \
+    DSM_CUDA(cudaFuncSetAttribute(refine_kernel<B, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)sizeof(RefSmem<K, false>)));                                           \
+    DSM_CUDA(cudaFuncSetAttribute(refine_kernel<B, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)sizeof(RefSmem<K, true>)))
         SET(3, 1); SET(4, 1); SET(8, 1); SET(3, 2); SET(4, 2); SET(8, 2);
 #undef SET
         attr_set = true;
     }
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
+#define REFINE(B, K, W)                                                                                             \
+    refine_kernel<B, K, W><<<grid, kRefThreads, sizeof(RefSmem<K, W>), st>>>(                                       \
+        packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,   \
+        win_next, win_next_count, nwin, bwt, max_steps, sa_hi, lo_bits)
 #define CALL(B)                                                                                                     \
     do {                                                                                                            \
-        if (key_words == 2)                                                                                         \
-            refine_kernel<B, 2><<<grid, kRefThreads, sizeof(RefSmem<2>), st>>>(                                     \
-                packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining,     \
-                win_flag, win_next, win_next_count, nwin, bwt, max_steps);                                          \
-        else                                                                                                        \
-            refine_kernel<B, 1><<<grid, kRefThreads, sizeof(RefSmem<1>), st>>>(                                     \
-                packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining,     \
-                win_flag, win_next, win_next_count, nwin, bwt, max_steps);                                          \
+        if (key_words == 2) {                                                                                       \
+            if (sa_hi) REFINE(B, 2, true); else REFINE(B, 2, false);                                                \
+        } else {                                                                                                    \
+            if (sa_hi) REFINE(B, 1, true); else REFINE(B, 1, false);                                                \
+        }                                                                                                           \
     } while (0)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
+#undef REFINE
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }
@@ -1118,11 +1159,12 @@ void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, co
 
 void launch_big_gather(cudaStream_t st, int bits, const uint64_t *packed, const uint32_t *sa, uint32_t depth,
                        const uint32_t *big_heads, const uint64_t *big_off, uint32_t nbig, uint64_t total, uint32_t *bsa,
-                       uint64_t *bkey, uint32_t *bgid, uint32_t *launches)
+                       uint64_t *bkey, uint32_t *bgid, const uint8_t *sa_hi, uint8_t *bhi, int lo_bits,
+                       uint32_t *launches)
 {
 #define CALL(B)                                                                                                    \
     big_gather_kernel<B><<<grid_for(total, 256 * 4), 256, 0, st>>>(packed, sa, depth, big_heads, big_off, nbig, total, \
-                                                                   bsa, bkey, bgid)
+                                                                   bsa, bkey, bgid, sa_hi, bhi, lo_bits)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -1141,14 +1183,23 @@ void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const u
                         const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
                         uint32_t *sa, uint32_t *head_next, uint32_t *win_flag, uint32_t *win_next,
                         uint32_t *win_next_count, const uint64_t *packed, const uint8_t *inv_map, uint8_t *bwt,
-                        uint32_t *launches)
+                        const uint8_t *bhi, uint8_t *sa_hi, int lo_bits, uint32_t *launches)
 {
 #define CALL(B)                                                                                                   \
     big_scatter_kernel<B><<<grid_for(total, 256 * 4), 256, 0, st>>>(perm, bsa, bkey, bgid, big_heads, big_off, total, \
                                                                     sa, head_next, win_flag, win_next, win_next_count,      \
-                                                                    packed, inv_map, bwt)
+                                                                    packed, inv_map, bwt, bhi, sa_hi, lo_bits)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_widen_sa(cudaStream_t st, const uint32_t *lo, const uint8_t *hi, int lo_bits, uint64_t n, uint64_t *out,
+                     uint32_t *launches)
+{
+    if (n == 0) return;
+    widen_sa_kernel<<<grid_for(n, 256 * 4), 256, 0, st>>>(lo, hi, lo_bits, n, out);
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

@@ -45,13 +45,17 @@ void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint
 // (key, position) pairs of those suffixes, in text order; tile_off = exclusive scan of the counts
 void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
                          uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
-                         uint32_t *launches);
+                         int lo_bits, int hi_shift, uint32_t *launches);
+// Wide builds (more than 2^lo_bits symbols in the collection): a text position is hi << lo_bits | lo with
+// lo in the u32 value of the sort and hi (<= 8 bits) riding in the key bits from hi_shift upwards
+// (hi_shift = 0: not wide); launch_heads then unloads hi into a byte array that travels with the suffix
+// array through the refinement, like the BWT bytes do.
 
 // Only the low key_bits of a key are compared.  If bwt != nullptr, bwt[i] = inv_map[code carried above
 // the key bits] is written for every rank i.
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
                   uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
-                  uint8_t *bwt, uint32_t *launches);
+                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *launches);
 
 constexpr int kRefThreads = 256;
 constexpr int kRefWindow = 1024;   // group heads owned by one CTA lie in a window of this many slots
@@ -75,7 +79,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   int key_words, uint32_t *launches);
+                   int key_words, uint8_t *sa_hi, int lo_bits, uint32_t *launches);
 
 // Large-group path, step 1: length of each listed group (distance to the next head).
 void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,
@@ -83,7 +87,8 @@ void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, co
 // step 2: gather (suffix, next key, group ordinal) of all listed groups into dense arrays
 void launch_big_gather(cudaStream_t st, int bits, const uint64_t *packed, const uint32_t *sa, uint32_t depth,
                        const uint32_t *big_heads, const uint64_t *big_off, uint32_t nbig, uint64_t total,
-                       uint32_t *bsa, uint64_t *bkey, uint32_t *bgid, uint32_t *launches);
+                       uint32_t *bsa, uint64_t *bkey, uint32_t *bgid, const uint8_t *sa_hi, uint8_t *bhi, int lo_bits,
+                       uint32_t *launches);
 // step 3 helper: k2[j] = gid[perm[j]]
 void launch_gather_u32_to_u64(cudaStream_t st, const uint32_t *src, const uint32_t *perm, uint64_t n, uint64_t *dst,
                               uint32_t *launches);
@@ -92,7 +97,11 @@ void launch_big_scatter(cudaStream_t st, int bits, const uint32_t *perm, const u
                         const uint32_t *bgid, const uint32_t *big_heads, const uint64_t *big_off, uint64_t total,
                         uint32_t *sa, uint32_t *head_next, uint32_t *win_flag, uint32_t *win_next,
                         uint32_t *win_next_count, const uint64_t *packed, const uint8_t *inv_map, uint8_t *bwt,
-                        uint32_t *launches);
+                        const uint8_t *bhi, uint8_t *sa_hi, int lo_bits, uint32_t *launches);
+
+// out[i] = hi[i] << lo_bits | lo[i]  (hi may be nullptr)
+void launch_widen_sa(cudaStream_t st, const uint32_t *lo, const uint8_t *hi, int lo_bits, uint64_t n, uint64_t *out,
+                     uint32_t *launches);
 
 // ---- BWT --------------------------------------------------------------------
 // bwt[i] = byte of text[sa[i]-1], or 0 when suffix i is a whole document (incbwt/rlcsa.cpp:815-845);

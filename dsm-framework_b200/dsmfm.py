@@ -18,7 +18,8 @@ FLAG_KEEP_BWT, FLAG_KEEP_SA = 1, 2
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("samplerate", C.c_uint32), ("expected_bytes", C.c_uint64),
                 ("stream", C.c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32),
-                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32)]
+                ("shard_index", C.c_uint32), ("shard_count", C.c_uint32), ("shard_span", C.c_uint32),
+                ("reserved2", C.c_uint32)]
 
 
 class Shard(C.Structure):
@@ -101,6 +102,7 @@ def lib():
     L.dsmfm_release_cached.argtypes = [C.c_int]
     L.dsmfm_shard_info.argtypes = [B, C.POINTER(Shard)]
     L.dsmfm_assemble.argtypes = [B, C.c_void_p, C.c_uint64]
+    L.dsmfm_shard_export.argtypes = [B, C.c_void_p, C.c_void_p]
     L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
     L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]
@@ -137,10 +139,12 @@ def fmi_bytes(index):
 class Builder:
     """Mirror of the reference's TextCollectionBuilder over the C ABI."""
 
-    def __init__(self, device=-1, samplerate=0, expected_bytes=0, stream=None, flags=0, shard_index=0, shard_count=1):
+    def __init__(self, device=-1, samplerate=0, expected_bytes=0, stream=None, flags=0, shard_index=0, shard_count=1,
+                 shard_span=1):
         self._L = lib()
         opt = Options(device=device, samplerate=samplerate, expected_bytes=expected_bytes,
-                      stream=stream, flags=flags, reserved=0, shard_index=shard_index, shard_count=shard_count)
+                      stream=stream, flags=flags, reserved=0, shard_index=shard_index, shard_count=shard_count,
+                      shard_span=shard_span, reserved2=0)
         self._h = C.c_void_p()
         rc = self._L.dsmfm_create(C.byref(opt), C.byref(self._h))
         if rc != OK:
@@ -175,6 +179,11 @@ class Builder:
         sh = Shard()
         self._check(self._L.dsmfm_shard_info(self._h, C.byref(sh)))
         return sh
+
+    def shard_export(self, bwt_dst=None, sa_dst=None):
+        """Copies the slice into CUDA tensors: bwt_dst uint8[count], sa_dst int64/uint64[count]."""
+        self._check(self._L.dsmfm_shard_export(self._h, bwt_dst.data_ptr() if bwt_dst is not None else None,
+                                               sa_dst.data_ptr() if sa_dst is not None else None))
 
     def assemble(self, bwt_dev, n_total):
         """bwt_dev: device address (int) or torch CUDA tensor holding the concatenated BWT."""

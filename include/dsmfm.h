@@ -55,11 +55,17 @@ typedef struct dsmfm_options {
     uint32_t flags;          /* DSMFM_FLAG_*                                                      */
     uint32_t reserved;
     /* Key-range sharding of ONE collection over several GPUs (one builder per GPU, every builder is
-     * given the WHOLE collection): builder `shard_index` of `shard_count` sorts the suffixes whose
-     * first key falls into its range and produces the matching contiguous slice of the global suffix
-     * array / BWT (dsmfm_shard_info).  shard_count 0 or 1 = the whole index on this GPU. */
+     * given the WHOLE collection): the suffixes are cut into `shard_count` ranges of their first key
+     * with about equal population; this builder sorts ranges [shard_index, shard_index + shard_span)
+     * one after the other and produces the matching contiguous slice of the global suffix array / BWT
+     * (dsmfm_shard_info).  shard_count 0 or 1 = the whole index on this GPU (limit: 2^32 symbols).
+     * Sharded builds index collections of up to 2^40 symbols; each single range must hold fewer than
+     * 2^32 suffixes and bounds the sort buffers (24 bytes x 2 per suffix of the range), so G GPUs
+     * with K ranges each use shard_count = G*K, shard_index = g*K, shard_span = K. */
     uint32_t shard_index;
     uint32_t shard_count;
+    uint32_t shard_span;     /* 0 -> 1 */
+    uint32_t reserved2;
 } dsmfm_options;
 
 #define DSMFM_FLAG_KEEP_BWT 1u /* keep the plain BWT in host memory after finish (dsmfm_index.bwt)   */
@@ -171,9 +177,14 @@ typedef struct dsmfm_shard {
     uint64_t rank_begin;  /* global rank of the first suffix of this slice                    */
     uint64_t count;       /* suffixes in this slice                                           */
     const void *bwt_dev;  /* DEVICE pointer: BWT bytes of the slice [count]                   */
-    const void *sa_dev;   /* DEVICE pointer: text positions (u32) [count], needs KEEP_SA      */
+    const void *sa_dev;   /* reserved (use dsmfm_shard_export for the suffix array)           */
 } dsmfm_shard;
 DSMFM_API int dsmfm_shard_info(dsmfm_builder *b, dsmfm_shard *out);
+
+/* Copies the slice into caller-provided DEVICE buffers on the builder's device (either may be NULL),
+ * on the builder's stream, and waits for the copy: bwt_dst_dev[count] bytes; sa_dst_dev[count]
+ * text positions as u64 (needs DSMFM_FLAG_KEEP_SA). */
+DSMFM_API int dsmfm_shard_export(dsmfm_builder *b, void *bwt_dst_dev, void *sa_dst_dev);
 
 /* On the assembling GPU: build C[], the code table, the wavelet tree and the BitRank directories
  * from the concatenated BWT (`bwt_dev`, device memory, n_total bytes, slices in shard order).

@@ -265,3 +265,88 @@ def test_toydata_shaped_sample_matches_live_reference(tmp_path):
     fasta = dsmgen.fasta(**kw).tobytes()
     want = oracle.reference_build(fasta, tmp_path)
     _assert_same_fmi(_build(dsmgen.docs(**kw)), want)
+
+
+# ---- one collection cut into key ranges (the multi-GPU path, here with every range on one device) ------
+
+def _sharded_build(docs, shard_count, span=1):
+    """Builds every slice of the global suffix order with its own builder, concatenates the BWT slices
+    on the device and assembles the index on the first builder.  Returns (fmi, bwt, sa)."""
+    import torch
+    import dsmfm
+    builders, bw, sa, nxt = [], [], [], 0
+    try:
+        for first in range(0, shard_count, span):
+            b = dsmfm.Builder(flags=dsmfm.FLAG_KEEP_SA, shard_index=first, shard_count=shard_count,
+                              shard_span=min(span, shard_count - first))
+            builders.append(b)
+            b.append_batch(docs)
+            b.build_device()
+            info = b.shard_info()
+            assert info.n_total == len(docs)
+            assert info.rank_begin == nxt, "slices are not contiguous"
+            nxt += info.count
+            bw.append(torch.empty(info.count, dtype=torch.uint8, device="cuda"))
+            sa.append(torch.empty(info.count, dtype=torch.int64, device="cuda"))
+            b.shard_export(bw[-1], sa[-1])
+        assert nxt == len(docs)
+        full = torch.cat(bw)
+        builders[0].assemble(full, len(docs))
+        builders[0].fetch()
+        return builders[0].fmi(), full.cpu().numpy().tobytes(), torch.cat(sa).cpu().numpy()
+    finally:
+        for b in builders:
+            b.close()
+
+
+@pytest.mark.parametrize("shards,span", [(2, 1), (3, 1), (8, 1), (8, 4), (5, 2), (64, 16)])
+@pytest.mark.parametrize("name", ["reads100", "poly_a", "duplicates", "mixed_alphabet", "one_base_reads", "single"])
+def test_key_range_shards_concatenate_to_the_reference_index(name, shards, span):
+    docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+    want_bwt, want_sa = oracle.bwt(docs, want_sa=True)
+    fmi, bwt, sa = _sharded_build(docs, shards, span)
+    assert np.array_equal(sa.astype(np.uint64), want_sa)
+    assert bwt == want_bwt
+    _assert_same_fmi(fmi, _golden(name, ".fmi"))
+
+
+@pytest.mark.parametrize("lo_bits", ["12", "15"])
+def test_wide_positions_on_small_inputs(monkeypatch, lo_bits):
+    """Collections beyond 2^32 symbols keep the high part of a text position in the key's spare bits and
+    then in a byte array next to the suffix array; DSMFM_POS_LO_BITS shrinks the low part so that the
+    same code runs on inputs the oracle can check."""
+    monkeypatch.setenv("DSMFM_POS_LO_BITS", lo_bits)
+    for name, shards, span in [("reads100", 3, 1), ("poly_a", 2, 1), ("colour_space", 4, 2), ("two_letter", 2, 2)]:
+        docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+        want_bwt, want_sa = oracle.bwt(docs, want_sa=True)
+        fmi, bwt, sa = _sharded_build(docs, shards, span)
+        assert np.array_equal(sa.astype(np.uint64), want_sa)
+        assert bwt == want_bwt
+        _assert_same_fmi(fmi, _golden(name, ".fmi"))
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()["high_coverage"])
+    fmi, _, _ = _sharded_build(docs, 3, 1)
+    assert hashlib.sha256(fmi).hexdigest() == MANIFEST["digests"]["high_coverage"]["fmi_sha256"]
+
+
+def test_sharded_arbitrary_byte_alphabet(monkeypatch):
+    monkeypatch.setenv("DSMFM_POS_LO_BITS", "10")
+    rng = np.random.default_rng(12)
+    docs = b"".join(rng.integers(1, 256, size=int(rng.integers(1, 90)), dtype=np.uint8).tobytes() + b"\0"
+                    for _ in range(200))
+    fmi, bwt, sa = _sharded_build(docs, 3, 1)
+    want_bwt, want_sa = oracle.bwt(docs, want_sa=True)
+    assert np.array_equal(sa.astype(np.uint64), want_sa) and bwt == want_bwt
+    _assert_same_fmi(fmi, oracle.fmi_from_docs(docs))
+
+
+def test_sharded_builder_errors():
+    import dsmfm
+    with pytest.raises(dsmfm.DsmfmError):
+        dsmfm.Builder(shard_index=2, shard_count=2)
+    with pytest.raises(dsmfm.DsmfmError):
+        dsmfm.Builder(shard_index=1, shard_count=4, shard_span=4)
+    with dsmfm.Builder(shard_index=0, shard_count=2) as b:
+        b.append_batch(b"ACGT\0")
+        b.build_device()
+        with pytest.raises(dsmfm.DsmfmError):   # a slice is not an index
+            b.fetch()
