@@ -6,9 +6,11 @@
 
 A step = one complete FM-index build (pack, suffix sort, BWT, HuffWT + BitRank) of one synthetic
 sample.  N=1: the 1 Gbp sample of BASELINE.json configs[2] (SURVEY 8d "C3": 10M x 100-bp reads,
-n = 2.02 G indexed symbols).  N>1 (torchrun, one rank per GPU): every rank builds the index of its
-own 1 Gbp block of reads (weak scaling, no data-path collective; the cross-GPU BWT merge of the
-north star is not built yet, so the result is one index per GPU).
+n = 2.02 G indexed symbols).  N>1 (torchrun, one rank per GPU): every rank holds its own 1 Gbp block
+of reads and the N GPUs build ONE index of the N Gbp collection (weak scaling; BASELINE.json
+configs[3] shape): NCCL all-gather of the raw text, key-range sharded suffix sort (every GPU sorts
+its share of the global suffix order from the replicated text), BWT slices sent to rank 0, which
+builds the wavelet tree (dsm-framework_b200/multigpu.py).
 
 value   = input bases of all ranks / max-over-ranks device time, documents already resident in HBM.
 e2e     = the same through the C ABI with HOST buffers: dsmfm_append_batch from pinned host memory
@@ -48,6 +50,7 @@ def parse_args():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ranges-per-gpu", type=int, default=1, help="N>1: key ranges sorted one after the other per GPU")
     return ap.parse_args()
 
 
@@ -203,7 +206,8 @@ def main():
         torch.cuda.synchronize()
 
     kw = dict(dsmgen.CONFIGS[WORKLOADS[args.workload]])
-    kw["seed"] += 1000 * rank  # every rank indexes its own block of reads
+    kw["seed"] += 1000 * rank  # every rank holds its own block of reads, drawn from its own genomes
+    kw["pool_seed"] += 1000 * rank  # (coverage stays that of the workload as N grows, like C4 vs C3)
     if args.reads:
         kw["n_reads"] = args.reads
     n_reads, L = kw["n_reads"], kw["read_len"]
@@ -216,22 +220,44 @@ def main():
     stream = torch.cuda.current_stream()
     flags = 0
 
-    def device_step():
-        b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
-        b.append_batch_device(dev_docs)
-        b.build_device()
-        s = b.stats()
-        b.close()
-        return s
+    if world > 1:
+        import multigpu
+        engine = multigpu.CudaEngine(local, stream=stream.cuda_stream, flags=flags)
+        launches = [0]
 
-    def e2e_step():
-        b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
-        b.append_batch(host_docs)
-        idx = b.finish()
-        out_bytes = section_bytes(idx)
-        s = b.stats()
-        b.close()
-        return s, out_bytes
+        def sharded(docs, fetch):
+            handle, info = multigpu.build_sharded(dist, docs, engine, ranges_per_gpu=args.ranges_per_gpu)
+            s, out_bytes = info["stats"], 0
+            if handle is not None:
+                if fetch:
+                    out_bytes = section_bytes(handle.fetch())
+                s = handle.stats()
+                handle.close()
+            launches[0] += s.kernel_launches
+            return s, out_bytes
+
+        def device_step():
+            return sharded(dev_docs, False)[0]
+
+        def e2e_step():
+            return sharded(host_docs, True)
+    else:
+        def device_step():
+            b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
+            b.append_batch_device(dev_docs)
+            b.build_device()
+            s = b.stats()
+            b.close()
+            return s
+
+        def e2e_step():
+            b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
+            b.append_batch(host_docs)
+            idx = b.finish()
+            out_bytes = section_bytes(idx)
+            s = b.stats()
+            b.close()
+            return s, out_bytes
 
     # ---- device-resident throughput ("value") ------------------------------------------------------
     for _ in range(args.warmup):
@@ -266,6 +292,10 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     barrier()
     t_e2e = float(t_e2e.item())
+    n_launch = torch.tensor([sum(s.kernel_launches for s in stats)], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(n_launch)
+    n_launch = int(n_launch.item())
 
     if rank != 0:
         if dist is not None:
@@ -304,7 +334,10 @@ def main():
         "config": {
             "workload": "%s: %d x %d-bp ACGTN reads per GPU (%.2f Gbp, n = %d indexed symbols), SA + BWT + HuffWT + BitRank"
                         % (args.workload, n_reads, L, bases / 1e9, nbytes),
-            "parallelism": "1 GPU" if world == 1 else "%d independent samples, one index per GPU (no cross-GPU BWT merge yet)" % world,
+            "parallelism": "1 GPU" if world == 1 else
+                           "%d GPUs build ONE index of %.2f Gbp: NCCL all-gather of the raw text, key-range sharded suffix "
+                           "sort (%d range(s) per GPU), BWT slices gathered on rank 0 for the wavelet tree"
+                           % (world, world * bases / 1e9, args.ranges_per_gpu),
             "cache": "inputs (%.2f GB) and sort buffers are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
             "bits_per_symbol": s0.bits_per_symbol,
             "refine_rounds": s0.rounds,
@@ -321,12 +354,12 @@ def main():
         "e2e": {
             "value": round(world * bases * args.steps / t_e2e / 1e6, 2),
             "unit": "Mbp/s",
-            "h2d_bytes_per_step": nbytes,
+            "h2d_bytes_per_step": world * nbytes,
             "d2h_bytes_per_step": e2e_out[-1][1],
             "ms_per_step": round(1000 * t_e2e / args.steps, 2),
             "api": "dsmfm_create / dsmfm_append_batch (pinned host buffer) / dsmfm_finish / dsmfm_destroy",
         },
-        "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+        "gpu_launches": n_launch,
         "roofline": {
             "bound": "hbm",
             "kernel": "onesweep_kernel (one LSD radix pass over (u64 key, u32 suffix) pairs; %d passes per build)" % s0.sort_passes,
