@@ -220,19 +220,17 @@ struct WaveletResult {
     }
 };
 
-void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, const dsmfm_code *tab, WaveletResult &r,
-                          uint32_t *launches, size_t *dev_bytes)
+// shape of the tree and layout of the sections for a code table
+void wavelet_prepare(const dsmfm_code *tab, WaveletResult &r)
 {
     r.shape = WtShape();
     shape_rec(tab, 0u, 0u, r.shape);
     const int m = r.shape.n_internal;
-    if (m == 0) return;
     if (m > kWtMaxNodes) throw CudaError{cudaErrorInvalidValue, "too many wavelet tree nodes", __FILE__, __LINE__};
-    r.off_data.resize(m);
-    r.off_rs.resize(m);
-    r.off_rb.resize(m);
+    r.off_data.assign(m, 0);
+    r.off_rs.assign(m, 0);
+    r.off_rb.assign(m, 0);
     size_t off = 0;
-    uint64_t max_sb = 0;
     for (size_t i = 0; i < r.shape.nodes.size(); ++i) {
         const int v = r.shape.internal_of_node[i];
         if (v < 0) continue;
@@ -243,32 +241,62 @@ void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, con
         off += (nd.nbits / 256 + 1) * 8;
         r.off_rb[v] = off;
         off += align8(nd.nbits / 64 + 1);
-        max_sb = std::max<uint64_t>(max_sb, nd.nbits / 256 + 1);
     }
     r.section_bytes = off;
-    r.d_sections = static_cast<uint8_t *>(dev_alloc(off, st));
-    r.d_ch = static_cast<uint8_t *>(dev_alloc((size_t)m, st));
-    DSM_CUDA(cudaMemsetAsync(r.d_sections, 0, off, st));
-    DSM_CUDA(cudaMemsetAsync(r.d_ch, 0, (size_t)m, st));
+}
 
+void wavelet_alloc(cudaStream_t st, WaveletResult &r)
+{
+    const int m = r.shape.n_internal;
+    r.d_sections = static_cast<uint8_t *>(dev_alloc(r.section_bytes, st));
+    r.d_ch = static_cast<uint8_t *>(dev_alloc((size_t)(m ? m : 1), st));
+    DSM_CUDA(cudaMemsetAsync(r.d_sections, 0, r.section_bytes, st));
+    DSM_CUDA(cudaMemsetAsync(r.d_ch, 0, (size_t)(m ? m : 1), st));
+}
+
+// Bits of every internal node for the byte sequence d_seq: node v's bits go to ptrs[v] (device pointers,
+// zero-initialised arrays) starting at bit bit_base[v] (empty = 0); d_ch[v] = first member symbol.
+// Synchronises the stream.  Returns the scratch bytes it used.
+size_t wavelet_fill_bits(cudaStream_t st, const uint8_t *d_seq, uint64_t n, const WtShape &shape,
+                         const std::vector<uint64_t *> &ptrs, const std::vector<uint64_t> &bit_base, uint8_t *d_ch,
+                         uint32_t *launches)
+{
+    const int m = shape.n_internal;
+    if (m == 0 || n == 0) return 0;
     const uint64_t ntiles = div_up(n, kWtTile);
-    uint8_t *d_info = nullptr;
-    uint64_t *d_tile = nullptr, **d_ptrs = nullptr, *d_scratch = nullptr;
     const size_t tile_bytes = sizeof(uint64_t) * (size_t)m * ntiles;
-    const size_t scratch_bytes = sizeof(uint64_t) * (div_up(max_sb, kRankChunk) + 1);
-    d_info = static_cast<uint8_t *>(dev_alloc((size_t)m * 256, st));
-    d_tile = static_cast<uint64_t *>(dev_alloc(tile_bytes, st));
-    d_ptrs = static_cast<uint64_t **>(dev_alloc(sizeof(uint64_t *) * m, st));
-    d_scratch = static_cast<uint64_t *>(dev_alloc(scratch_bytes, st));
-    if (dev_bytes) *dev_bytes = off + m + (size_t)m * 256 + tile_bytes + sizeof(uint64_t *) * m + scratch_bytes;
-    std::vector<uint64_t *> ptrs(m);
-    for (int v = 0; v < m; ++v) ptrs[v] = reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]);
+    uint8_t *d_info = static_cast<uint8_t *>(dev_alloc((size_t)m * 256, st));
+    uint64_t *d_tile = static_cast<uint64_t *>(dev_alloc(tile_bytes, st));
+    uint64_t **d_ptrs = static_cast<uint64_t **>(dev_alloc(sizeof(uint64_t *) * m, st));
+    uint64_t *d_base = bit_base.empty() ? nullptr : static_cast<uint64_t *>(dev_alloc(sizeof(uint64_t) * m, st));
     try {
-        DSM_CUDA(cudaMemcpyAsync(d_info, r.shape.info.data(), (size_t)m * 256, cudaMemcpyHostToDevice, st));
+        DSM_CUDA(cudaMemcpyAsync(d_info, shape.info.data(), (size_t)m * 256, cudaMemcpyHostToDevice, st));
         DSM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(uint64_t *) * m, cudaMemcpyHostToDevice, st));
+        if (d_base) DSM_CUDA(cudaMemcpyAsync(d_base, bit_base.data(), sizeof(uint64_t) * m, cudaMemcpyHostToDevice, st));
         launch_wt_count(st, d_seq, n, d_info, m, ntiles, d_tile, launches);
         launch_wt_scan(st, d_tile, m, ntiles, launches);
-        launch_wt_fill(st, d_seq, n, d_info, m, ntiles, d_tile, d_ptrs, r.d_ch, launches);
+        launch_wt_fill(st, d_seq, n, d_info, m, ntiles, d_tile, d_ptrs, d_ch, d_base, launches);
+        DSM_CUDA(cudaStreamSynchronize(st)); // the host vectors are consumed
+    } catch (...) {
+        dev_free(d_info, st); dev_free(d_tile, st); dev_free(d_ptrs, st); dev_free(d_base, st);
+        throw;
+    }
+    dev_free(d_info, st);
+    dev_free(d_tile, st);
+    dev_free(d_ptrs, st);
+    dev_free(d_base, st);
+    return (size_t)m * 256 + tile_bytes + sizeof(uint64_t *) * m;
+}
+
+// BitRank directories of every internal node (data already in r.d_sections)
+void wavelet_ranks(cudaStream_t st, WaveletResult &r, uint32_t *launches)
+{
+    uint64_t max_sb = 0;
+    for (size_t i = 0; i < r.shape.nodes.size(); ++i)
+        if (r.shape.internal_of_node[i] >= 0) max_sb = std::max<uint64_t>(max_sb, r.shape.nodes[i].nbits / 256 + 1);
+    if (!max_sb) return;
+    uint64_t *d_scratch = static_cast<uint64_t *>(dev_alloc(sizeof(uint64_t) * (div_up(max_sb, kRankChunk) + 1), st));
+    try {
         for (size_t i = 0; i < r.shape.nodes.size(); ++i) {
             const int v = r.shape.internal_of_node[i];
             if (v < 0) continue;
@@ -276,15 +304,74 @@ void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, con
                            reinterpret_cast<uint64_t *>(r.d_sections + r.off_rs[v]), r.d_sections + r.off_rb[v],
                            d_scratch, launches);
         }
-        DSM_CUDA(cudaStreamSynchronize(st)); // ptrs / info are host vectors: keep them alive until consumed
     } catch (...) {
-        dev_free(d_info, st); dev_free(d_tile, st); dev_free(d_ptrs, st); dev_free(d_scratch, st);
+        dev_free(d_scratch, st);
         throw;
     }
-    dev_free(d_info, st);
-    dev_free(d_tile, st);
-    dev_free(d_ptrs, st);
     dev_free(d_scratch, st);
+}
+
+void wavelet_build_device(cudaStream_t st, const uint8_t *d_seq, uint64_t n, const dsmfm_code *tab, WaveletResult &r,
+                          uint32_t *launches, size_t *dev_bytes)
+{
+    wavelet_prepare(tab, r);
+    const int m = r.shape.n_internal;
+    if (m == 0) return;
+    wavelet_alloc(st, r);
+    std::vector<uint64_t *> ptrs(m);
+    for (int v = 0; v < m; ++v) ptrs[v] = reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]);
+    const size_t scratch = wavelet_fill_bits(st, d_seq, n, r.shape, ptrs, std::vector<uint64_t>(), r.d_ch, launches);
+    wavelet_ranks(st, r, launches);
+    if (dev_bytes) *dev_bytes = r.section_bytes + m + scratch;
+}
+
+// ---- wavelet tree built by several GPUs ---------------------------------------------------------
+// GPU r holds slice r of the BWT.  hist_all[r][c] = occurrences of byte c in slice r, so the number of
+// members of node v in slice r, and with it the global bit offset of slice r's contribution to node v,
+// follow for every (r, v) without looking at any data.  GPU r builds its contributions ("pieces")
+// already shifted to their global bit offset modulo 64, so that the assembling GPU only copies words
+// (and ORs the shared boundary words).
+struct PiecePlan {
+    std::vector<uint64_t> count, bit_off, words, word_off; // [world][m]
+    std::vector<uint64_t> rank_words, rank_bytes, rank_byte_off; // [world]
+    uint64_t total_bytes = 0;
+};
+
+PiecePlan plan_pieces(const WtShape &shape, const uint64_t *hist_all, uint32_t world)
+{
+    const int m = shape.n_internal;
+    PiecePlan p;
+    p.count.assign((size_t)world * m, 0);
+    p.bit_off.assign((size_t)world * m, 0);
+    p.words.assign((size_t)world * m, 0);
+    p.word_off.assign((size_t)world * m, 0);
+    p.rank_words.assign(world, 0);
+    p.rank_bytes.assign(world, 0);
+    p.rank_byte_off.assign(world, 0);
+    for (int v = 0; v < m; ++v) {
+        uint64_t run = 0;
+        for (uint32_t r = 0; r < world; ++r) {
+            uint64_t c = 0;
+            for (int s = 0; s < 256; ++s)
+                if (shape.info[(size_t)v * 256 + s] & 1u) c += hist_all[(size_t)r * 256 + s];
+            p.count[(size_t)r * m + v] = c;
+            p.bit_off[(size_t)r * m + v] = run;
+            p.words[(size_t)r * m + v] = c ? div_up((run & 63) + c, 64) : 0;
+            run += c;
+        }
+    }
+    for (uint32_t r = 0; r < world; ++r) {
+        uint64_t w = 0;
+        for (int v = 0; v < m; ++v) {
+            p.word_off[(size_t)r * m + v] = w;
+            w += p.words[(size_t)r * m + v];
+        }
+        p.rank_words[r] = w;
+        p.rank_bytes[r] = w * 8 + align8((size_t)(m ? m : 1)); // words, then the first member symbol of every node
+        p.rank_byte_off[r] = p.total_bytes;
+        p.total_bytes += p.rank_bytes[r];
+    }
+    return p;
 }
 
 void wavelet_fetch(cudaStream_t st, WaveletResult &r)
@@ -592,10 +679,10 @@ void dsmfm_builder::build()
     std::vector<Range> ranges;
     const int key_bits = first_syms * bits; // sorted bits of the first key
     const int hi_shift = wide ? key_bits + bits : 0;
+    const int top_bits = key_bits < 12 ? key_bits : 12; // key ranges are cut at multiples of 2^(key_bits - top_bits)
     if (!sharded) {
         ranges.push_back(Range{0, 0, n, 0});
     } else {
-        const int top_bits = key_bits < 12 ? key_bits : 12;
         const int nbins = 1 << top_bits;
         unsigned long long *d_top = static_cast<unsigned long long *>(dmalloc(4096 * 8));
         DSM_CUDA(cudaMemsetAsync(d_top, 0, 4096 * 8, st));
@@ -702,12 +789,12 @@ void dsmfm_builder::build()
         if (!sharded) {
             launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
         } else {
-            const uint64_t ntile = select_tiles(n);
+            const uint64_t ntile = select_tiles(n, bits, first_syms, top_bits);
             uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
-            launch_select_count(st, bits, d_packed, n, first_syms, rg.key_lo, rg.key_hi, d_tile, L);
+            launch_select_count(st, bits, d_packed, n, first_syms, top_bits, rg.key_lo, rg.key_hi, d_tile, L);
             launch_wt_scan(st, d_tile, 1, ntile, L);
-            launch_select_write(st, bits, d_packed, n, first_syms, carry_bwt, rg.key_lo, rg.key_hi, d_tile, d_keys_a,
-                                d_vals_a, lo_bits, hi_shift, L);
+            launch_select_write(st, bits, d_packed, n, first_syms, top_bits, carry_bwt, rg.key_lo, rg.key_hi, d_tile,
+                                d_keys_a, d_vals_a, lo_bits, hi_shift, L);
             dfree(d_tile);
         }
         const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
@@ -1156,6 +1243,143 @@ DSMFM_API int dsmfm_assemble(dsmfm_builder *b, const void *bwt_dev, uint64_t n_t
         DSM_CUDA(cudaEventRecord(e0, b->stream));
         wavelet_build_device(b->stream, static_cast<const uint8_t *>(bwt_dev), n_total, b->index.codetable, b->wt,
                              &b->stats.kernel_launches, nullptr);
+        DSM_CUDA(cudaEventRecord(e1, b->stream));
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        b->stats.ms_wt = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    b->assembled = true;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_slice_hist(dsmfm_builder *b, uint64_t *out256)
+{
+    API_GUARD(b);
+    if (!out256) return DSMFM_EINVAL;
+    if (!b->built || !b->d_bwt) return b->fail(DSMFM_EINVAL, "dsmfm_slice_hist: nothing built (or already fetched)");
+    const uint64_t m = b->shard_count > 1 ? b->shard_m : b->index.n;
+    try {
+        uint64_t *d_counts = static_cast<uint64_t *>(dev_alloc(256 * 8, b->stream));
+        DSM_CUDA(cudaMemsetAsync(d_counts, 0, 256 * 8, b->stream));
+        if (m) launch_byte_hist(b->stream, b->d_bwt, m, d_counts, &b->stats.kernel_launches);
+        DSM_CUDA(cudaMemcpyAsync(out256, d_counts, 256 * 8, cudaMemcpyDeviceToHost, b->stream));
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+        dev_free(d_counts, b->stream);
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
+static int check_pieces_args(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, const char *who)
+{
+    if (!b->built || b->shard_count <= 1) return b->fail(DSMFM_EINVAL, "%s: needs a built sharded builder", who);
+    if (!hist_all || world == 0) return b->fail(DSMFM_EINVAL, "%s: bad histogram table", who);
+    // the slices together must hold exactly the symbols of the collection
+    for (int c = 0; c < 256; ++c) {
+        uint64_t t = 0;
+        for (uint32_t r = 0; r < world; ++r) t += hist_all[(size_t)r * 256 + c];
+        if (t != b->counts[c]) return b->fail(DSMFM_EINVAL, "%s: slice histograms do not add up to the collection's", who);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API uint64_t dsmfm_pieces_bytes(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank)
+{
+    if (!b || !hist_all || rank > world) return 0;
+    try {
+        WaveletResult tmp;
+        wavelet_prepare(b->index.codetable, tmp);
+        const PiecePlan p = plan_pieces(tmp.shape, hist_all, world);
+        return rank == world ? p.total_bytes : p.rank_bytes[rank];
+    } catch (const CudaError &) {
+        return 0;
+    }
+}
+
+DSMFM_API int dsmfm_build_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, void *dst_dev)
+{
+    API_GUARD(b);
+    int rc = check_pieces_args(b, hist_all, world, "dsmfm_build_pieces");
+    if (rc) return rc;
+    if (rank >= world || !dst_dev || !b->d_bwt) return b->fail(DSMFM_EINVAL, "dsmfm_build_pieces: bad arguments");
+    try {
+        WaveletResult tmp;
+        wavelet_prepare(b->index.codetable, tmp);
+        const int m = tmp.shape.n_internal;
+        const PiecePlan p = plan_pieces(tmp.shape, hist_all, world);
+        uint64_t mine = 0;
+        for (int c = 0; c < 256; ++c) mine += hist_all[(size_t)rank * 256 + c];
+        if (mine != b->shard_m) return b->fail(DSMFM_EINVAL, "dsmfm_build_pieces: histogram row %u is not this slice's", rank);
+        uint8_t *dst = static_cast<uint8_t *>(dst_dev);
+        DSM_CUDA(cudaMemsetAsync(dst, 0, p.rank_bytes[rank], b->stream));
+        std::vector<uint64_t *> ptrs(m);
+        std::vector<uint64_t> base(m);
+        for (int v = 0; v < m; ++v) {
+            ptrs[v] = reinterpret_cast<uint64_t *>(dst) + p.word_off[(size_t)rank * m + v];
+            base[v] = p.bit_off[(size_t)rank * m + v] & 63;
+        }
+        wavelet_fill_bits(b->stream, b->d_bwt, b->shard_m, tmp.shape, ptrs, base, dst + p.rank_words[rank] * 8,
+                          &b->stats.kernel_launches);
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, const void *pieces_dev)
+{
+    API_GUARD(b);
+    int rc = check_pieces_args(b, hist_all, world, "dsmfm_assemble_pieces");
+    if (rc) return rc;
+    if (b->assembled) return b->fail(DSMFM_EINVAL, "dsmfm_assemble_pieces: already assembled");
+    if (!pieces_dev) return b->fail(DSMFM_EINVAL, "dsmfm_assemble_pieces: null piece buffer");
+    try {
+        cudaEvent_t e0, e1;
+        DSM_CUDA(cudaEventCreate(&e0));
+        DSM_CUDA(cudaEventCreate(&e1));
+        DSM_CUDA(cudaEventRecord(e0, b->stream));
+        WaveletResult &r = b->wt;
+        wavelet_prepare(b->index.codetable, r);
+        const int m = r.shape.n_internal;
+        if (m > 0) {
+            wavelet_alloc(b->stream, r);
+            const PiecePlan p = plan_pieces(r.shape, hist_all, world);
+            const uint8_t *src = static_cast<const uint8_t *>(pieces_dev);
+            std::vector<WtPiece> table;
+            std::vector<uint8_t> ch(m, 0), trailers((size_t)world * m);
+            for (uint32_t q = 0; q < world; ++q) // first member symbols reported by every rank
+                DSM_CUDA(cudaMemcpyAsync(trailers.data() + (size_t)q * m, src + p.rank_byte_off[q] + p.rank_words[q] * 8,
+                                         (size_t)m, cudaMemcpyDeviceToHost, b->stream));
+            for (int v = 0; v < m; ++v)
+                for (uint32_t q = 0; q < world; ++q) {
+                    const size_t i = (size_t)q * m + v;
+                    if (!p.count[i]) continue;
+                    table.push_back(WtPiece{p.rank_byte_off[q] / 8 + p.word_off[i],
+                                            reinterpret_cast<uint64_t *>(r.d_sections + r.off_data[v]) + (p.bit_off[i] >> 6),
+                                            p.words[i]});
+                }
+            WtPiece *d_table = static_cast<WtPiece *>(dev_alloc(sizeof(WtPiece) * (table.size() + 1), b->stream));
+            DSM_CUDA(cudaMemcpyAsync(d_table, table.data(), sizeof(WtPiece) * table.size(), cudaMemcpyHostToDevice, b->stream));
+            launch_wt_merge_pieces(b->stream, reinterpret_cast<const uint64_t *>(src), d_table, (uint32_t)table.size(),
+                                   &b->stats.kernel_launches);
+            DSM_CUDA(cudaStreamSynchronize(b->stream));
+            dev_free(d_table, b->stream);
+            for (int v = 0; v < m; ++v) // HuffWT.cpp:8: ch = first symbol of the node's subsequence
+                for (uint32_t q = 0; q < world; ++q)
+                    if (p.count[(size_t)q * m + v]) {
+                        ch[v] = trailers[(size_t)q * m + v];
+                        break;
+                    }
+            DSM_CUDA(cudaMemcpyAsync(r.d_ch, ch.data(), (size_t)m, cudaMemcpyHostToDevice, b->stream));
+            wavelet_ranks(b->stream, r, &b->stats.kernel_launches);
+        }
         DSM_CUDA(cudaEventRecord(e1, b->stream));
         DSM_CUDA(cudaStreamSynchronize(b->stream));
         float ms = 0;

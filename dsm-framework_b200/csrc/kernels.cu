@@ -301,6 +301,146 @@ select_write_kernel(const uint64_t *__restrict__ packed, uint64_t n, int drop_bi
     }
 }
 
+// ---- fast selection: one thread per packed word --------------------------------------------------
+// Range membership only needs the top 12 key bits, i.e. the first kTopSyms symbols of the suffix cut at
+// its terminator.  A thread takes one packed word (SPW consecutive suffixes) plus its successor as a
+// 128-bit stream and classifies every suffix with a handful of 32-bit operations; the full first key
+// is computed only for the suffixes that were selected.  (The generic kernels above recompute word
+// index, two loads and 64-bit shifts per suffix: on G GPUs every GPU scans the whole text, so this
+// scan is the part of a sharded build that does not shrink with G.)
+template <int BITS> struct TopBits {
+    static constexpr int SYMS = BITS == 8 ? 2 : 12 / BITS; // 4, 3, 2 symbols
+    static constexpr int RAW = SYMS * BITS;                // 12, 12, 16 bits
+};
+
+// bin (top 12 key bits) of the suffix starting at symbol j of the stream s[0..3] (MSB first)
+template <int BITS> __device__ __forceinline__ uint32_t top_bin(const uint32_t (&s)[4], int j)
+{
+    using T = TopBits<BITS>;
+    const int b = BITS * j, q = b >> 5, r = b & 31;
+    const uint32_t top32 = __funnelshift_l(s[q + 1 < 4 ? q + 1 : 3], s[q], r);
+    uint32_t x = top32 >> (32 - T::RAW);
+    // cut at the terminator: zero every field after the first zero field
+    uint32_t nz = x;
+#pragma unroll
+    for (int i = 1; i < BITS; ++i) nz |= x >> i;
+    constexpr uint32_t LSB = BITS == 3 ? 0x249u : (BITS == 4 ? 0x111u : 0x101u);
+    const uint32_t z = ~nz & LSB;
+    if (z) {
+        const int top = 31 - __clz(z) + BITS; // bit just above the most significant zero field
+        x = top >= 32 ? 0u : (x & ~((1u << top) - 1u));
+    }
+    return x >> (T::RAW - 12);
+}
+
+template <int BITS> __device__ __forceinline__ void load_stream(const uint64_t *__restrict__ packed, uint64_t w,
+                                                                uint64_t nwords, uint32_t (&s)[4])
+{
+    using P = Pack<BITS>;
+    uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
+    if (P::USED == 63) { // 3-bit symbols sit in bits 62..0: close the gap so that symbol j starts at stream bit 3j
+        x0 = (x0 << 1) | (x1 >> 62);
+        x1 <<= 2;
+    }
+    s[0] = (uint32_t)(x0 >> 32);
+    s[1] = (uint32_t)x0;
+    s[2] = (uint32_t)(x1 >> 32);
+    s[3] = (uint32_t)x1;
+}
+
+constexpr int kSelWords = 256; // packed words per CTA of the fast selection kernels
+
+// selection mask of the SPW suffixes starting in word w: bit j set iff suffix w*SPW+j exists and its bin is in range
+template <int BITS>
+__device__ __forceinline__ uint32_t select_mask(const uint64_t *__restrict__ packed, uint64_t w, uint64_t nwords,
+                                                uint64_t n, uint32_t bin_lo, uint32_t bin_hi)
+{
+    using P = Pack<BITS>;
+    if (w >= nwords) return 0u;
+    uint32_t s[4];
+    load_stream<BITS>(packed, w, nwords, s);
+    uint32_t sel = 0;
+#pragma unroll
+    for (int j = 0; j < P::SPW; ++j) {
+        const uint32_t bin = top_bin<BITS>(s, j);
+        sel |= (uint32_t)(bin >= bin_lo && bin < bin_hi) << j;
+    }
+    const uint64_t p0 = w * P::SPW;
+    if (p0 + P::SPW > n) sel &= p0 >= n ? 0u : ((1u << (n - p0)) - 1u);
+    return sel;
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+key_top_hist_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords,
+                         unsigned long long *__restrict__ hist)
+{
+    using P = Pack<BITS>;
+    __shared__ uint32_t h[4096];
+    for (int i = threadIdx.x; i < 4096; i += 256) h[i] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t w = (uint64_t)blockIdx.x * 256 + threadIdx.x; w < nwords; w += stride) {
+        uint32_t s[4];
+        load_stream<BITS>(packed, w, nwords, s);
+        const uint64_t p0 = w * P::SPW;
+        // runs of equal bins are common (a word holds consecutive suffixes of few distinct leading symbols
+        // only by chance), so counts are added one by one; shared-memory atomics on 4096 bins
+#pragma unroll
+        for (int j = 0; j < P::SPW; ++j)
+            if (p0 + j < n) atomicAdd(&h[top_bin<BITS>(s, j)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4096; i += 256)
+        if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+select_count_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, uint32_t bin_lo,
+                         uint32_t bin_hi, uint64_t *__restrict__ tile_count)
+{
+    __shared__ uint32_t s_sum[8];
+    const uint64_t w = (uint64_t)blockIdx.x * kSelWords + threadIdx.x;
+    uint32_t c = __popc(select_mask<BITS>(packed, w, nwords, n, bin_lo, bin_hi));
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += s_sum[k];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+select_write_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, int drop_bits, int key_bits,
+                         uint32_t bin_lo, uint32_t bin_hi, const uint64_t *__restrict__ tile_off,
+                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int lo_bits, int hi_shift)
+{
+    using P = Pack<BITS>;
+    __shared__ uint32_t scratch[9];
+    const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
+    const uint64_t w = (uint64_t)blockIdx.x * kSelWords + threadIdx.x;
+    uint32_t sel = select_mask<BITS>(packed, w, nwords, n, bin_lo, bin_hi);
+    uint32_t total;
+    const uint32_t e = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
+    uint64_t o = tile_off[blockIdx.x] + e;
+    const uint64_t p0 = w * P::SPW;
+    while (sel) {
+        const int j = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const uint64_t p = p0 + j;
+        uint64_t k = first_key<BITS>(packed, p, drop_bits);
+        if (p) k |= (uint64_t)text_symbol<BITS>(packed, p - 1) << key_bits; // the BWT symbol rides along
+        if (hi_shift) k |= (p >> lo_bits) << hi_shift;
+        keys[o] = k;
+        vals[o] = (uint32_t)(p & lo_mask);
+        ++o;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // group heads after the initial sort
 // ---------------------------------------------------------------------------
@@ -884,7 +1024,7 @@ __global__ void __launch_bounds__(1024) wt_scan_kernel(uint64_t *__restrict__ ti
 __global__ void __launch_bounds__(256)
 wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
                uint64_t ntiles, const uint64_t *__restrict__ tile_off, uint64_t *const *__restrict__ node_data,
-               uint8_t *__restrict__ node_ch)
+               uint8_t *__restrict__ node_ch, const uint64_t *__restrict__ bit_base)
 {
     extern __shared__ uint8_t s_info[];
     __shared__ uint32_t scratch[9];
@@ -916,15 +1056,35 @@ wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__res
                 ++out;
                 mm &= mm - 1;
             }
-            const uint64_t o = tile_off[(uint64_t)v * ntiles + tile] + e; // bit offset in the node's array
+            const uint64_t local = tile_off[(uint64_t)v * ntiles + tile] + e; // rank among the node's members
+            const uint64_t o = local + (bit_base ? bit_base[v] : 0ull);        // bit offset in the node's array
             unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]);
             const int sh = (int)(o & 63);
             if (bits << sh) atomicOr(d + (o >> 6), (unsigned long long)(bits << sh));
             if (sh + (int)c > 64 && (bits >> (64 - sh))) atomicOr(d + (o >> 6) + 1, (unsigned long long)(bits >> (64 - sh)));
-            if (o == 0) { // first symbol of the node's subsequence (HuffWT.cpp:8)
+            if (local == 0) { // first symbol of the node's subsequence (HuffWT.cpp:8)
                 const int j = __ffs(m) - 1;
                 node_ch[v] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
             }
+        }
+    }
+}
+
+// Pieces of node bit arrays built by different GPUs (each already shifted to its global bit offset modulo
+// 64) are merged into the node arrays: interior words are plain copies, the first and last word of a piece
+// may share their destination word with a neighbouring piece and are OR-ed in.
+__global__ void __launch_bounds__(256) wt_merge_pieces_kernel(const uint64_t *__restrict__ src, const WtPiece *__restrict__ pieces)
+{
+    const WtPiece pc = pieces[blockIdx.y];
+    const uint64_t *from = src + pc.src_word;
+    unsigned long long *to = reinterpret_cast<unsigned long long *>(pc.dst);
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < pc.nwords; i += stride) {
+        const uint64_t x = from[i];
+        if (i == 0 || i + 1 == pc.nwords) {
+            if (x) atomicOr(to + i, (unsigned long long)x);
+        } else {
+            to[i] = x;
         }
     }
 }
@@ -1055,43 +1215,83 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
     if (launches) ++*launches;
 }
 
+// The fast kernels classify by the top 12 key bits; they apply when the first key has at least 12 bits
+// and at least TopBits::SYMS symbols (always, except under DSMFM_FIRST_KEY_BITS experiments).
+static bool select_fast_ok(int bits, int first_syms, int top_bits)
+{
+    const int syms = bits == 8 ? 2 : 12 / bits;
+    return top_bits == 12 && first_syms >= syms;
+}
+
 void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
                          unsigned long long *hist, uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
     const int top_shift = first_syms * bits - top_bits;
-#define CALL(B) key_top_hist_kernel<B><<<grid_for(n, 256 * 16), 256, 0, st>>>(packed, n, drop_bits, top_shift, hist)
-    DISPATCH_BITS(bits, CALL);
+    const uint64_t nwords = div_up(n, 64 / bits);
+    if (select_fast_ok(bits, first_syms, top_bits)) {
+#define CALL(B) key_top_hist_fast_kernel<B><<<grid_for(nwords, 256 * 4), 256, 0, st>>>(packed, n, nwords, hist)
+        DISPATCH_BITS(bits, CALL);
 #undef CALL
+    } else {
+#define CALL(B) key_top_hist_kernel<B><<<grid_for(n, 256 * 16), 256, 0, st>>>(packed, n, drop_bits, top_shift, hist)
+        DISPATCH_BITS(bits, CALL);
+#undef CALL
+    }
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }
 
-uint64_t select_tiles(uint64_t n) { return div_up(n, kSelTile); }
+uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits)
+{
+    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(div_up(n, 64 / bits), kSelWords);
+    return div_up(n, kSelTile);
+}
 
-void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, uint64_t key_lo,
-                         uint64_t key_hi, uint64_t *tile_count, uint32_t *launches)
+void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         uint64_t key_lo, uint64_t key_hi, uint64_t *tile_count, uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
+    const unsigned tiles = (unsigned)select_tiles(n, bits, first_syms, top_bits);
+    if (select_fast_ok(bits, first_syms, top_bits)) {
+        const int sh = first_syms * bits - 12;
+        const uint64_t nwords = div_up(n, 64 / bits);
 #define CALL(B) \
-    select_count_kernel<B><<<(unsigned)select_tiles(n), 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_count)
-    DISPATCH_BITS(bits, CALL);
+    select_count_fast_kernel<B><<<tiles, 256, 0, st>>>(packed, n, nwords, (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh), tile_count)
+        DISPATCH_BITS(bits, CALL);
 #undef CALL
+    } else {
+#define CALL(B) select_count_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_count)
+        DISPATCH_BITS(bits, CALL);
+#undef CALL
+    }
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }
 
-void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
-                         uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
-                         int lo_bits, int hi_shift, uint32_t *launches)
+void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         bool carry_prev, uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys,
+                         uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
     const int key_bits = first_syms * bits;
-#define CALL(B)                                                                                                   \
-    select_write_kernel<B><<<(unsigned)select_tiles(n), 256, 0, st>>>(packed, n, drop_bits, key_bits, carry_prev, \
-                                                                      key_lo, key_hi, tile_off, keys, vals, lo_bits, hi_shift)
-    DISPATCH_BITS(bits, CALL);
+    const unsigned tiles = (unsigned)select_tiles(n, bits, first_syms, top_bits);
+    if (select_fast_ok(bits, first_syms, top_bits) && carry_prev) {
+        const int sh = key_bits - 12;
+        const uint64_t nwords = div_up(n, 64 / bits);
+#define CALL(B)                                                                                              \
+    select_write_fast_kernel<B><<<tiles, 256, 0, st>>>(packed, n, nwords, drop_bits, key_bits,               \
+                                                       (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh),   \
+                                                       tile_off, keys, vals, lo_bits, hi_shift)
+        DISPATCH_BITS(bits, CALL);
 #undef CALL
+    } else {
+#define CALL(B)                                                                                                   \
+    select_write_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_bits, carry_prev, key_lo, key_hi,     \
+                                                  tile_off, keys, vals, lo_bits, hi_shift)
+        DISPATCH_BITS(bits, CALL);
+#undef CALL
+    }
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }
@@ -1234,10 +1434,19 @@ void launch_wt_scan(cudaStream_t st, uint64_t *tile_count, int n_internal, uint6
 
 void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
                     uint64_t ntiles, const uint64_t *tile_off, uint64_t *const *node_data, uint8_t *node_ch,
-                    uint32_t *launches)
+                    const uint64_t *bit_base, uint32_t *launches)
 {
     wt_fill_kernel<<<(unsigned)ntiles, 256, wt_info_smem(n_internal), st>>>(seq, n, node_info, n_internal, ntiles,
-                                                                           tile_off, node_data, node_ch);
+                                                                           tile_off, node_data, node_ch, bit_base);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_wt_merge_pieces(cudaStream_t st, const uint64_t *src, const WtPiece *pieces, uint32_t npieces,
+                            uint32_t *launches)
+{
+    if (npieces == 0) return;
+    wt_merge_pieces_kernel<<<dim3(kNumSMs * 2, npieces), 256, 0, st>>>(src, pieces);
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

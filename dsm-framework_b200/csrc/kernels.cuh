@@ -38,14 +38,15 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
 // hist[4096]: counts of the top `top_bits` (<= 12) bits of every suffix's first key
 void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
                          unsigned long long *hist, uint32_t *launches);
-// per-tile counts (select_tiles(n) entries) of the suffixes whose first key lies in [key_lo, key_hi)
-uint64_t select_tiles(uint64_t n);
-void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, uint64_t key_lo,
-                         uint64_t key_hi, uint64_t *tile_count, uint32_t *launches);
+// per-tile counts (select_tiles(...) entries) of the suffixes whose first key lies in [key_lo, key_hi);
+// the bounds are multiples of 2^(key_bits - top_bits) (bin boundaries of the histogram above)
+uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits);
+void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         uint64_t key_lo, uint64_t key_hi, uint64_t *tile_count, uint32_t *launches);
 // (key, position) pairs of those suffixes, in text order; tile_off = exclusive scan of the counts
-void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, bool carry_prev,
-                         uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys, uint32_t *vals,
-                         int lo_bits, int hi_shift, uint32_t *launches);
+void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                         bool carry_prev, uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys,
+                         uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches);
 // Wide builds (more than 2^lo_bits symbols in the collection): a text position is hi << lo_bits | lo with
 // lo in the u32 value of the sort and hi (<= 8 bits) riding in the key bits from hi_shift upwards
 // (hi_shift = 0: not wide); launch_heads then unloads hi into a byte array that travels with the suffix
@@ -119,9 +120,20 @@ void launch_wt_count(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint
 // in-place exclusive scan of tile_count[v][0..ntiles) for every node v
 void launch_wt_scan(cudaStream_t st, uint64_t *tile_count, int n_internal, uint64_t ntiles, uint32_t *launches);
 // node_data[v] = device pointer of node v's (zeroed) bit array; node_ch[v] receives the first member symbol
+// bit_base[v] (optional, device): bit offset of the sequence's first member inside node_data[v] (multi-GPU pieces)
 void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
                     uint64_t ntiles, const uint64_t *tile_off, uint64_t *const *node_data, uint8_t *node_ch,
-                    uint32_t *launches);
+                    const uint64_t *bit_base, uint32_t *launches);
+
+// Multi-GPU: node bit arrays arrive as pieces built on different GPUs.  nwords words from src + src_word
+// are merged into dst (first / last word OR-ed, interior copied); gridDim.y = pieces.
+struct WtPiece {
+    uint64_t src_word;
+    uint64_t *dst;
+    uint64_t nwords;
+};
+void launch_wt_merge_pieces(cudaStream_t st, const uint64_t *src, const WtPiece *pieces, uint32_t npieces,
+                            uint32_t *launches);
 
 // BitRank directories of one bit array (BitRank.cpp:154-187): Rs[j] = ones in
 // words [0,4j), j <= nbits/256; Rb[k] = ones in words [4*(k/4), k), k <= nbits/64.

@@ -103,6 +103,11 @@ def lib():
     L.dsmfm_shard_info.argtypes = [B, C.POINTER(Shard)]
     L.dsmfm_assemble.argtypes = [B, C.c_void_p, C.c_uint64]
     L.dsmfm_shard_export.argtypes = [B, C.c_void_p, C.c_void_p]
+    L.dsmfm_slice_hist.argtypes = [B, C.c_void_p]
+    L.dsmfm_pieces_bytes.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.dsmfm_pieces_bytes.restype = C.c_uint64
+    L.dsmfm_build_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.dsmfm_assemble_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_void_p]
     L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
     L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]
@@ -184,6 +189,35 @@ class Builder:
         """Copies the slice into CUDA tensors: bwt_dst uint8[count], sa_dst int64/uint64[count]."""
         self._check(self._L.dsmfm_shard_export(self._h, bwt_dst.data_ptr() if bwt_dst is not None else None,
                                                sa_dst.data_ptr() if sa_dst is not None else None))
+
+    # ---- wavelet tree built by several GPUs (include/dsmfm.h) ----
+    def slice_hist(self):
+        """Byte histogram of this builder's BWT slice: numpy uint64[256]."""
+        import numpy as np
+        out = np.zeros(256, dtype=np.uint64)
+        self._check(self._L.dsmfm_slice_hist(self._h, out.ctypes.data))
+        return out
+
+    @staticmethod
+    def _hist_table(hist_all):
+        import numpy as np
+        h = np.ascontiguousarray(hist_all, dtype=np.uint64)
+        assert h.ndim == 2 and h.shape[1] == 256
+        return h
+
+    def pieces_bytes(self, hist_all, rank):
+        """Size of slice `rank`'s piece buffer (rank == number of slices: all of them together)."""
+        h = self._hist_table(hist_all)
+        return int(self._L.dsmfm_pieces_bytes(self._h, h.ctypes.data, h.shape[0], rank))
+
+    def build_pieces(self, hist_all, rank, dst):
+        h = self._hist_table(hist_all)
+        self._check(self._L.dsmfm_build_pieces(self._h, h.ctypes.data, h.shape[0], rank, dst.data_ptr()))
+
+    def assemble_pieces(self, hist_all, pieces):
+        h = self._hist_table(hist_all)
+        self._keep.append(pieces)
+        self._check(self._L.dsmfm_assemble_pieces(self._h, h.ctypes.data, h.shape[0], pieces.data_ptr()))
 
     def assemble(self, bwt_dev, n_total):
         """bwt_dev: device address (int) or torch CUDA tensor holding the concatenated BWT."""

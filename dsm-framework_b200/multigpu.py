@@ -11,9 +11,12 @@ the other into one TextCollectionBuilder).  The build:
      derives from the same histogram without talking to the others.  The refinement keys come from the
      replicated text, so no rank exchange is needed -- this replaces incbwt's merge by backward search
      (rlcsa_builder.cpp:245-318) and yields the same order, because the order is a property of the text;
-  3. the BWT slices -- contiguous pieces of the global BWT, in rank order -- are sent to rank 0 (NCCL
-     point-to-point), which builds C[], the Huffman-shaped wavelet tree and the BitRank directories
-     (dsmfm_assemble) and owns the finished index.
+  3. the BWT slices are contiguous pieces of the global BWT, in rank order.  Every GPU turns its slice into
+     the bits it contributes to each node of the Huffman-shaped wavelet tree, already shifted to their
+     global bit offset (known from an all-gather of the slices' 256-bin histograms), and sends these
+     pieces (0.28 bytes per symbol) to rank 0 (NCCL point-to-point), which copies them into place, builds
+     the BitRank directories and owns the finished index.  (Engines without piece support -- and
+     wavelet="root" -- ship the BWT slices themselves and rank 0 builds the whole tree, dsmfm_assemble.)
 
 torch.distributed is plumbing only.  `engine` abstracts the device work so that the host logic (block
 offsets, uneven sizes, slice order) is testable with the gloo backend on CPU tensors.
@@ -58,6 +61,19 @@ class CudaEngine:
         handle.assemble(bwt, n_total)
         return handle
 
+    def slice_hist(self, handle):
+        return handle.slice_hist()
+
+    def pieces_bytes(self, handle, hist_all, rank):
+        return handle.pieces_bytes(hist_all, rank)
+
+    def build_pieces(self, handle, hist_all, rank, out):
+        handle.build_pieces(hist_all, rank, out)
+
+    def assemble_pieces(self, handle, hist_all, pieces):
+        handle.assemble_pieces(hist_all, pieces)
+        return handle
+
     def stats(self, handle):
         return handle.stats()
 
@@ -100,38 +116,62 @@ def gather_text(dist, local, device):
     return full, sizes
 
 
-def gather_slices(dist, piece, rank_begin, n_total, device, root=0):
-    """Collects the ranks' BWT slices on `root` in global rank order.  Returns the whole BWT there, None elsewhere."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    counts = _all_gather_sizes(dist, piece.numel(), device)
+def check_tiling(dist, rank_begin, count, n_total, device):
+    """The ranks' slices must tile the suffix order [0, n_total) in rank order, without gaps."""
+    counts = _all_gather_sizes(dist, count, device)
     begins = _all_gather_sizes(dist, rank_begin, device)
-    order = sorted(range(world), key=lambda r: (begins[r], r))
     pos = 0
-    for r in order:  # the slices must tile [0, n_total) without gaps
+    for r in range(dist.get_world_size()):
         if counts[r] and begins[r] != pos:
             raise RuntimeError("BWT slices do not tile the suffix order: rank %d begins at %d, expected %d"
                                % (r, begins[r], pos))
         pos += counts[r]
     if pos != n_total:
         raise RuntimeError("BWT slices cover %d of %d suffixes" % (pos, n_total))
+    return counts
+
+
+def gather_to_root(dist, piece, sizes, device, root=0):
+    """Concatenates the ranks' uint8 buffers (sizes[r] bytes each) on `root` in rank order; None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert piece.numel() == sizes[rank]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
     if rank == root:
-        full = torch.empty(n_total, dtype=torch.uint8, device=device)
-        full[begins[rank]:begins[rank] + counts[rank]].copy_(piece)
-        ops = [dist.P2POp(dist.irecv, full[begins[r]:begins[r] + counts[r]], r)
-               for r in range(world) if r != root and counts[r]]
+        full = torch.empty(offs[-1], dtype=torch.uint8, device=device)
+        full[offs[rank]:offs[rank + 1]].copy_(piece)
+        ops = [dist.P2POp(dist.irecv, full[offs[r]:offs[r + 1]], r) for r in range(world) if r != root and sizes[r]]
     else:
         full = None
-        ops = [dist.P2POp(dist.isend, piece, root)] if counts[rank] else []
+        ops = [dist.P2POp(dist.isend, piece, root)] if sizes[rank] else []
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return full
 
 
-def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0):
+def gather_slices(dist, piece, rank_begin, n_total, device, root=0):
+    """Collects the ranks' BWT slices on `root` in global rank order.  Returns the whole BWT there, None elsewhere."""
+    counts = check_tiling(dist, rank_begin, piece.numel(), n_total, device)
+    return gather_to_root(dist, piece, counts, device, root)
+
+
+def all_gather_hist(dist, hist, device):
+    """hist: numpy uint64[256] of this rank -> numpy uint64[world, 256]."""
+    import numpy as np
+    t = torch.from_numpy(hist.astype(np.int64)).to(device)
+    out = torch.empty(dist.get_world_size() * 256, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t)
+    return out.cpu().numpy().astype(np.uint64).reshape(dist.get_world_size(), 256)
+
+
+def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0, wavelet="distributed"):
     """Builds ONE index over the documents of all ranks (rank order = document order).
 
     local_docs: uint8 tensor (pinned host or device) with this rank's '\\0'-terminated documents.
+    wavelet: "distributed" (every GPU builds its pieces of the wavelet tree) or "root" (BWT slices go to
+    the root, which builds the whole tree).
     Returns (handle, info): on `root` handle is the engine's builder holding the assembled index
     (fetch()/fmi()/save() as for a single-GPU build), None elsewhere; info has the slice layout.
     """
@@ -145,18 +185,33 @@ def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0):
     handle, rank_begin, count = engine.sort_slice(full, rank * k, world * k, k)
     del full
     if trace: trace.mark("sort_slice")
-    piece = torch.empty(count, dtype=torch.uint8, device=device)
-    engine.export_bwt(handle, piece)
-    bwt = gather_slices(dist, piece, rank_begin, n, device, root)
-    if trace: trace.mark("gather_slices")
     info = {"n_total": n, "block_bytes": sizes, "rank_begin": rank_begin, "count": count}
+    distributed = wavelet == "distributed" and hasattr(engine, "build_pieces")
+    if distributed:
+        check_tiling(dist, rank_begin, count, n, device)
+        hist_all = all_gather_hist(dist, engine.slice_hist(handle), device)
+        if int(hist_all[rank].sum()) != count:
+            raise RuntimeError("slice histogram of rank %d does not match its slice" % rank)
+        psizes = [engine.pieces_bytes(handle, hist_all, r) for r in range(world)]
+        piece = torch.empty(psizes[rank], dtype=torch.uint8, device=device)
+        engine.build_pieces(handle, hist_all, rank, piece)
+        if trace: trace.mark("build_pieces")
+        gathered = gather_to_root(dist, piece, psizes, device, root)
+    else:
+        piece = torch.empty(count, dtype=torch.uint8, device=device)
+        engine.export_bwt(handle, piece)
+        gathered = gather_slices(dist, piece, rank_begin, n, device, root)
+    if trace: trace.mark("gather")
     if rank != root:
         if hasattr(engine, "stats"):
             info["stats"] = engine.stats(handle)
         engine.close(handle)
         if trace: trace.report(rank, info)
         return None, info
-    engine.assemble(handle, bwt, n)
+    if distributed:
+        engine.assemble_pieces(handle, hist_all, gathered)
+    else:
+        engine.assemble(handle, gathered, n)
     if trace: trace.mark("assemble")
     if hasattr(engine, "stats"):
         info["stats"] = engine.stats(handle)

@@ -191,6 +191,21 @@ DSMFM_API int dsmfm_shard_export(dsmfm_builder *b, void *bwt_dst_dev, void *sa_d
  * dsmfm_fetch then returns the index of the whole collection. */
 DSMFM_API int dsmfm_assemble(dsmfm_builder *b, const void *bwt_dev, uint64_t n_total);
 
+/* ---- wavelet tree built by several GPUs ----
+ * Instead of shipping whole BWT slices to one GPU (dsmfm_assemble), every GPU turns its slice into
+ * the bits it contributes to each wavelet-tree node ("pieces", about 0.28 bytes per symbol), already
+ * shifted to their global bit offset modulo 64; the assembling GPU copies them into place and builds
+ * the BitRank directories.  All that has to be agreed on is the table hist_all[world][256] of the
+ * slices' byte histograms (dsmfm_slice_hist of every builder, in slice order).
+ *   dsmfm_pieces_bytes(b, hist_all, world, r)      size of builder r's piece buffer (r == world: sum of all)
+ *   dsmfm_build_pieces(b, hist_all, world, r, dst) fills dst (DEVICE memory of that size) on builder r
+ *   dsmfm_assemble_pieces(b, hist_all, world, src) src = the world piece buffers back to back in slice
+ *                                                  order (DEVICE memory); dsmfm_fetch then returns the index */
+DSMFM_API int dsmfm_slice_hist(dsmfm_builder *b, uint64_t *out256);
+DSMFM_API uint64_t dsmfm_pieces_bytes(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank);
+DSMFM_API int dsmfm_build_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, void *dst_dev);
+DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, const void *pieces_dev);
+
 /* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
  * byte-for-byte in the reference layout (version 17). */
 DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix);

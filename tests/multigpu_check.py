@@ -30,8 +30,8 @@ def main():
             mine = b"".join(d + b"\0" for d in doc_list[b:e])
             host = torch.frombuffer(bytearray(mine), dtype=torch.uint8).pin_memory()
             engine = multigpu.CudaEngine(local, stream=torch.cuda.current_stream().cuda_stream)
-            for src in (host, host.cuda()):
-                handle, info = multigpu.build_sharded(dist, src, engine, ranges_per_gpu=ranges)
+            for src, wavelet in ((host, "distributed"), (host.cuda(), "distributed"), (host, "root")):
+                handle, info = multigpu.build_sharded(dist, src, engine, ranges_per_gpu=ranges, wavelet=wavelet)
                 assert info["n_total"] == len(docs)
                 if rank == 0:
                     handle.fetch()

@@ -269,7 +269,7 @@ def test_toydata_shaped_sample_matches_live_reference(tmp_path):
 
 # ---- one collection cut into key ranges (the multi-GPU path, here with every range on one device) ------
 
-def _sharded_build(docs, shard_count, span=1):
+def _sharded_build(docs, shard_count, span=1, pieces=False):
     """Builds every slice of the global suffix order with its own builder, concatenates the BWT slices
     on the device and assembles the index on the first builder.  Returns (fmi, bwt, sa)."""
     import torch
@@ -291,7 +291,18 @@ def _sharded_build(docs, shard_count, span=1):
             b.shard_export(bw[-1], sa[-1])
         assert nxt == len(docs)
         full = torch.cat(bw)
-        builders[0].assemble(full, len(docs))
+        if pieces:  # every slice contributes its bits of every wavelet-tree node; the first builder merges them
+            hist_all = np.stack([b.slice_hist() for b in builders])
+            assert np.array_equal(hist_all.sum(axis=0), np.bincount(np.frombuffer(docs, dtype=np.uint8), minlength=256))
+            bufs = []
+            for r, b in enumerate(builders):
+                bufs.append(torch.empty(b.pieces_bytes(hist_all, r), dtype=torch.uint8, device="cuda"))
+                b.build_pieces(hist_all, r, bufs[-1])
+            allp = torch.cat(bufs)
+            assert allp.numel() == builders[0].pieces_bytes(hist_all, len(builders))
+            builders[0].assemble_pieces(hist_all, allp)
+        else:
+            builders[0].assemble(full, len(docs))
         builders[0].fetch()
         return builders[0].fmi(), full.cpu().numpy().tobytes(), torch.cat(sa).cpu().numpy()
     finally:
@@ -350,3 +361,22 @@ def test_sharded_builder_errors():
         b.build_device()
         with pytest.raises(dsmfm.DsmfmError):   # a slice is not an index
             b.fetch()
+
+
+@pytest.mark.parametrize("shards,span", [(2, 1), (3, 1), (8, 2), (37, 1)])
+@pytest.mark.parametrize("name", ["reads100", "poly_a", "duplicates", "mixed_alphabet", "one_base_reads", "single",
+                                  "two_letter", "empty"])
+def test_wavelet_tree_assembled_from_per_slice_pieces(name, shards, span):
+    """The multi-GPU wavelet tree: every slice's bits are built at their global bit offset and merged."""
+    docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+    if not docs:
+        pytest.skip("the empty collection is built unsharded")
+    fmi, _, _ = _sharded_build(docs, shards, span, pieces=True)
+    _assert_same_fmi(fmi, _golden(name, ".fmi"))
+
+
+def test_pieces_on_a_generated_sample():
+    import dsmgen
+    g = MANIFEST["generated"]["gen_20k"]
+    fmi, _, _ = _sharded_build(dsmgen.docs(**g["params"]).tobytes(), 5, 1, pieces=True)
+    assert hashlib.sha256(fmi).hexdigest() == g["fmi_sha256"]
