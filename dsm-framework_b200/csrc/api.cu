@@ -791,10 +791,8 @@ void dsmfm_builder::build()
         } else {
             const uint64_t ntile = select_tiles(n, bits, first_syms, top_bits);
             uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
-            launch_select_count(st, bits, d_packed, n, first_syms, top_bits, rg.key_lo, rg.key_hi, d_tile, L);
-            launch_wt_scan(st, d_tile, 1, ntile, L);
-            launch_select_write(st, bits, d_packed, n, first_syms, top_bits, carry_bwt, rg.key_lo, rg.key_hi, d_tile,
-                                d_keys_a, d_vals_a, lo_bits, hi_shift, L);
+            launch_select(st, bits, d_packed, n, first_syms, top_bits, carry_bwt, rg.key_lo, rg.key_hi, d_tile,
+                          ws.counter, d_keys_a, d_vals_a, lo_bits, hi_shift, L);
             dfree(d_tile);
         }
         const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,

@@ -90,20 +90,36 @@ __global__ void __launch_bounds__(256) doc_stats_kernel(const uint8_t *__restric
     const uint64_t begin = (uint64_t)blockIdx.x * kStatChunk + (uint64_t)threadIdx.x * PER;
     long long first = -1, last = -1;
     unsigned long long gmax = 0, gmin = ~0ull;
-    if (begin < n) {
-        const uint64_t end = begin + PER < n ? begin + PER : n;
-        for (uint64_t p = begin; p < end; ++p) {
-            if (raw[p] == 0) {
-                if (last >= 0) {
-                    const unsigned long long g = p - (uint64_t)last;
-                    gmax = g > gmax ? g : gmax;
-                    gmin = g < gmin ? g : gmin;
-                } else {
-                    first = (long long)p;
+    auto terminator_at = [&](uint64_t p) {
+        if (last >= 0) {
+            const unsigned long long g = p - (uint64_t)last;
+            gmax = g > gmax ? g : gmax;
+            gmin = g < gmin ? g : gmin;
+        } else {
+            first = (long long)p;
+        }
+        last = (long long)p;
+    };
+    if (begin + PER <= n && (reinterpret_cast<uintptr_t>(raw) & 15) == 0) {
+        // terminators are rare (one per document): test four bytes at a time
+        static_assert(PER % 16 == 0, "whole 16-byte vectors per thread");
+#pragma unroll
+        for (int q = 0; q < PER / 16; ++q) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(raw + begin) + q);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if ((w[i] - 0x01010101u) & ~w[i] & 0x80808080u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (((w[i] >> (8 * j)) & 0xffu) == 0) terminator_at(begin + 16 * q + 4 * i + j);
                 }
-                last = (long long)p;
             }
         }
+    } else if (begin < n) {
+        const uint64_t end = begin + PER < n ? begin + PER : n;
+        for (uint64_t p = begin; p < end; ++p)
+            if (raw[p] == 0) terminator_at(p);
     }
     // inclusive max-scan of `last` over the block -> previous terminator of each thread
     long long incl = last;
@@ -348,7 +364,6 @@ template <int BITS> __device__ __forceinline__ void load_stream(const uint64_t *
     s[3] = (uint32_t)x1;
 }
 
-constexpr int kSelWords = 256; // packed words per CTA of the fast selection kernels
 
 // selection mask of the SPW suffixes starting in word w: bit j set iff suffix w*SPW+j exists and its bin is in range
 template <int BITS>
@@ -395,49 +410,98 @@ key_top_hist_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64
         if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(256)
-select_count_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, uint32_t bin_lo,
-                         uint32_t bin_hi, uint64_t *__restrict__ tile_count)
-{
-    __shared__ uint32_t s_sum[8];
-    const uint64_t w = (uint64_t)blockIdx.x * kSelWords + threadIdx.x;
-    uint32_t c = __popc(select_mask<BITS>(packed, w, nwords, n, bin_lo, bin_hi));
-    c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int k = 0; k < 8; ++k) t += s_sum[k];
-        tile_count[blockIdx.x] = t;
-    }
-}
+// One pass: select, compute the keys of the selected suffixes and write the (key, position) pairs out in
+// text order.  A CTA takes the next tile of kSweepSelWords packed words (dynamic tile id, so that a tile's
+// predecessors are always running or done), counts its selected suffixes, publishes the count and obtains
+// its output offset by decoupled look-back over the preceding tiles (64-bit status words: 2 flag bits + 62
+// value bits); meanwhile the keys are staged in shared memory in text order, so that the tile leaves the SM
+// as one contiguous burst instead of 12-byte stores scattered per thread.
+constexpr int kSweepSelThreads = 128;
+constexpr int kSweepSelWords = kSweepSelThreads; // one packed word per thread
+constexpr unsigned long long kSelFlagAgg = 1ull << 62, kSelFlagPrefix = 2ull << 62, kSelValueMask = (1ull << 62) - 1;
 
 template <int BITS>
-__global__ void __launch_bounds__(256)
-select_write_fast_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, int drop_bits, int key_bits,
-                         uint32_t bin_lo, uint32_t bin_hi, const uint64_t *__restrict__ tile_off,
-                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int lo_bits, int hi_shift)
+__global__ void __launch_bounds__(kSweepSelThreads)
+select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, int drop_bits, int key_bits,
+                    uint32_t bin_lo, uint32_t bin_hi, volatile unsigned long long *status, uint32_t *counter,
+                    uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int lo_bits, int hi_shift)
 {
     using P = Pack<BITS>;
-    __shared__ uint32_t scratch[9];
+    constexpr int CAP = kSweepSelWords * P::SPW; // suffixes per tile
+    __shared__ uint64_t s_key[CAP];
+    __shared__ uint32_t s_val[CAP];
+    __shared__ uint32_t scratch[kSweepSelThreads / 32 + 1];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
     const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
-    const uint64_t w = (uint64_t)blockIdx.x * kSelWords + threadIdx.x;
+    const uint64_t w = (uint64_t)tile * kSweepSelWords + tid;
     uint32_t sel = select_mask<BITS>(packed, w, nwords, n, bin_lo, bin_hi);
     uint32_t total;
-    const uint32_t e = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
-    uint64_t o = tile_off[blockIdx.x] + e;
+    uint32_t o = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
+    if (tid == 0) status[tile] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
+
+    // Keys of the selected suffixes, staged in text order.  The word and its successor hold every symbol a
+    // first key can need (first_syms <= SPW), so keys are cut out of two registers; the symbol before the
+    // suffix (the BWT symbol, which rides above the key bits) is the previous symbol of the same stream.
     const uint64_t p0 = w * P::SPW;
-    while (sel) {
-        const int j = __ffs(sel) - 1;
-        sel &= sel - 1;
-        const uint64_t p = p0 + j;
-        uint64_t k = first_key<BITS>(packed, p, drop_bits);
-        if (p) k |= (uint64_t)text_symbol<BITS>(packed, p - 1) << key_bits; // the BWT symbol rides along
-        if (hi_shift) k |= (p >> lo_bits) << hi_shift;
-        keys[o] = k;
-        vals[o] = (uint32_t)(p & lo_mask);
-        ++o;
+    if (sel) {
+        uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
+        uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u; // last symbol of the previous word
+        if (P::USED == 63) {
+            x0 = (x0 << 1) | (x1 >> 62);
+            x1 <<= 2;
+        }
+        const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
+        while (sel) {
+            const int j = __ffs(sel) - 1;
+            sel &= sel - 1;
+            const int b = BITS * j;
+            const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0;     // stream from symbol j on
+            uint64_t k = (v >> (64 - key_bits)) | ~kmask;                  // ones above: only real fields can be zero
+            k = cut_at_terminator<BITS>(k) & kmask;
+            const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
+            k |= (uint64_t)prev << key_bits;                               // the BWT symbol rides along
+            const uint64_t p = p0 + j;
+            if (hi_shift) k |= (p >> lo_bits) << hi_shift;
+            s_key[o] = k;
+            s_val[o] = (uint32_t)(p & lo_mask);
+            ++o;
+        }
+    }
+
+    // look-back by the first warp: 32 predecessors per step
+    if (tid < 32) {
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            long long t = (long long)tile - 1;
+            for (;;) {
+                const long long idx = t - lane;
+                unsigned long long x = 2ull << 62; // before the first tile: an empty prefix
+                if (idx >= 0) x = status[idx];
+                while (__any_sync(0xffffffffu, (x >> 62) == 0))
+                    if ((x >> 62) == 0) x = status[idx];
+                const uint32_t pm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+                const int stop = pm ? __ffs(pm) - 1 : 32;
+                unsigned long long v = lane <= stop ? (x & kSelValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (pm) break;
+                t -= 32;
+            }
+            if (lane == 0) status[tile] = kSelFlagPrefix | (excl + total);
+        }
+        if (lane == 0) s_base = excl;
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
+    for (uint32_t i = tid; i < total; i += kSweepSelThreads) {
+        keys[base + i] = s_key[i];
+        vals[base + i] = s_val[i];
     }
 }
 
@@ -1244,34 +1308,13 @@ void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint
 
 uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits)
 {
-    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(div_up(n, 64 / bits), kSelWords);
+    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(div_up(n, 64 / bits), kSweepSelWords);
     return div_up(n, kSelTile);
 }
 
-void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
-                         uint64_t key_lo, uint64_t key_hi, uint64_t *tile_count, uint32_t *launches)
-{
-    const int drop_bits = (64 / bits - first_syms) * bits;
-    const unsigned tiles = (unsigned)select_tiles(n, bits, first_syms, top_bits);
-    if (select_fast_ok(bits, first_syms, top_bits)) {
-        const int sh = first_syms * bits - 12;
-        const uint64_t nwords = div_up(n, 64 / bits);
-#define CALL(B) \
-    select_count_fast_kernel<B><<<tiles, 256, 0, st>>>(packed, n, nwords, (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh), tile_count)
-        DISPATCH_BITS(bits, CALL);
-#undef CALL
-    } else {
-#define CALL(B) select_count_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_count)
-        DISPATCH_BITS(bits, CALL);
-#undef CALL
-    }
-    DSM_LAUNCH_CHECK();
-    if (launches) ++*launches;
-}
-
-void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
-                         bool carry_prev, uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys,
-                         uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches)
+void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                   bool carry_prev, uint64_t key_lo, uint64_t key_hi, uint64_t *tile_scratch, uint32_t *counter,
+                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
     const int key_bits = first_syms * bits;
@@ -1279,21 +1322,31 @@ void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint
     if (select_fast_ok(bits, first_syms, top_bits) && carry_prev) {
         const int sh = key_bits - 12;
         const uint64_t nwords = div_up(n, 64 / bits);
-#define CALL(B)                                                                                              \
-    select_write_fast_kernel<B><<<tiles, 256, 0, st>>>(packed, n, nwords, drop_bits, key_bits,               \
-                                                       (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh),   \
-                                                       tile_off, keys, vals, lo_bits, hi_shift)
+        DSM_CUDA(cudaMemsetAsync(tile_scratch, 0, (size_t)tiles * 8, st));
+        DSM_CUDA(cudaMemsetAsync(counter, 0, 4, st));
+#define CALL(B)                                                                                                        \
+    select_sweep_kernel<B><<<tiles, kSweepSelThreads, 0, st>>>(                                                        \
+        packed, n, nwords, drop_bits, key_bits, (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh),                    \
+        reinterpret_cast<volatile unsigned long long *>(tile_scratch), counter, keys, vals, lo_bits, hi_shift)
         DISPATCH_BITS(bits, CALL);
 #undef CALL
-    } else {
+        DSM_LAUNCH_CHECK();
+        if (launches) ++*launches;
+        return;
+    }
+    // generic path (first keys shorter than 12 bits: only under DSMFM_FIRST_KEY_BITS experiments)
+#define CALL(B) select_count_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_scratch)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    launch_wt_scan(st, tile_scratch, 1, tiles, launches);
 #define CALL(B)                                                                                                   \
     select_write_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_bits, carry_prev, key_lo, key_hi,     \
-                                                  tile_off, keys, vals, lo_bits, hi_shift)
-        DISPATCH_BITS(bits, CALL);
+                                                  tile_scratch, keys, vals, lo_bits, hi_shift)
+    DISPATCH_BITS(bits, CALL);
 #undef CALL
-    }
     DSM_LAUNCH_CHECK();
-    if (launches) ++*launches;
+    if (launches) *launches += 2;
 }
 
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,

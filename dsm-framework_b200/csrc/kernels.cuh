@@ -38,15 +38,13 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
 // hist[4096]: counts of the top `top_bits` (<= 12) bits of every suffix's first key
 void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
                          unsigned long long *hist, uint32_t *launches);
-// per-tile counts (select_tiles(...) entries) of the suffixes whose first key lies in [key_lo, key_hi);
-// the bounds are multiples of 2^(key_bits - top_bits) (bin boundaries of the histogram above)
+// (key, position) pairs of the suffixes whose first key lies in [key_lo, key_hi), in text order.  The bounds
+// are multiples of 2^(key_bits - top_bits) (bin boundaries of the histogram above).  tile_scratch holds
+// select_tiles(...) u64, counter one u32.
 uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits);
-void launch_select_count(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
-                         uint64_t key_lo, uint64_t key_hi, uint64_t *tile_count, uint32_t *launches);
-// (key, position) pairs of those suffixes, in text order; tile_off = exclusive scan of the counts
-void launch_select_write(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
-                         bool carry_prev, uint64_t key_lo, uint64_t key_hi, const uint64_t *tile_off, uint64_t *keys,
-                         uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches);
+void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+                   bool carry_prev, uint64_t key_lo, uint64_t key_hi, uint64_t *tile_scratch, uint32_t *counter,
+                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches);
 // Wide builds (more than 2^lo_bits symbols in the collection): a text position is hi << lo_bits | lo with
 // lo in the u32 value of the sort and hi (<= 8 bits) riding in the key bits from hi_shift upwards
 // (hi_shift = 0: not wide); launch_heads then unloads hi into a byte array that travels with the suffix
