@@ -185,11 +185,13 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # torchrun pins OMP_NUM_THREADS to 1; the read generator (input preparation) is OpenMP code
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import torch
     import dsmfm
     import dsmgen
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():

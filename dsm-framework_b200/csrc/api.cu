@@ -1065,8 +1065,8 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
         g_create_error = "device ordinal out of range";
         return DSMFM_EINVAL;
     }
-    cudaDeviceProp prop;
-    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess || prop.major < 10) {
+    int cc_major = 0; // (cudaGetDeviceProperties takes tens of milliseconds; one attribute does not)
+    if ((e = cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess || cc_major < 10) {
         g_create_error = "device is not sm_100 or newer (kernels are built for sm_100a only)";
         return DSMFM_ECUDA;
     }

@@ -22,6 +22,7 @@ torch.distributed is plumbing only.  `engine` abstracts the device work so that 
 offsets, uneven sizes, slice order) is testable with the gloo backend on CPU tensors.
 """
 import os
+import time
 
 import torch
 
@@ -46,12 +47,16 @@ class CudaEngine:
                                 samplerate=self.samplerate, shard_index=shard_index, shard_count=shard_count,
                                 shard_span=shard_span)
         try:
+            t0 = time.perf_counter()
             b.append_batch_device(text)
+            t1 = time.perf_counter()
             b.build_device()
+            t2 = time.perf_counter()
             info = b.shard_info()
         except Exception:
             b.close()
             raise
+        self.last_walls = (1000 * (t1 - t0), 1000 * (t2 - t1))  # append, build (host wall, for DSMFM_MG_TRACE)
         return b, info.rank_begin, info.count
 
     def export_bwt(self, handle, out):
@@ -185,6 +190,7 @@ def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0, wavelet="d
     handle, rank_begin, count = engine.sort_slice(full, rank * k, world * k, k)
     del full
     if trace: trace.mark("sort_slice")
+    if trace and hasattr(engine, "last_walls"): trace.marks.append(("(append %.1f build %.1f)" % engine.last_walls, 0.0))
     info = {"n_total": n, "block_bytes": sizes, "rank_begin": rank_begin, "count": count}
     distributed = wavelet == "distributed" and hasattr(engine, "build_pieces")
     if distributed:
@@ -244,6 +250,6 @@ class _Trace:
         s = info.get("stats")
         extra = ""
         if s is not None:
-            extra = " | build: pack %.1f sort %.1f refine %.1f wt %.1f total %.1f, count %d" % (
-                s.ms_pack, s.ms_sort, s.ms_refine, s.ms_wt, s.ms_total, info["count"])
+            extra = " | build: pack %.1f sort %.1f refine %.1f wt %.1f total %.1f, wall %.1f of which alloc %.1f, count %d" % (
+                s.ms_pack, s.ms_sort, s.ms_refine, s.ms_wt, s.ms_total, s.ms_wall_build, s.ms_wall_alloc, info["count"])
         print("[multigpu rank %d] " % rank + " ".join("%s %.1f ms" % m for m in self.marks) + extra, file=sys.stderr)
