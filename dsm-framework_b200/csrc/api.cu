@@ -432,6 +432,8 @@ struct dsmfm_builder {
     uint32_t *d_sa = nullptr;      // suffix array of the slice, low position bits (DSMFM_FLAG_KEEP_SA)
     uint8_t *d_sa_hi = nullptr;    // wide builds: position = d_sa_hi << pos_lo_bits | d_sa
     int pos_lo_bits = 32;
+    uint32_t *d_doc_end = nullptr; // text position of every document's terminator (DSMFM_FLAG_KEEP_SA, unsharded)
+    std::vector<uint8_t> sa_image; // bytes of the .sa file, built on first use
     uint8_t *d_bwt = nullptr;      // lives in the first key buffer of the sort
     WaveletResult wt;
     uint8_t *h_bwt = nullptr;
@@ -518,12 +520,14 @@ struct dsmfm_builder {
         d_sa = nullptr;
         d_sa_hi = nullptr;
         d_bwt = nullptr;
+        d_doc_end = nullptr;
         dev_now = 0;
         wt.release(stream);
     }
 
     void build();
     void fetch();
+    void make_sa_image();
 };
 
 // ---------------------------------------------------------------------------
@@ -988,6 +992,13 @@ void dsmfm_builder::build()
         dfree(d_last_sorted_vals);
     }
     pos_lo_bits = lo_bits;
+    if (keep_sa && !sharded) { // the .sa writer needs the document boundaries
+        d_doc_end = static_cast<uint32_t *>(dmalloc((size_t)counts[0] * 4 + 16));
+        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(term_tiles(n) * 8));
+        launch_term_positions(st, d_raw, n, d_tile, d_doc_end, L);
+        DSM_CUDA(cudaStreamSynchronize(st));
+        dfree(d_tile);
+    }
     dfree(d_raw);
     chunks.clear();
     d_raw = nullptr;
@@ -1028,13 +1039,115 @@ void dsmfm_builder::fetch()
     index.n_nodes = (uint32_t)wt.shape.nodes.size();
     index.nodes = wt.shape.nodes.data();
     index.bwt = h_bwt;
-    // the device copies are no longer needed
-    dfree(d_bwt);
-    d_bwt = nullptr;
+    // the device copies are no longer needed (the .sa writer still wants the BWT)
+    if (!(flags & DSMFM_FLAG_KEEP_SA)) {
+        dfree(d_bwt);
+        d_bwt = nullptr;
+    }
     dev_free(wt.d_sections, stream);
     dev_free(wt.d_ch, stream);
     wt.d_sections = wt.d_ch = nullptr;
     fetched = true;
+}
+
+// ---------------------------------------------------------------------------
+// .sa image: FMIndex::saveSamples over maketables (FMIndex.cpp:125-147, 572-714).  The reference
+// walks the whole text backwards by LF-mapping to find the sampled BWT positions and the order of
+// the end markers; with the suffix array in HBM the same tables fall out of three passes over it.
+// ---------------------------------------------------------------------------
+namespace {
+unsigned ceil_log2(uint64_t i) // Tools::CeilLog2, Tools.cpp:43-64
+{
+    unsigned b = 0;
+    uint64_t t = i;
+    while (t) { ++b; t >>= 1; }
+    const unsigned fl = b ? b - 1 : 0;
+    return ((uint64_t)1 << fl) != i ? fl + 1 : fl;
+}
+
+// BlockArray::Save (BlockArray.h:54-64): n, blockLength, n*blockLength/64+1 words, fields LSB first (Tools.h:49-61)
+void put_block_array(std::vector<uint8_t> &out, const uint32_t *v, uint64_t count, unsigned len)
+{
+    std::vector<uint64_t> data(count * len / 64 + 1, 0);
+    if (len)
+        for (uint64_t i = 0; i < count; ++i) {
+            const uint64_t bit = i * len, w = bit >> 6, j = bit & 63, x = v[i];
+            data[w] |= x << j;
+            if (j + len > 64) data[w + 1] |= x >> (64 - j);
+        }
+    const uint64_t hdr[2] = {count, len};
+    const uint8_t *h = reinterpret_cast<const uint8_t *>(hdr), *d = reinterpret_cast<const uint8_t *>(data.data());
+    out.insert(out.end(), h, h + 16);
+    out.insert(out.end(), d, d + data.size() * 8);
+}
+} // namespace
+
+void dsmfm_builder::make_sa_image()
+{
+    cudaStream_t st = stream;
+    uint32_t *L = &stats.kernel_launches;
+    const uint64_t nn = index.n;
+    const uint32_t D = index.number_of_texts;
+    const uint64_t words = nn / 64 + 1, nsb = nn / 256 + 1, nb = nn / 64 + 1;
+    struct Bits {
+        uint64_t *data = nullptr, *Rs = nullptr;
+        uint8_t *Rb = nullptr;
+    };
+    uint32_t *d_mark = static_cast<uint32_t *>(dmalloc(((nn >> 5) + 2) * 4));
+    uint64_t *d_scratch = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * (div_up(nsb, kRankChunk) + 1)));
+    Bits sampled, starts;
+    for (Bits *b : {&sampled, &starts}) {
+        b->data = static_cast<uint64_t *>(dmalloc(words * 8));
+        b->Rs = static_cast<uint64_t *>(dmalloc(nsb * 8));
+        b->Rb = static_cast<uint8_t *>(dmalloc(nb + 8));
+    }
+    DSM_CUDA(cudaMemsetAsync(d_mark, 0, ((nn >> 5) + 2) * 4, st));
+    launch_sa_mark(st, d_doc_end, D, samplerate, d_mark, L);
+    launch_sa_rank_bits(st, d_sa, nullptr, d_mark, nn, reinterpret_cast<uint32_t *>(sampled.data), words * 2, L);
+    launch_bitrank(st, sampled.data, nn, sampled.Rs, sampled.Rb, d_scratch, L);
+    launch_sa_rank_bits(st, d_sa, d_bwt, nullptr, nn, reinterpret_cast<uint32_t *>(starts.data), words * 2, L);
+    launch_bitrank(st, starts.data, nn, starts.Rs, starts.Rb, d_scratch, L);
+
+    std::vector<uint64_t> h_data(words), h_rs(nsb);
+    std::vector<uint8_t> h_rb(nb);
+    DSM_CUDA(cudaMemcpyAsync(h_data.data(), sampled.data, words * 8, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(h_rs.data(), sampled.Rs, nsb * 8, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(h_rb.data(), sampled.Rb, nb, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    uint64_t samples = h_rs[nsb - 1];
+    for (uint64_t w = 4 * (nsb - 1); w < words; ++w) samples += (uint64_t)__builtin_popcountll(h_data[w]);
+
+    uint32_t *d_sdoc = static_cast<uint32_t *>(dmalloc(samples * 4 + 16));
+    uint32_t *d_soff = static_cast<uint32_t *>(dmalloc(samples * 4 + 16));
+    uint32_t *d_emdoc = static_cast<uint32_t *>(dmalloc((size_t)D * 4 + 16));
+    launch_sa_emit(st, d_sa, sampled.data, sampled.Rs, sampled.Rb, nn, d_doc_end, D, d_sdoc, d_soff, L);
+    launch_sa_emit(st, d_sa, starts.data, starts.Rs, starts.Rb, nn, d_doc_end, D, d_emdoc, nullptr, L);
+    std::vector<uint32_t> h_sdoc(samples + 1), h_soff(samples + 1), h_emdoc(D), h_end(D), h_len(D);
+    DSM_CUDA(cudaMemcpyAsync(h_sdoc.data(), d_sdoc, samples * 4, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(h_soff.data(), d_soff, samples * 4, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(h_emdoc.data(), d_emdoc, (size_t)D * 4, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(h_end.data(), d_doc_end, (size_t)D * 4, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    dfree(d_mark); dfree(d_scratch); dfree(d_sdoc); dfree(d_soff); dfree(d_emdoc);
+    for (Bits *b : {&sampled, &starts}) { dfree(b->data); dfree(b->Rs); dfree(b->Rb); }
+    for (uint32_t k = 0; k < D; ++k) h_len[k] = h_end[k] - (k ? h_end[k - 1] + 1 : 0u); // FMIndex.cpp:703-707
+
+    // saveSamples order: sampled (BitRank::save), suffixes, suffixDocId, textLength, Doc (FMIndex.cpp:134-143)
+    std::vector<uint8_t> &out = sa_image;
+    out.clear();
+    const uint64_t integers = (nn + 1) % 64 ? (nn + 1) / 64 + 1 : (nn + 1) / 64;
+    const uint32_t b64 = 64, s256 = 256;
+    auto put = [&](const void *p, size_t bytes) {
+        const uint8_t *q = static_cast<const uint8_t *>(p);
+        out.insert(out.end(), q, q + bytes);
+    };
+    put(&nn, 8); put(&integers, 8); put(&b64, 4); put(&s256, 4);
+    put(h_data.data(), integers * 8); put(h_rs.data(), nsb * 8); put(h_rb.data(), nb);
+    const unsigned wlen = ceil_log2(index.max_text_length), wdoc = ceil_log2(D);
+    put_block_array(out, h_soff.data(), samples, wlen);
+    put_block_array(out, h_sdoc.data(), samples, wdoc);
+    put_block_array(out, h_len.data(), D, wlen);
+    put_block_array(out, h_emdoc.data(), D, wdoc);
 }
 
 // ---------------------------------------------------------------------------
@@ -1425,6 +1538,54 @@ DSMFM_API int dsmfm_copy_sa(dsmfm_builder *b, uint32_t *out, uint64_t first, uin
     cudaError_t e = cudaMemcpy(out, b->d_sa + first, count * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return b->fail(DSMFM_ECUDA, "dsmfm_copy_sa: %s", cudaGetErrorString(e));
     return DSMFM_OK;
+}
+
+static int ensure_sa_image(dsmfm_builder *b, const char *who)
+{
+    if (!b->built || !b->d_sa || !b->d_doc_end || !b->d_bwt)
+        return b->fail(DSMFM_EINVAL, "%s: needs a finished, unsharded build with DSMFM_FLAG_KEEP_SA", who);
+    if (!b->sa_image.empty()) return DSMFM_OK;
+    try {
+        b->make_sa_image();
+    } catch (const CudaError &e) {
+        b->sa_image.clear();
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        b->sa_image.clear();
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API uint64_t dsmfm_sa_size(dsmfm_builder *b)
+{
+    if (!b) return 0;
+    cudaSetDevice(b->device);
+    return ensure_sa_image(b, "dsmfm_sa_size") == DSMFM_OK ? b->sa_image.size() : 0;
+}
+
+DSMFM_API int dsmfm_sa_serialize(dsmfm_builder *b, uint8_t *out, uint64_t out_cap)
+{
+    API_GUARD(b);
+    int rc = ensure_sa_image(b, "dsmfm_sa_serialize");
+    if (rc) return rc;
+    if (!out || out_cap < b->sa_image.size()) return b->fail(DSMFM_EINVAL, "dsmfm_sa_serialize: buffer too small");
+    std::memcpy(out, b->sa_image.data(), b->sa_image.size());
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_write_sa(dsmfm_builder *b, const char *path_prefix)
+{
+    API_GUARD(b);
+    if (!path_prefix) return DSMFM_EINVAL;
+    int rc = ensure_sa_image(b, "dsmfm_write_sa");
+    if (rc) return rc;
+    const std::string name = std::string(path_prefix) + ".sa"; // FMIndex.cpp:131
+    FILE *f = std::fopen(name.c_str(), "wb");
+    if (!f) return b->fail(DSMFM_EIO, "dsmfm_write_sa: can not open %s", name.c_str());
+    const bool ok = std::fwrite(b->sa_image.data(), 1, b->sa_image.size(), f) == b->sa_image.size() && std::fflush(f) == 0;
+    std::fclose(f);
+    return ok ? DSMFM_OK : b->fail(DSMFM_EIO, "dsmfm_write_sa: write error");
 }
 
 DSMFM_API int dsmfm_get_stats(const dsmfm_builder *b, dsmfm_stats *out)

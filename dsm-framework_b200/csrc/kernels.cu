@@ -987,6 +987,109 @@ __global__ void __launch_bounds__(256) bwt_kernel(const uint64_t *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------
+// suffix-array samples (the reference's dormant FMIndex::maketables, FMIndex.cpp:572-714)
+// ---------------------------------------------------------------------------
+constexpr int kTermTile = 4096; // raw bytes per CTA (256 threads x 16)
+
+// terminators per tile / their positions in text order (document k ends at doc_end[k])
+__global__ void __launch_bounds__(256) term_count_kernel(const uint8_t *__restrict__ raw, uint64_t n,
+                                                         uint64_t *__restrict__ tile_count)
+{
+    __shared__ uint32_t s_sum[8];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kTermTile + (uint64_t)threadIdx.x * 16;
+    uint32_t c = 0;
+    for (int j = 0; j < 16; ++j)
+        if (p0 + j < n) c += raw[p0 + j] == 0;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += s_sum[k];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) term_write_kernel(const uint8_t *__restrict__ raw, uint64_t n,
+                                                         const uint64_t *__restrict__ tile_off,
+                                                         uint32_t *__restrict__ doc_end)
+{
+    __shared__ uint32_t scratch[9];
+    const uint64_t p0 = (uint64_t)blockIdx.x * kTermTile + (uint64_t)threadIdx.x * 16;
+    uint32_t mask = 0;
+    for (int j = 0; j < 16; ++j)
+        if (p0 + j < n && raw[p0 + j] == 0) mask |= 1u << j;
+    uint32_t total;
+    uint64_t o = tile_off[blockIdx.x] + block_excl_sum((uint32_t)__popc(mask), scratch, &total);
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        doc_end[o++] = (uint32_t)(p0 + j);
+    }
+}
+
+// FMIndex.cpp:624: the suffix at text position x = i+1 is sampled iff (end marker of its document - i) is a
+// positive multiple of the sample rate and i lies in the same document.  One thread per document marks them
+// in a bitmap indexed by text position.
+__global__ void __launch_bounds__(256) sa_mark_kernel(const uint32_t *__restrict__ doc_end, uint32_t ndocs,
+                                                      uint32_t rate, uint32_t *__restrict__ mark)
+{
+    const uint32_t k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= ndocs) return;
+    const int64_t e = doc_end[k], s = k ? (int64_t)doc_end[k - 1] + 1 : 0;
+    for (int64_t i = e - rate; i >= s; i -= rate) {
+        const uint64_t x = (uint64_t)i + 1;
+        atomicOr(&mark[x >> 5], 1u << (x & 31));
+    }
+}
+
+// bit p of `out` (rank order) = mark[sa[p]] (by_mark) or bwt[p] == 0
+__global__ void __launch_bounds__(256) sa_rank_bits_kernel(const uint32_t *__restrict__ sa, const uint8_t *__restrict__ bwt,
+                                                           const uint32_t *__restrict__ mark, uint64_t n,
+                                                           uint32_t *__restrict__ out, uint64_t out_words)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * 8;
+    for (uint64_t w = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < out_words; w += warps) {
+        const uint64_t p = w * 32 + lane;
+        bool bit = false;
+        if (p < n) {
+            if (mark) {
+                const uint32_t x = sa[p];
+                bit = (mark[x >> 5] >> (x & 31)) & 1u;
+            } else {
+                bit = bwt[p] == 0;
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) out[w] = word;
+    }
+}
+
+// For every set bit p of `bits` (with its BitRank directories): j = rank1(p) - 1; doc = document holding text
+// position sa[p]; out_doc[j] = doc; out_off[j] = sa[p] - start of doc  (FMIndex.cpp:676-699, 636-637).
+__global__ void __launch_bounds__(256) sa_emit_kernel(const uint32_t *__restrict__ sa, const uint64_t *__restrict__ bits,
+                                                      const uint64_t *__restrict__ Rs, const uint8_t *__restrict__ Rb,
+                                                      uint64_t n, const uint32_t *__restrict__ doc_end, uint32_t ndocs,
+                                                      uint32_t *__restrict__ out_doc, uint32_t *__restrict__ out_off)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t p = (uint64_t)blockIdx.x * 256 + threadIdx.x; p < n; p += stride) {
+        const uint64_t word = bits[p >> 6];
+        if (!((word >> (p & 63)) & 1ull)) continue;
+        const uint64_t j = Rs[p >> 8] + Rb[p >> 6] + __popcll(word & ((1ull << (p & 63)) - 1)); // ones before p
+        const uint32_t x = sa[p];
+        uint32_t lo = 0, hi = ndocs - 1; // first document whose end marker is at or after x
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (doc_end[mid] >= x) hi = mid; else lo = mid + 1;
+        }
+        out_doc[j] = lo;
+        if (out_off) out_off[j] = x - (lo ? doc_end[lo - 1] + 1 : 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // wavelet tree
 // ---------------------------------------------------------------------------
 constexpr int kWtInfoSmemNodes = 64; // node tables of up to this many internal nodes are staged in shared memory
@@ -1463,6 +1566,45 @@ void launch_bwt(cudaStream_t st, int bits, const uint64_t *packed, const uint8_t
 #define CALL(B) bwt_kernel<B><<<grid_for(n, 256 * 16), 256, 0, st>>>(packed, inv_map, sa, n, bwt)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+uint64_t term_tiles(uint64_t n) { return div_up(n, kTermTile); }
+
+void launch_term_positions(cudaStream_t st, const uint8_t *raw, uint64_t n, uint64_t *tile_scratch, uint32_t *doc_end,
+                           uint32_t *launches)
+{
+    const unsigned tiles = (unsigned)term_tiles(n);
+    term_count_kernel<<<tiles, 256, 0, st>>>(raw, n, tile_scratch);
+    DSM_LAUNCH_CHECK();
+    launch_wt_scan(st, tile_scratch, 1, tiles, launches);
+    term_write_kernel<<<tiles, 256, 0, st>>>(raw, n, tile_scratch, doc_end);
+    DSM_LAUNCH_CHECK();
+    if (launches) *launches += 2;
+}
+
+void launch_sa_mark(cudaStream_t st, const uint32_t *doc_end, uint32_t ndocs, uint32_t rate, uint32_t *mark,
+                    uint32_t *launches)
+{
+    sa_mark_kernel<<<(unsigned)div_up(ndocs, 256), 256, 0, st>>>(doc_end, ndocs, rate, mark);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_sa_rank_bits(cudaStream_t st, const uint32_t *sa, const uint8_t *bwt, const uint32_t *mark, uint64_t n,
+                         uint32_t *out, uint64_t out_words, uint32_t *launches)
+{
+    sa_rank_bits_kernel<<<grid_for(out_words, 8 * 4), 256, 0, st>>>(sa, bwt, mark, n, out, out_words);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+void launch_sa_emit(cudaStream_t st, const uint32_t *sa, const uint64_t *bits, const uint64_t *Rs, const uint8_t *Rb,
+                    uint64_t n, const uint32_t *doc_end, uint32_t ndocs, uint32_t *out_doc, uint32_t *out_off,
+                    uint32_t *launches)
+{
+    sa_emit_kernel<<<grid_for(n, 256 * 8), 256, 0, st>>>(sa, bits, Rs, Rb, n, doc_end, ndocs, out_doc, out_off);
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

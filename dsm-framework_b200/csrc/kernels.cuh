@@ -108,6 +108,22 @@ void launch_widen_sa(cudaStream_t st, const uint32_t *lo, const uint8_t *hi, int
 void launch_bwt(cudaStream_t st, int bits, const uint64_t *packed, const uint8_t *inv_map, const uint32_t *sa,
                 uint64_t n, uint8_t *bwt, uint32_t *launches);
 
+// ---- suffix-array samples (.sa; FMIndex::maketables, FMIndex.cpp:572-714) ---------------
+// doc_end[k] = text position of document k's terminator; tile_scratch holds term_tiles(n) u64
+uint64_t term_tiles(uint64_t n);
+void launch_term_positions(cudaStream_t st, const uint8_t *raw, uint64_t n, uint64_t *tile_scratch, uint32_t *doc_end,
+                           uint32_t *launches);
+// mark (zeroed bitmap over text positions): sampled suffixes by the rule of FMIndex.cpp:624
+void launch_sa_mark(cudaStream_t st, const uint32_t *doc_end, uint32_t ndocs, uint32_t rate, uint32_t *mark,
+                    uint32_t *launches);
+// out (u32 words, rank order): bit p = mark[sa[p]], or bwt[p] == 0 when mark is nullptr
+void launch_sa_rank_bits(cudaStream_t st, const uint32_t *sa, const uint8_t *bwt, const uint32_t *mark, uint64_t n,
+                         uint32_t *out, uint64_t out_words, uint32_t *launches);
+// for every set bit p (j-th set bit): out_doc[j] = document of text position sa[p], out_off[j] = offset in it
+void launch_sa_emit(cudaStream_t st, const uint32_t *sa, const uint64_t *bits, const uint64_t *Rs, const uint8_t *Rb,
+                    uint64_t n, const uint32_t *doc_end, uint32_t ndocs, uint32_t *out_doc, uint32_t *out_off,
+                    uint32_t *launches);
+
 // ---- wavelet tree -------------------------------------------------------------
 constexpr int kWtTile = 8192; // symbols per CTA
 constexpr int kWtMaxNodes = 255;

@@ -103,6 +103,10 @@ def lib():
     L.dsmfm_shard_info.argtypes = [B, C.POINTER(Shard)]
     L.dsmfm_assemble.argtypes = [B, C.c_void_p, C.c_uint64]
     L.dsmfm_shard_export.argtypes = [B, C.c_void_p, C.c_void_p]
+    L.dsmfm_write_sa.argtypes = [B, C.c_char_p]
+    L.dsmfm_sa_size.argtypes = [B]
+    L.dsmfm_sa_size.restype = C.c_uint64
+    L.dsmfm_sa_serialize.argtypes = [B, C.c_void_p, C.c_uint64]
     L.dsmfm_slice_hist.argtypes = [B, C.c_void_p]
     L.dsmfm_pieces_bytes.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32]
     L.dsmfm_pieces_bytes.restype = C.c_uint64
@@ -259,6 +263,21 @@ class Builder:
         rc = self._L.dsmfm_write_fmi(C.byref(self.index), os.fsencode(prefix))
         if rc != OK:
             raise DsmfmError(rc, "dsmfm_write_fmi failed")
+
+    def sa_file(self):
+        """Bytes of the `.sa` file (FMIndex::saveSamples); needs FLAG_KEEP_SA."""
+        size = self._L.dsmfm_sa_size(self._h)
+        if size == 0:
+            raise DsmfmError(EINVAL, (self._L.dsmfm_last_error(self._h) or b"").decode())
+        out = bytearray(size)
+        arr = (C.c_char * size).from_buffer(out)
+        self._check(self._L.dsmfm_sa_serialize(self._h, C.addressof(arr), size))
+        del arr
+        return bytes(out)
+
+    def save_samples(self, prefix):
+        """TextCollection::saveSamples: writes <prefix>.sa"""
+        self._check(self._L.dsmfm_write_sa(self._h, os.fsencode(prefix)))
 
     def stats(self):
         s = Stats()

@@ -32,6 +32,12 @@ void TextCollection::save(std::string const &filename) const
         throw std::runtime_error("TextCollection::save(): file write error.");
 }
 
+void TextCollection::saveSamples(std::string const &filename) const
+{
+    if (dsmfm_write_sa(owner, filename.c_str()) != DSMFM_OK)
+        throw std::runtime_error(std::string("TextCollection::saveSamples(): ") + dsmfm_last_error(owner));
+}
+
 std::string TextCollection::buildReport() const
 {
     dsmfm_stats s;

@@ -46,6 +46,10 @@ public:
     // std::runtime_error on an i/o error, like FMIndex::save.
     void save(std::string const &filename) const;
 
+    // Writes `<filename>.sa` (FMIndex::saveSamples, FMIndex.cpp:125-147).  Available when the builder
+    // kept the suffix array (environment DSMFM_KEEP_SA=1 / `builder --samples`); throws std::runtime_error otherwise.
+    void saveSamples(std::string const &filename) const;
+
     ~TextCollection();
 
     bool isColorCoded() const { return colorCoded; }

@@ -35,6 +35,8 @@ TextCollectionBuilder::TextCollectionBuilder(unsigned samplerate, ulong estimate
     // builder.cpp:411 always passes an estimate of 1; anything below the default is "unknown"
     opt.expected_bytes = estimatedInputLength > TEXTCOLLECTION_DEFAULT_INPUT_LENGTH ? estimatedInputLength : 0;
     if (const char *dev = std::getenv("DSMFM_DEVICE")) opt.device = std::atoi(dev);
+    if (const char *k = std::getenv("DSMFM_KEEP_SA"))
+        if (std::atoi(k)) opt.flags |= DSMFM_FLAG_KEEP_SA; // TextCollection::saveSamples will be called
     if (dsmfm_create(&opt, &p_->gpu) != DSMFM_OK)
     {
         // no CPU fallback: without the GPU path there is no builder

@@ -17,6 +17,7 @@
 namespace {
 
 bool g_verbose = false;
+bool g_samples = false; // --samples: also write <output>.sa (the reference's dormant FMIndex::saveSamples)
 
 struct Clock
 {
@@ -79,7 +80,9 @@ void help(char const *name)
               << "                               yields a bigger index but can decrease search " << std::endl
               << "                               time (default: " << TEXTCOLLECTION_DEFAULT_SAMPLERATE << ")." << std::endl
               << " -h, --help                    Display command line options." << std::endl
-              << " -v, --verbose                 Print progress information." << std::endl;
+              << " -v, --verbose                 Print progress information." << std::endl
+              << "     --samples                 Also write <output>.sa, the suffix array samples of" << std::endl
+              << "                               FMIndex::saveSamples (extension; off in the reference)." << std::endl;
 }
 
 int parse_int_at_least(char const *value, int min, char const *parameter, char const *name)
@@ -158,6 +161,7 @@ void build(std::istream &in, std::string const &outputfile, unsigned samplerate,
                   << "(total wall-clock time " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)"
                   << std::endl;
     tc->save(outputfile);
+    if (g_samples) tc->saveSamples(outputfile);
     delete tc;
 }
 
@@ -175,6 +179,7 @@ int main(int argc, char **argv)
     static struct option long_options[] = {{"sample-rate", required_argument, 0, 's'},
                                            {"help", no_argument, 0, 'h'},
                                            {"verbose", no_argument, 0, 'v'},
+                                           {"samples", no_argument, 0, 1000},
                                            {0, 0, 0, 0}};
     int option_index = 0, c;
     // same option string as the reference (builder.cpp:353): -c, -R and -F are accepted by getopt
@@ -186,6 +191,10 @@ int main(int argc, char **argv)
         case 's': samplerate = (unsigned)parse_int_at_least(optarg, 1, "-s, --sample-rate", argv[0]); break;
         case 'h': help(argv[0]); return 0;
         case 'v': g_verbose = true; break;
+        case 1000: // not in the reference CLI: keeps the suffix array on the GPU and writes the .sa samples too
+            g_samples = true;
+            setenv("DSMFM_KEEP_SA", "1", 1);
+            break;
         case '?': usage(argv[0]); return 1;
         default: usage(argv[0]); std::abort();
         }

@@ -69,7 +69,7 @@ typedef struct dsmfm_options {
 } dsmfm_options;
 
 #define DSMFM_FLAG_KEEP_BWT 1u /* keep the plain BWT in host memory after finish (dsmfm_index.bwt)   */
-#define DSMFM_FLAG_KEEP_SA 2u  /* keep the suffix array on the device for dsmfm_write_sa / debugging */
+#define DSMFM_FLAG_KEEP_SA 2u  /* keep suffix array, BWT and document boundaries on the device (dsmfm_write_sa) */
 
 /* One Huffman code-table entry: HuffWT::TCodeEntry, HuffWT.h:13-19. */
 typedef struct dsmfm_code {
@@ -209,6 +209,16 @@ DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, 
 /* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
  * byte-for-byte in the reference layout (version 17). */
 DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix);
+
+/* Replaces: FMIndex::saveSamples -> FMIndex::maketables (FMIndex.cpp:125-147, 572-714), the SA sampling
+ * the reference builder leaves dormant.  Writes `<path_prefix>.sa`: BitRank `sampled` (one bit per BWT
+ * position), BlockArray `suffixes` (offset of each sampled suffix in its document), `suffixDocId`,
+ * `textLength`, and `Doc` (document of every end marker in BWT order), byte for byte what the reference
+ * writes at the index's sample rate.  Needs DSMFM_FLAG_KEEP_SA on an unsharded builder, after
+ * dsmfm_finish; the tables are derived on the device from the suffix array. */
+DSMFM_API int dsmfm_write_sa(dsmfm_builder *b, const char *path_prefix);
+DSMFM_API uint64_t dsmfm_sa_size(dsmfm_builder *b);
+DSMFM_API int dsmfm_sa_serialize(dsmfm_builder *b, uint8_t *out, uint64_t out_cap);
 
 /* Serialise the same bytes into memory.  dsmfm_fmi_size gives the exact size. */
 DSMFM_API uint64_t dsmfm_fmi_size(const dsmfm_index *idx);

@@ -48,3 +48,11 @@ def digest_cases():
     c["ragged_2k"] = rnd_fasta(10, 2000, 150, genome=4000, dup=0.3)
     c["high_coverage"] = rnd_fasta(11, 4000, 60, minlen=60, genome=600, dup=0.0, pn=0.0)
     return c
+
+
+# (golden case, sample rate) pairs whose `.sa` file (FMIndex::saveSamples) is committed as <case>.s<rate>.sa
+SA_CASES = [("reads100", 124), ("reads100", 16), ("small_random", 32), ("small_random", 3), ("duplicates", 5),
+            ("one_base_reads", 2), ("poly_a", 7), ("mixed_alphabet", 16), ("single", 3), ("single", 124),
+            ("multiline_and_blank", 4), ("two_letter", 9), ("colour_space", 11)]
+# digest-only
+SA_DIGEST_CASES = [("reads100_3k", 124), ("ragged_2k", 40), ("high_coverage", 13)]

@@ -55,12 +55,26 @@ def main():
             fmi = oracle.reference_build(fa, tmp)
             manifest["digests"][name] = {"fasta_sha256": hashlib.sha256(fa).hexdigest(), "fmi_bytes": len(fmi),
                                          "fmi_sha256": hashlib.sha256(fmi).hexdigest()}
+        # the dormant SA sampling (FMIndex::saveSamples), driven by oracle/ref_driver.cpp over the reference classes
+        manifest["sa"], manifest["sa_digests"] = {}, {}
+        for name, rate in cases.SA_CASES:
+            sa = oracle.reference_sa(cases.golden_cases()[name], tmp, samplerate=rate)
+            fn = "%s.s%d.sa" % (name, rate)
+            with open(os.path.join(HERE, fn), "wb") as f:
+                f.write(sa)
+            manifest["sa"][fn] = {"case": name, "samplerate": rate, "bytes": len(sa), "sha256": hashlib.sha256(sa).hexdigest()}
+        for name, rate in cases.SA_DIGEST_CASES:
+            sa = oracle.reference_sa(cases.digest_cases()[name], tmp, samplerate=rate)
+            manifest["sa_digests"]["%s.s%d" % (name, rate)] = {"case": name, "samplerate": rate, "bytes": len(sa),
+                                                            "sha256": hashlib.sha256(sa).hexdigest()}
         import dsmgen
         for name, kw in GEN_CASES.items():
             fa = dsmgen.fasta(**kw).tobytes()
             fmi = oracle.reference_build(fa, tmp)
+            sa = oracle.reference_sa(fa, tmp)
             manifest["generated"][name] = {"params": kw, "fasta_sha256": hashlib.sha256(fa).hexdigest(),
-                                           "fmi_bytes": len(fmi), "fmi_sha256": hashlib.sha256(fmi).hexdigest()}
+                                           "fmi_bytes": len(fmi), "fmi_sha256": hashlib.sha256(fmi).hexdigest(),
+                                           "sa_bytes": len(sa), "sa_sha256": hashlib.sha256(sa).hexdigest()}
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print("wrote", len(manifest["files"]), "file cases,", len(manifest["digests"]), "digest cases,",

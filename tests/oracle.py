@@ -33,6 +33,8 @@ def lib():
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.dsm_oracle_build.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_size_t)]
+        L.dsm_oracle_sa_file.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.dsm_oracle_free.argtypes = [C.c_void_p]
         L.dsm_oracle_free.restype = None
         _lib = L
@@ -92,6 +94,34 @@ def fmi_from_docs(docs, samplerate=124):
         return fmi_from_bwt(b"\0", samplerate, 1, 1)  # TextCollectionBuilder.cpp:111-119
     nd, maxlen = doc_stats(docs)
     return fmi_from_bwt(bwt(docs), samplerate, nd, maxlen)
+
+
+def sa_file_from_bwt(bwt_bytes, samplerate, ntexts, maxlen):
+    """Bytes of the `.sa` file FMIndex::saveSamples writes for this index."""
+    bwt_bytes = bytes(bwt_bytes)
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = lib().dsm_oracle_sa_file(bwt_bytes, len(bwt_bytes), samplerate, ntexts, maxlen, C.byref(out), C.byref(n))
+    assert rc == 0, rc
+    return _take(out, n)
+
+
+def sa_file_from_docs(docs, samplerate=124):
+    docs = bytes(docs)
+    if len(docs) == 0:
+        return sa_file_from_bwt(b"\0", samplerate, 1, 1)
+    nd, maxlen = doc_stats(docs)
+    return sa_file_from_bwt(bwt(docs), samplerate, nd, maxlen)
+
+
+def reference_sa(fasta, tmpdir, samplerate=None):
+    """`.sa` bytes from the UNMODIFIED reference: builder [-s R], then its dormant FMIndex::saveSamples
+    driven by oracle/_ref/ref_driver (oracle/ref_driver.cpp)."""
+    reference_build(fasta, tmpdir, samplerate)
+    base = os.path.join(str(tmpdir), "ref_input.fasta")
+    subprocess.run([os.path.join(REF_DIR, "ref_driver"), "sa", base + ".fmi", base], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    with open(base + ".sa", "rb") as f:
+        return f.read()
 
 
 def build(fasta, samplerate=0):

@@ -380,3 +380,59 @@ def test_pieces_on_a_generated_sample():
     g = MANIFEST["generated"]["gen_20k"]
     fmi, _, _ = _sharded_build(dsmgen.docs(**g["params"]).tobytes(), 5, 1, pieces=True)
     assert hashlib.sha256(fmi).hexdigest() == g["fmi_sha256"]
+
+
+# ---- suffix-array samples: the `.sa` file of the reference's dormant FMIndex::saveSamples -----------------
+
+def _sa_file(docs, samplerate):
+    import dsmfm
+    with dsmfm.Builder(flags=dsmfm.FLAG_KEEP_SA, samplerate=samplerate) as b:
+        if len(docs):
+            b.append_batch(docs)
+        b.finish()
+        return b.sa_file(), b.fmi()
+
+
+@pytest.mark.parametrize("fn", sorted(MANIFEST["sa"]))
+def test_sa_file_matches_reference_golden(fn):
+    e = MANIFEST["sa"][fn]
+    docs, _ = oracle.fasta_to_docs(_golden(e["case"], ".fasta"))
+    got, _ = _sa_file(docs, e["samplerate"])
+    assert got == _golden(fn, "")
+
+
+@pytest.mark.parametrize("key", sorted(MANIFEST["sa_digests"]))
+def test_sa_file_matches_reference_digest(key):
+    e = MANIFEST["sa_digests"][key]
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()[e["case"]])
+    got, _ = _sa_file(docs, e["samplerate"])
+    assert len(got) == e["bytes"] and hashlib.sha256(got).hexdigest() == e["sha256"]
+
+
+def test_sa_file_on_generated_reads_and_empty_collection():
+    import dsmgen
+    g = MANIFEST["generated"]["gen_20k"]
+    got, fmi = _sa_file(dsmgen.docs(**g["params"]).tobytes(), 0)
+    assert hashlib.sha256(fmi).hexdigest() == g["fmi_sha256"]
+    assert len(got) == g["sa_bytes"] and hashlib.sha256(got).hexdigest() == g["sa_sha256"]
+    got, _ = _sa_file(b"", 124)
+    assert got == oracle.sa_file_from_docs(b"", 124)
+
+
+def test_sa_file_needs_the_suffix_array():
+    import dsmfm
+    with dsmfm.Builder() as b:
+        b.append_batch(b"ACGT\0")
+        b.finish()
+        with pytest.raises(dsmfm.DsmfmError) as e:
+            b.sa_file()
+        assert e.value.code == dsmfm.EINVAL
+
+
+def test_builder_cli_samples_option(tmp_path):
+    exe = os.path.join(ROOT, "dsm-framework_b200", "builder")
+    fa = tmp_path / "r.fasta"
+    fa.write_bytes(_golden("reads100", ".fasta"))
+    r = subprocess.run([exe, "--samples", "-s", "16", str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(str(fa) + ".sa", "rb").read() == _golden("reads100.s16", ".sa")

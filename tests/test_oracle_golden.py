@@ -83,3 +83,37 @@ def test_bwt_definition_small():
 def test_oracle_matches_live_reference(seed, tmp_path):
     fasta = cases.rnd_fasta(seed, 300, 80, genome=1500, dup=0.25, lower=0.2, wrap=50)
     assert oracle.build(fasta) == oracle.reference_build(fasta, tmp_path)
+
+
+# ---- the dormant SA sampling: `.sa` files written by the reference's FMIndex::saveSamples -------------
+
+@pytest.mark.parametrize("fn", sorted(MANIFEST["sa"]))
+def test_oracle_sa_file_matches_reference(fn):
+    e = MANIFEST["sa"][fn]
+    docs, _ = oracle.fasta_to_docs(_golden(e["case"], ".fasta"))
+    want = _golden(fn, "")
+    assert hashlib.sha256(want).hexdigest() == e["sha256"]
+    assert oracle.sa_file_from_docs(docs, e["samplerate"]) == want
+
+
+@pytest.mark.parametrize("key", sorted(MANIFEST["sa_digests"]))
+def test_oracle_sa_file_matches_reference_digest(key):
+    e = MANIFEST["sa_digests"][key]
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()[e["case"]])
+    got = oracle.sa_file_from_docs(docs, e["samplerate"])
+    assert len(got) == e["bytes"] and hashlib.sha256(got).hexdigest() == e["sha256"]
+
+
+def test_oracle_sa_file_generated_case():
+    import dsmgen
+    g = MANIFEST["generated"]["gen_20k"]
+    got = oracle.sa_file_from_docs(dsmgen.docs(**g["params"]).tobytes())
+    assert len(got) == g["sa_bytes"] and hashlib.sha256(got).hexdigest() == g["sa_sha256"]
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not present")
+def test_oracle_sa_file_matches_live_reference(tmp_path):
+    fa = cases.rnd_fasta(77, 300, 90, genome=1500, dup=0.3)
+    docs, _ = oracle.fasta_to_docs(fa)
+    for rate in (6, 31):
+        assert oracle.sa_file_from_docs(docs, rate) == oracle.reference_sa(fa, tmp_path, samplerate=rate)
