@@ -36,6 +36,7 @@ WORKLOADS = {
     # name -> generator parameters (dsmgen.CONFIGS) ; per-rank seed offset is added for N>1
     "C3": "C3",
     "C1": "C1",
+    "C5": "C5",  # high repetition: 4 genomes at 200x coverage, error free (BASELINE.json configs[4])
 }
 CPU_SAMPLE = dict(seed=1, pool_seed=1, pool_size=10, n_genomes=10, genome_len=100_000, n_reads=100_000,
                   read_len=100, sub=0.005, pn=0.001)  # 10 Mbp at the 10x coverage of C1

@@ -52,11 +52,49 @@ def _check_index_properties(docs, nreads, doc_len, b, idx, rng, windows=24, wind
     assert np.array_equal(rs, cum[0:4 * (n // 256) + 1:4])
 
 
-@pytest.mark.parametrize("config,scale", [("C1", 1.0), ("C3", 1.0)])
+def _check_sa_file(sa_bytes, n, nreads, doc_len, rate=124):
+    """Sections of the `.sa` image (FMIndex.cpp:134-143) for equal-length documents: one sample per document
+    at offset doc_len - rate (FMIndex.cpp:624), every document id exactly once, end markers listed once each."""
+    u64 = lambda off: int.from_bytes(sa_bytes[off:off + 8], "little")
+    assert u64(0) == n
+    integers = u64(8)
+    assert integers == n // 64 + 1
+    off = 24
+    words = np.frombuffer(sa_bytes, dtype=np.uint64, count=integers, offset=off)
+    ones = int(np.bitwise_count(words).sum()) if hasattr(np, "bitwise_count") else sum(bin(int(x)).count("1") for x in words)
+    assert ones == nreads
+    off += 8 * integers + 8 * (n // 256 + 1) + (n // 64 + 1)
+
+    def block_array(off):
+        cnt, width = u64(off), u64(off + 8)
+        nw = cnt * width // 64 + 1
+        data = np.frombuffer(sa_bytes, dtype=np.uint64, count=nw, offset=off + 16)
+        bits = np.unpackbits(data.view(np.uint8), bitorder="little")[:cnt * width].reshape(cnt, width)
+        vals = (bits.astype(np.uint64) << np.arange(width, dtype=np.uint64)).sum(axis=1)
+        return vals, off + 16 + 8 * nw
+
+    suffixes, off = block_array(off)
+    suffix_doc, off = block_array(off)
+    text_len, off = block_array(off)
+    doc, off = block_array(off)
+    assert off == len(sa_bytes)
+    assert suffixes.size == nreads and np.all(suffixes == doc_len - rate)
+    assert np.array_equal(np.sort(suffix_doc), np.arange(nreads, dtype=np.uint64))
+    assert text_len.size == nreads and np.all(text_len == doc_len - 1)
+    assert np.array_equal(np.sort(doc), np.arange(nreads, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("config,scale", [("C1", 1.0), ("C3", 1.0), ("C5", 0.1)])
 def test_full_size_build_properties(config, scale):
+    """C1 / C3: BASELINE.json configs[0..2] at full size.  C5 (configs[4], few genomes at 200x coverage, error
+    free: every suffix sits in a deep tie group that only the document order resolves) at a tenth of its
+    size with the same coverage -- DSMFM_TEST_FULL_C5=1 runs all 16M reads (3.2 G symbols, ~90 GB of HBM)."""
     import dsmfm
     import dsmgen
     kw = dict(dsmgen.CONFIGS[config])
+    if scale != 1.0 and not os.environ.get("DSMFM_TEST_FULL_" + config):
+        kw["n_reads"] = int(kw["n_reads"] * scale)
+        kw["genome_len"] = int(kw["genome_len"] * scale)
     if os.environ.get("DSMFM_TEST_SMALL"):
         kw["n_reads"] //= 10
     nreads, L = kw["n_reads"], kw["read_len"]
@@ -68,3 +106,5 @@ def test_full_size_build_properties(config, scale):
         _check_index_properties(docs, nreads, 2 * L + 2, b, idx, rng)
         s = b.stats()
         assert s.fallback_elems == 0 or config != "C1"
+        if config == "C1":
+            _check_sa_file(b.sa_file(), idx.n, nreads, 2 * L + 2)

@@ -436,3 +436,37 @@ def test_builder_cli_samples_option(tmp_path):
     r = subprocess.run([exe, "--samples", "-s", "16", str(fa)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(str(fa) + ".sa", "rb").read() == _golden("reads100.s16", ".sa")
+
+
+# ---- BASELINE.json configs[1]: several samples, then the reference's own mining pipeline on both sets of indexes ----
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not present")
+def test_five_samples_and_identical_mining_output(tmp_path):
+    """Five toydata-shaped samples (each draws 10 genomes of a shared pool of 16) are built by the
+    reference `builder` and by the GPU `builder` CLI: the `.fmi` files must be identical, and the unmodified
+    metaserver x4 + metaenumerate x5 must print the same mined substrings from either set.  Reduced to 12k reads
+    per sample here; DSMFM_TEST_FULL_C2=1 runs the full 250k-read samples (minutes of CPU time)."""
+    import dsmgen
+    import mining
+    full = bool(os.environ.get("DSMFM_TEST_FULL_C2"))
+    exe = os.path.join(ROOT, "dsm-framework_b200", "builder")
+    ours, theirs = {}, {}
+    for i in range(1, 6):
+        kw = dict(dsmgen.CONFIGS["C2-%d" % i])
+        if not full:
+            kw.update(n_reads=12_000, genome_len=12_000)
+        name = "toydata-%d" % i
+        for which, table in (("gpu", ours), ("ref", theirs)):
+            d = tmp_path / which
+            d.mkdir(exist_ok=True)
+            fa = d / (name + ".fasta")
+            dsmgen.fasta(**kw).tofile(str(fa))
+            cmd = [exe, str(fa)] if which == "gpu" else [os.path.join(oracle.REF_DIR, "builder"), str(fa)]
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            table[name] = str(fa) + ".fmi"
+        assert open(ours[name], "rb").read() == open(theirs[name], "rb").read(), name
+    got = mining.mine(ours, str(tmp_path / "mine_gpu"))
+    want = mining.mine(theirs, str(tmp_path / "mine_ref"))
+    assert sum(len(v) for v in want.values()) > 1000, "the mining run printed nothing"
+    for h in want:
+        assert hashlib.sha256(got[h]).hexdigest() == hashlib.sha256(want[h]).hexdigest(), "server %s output differs" % h
