@@ -32,7 +32,8 @@ def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900):
     names_txt = ("\n".join(names) + "\n").encode()
     hashes = ["A", "C", "G", "T"]
     ports = _free_ports(len(hashes))
-    hosts = "".join("localhost\t%d\t%s\n" % (p, h) for p, h in zip(ports, hashes)).encode()
+    # a numeric address: the box's hostname / "localhost" need not resolve
+    hosts = "".join("127.0.0.1\t%d\t%s\n" % (p, h) for p, h in zip(ports, hashes)).encode()
     servers, clients, outs = [], [], {}
     try:
         for p, h in zip(ports, hashes):
@@ -55,7 +56,7 @@ def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900):
         for cp, log in clients:
             rc = cp.wait(timeout=max(1, deadline - time.time()))
             log.close()
-            assert rc == 0, "metaenumerate failed"
+            assert rc == 0, "metaenumerate failed: " + open(log.name, "rb").read()[-2000:].decode(errors="replace")
         for sp, out, err in servers:
             rc = sp.wait(timeout=max(1, deadline - time.time()))
             out.close()
@@ -68,4 +69,11 @@ def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900):
     for h in hashes:
         with open(os.path.join(workdir, "out.%s.txt" % h), "rb") as f:
             outs[h] = f.read()
+    if not any(outs.values()):  # nothing mined: show what the processes said
+        logs = []
+        for fn in sorted(os.listdir(workdir)):
+            if fn.endswith(".log"):
+                with open(os.path.join(workdir, fn), "rb") as f:
+                    logs.append("== %s ==\n%s" % (fn, f.read()[-1500:].decode(errors="replace")))
+        raise AssertionError("the mining run printed nothing\n" + "\n".join(logs))
     return outs
