@@ -15,9 +15,10 @@ builds the wavelet tree (dsm-framework_b200/multigpu.py).
 value   = input bases of all ranks / max-over-ranks device time, documents already resident in HBM.
 e2e     = the same through the C ABI with HOST buffers: dsmfm_append_batch from pinned host memory
           (H2D inside the timed region) ... dsmfm_finish (sections copied back to the host).
-roofline: the dominant kernel is one LSD pass of the one-sweep radix sort (8 launches per build);
-          achieved = 24 B/pair (8+4 read, 8+4 written) x n pairs / mean pass time (CUDA events on
-          the build stream, recorded inside the library around the 8 passes of every timed step).
+roofline: the dominant kernel is the one-sweep LSD radix pass (6 passes, each one launch per portion of
+          <= 2^29 pairs: 24 launches per 1 Gbp build); achieved = 24 B/pair (8+4 read, 8+4 written) x
+          pairs of a launch / mean launch time (CUDA events on the build stream, recorded inside the
+          library around the passes of every timed step, divided by the number of launches).
 cpu_baseline: the UNMODIFIED reference `builder` (oracle/_ref/builder, single-threaded as shipped)
           on a bounded toydata-shaped sample, on this box's host cores, rank 0 at N=1 only.
 """
@@ -366,7 +367,9 @@ def main():
         "gpu_launches": n_launch,
         "roofline": {
             "bound": "hbm",
-            "kernel": "onesweep_kernel (one LSD radix pass over (u64 key, u32 suffix) pairs; %d passes per build)" % s0.sort_passes,
+            "kernel": "onesweep_kernel: one launch of the LSD radix sort over (u64 key, u32 suffix) pairs; %d passes x %d "
+                      "portion(s) of <= 2^29 pairs = %d launches per build" % (
+                          s0.sort_passes, max(1, s0.sort_launches // max(1, s0.sort_passes)), s0.sort_launches),
             "achieved": round(achieved, 1),
             "peak": peak,
             "unit": "GB/s",
@@ -375,6 +378,7 @@ def main():
             "algorithmic_bytes_per_launch": s0.sort_pass_bytes,
             "ms_per_launch": round(pass_ms, 4),
             "traffic": profile.get("onesweep_dram_bytes_per_launch"),
+            "traffic_note": profile.get("note"),
         },
     }
 

@@ -807,7 +807,7 @@ void dsmfm_builder::build()
         d_last_sorted_vals = d_sorted_vals;
         d_last_other_vals = d_other_vals;
         stats.sort_passes = passes;
-        pass_launches += (uint32_t)passes;
+        pass_launches += (uint32_t)passes * (uint32_t)div_up(m, kSweepPortion); // a pass is one launch per portion
         pass_launch_bytes += (uint64_t)passes * m * 24ull;
 
         DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
@@ -946,6 +946,7 @@ void dsmfm_builder::build()
     dfree(d_win_count);
     stats.rounds = rounds_max;
     stats.sort_pass_bytes = pass_launches ? pass_launch_bytes / pass_launches : 0;
+    stats.sort_launches = pass_launches;
     DSM_CUDA(cudaEventRecord(ev[3], st));
     DSM_CUDA(cudaEventRecord(ev[4], st));
 

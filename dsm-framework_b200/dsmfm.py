@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("fallback_elems", C.c_uint64), ("ms_total", C.c_float), ("ms_pack", C.c_float),
                 ("ms_sort", C.c_float), ("ms_sort_pass", C.c_float), ("ms_refine", C.c_float), ("ms_bwt", C.c_float),
                 ("ms_wt", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("sort_passes", C.c_uint32),
-                ("reserved", C.c_uint32), ("sort_pass_bytes", C.c_uint64), ("device_bytes_peak", C.c_uint64),
+                ("sort_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64), ("device_bytes_peak", C.c_uint64),
                 ("ms_wall_build", C.c_float), ("ms_wall_fetch", C.c_float), ("ms_wall_alloc", C.c_float),
                 ("reserved2", C.c_float)]
 

@@ -119,15 +119,16 @@ typedef struct dsmfm_stats {
     float ms_total;              /* whole device build                                      */
     float ms_pack;               /* histogram + pack                                        */
     float ms_sort;               /* key build + LSD radix sort + head marking               */
-    float ms_sort_pass;          /* mean duration of one onesweep pass (dominant kernel)    */
+    float ms_sort_pass;          /* mean duration of one onesweep LAUNCH (dominant kernel)  */
     float ms_refine;             /* all refinement rounds                                   */
     float ms_bwt;                /* BWT emission                                            */
     float ms_wt;                 /* wavelet tree + BitRank directories                      */
     float ms_h2d;                /* last finish: host->device copies not overlapped         */
     float ms_d2h;                /* last finish: device->host of the sections               */
-    uint32_t sort_passes;        /* onesweep launches in the initial sort                   */
-    uint32_t reserved;
-    uint64_t sort_pass_bytes;    /* algorithmic bytes moved by ONE onesweep pass            */
+    uint32_t sort_passes;        /* LSD passes of the initial sort (of the last key range)  */
+    uint32_t sort_launches;      /* onesweep launches of the initial sorts: a pass over more */
+                                 /* than 2^29 pairs runs as several launches                 */
+    uint64_t sort_pass_bytes;    /* mean algorithmic bytes moved by ONE onesweep launch      */
     uint64_t device_bytes_peak;  /* peak device memory held by the builder                  */
     float ms_wall_build;         /* host wall time of dsmfm_build_device                    */
     float ms_wall_fetch;         /* host wall time of dsmfm_fetch                           */
