@@ -382,6 +382,22 @@ def main():
         },
     }
 
+    # The kernel with the largest share of the step is the refinement (one launch, random 8-byte gathers from the
+    # packed text); its algorithmic bytes: per suffix in a tie group 4+1 B read and 4+1 B written (suffix, BWT
+    # symbol), 8 B per key gathered, n/4 B of group-head bitmaps.
+    act = sum(s0.active[r] for r in range(min(s0.rounds, 32)))
+    ref_bytes = 10 * act + 8 * s0.refine_key_fetches + s0.n // 4
+    ref_ms = sum(s.ms_refine for s in stats) / len(stats)
+    ref_ach = ref_bytes / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else 0.0
+    line["roofline_refine"] = {
+        "bound": "hbm", "kernel": "refine_kernel (%d launch(es) per build; all tie groups resolved in shared memory, keys "
+                                  "gathered from the packed text)" % s0.refine_launches,
+        "achieved": round(ref_ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ref_ach / peak, 4),
+        "algorithmic_bytes_per_launch": ref_bytes // max(1, s0.refine_launches),
+        "ms_per_launch": round(ref_ms / max(1, s0.refine_launches), 3),
+        "keys_gathered": s0.refine_key_fetches, "traffic": profile.get("refine_dram_bytes_per_launch"),
+        "traffic_note": profile.get("refine_note")}
+
     if world == 1 and not args.no_cpu_baseline:
         import tempfile
         try:

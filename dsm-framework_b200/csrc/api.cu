@@ -746,7 +746,8 @@ void dsmfm_builder::build()
     uint32_t *d_head[2];
     d_head[0] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
-    unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(64 * 8));
+    // [0,64): suffixes left in groups of >= 2; [64,128): keys the refinement gathered from the text
+    unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(128 * 8));
     const uint32_t big_cap = (uint32_t)(m_max / kRefGroupMax + 2);
     uint32_t *d_big_heads = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
@@ -790,8 +791,12 @@ void dsmfm_builder::build()
         // ---- initial sort by the first `first_syms` symbols -------------------------------
         // When the key leaves room, the symbol before each suffix rides above the sorted bits and the
         // BWT falls out of the sort; otherwise it is gathered from the text at the end.
+        bool hist_ready = false;
         if (!sharded) {
-            launch_make_keys(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, L);
+            // keys and their digit histogram in one pass over the packed text
+            DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * kMaxPasses * kRadix, st));
+            launch_make_keys_hist(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, ws.hist, L);
+            hist_ready = true;
         } else {
             const uint64_t ntile = select_tiles(n, bits, first_syms, top_bits);
             uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
@@ -800,7 +805,7 @@ void dsmfm_builder::build()
             dfree(d_tile);
         }
         const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
-                                            ev_pass0, ev_pass1);
+                                            ev_pass0, ev_pass1, hist_ready);
         uint64_t *d_sorted_keys = (passes & 1) ? d_keys_b : d_keys_a;
         uint32_t *d_sorted_vals = (passes & 1) ? d_vals_b : d_vals_a;
         uint32_t *d_other_vals = (passes & 1) ? d_vals_a : d_vals_b;
@@ -810,18 +815,19 @@ void dsmfm_builder::build()
         pass_launches += (uint32_t)passes * (uint32_t)div_up(m, kSweepPortion); // a pass is one launch per portion
         pass_launch_bytes += (uint64_t)passes * m * 24ull;
 
-        DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+        DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 128 * 8, st));
         const uint64_t hw = head_words_for(m);
         launch_heads(st, bits, d_sorted_keys, m, d_head[0], hw, d_remaining, key_bits, d_inv,
                      carry_bwt ? bwt_out : nullptr, hi_out, hi_shift, L);
         DSM_CUDA(cudaEventRecord(evr[1], st));
 
         auto read_remaining = [&]() -> uint64_t {
-            unsigned long long h[64];
+            unsigned long long h[128];
             DSM_CUDA(cudaMemcpyAsync(h, d_remaining, sizeof h, cudaMemcpyDeviceToHost, st));
             DSM_CUDA(cudaStreamSynchronize(st));
             uint64_t t = 0;
-            for (auto x : h) t += x;
+            for (int i = 0; i < 64; ++i) t += h[i];
+            for (int i = 64; i < 128; ++i) stats.refine_key_fetches += h[i];
             return t;
         };
         uint64_t remaining = read_remaining();
@@ -848,10 +854,11 @@ void dsmfm_builder::build()
             ++round;
             const uint32_t depth = depth_next;
             DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hw * 4, cudaMemcpyDeviceToDevice, st));
-            DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 64 * 8, st));
+            DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 128 * 8, st));
             DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
             DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
             DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
+            ++stats.refine_launches;
             launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
                           d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
                           carry_bwt ? bwt_out : nullptr, multi_step, key_words, hi_out, lo_bits, L);

@@ -225,6 +225,66 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
     }
 }
 
+// Same keys, one thread per packed word: the word and its successor hold every symbol the SPW first keys
+// starting in it can need, so the keys are cut out of two registers instead of two loads and a division
+// per suffix; they are staged in shared memory and leave the SM as one contiguous burst.  While the keys
+// are in registers the kernel also counts their radix digits, which saves the sort's own histogram pass
+// over the key array (8 bytes per suffix read back from HBM).
+constexpr int kKeyTileThreads = 128; // one packed word per thread and tile
+constexpr int kMaxKeyPasses = 8;     // 64 key bits / 8-bit digits
+
+template <int BITS>
+__global__ void __launch_bounds__(kKeyTileThreads)
+make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, uint64_t *__restrict__ keys,
+                      int key_bits, bool carry_prev, int npass, uint64_t *__restrict__ ghist)
+{
+    using P = Pack<BITS>;
+    constexpr int CAP = kKeyTileThreads * P::SPW;
+    __shared__ uint64_t s_key[CAP];
+    __shared__ uint32_t s_hist[kMaxKeyPasses][256];
+    for (int i = threadIdx.x; i < kMaxKeyPasses * 256; i += kKeyTileThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
+    const uint64_t ntiles = (nwords + kKeyTileThreads - 1) / kKeyTileThreads;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t w = tile * kKeyTileThreads + threadIdx.x;
+        if (w < nwords) {
+            uint64_t x0 = __ldg(packed + w), x1 = __ldg(packed + w + 1); // the text is followed by zero words
+            const uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u;
+            if (P::USED == 63) { // 3-bit symbols sit in bits 62..0: close the gap, symbol j starts at stream bit 3j
+                x0 = (x0 << 1) | (x1 >> 62);
+                x1 <<= 2;
+            }
+            const uint64_t p0 = w * P::SPW;
+#pragma unroll
+            for (int j = 0; j < P::SPW; ++j) {
+                if (p0 + j >= n) break; // positions behind the text (last word only)
+                const int b = BITS * j;
+                const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0; // stream from symbol j on
+                uint64_t k = (v >> (64 - key_bits)) | ~kmask;                // ones above: only real fields can be zero
+                k = cut_at_terminator<BITS>(k) & kmask;
+#pragma unroll
+                for (int q = 0; q < kMaxKeyPasses; ++q)
+                    if (q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu], 1u);
+                if (carry_prev) {
+                    const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
+                    k |= (uint64_t)prev << key_bits;
+                }
+                s_key[threadIdx.x * P::SPW + j] = k;
+            }
+        }
+        __syncthreads();
+        const uint64_t t0 = tile * CAP;
+        const uint32_t valid = (uint32_t)(n - t0 < (uint64_t)CAP ? n - t0 : (uint64_t)CAP);
+        for (uint32_t i = threadIdx.x; i < valid; i += kKeyTileThreads) keys[t0 + i] = s_key[i];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < npass * 256; i += kKeyTileThreads) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd((unsigned long long *)&ghist[i], (unsigned long long)c);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // key-range sharding (multi-GPU): every GPU holds the whole packed text and sorts the suffixes
 // whose first key falls into its range
@@ -732,9 +792,11 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     __syncthreads();
 
     int c = 0, lc = 0;
+    unsigned long long fetched = 0; // keys gathered from the text by this CTA (statistics)
     for (int step = 0; step < max_steps; ++step) {
         const int cnt = s_n[lc];
         if (cnt == 0) break;
+        fetched += (unsigned)cnt;
         if (tid == 0) s_n[lc ^ 1] = 0;
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
         // carries the same key (or its key holds the terminator, which makes it unique)
@@ -822,6 +884,7 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     const int any_next = __syncthreads_or(mine_next);
     if (tid == 0) {
         if (left) atomicAdd(&remaining[wid & 63], (unsigned long long)left);
+        if (fetched) atomicAdd(&remaining[64 + (wid & 63)], fetched);
         if (any_here && atomicExch(&win_flag[wid], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wid;
         if (any_next && wid + 1 < nwin && atomicExch(&win_flag[wid + 1], 1u) == 0u)
             win_next[atomicAdd(win_next_count, 1u)] = wid + 1;
@@ -1388,6 +1451,21 @@ static bool select_fast_ok(int bits, int first_syms, int top_bits)
 {
     const int syms = bits == 8 ? 2 : 12 / bits;
     return top_bits == 12 && first_syms >= syms;
+}
+
+void launch_make_keys_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
+                           bool carry_prev, uint64_t *ghist, uint32_t *launches)
+{
+    const int key_bits = first_syms * bits;
+    const int npass = (key_bits + 7) / 8;
+    const uint64_t nwords = div_up(n, 64 / bits);
+    const int grid = grid_for(nwords, kKeyTileThreads, 16);
+#define CALL(B) \
+    make_keys_hist_kernel<B><<<grid, kKeyTileThreads, 0, st>>>(packed, n, nwords, keys, key_bits, carry_prev, npass, ghist)
+    DISPATCH_BITS(bits, CALL);
+#undef CALL
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
 }
 
 void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,

@@ -31,6 +31,11 @@ void launch_pack(cudaStream_t st, int bits, const uint8_t *raw, uint64_t n, cons
 void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
                       bool carry_prev, uint32_t *launches);
 
+// The same keys plus, in ghist[pass][256] (zeroed u64), the counts of their 8-bit digits from bit 0 up to
+// first_syms*bits -- the histogram the LSD sort needs (radix_sort_pairs with hist_ready).
+void launch_make_keys_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
+                           bool carry_prev, uint64_t *ghist, uint32_t *launches);
+
 // Group heads after the initial sort: bit i set iff suffix i starts a new group
 // (key differs from its predecessor) or is already finished (key holds the
 // terminator).  Bits >= n are set.  *remaining += suffixes left in groups of >= 2.

@@ -255,7 +255,7 @@ void RadixWorkspace::release()
 
 int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b,
                      uint32_t *vals_b, uint64_t n, int begin_bit, int end_bit, bool iota_first,
-                     uint32_t *launches, cudaEvent_t ev_begin, cudaEvent_t ev_end)
+                     uint32_t *launches, cudaEvent_t ev_begin, cudaEvent_t ev_end, bool hist_ready)
 {
     const int npass = (int)div_up((uint64_t)(end_bit - begin_bit), kRadixBits);
     if (n == 0 || npass <= 0) return 0;
@@ -279,16 +279,17 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         attr_set = true;
     }
 
-    DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * npass * kRadix, stream));
-    {
+    if (!hist_ready) {
+        DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * npass * kRadix, stream));
         uint64_t want = div_up(n, 512 * 16);
         int grid = (int)(want < (uint64_t)kNumSMs * 4 ? (want ? want : 1) : (uint64_t)kNumSMs * 4);
         radix_hist_kernel<<<grid, 512, 0, stream>>>(keys_a, n, begin_bit, end_bit, npass, ws.hist);
         DSM_LAUNCH_CHECK();
-        radix_scan_kernel<<<npass, kRadix, 0, stream>>>(ws.hist);
-        DSM_LAUNCH_CHECK();
-        if (launches) *launches += 2;
+        if (launches) *launches += 1;
     }
+    radix_scan_kernel<<<npass, kRadix, 0, stream>>>(ws.hist);
+    DSM_LAUNCH_CHECK();
+    if (launches) *launches += 1;
     if (ev_begin) DSM_CUDA(cudaEventRecord(ev_begin, stream));
     for (int p = 0; p < npass; ++p) {
         const int shift = begin_bit + kRadixBits * p;

@@ -51,8 +51,11 @@ struct KeysFromArray {
 // (it must still be a valid buffer: it is the destination of odd passes).
 // `launches` (optional) is incremented per kernel launched.  ev_begin/ev_end
 // (optional) are recorded around the one-sweep passes (histogram excluded).
+// hist_ready: ws.hist[pass][256] already holds the digit counts of the keys (whoever produced the keys
+// counted them on the way), so the histogram pass over the key array is skipped.
 int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, uint32_t *vals_a, uint64_t *keys_b,
                      uint32_t *vals_b, uint64_t n, int begin_bit, int end_bit, bool iota_first,
-                     uint32_t *launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr);
+                     uint32_t *launches, cudaEvent_t ev_begin = nullptr, cudaEvent_t ev_end = nullptr,
+                     bool hist_ready = false);
 
 } // namespace dsmfm

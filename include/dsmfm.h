@@ -134,6 +134,8 @@ typedef struct dsmfm_stats {
     float ms_wall_fetch;         /* host wall time of dsmfm_fetch                           */
     float ms_wall_alloc;         /* of which: device allocation calls                       */
     float reserved2;
+    uint64_t refine_key_fetches; /* 8-byte keys the refinement kernel gathered from the text */
+    uint64_t refine_launches;    /* refine_kernel launches                                  */
 } dsmfm_stats;
 
 /* Replaces: TextCollectionBuilder::TextCollectionBuilder (TextCollectionBuilder.cpp:32-57). */
