@@ -17,9 +17,17 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d)
     uint32_t peers = 0xffffffffu;
 #pragma unroll
     for (int b = 0; b < kRadixBits; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? vote : ~vote;
+        // one predicate from a constant-mask test feeds both the ballot and the keep/flip mask
+        // (written in PTX: nvcc otherwise derives the two from separate shift/and/compare chains)
+        uint32_t vote, flip;
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                     "and.b32 t, %2, %3;\n\t"
+                     "setp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                     "selp.b32 %1, 0, 0xffffffff, p;\n\t}"
+                     : "=r"(vote), "=r"(flip)
+                     : "r"(d), "r"(1u << b));
+        peers &= vote ^ flip;
     }
     return peers;
 }
@@ -260,6 +268,7 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
     const int npass = (int)div_up((uint64_t)(end_bit - begin_bit), kRadixBits);
     if (n == 0 || npass <= 0) return 0;
     if (npass > kMaxPasses) throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: too many passes", __FILE__, __LINE__};
+    if (n >= (1ull << 32)) throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: 2^32 pairs or more", __FILE__, __LINE__};
     if (div_up(n < kSweepPortion ? n : kSweepPortion, kSweepTile) > ws.status_tiles)
         throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: workspace too small", __FILE__, __LINE__};
 
