@@ -41,14 +41,25 @@ class CudaEngine:
     def tensor_device(self):
         return torch.device("cuda", self.device)
 
-    def sort_slice(self, text, shard_index, shard_count, shard_span):
-        """text: uint8 CUDA tensor with the whole collection.  Returns (handle, rank_begin, count)."""
+    def open(self, text, shard_index, shard_count, shard_span):
+        """text: uint8 CUDA tensor with the whole collection; it is copied into the builder (the caller may drop
+        its tensor afterwards, which matters when the collection is tens of GB)."""
         b = self._dsmfm.Builder(device=self.device, stream=self.stream, expected_bytes=text.numel(), flags=self.flags,
                                 samplerate=self.samplerate, shard_index=shard_index, shard_count=shard_count,
                                 shard_span=shard_span)
         try:
             t0 = time.perf_counter()
             b.append_batch_device(text)
+            torch.cuda.current_stream().synchronize()
+            self._t_append = 1000 * (time.perf_counter() - t0)
+        except Exception:
+            b.close()
+            raise
+        return b
+
+    def sort(self, b):
+        """Returns (handle, rank_begin, count) of this builder's slice of the global suffix order."""
+        try:
             t1 = time.perf_counter()
             b.build_device()
             t2 = time.perf_counter()
@@ -56,8 +67,11 @@ class CudaEngine:
         except Exception:
             b.close()
             raise
-        self.last_walls = (1000 * (t1 - t0), 1000 * (t2 - t1))  # append, build (host wall, for DSMFM_MG_TRACE)
+        self.last_walls = (self._t_append, 1000 * (t2 - t1))  # append, build (host wall, for DSMFM_MG_TRACE)
         return b, info.rank_begin, info.count
+
+    def sort_slice(self, text, shard_index, shard_count, shard_span):
+        return self.sort(self.open(text, shard_index, shard_count, shard_span))
 
     def export_bwt(self, handle, out):
         handle.shard_export(bwt_dst=out)
@@ -187,8 +201,16 @@ def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0, wavelet="d
     if trace: trace.mark("gather_text")
     n = full.numel()
     k = max(1, int(ranges_per_gpu))
-    handle, rank_begin, count = engine.sort_slice(full, rank * k, world * k, k)
-    del full
+    if hasattr(engine, "open"):
+        opened = engine.open(full, rank * k, world * k, k)
+        big = full.numel() > (8 << 30)
+        del full  # the builder holds its own copy now
+        if big and device.type == "cuda":
+            torch.cuda.empty_cache()  # hand the gathered text's memory back before the sort buffers are allocated
+        handle, rank_begin, count = engine.sort(opened)
+    else:
+        handle, rank_begin, count = engine.sort_slice(full, rank * k, world * k, k)
+        del full
     if trace: trace.mark("sort_slice")
     if trace and hasattr(engine, "last_walls"): trace.marks.append(("(append %.1f build %.1f)" % engine.last_walls, 0.0))
     info = {"n_total": n, "block_bytes": sizes, "rank_begin": rank_begin, "count": count}

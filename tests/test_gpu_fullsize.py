@@ -108,3 +108,60 @@ def test_full_size_build_properties(config, scale):
         assert s.fallback_elems == 0 or config != "C1"
         if config == "C1":
             _check_sa_file(b.sa_file(), idx.n, nreads, 2 * L + 2)
+
+
+def test_collection_beyond_2_to_32_symbols_in_key_ranges():
+    """More than 2^32 symbols (22.2M reads, n = 4.48 G): the suffix order is cut into key ranges that are sorted
+    one after the other on this GPU (as every GPU of a multi-GPU build does for its ranges); text positions no
+    longer fit 32 bits, so their high part travels in the key's spare bits and next to the suffix array.
+    Size-independent checks: the slices tile the suffix order, the concatenated BWT is a permutation of the
+    text, its first D symbols are the documents' last symbols in document order, sampled windows of every
+    slice's suffix array are sorted under the reference rule and agree with the BWT."""
+    import torch
+    import dsmfm
+    import dsmgen
+    kw = dict(dsmgen.CONFIGS["C3"])
+    kw["n_reads"] = 22_200_000 if not os.environ.get("DSMFM_TEST_SMALL") else 300_000
+    nreads, L = kw["n_reads"], kw["read_len"]
+    doc_len = 2 * L + 2
+    host = torch.empty(nreads * doc_len, dtype=torch.uint8, pin_memory=True)
+    dsmgen.docs(out=host, **kw)
+    docs = host.numpy()
+    n = docs.size
+    dev = host.cuda()
+    shards, span = 6, 2
+    rng = np.random.default_rng(5)
+    counts = np.zeros(256, dtype=np.int64)
+    nxt = 0
+    head = None
+    for first in range(0, shards, span):
+        with dsmfm.Builder(flags=dsmfm.FLAG_KEEP_SA, shard_index=first, shard_count=shards, shard_span=span,
+                           expected_bytes=n) as b:
+            b.append_batch_device(dev)
+            b.build_device()
+            info = b.shard_info()
+            assert info.n_total == n and info.rank_begin == nxt
+            m = info.count
+            bw = torch.empty(m, dtype=torch.uint8, device="cuda")
+            sa = torch.empty(m, dtype=torch.int64, device="cuda")
+            b.shard_export(bw, sa)
+        counts += torch.bincount(bw.to(torch.int64), minlength=256).cpu().numpy()
+        if first == 0:
+            head = bw[:nreads].cpu().numpy()
+            sa0 = sa[:min(nreads, 200000)].cpu().numpy()
+            assert np.array_equal(sa0, np.arange(sa0.size, dtype=np.int64) * doc_len + doc_len - 1)
+        if n > 2**32:
+            assert int(sa.max()) >= 2**32 or first + span < shards  # high position bits are really in play
+        for _ in range(6):
+            w0 = int(rng.integers(0, max(1, m - 1024)))
+            win = sa[w0:w0 + 1024].cpu().numpy()
+            bwin = bw[w0:w0 + 1024].cpu().numpy()
+            prev = np.where(win > 0, docs[np.maximum(win - 1, 0)], 0)
+            assert np.array_equal(prev, bwin)
+            for j in range(0, win.size - 1, 5):
+                assert _suffix_less_equal(docs, int(win[j]), int(win[j + 1])), "order violated in slice %d" % first
+        nxt += m
+        del bw, sa
+    assert nxt == n
+    assert np.array_equal(counts, np.bincount(docs, minlength=256))
+    assert np.array_equal(head, docs.reshape(nreads, doc_len)[:, doc_len - 2])
