@@ -670,6 +670,16 @@ void dsmfm_builder::build()
     uint64_t *d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
     DSM_CUDA(cudaMemcpyAsync(d_map, code_map, 256, cudaMemcpyHostToDevice, st));
     launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
+    if ((flags & DSMFM_FLAG_KEEP_SA) && shard_count <= 1) { // the .sa writer needs the document boundaries
+        d_doc_end = static_cast<uint32_t *>(dmalloc((size_t)counts[0] * 4 + 16));
+        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(term_tiles(n) * 8));
+        launch_term_positions(st, d_raw, n, d_tile, d_doc_end, L);
+        dfree(d_tile);
+    }
+    // the raw text is not looked at again: everything downstream reads the packed text (3/8 of its size)
+    dfree(d_raw);
+    chunks.clear();
+    d_raw = nullptr;
     DSM_CUDA(cudaEventRecord(ev[1], st));
 
     // ---- which suffixes this builder sorts ------------------------------------------------
@@ -1000,16 +1010,6 @@ void dsmfm_builder::build()
         dfree(d_last_sorted_vals);
     }
     pos_lo_bits = lo_bits;
-    if (keep_sa && !sharded) { // the .sa writer needs the document boundaries
-        d_doc_end = static_cast<uint32_t *>(dmalloc((size_t)counts[0] * 4 + 16));
-        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(term_tiles(n) * 8));
-        launch_term_positions(st, d_raw, n, d_tile, d_doc_end, L);
-        DSM_CUDA(cudaStreamSynchronize(st));
-        dfree(d_tile);
-    }
-    dfree(d_raw);
-    chunks.clear();
-    d_raw = nullptr;
 
     float ms;
     cudaEventElapsedTime(&ms, ev[0], ev[5]); stats.ms_total = ms;
