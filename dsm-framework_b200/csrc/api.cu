@@ -663,7 +663,7 @@ void dsmfm_builder::build()
     stats.sigma = sigma;
 
     // ---- pack -----------------------------------------------------------------------
-    const uint64_t nwords = div_up(n, spw) + 4; // zero words behind the text: windows read up to 2 words ahead
+    const uint64_t nwords = div_up(n, spw) + 8; // zero words behind the text: refinement rows read up to 5 words ahead
     uint8_t *d_map = static_cast<uint8_t *>(dmalloc(256));
     uint8_t *d_inv = static_cast<uint8_t *>(dmalloc(256));
     DSM_CUDA(cudaMemcpyAsync(d_inv, inv_map, 256, cudaMemcpyHostToDevice, st));
@@ -758,7 +758,7 @@ void dsmfm_builder::build()
     d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     // [0,64): suffixes left in groups of >= 2; [64,128): keys the refinement gathered from the text
     unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(128 * 8));
-    const uint32_t big_cap = (uint32_t)(m_max / kRefGroupMax + 2);
+    const uint32_t big_cap = (uint32_t)(m_max / kRefGroupMaxWarps + 2);
     uint32_t *d_big_heads = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_len = static_cast<uint32_t *>(dmalloc((size_t)big_cap * 4));
     uint32_t *d_big_count = static_cast<uint32_t *>(dmalloc(4));

@@ -2,6 +2,7 @@
 // heads, segmented refinement rounds, BWT emission, Huffman-shaped wavelet tree
 // and BitRank directories.  All integer / byte work, HBM-bound; no tensor cores.
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace dsmfm {
 
@@ -891,6 +892,298 @@ refine_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, co
     }
 }
 
+// SPW-symbol window that starts `s` symbols into word x0 and runs on into x1, cut at the terminator
+template <int BITS> __device__ __forceinline__ uint64_t window_of(uint64_t x0, uint64_t x1, int s)
+{
+    using P = Pack<BITS>;
+    uint64_t x = (x0 << (BITS * s)) & P::USED_MASK;
+    if (s) x |= x1 >> (BITS * (P::SPW - s));
+    return cut_at_terminator<BITS>(x);
+}
+
+// ---------------------------------------------------------------------------
+// refinement with independent warps
+// ---------------------------------------------------------------------------
+// Same contract as the multi-step refine_kernel.  Groups never interact, so nothing forces the warps
+// of a CTA through the steps together: in refine_kernel every step costs two CTA-wide barriers and the
+// CTA runs as many steps as its slowest suffix needs, with most warps idle in the tail.  Here the CTA
+// only shares the window in shared memory.  Warp w owns the groups whose head lies in its 128-slot
+// part of the window -- a contiguous slot range [first head >= 128w, first head >= 128(w+1)) -- and
+// runs the rank / classify steps over that range on its own, synchronising with __syncwarp only.
+// Head bits of neighbouring ranges can share a 32-bit word: words are only ever OR-ed (atomically), a
+// warp publishes (head_b -> head_a) just the bits of its own range, and the bit scans stop at the
+// heads that bound the range, which are set from the start.  KW = 2 compares 2*SPW symbols per step
+// (128-bit keys): fewer steps per suffix, and every step has a fixed cost per suffix.
+constexpr int kRwGroupMax = kRefGroupMaxWarps;
+constexpr int kRwCap = kRefWindow + kRwGroupMax;
+
+template <int KW, bool WIDE> struct RwSmem {
+    uint64_t khi[kRwCap];
+    uint64_t klo[KW == 2 ? kRwCap : 1];
+    uint32_t sa[2][kRwCap];            // suffixes, double buffered across a step
+    uint16_t list[kRwCap];             // unresolved slots of each warp's range, compacted in place
+    uint8_t bw[2][kRwCap];             // BWT bytes travelling with the suffixes
+    uint8_t hi[2][WIDE ? kRwCap : 1];  // wide builds: text position = hi << lo_bits | sa
+    uint32_t head_a[kRwCap / 32 + 2];
+    uint32_t head_b[kRwCap / 32 + 2];
+    int range[2];
+};
+
+template <int BITS, int KW, bool WIDE>
+__global__ void __launch_bounds__(kRefThreads, 4)
+refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
+                    uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
+                    uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
+                    unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
+                    uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint8_t *__restrict__ bwt,
+                    uint8_t *__restrict__ sa_hi, int lo_bits)
+{
+    using P = Pack<BITS>;
+    constexpr int HW = kRwCap / 32 + 2;
+    constexpr int WIN_WORDS = kRefWindow / 32;
+    constexpr int OVER_WORDS = kRwGroupMax / 32;
+    constexpr int NWARP = kRefThreads / 32;
+    constexpr int PART = kRefWindow / NWARP; // slots of the window whose heads one warp owns
+    static_assert(WIN_WORDS == 32 && OVER_WORDS <= 32, "one warp scans the window / the overhang");
+    extern __shared__ __align__(16) unsigned char ref_smem_raw[];
+    RwSmem<KW, WIDE> &S = *reinterpret_cast<RwSmem<KW, WIDE> *>(ref_smem_raw);
+    uint64_t *s_khi = S.khi, *s_klo = S.klo;
+    uint32_t(*s_sa)[kRwCap] = S.sa;
+    uint8_t(*s_bw)[kRwCap] = S.bw;
+    uint8_t(*s_hi)[WIDE ? kRwCap : 1] = S.hi;
+    uint32_t *s_ha = S.head_a, *s_hb = S.head_b;
+    int *s_range = S.range;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t wid = win_list ? win_list[blockIdx.x] : blockIdx.x;
+    const uint64_t win = (uint64_t)wid * kRefWindow;
+    const uint64_t w0 = win >> 5;
+    for (int i = tid; i < HW; i += kRefThreads) {
+        const uint32_t h = head_cur[w0 + i];
+        s_ha[i] = h;
+        s_hb[i] = h;
+    }
+    __syncthreads();
+
+    // Ownership of the CTA: the groups whose head lies in [win, win+kRefWindow).
+    if (warp == 0) {
+        const uint32_t hw = s_ha[lane];
+        const uint32_t nz = __ballot_sync(0xffffffffu, hw != 0);
+        int start = -1, end = -1;
+        if (nz) {
+            const int fl = __ffs(nz) - 1, ll = 31 - __clz(nz);
+            const uint32_t fw = __shfl_sync(0xffffffffu, hw, fl), lw = __shfl_sync(0xffffffffu, hw, ll);
+            start = fl * 32 + __ffs(fw) - 1;
+            const int hl = ll * 32 + 31 - __clz(lw); // head of the last owned group
+            const uint32_t ew = lane < OVER_WORDS ? s_ha[WIN_WORDS + lane] : 0u;
+            const uint32_t enz = __ballot_sync(0xffffffffu, ew != 0);
+            int e = -1;
+            if (enz) {
+                const int el = __ffs(enz) - 1;
+                const uint32_t x = __shfl_sync(0xffffffffu, ew, el);
+                e = kRefWindow + el * 32 + __ffs(x) - 1;
+            }
+            if (e >= 0 && e - hl <= kRwGroupMax) {
+                end = e;
+            } else {
+                end = hl; // the last group is too large for shared memory: leave it to the global path
+                if (lane == 0) {
+                    const uint32_t slot = atomicAdd(big_count, 1u);
+                    if (slot < big_cap) big_heads[slot] = (uint32_t)(win + hl);
+                    // it comes back one depth deeper: this window is visited again
+                    if (atomicExch(&win_flag[wid], 1u) == 0u) win_next[atomicAdd(win_next_count, 1u)] = wid;
+                }
+            }
+        }
+        if (lane == 0) {
+            s_range[0] = start;
+            s_range[1] = end;
+        }
+    }
+    __syncthreads();
+    const int start = s_range[0], end = s_range[1];
+    if (start < 0 || end <= start) return;
+
+    // this warp's slot range (`end` is a head, so the scan stops there at the latest)
+    auto first_head_ge = [&](int x) -> int {
+        if (x >= end) return end;
+        int w = x >> 5;
+        uint32_t m = s_ha[w] & (0xffffffffu << (x & 31));
+        while (m == 0) m = s_ha[++w];
+        const int q = (w << 5) + __ffs(m) - 1;
+        return q < end ? q : end;
+    };
+    const int ws = first_head_ge(warp * PART);
+    const int we = warp == NWARP - 1 ? end : first_head_ge((warp + 1) * PART);
+    if (we <= ws) return;
+    uint16_t *list = &S.list[ws];
+
+    // keys of up to four suffixes per lane: all text words are requested before the first one is used
+    auto fetch4 = [&](const uint64_t (&pos)[4], const int (&slot)[4], uint32_t dd) {
+        uint64_t x0[4], x1[4], x2[4];
+        int sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (slot[u] >= 0) {
+                const uint64_t q = pos[u] + dd;
+                const uint64_t w = q / P::SPW;
+                sh[u] = (int)(q - w * P::SPW);
+                x0[u] = __ldg(packed + w);
+                x1[u] = __ldg(packed + w + 1);
+                if (KW == 2) x2[u] = __ldg(packed + w + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (slot[u] >= 0) {
+                const uint64_t h = window_of<BITS>(x0[u], x1[u], sh[u]);
+                s_khi[slot[u]] = h;
+                // a terminator inside hi ends the suffix: nothing after it may be looked at
+                if (KW == 2) s_klo[slot[u]] = key_terminated<BITS>(h) ? 0ull : window_of<BITS>(x1[u], x2[u], sh[u]);
+            }
+        }
+    };
+
+    // load the suffixes (and their BWT bytes) that sit in groups of >= 2, and their first keys
+    uint32_t d = depth;
+    int cnt = 0;
+    for (int b0 = ws; b0 < we; b0 += 128) {
+        uint64_t pos[4];
+        int slot[4];
+        uint32_t sv[4];
+        uint8_t bv[4], hv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { // the four loads of a lane are independent: issue them back to back
+            const int r = b0 + u * 32 + lane;
+            bool act = false;
+            if (r < we) {
+                const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
+                const bool h1 = (s_ha[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+                act = !(h0 && h1);
+            }
+            slot[u] = act ? r : -1;
+            sv[u] = 0;
+            bv[u] = hv[u] = 0;
+            if (act) {
+                sv[u] = sa[win + r];
+                if (bwt) bv[u] = bwt[win + r];
+                if (WIDE) hv[u] = sa_hi[win + r];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = b0 + u * 32 + lane;
+            const bool act = slot[u] >= 0;
+            pos[u] = sv[u];
+            if (act) {
+                s_sa[0][r] = sv[u];
+                s_bw[0][r] = bv[u];
+                if (WIDE) {
+                    s_hi[0][r] = hv[u];
+                    pos[u] |= (uint64_t)hv[u] << lo_bits;
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, act);
+            if (act) list[cnt + __popc(m & lanemask_lt())] = (uint16_t)r;
+            cnt += __popc(m);
+        }
+        fetch4(pos, slot, d);
+    }
+    __syncwarp();
+
+    int c = 0;
+    unsigned long long fetched = 0;
+    while (cnt > 0) {
+        fetched += (unsigned)cnt;
+        // rank: stable position inside the group; a suffix opens a new group iff no earlier member
+        // carries the same key (or its key holds the terminator, which makes it unique)
+        for (int i = lane; i < cnt; i += 32) {
+            const int r = list[i];
+            const int gs = prev_set_le(s_ha, r);
+            const int ge = next_set_gt(s_ha, r);
+            const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
+            int lt = 0, eq = 0;
+            if (KW == 2) {
+                for (int j = gs; j < ge; ++j) {
+                    const uint64_t oh = s_khi[j], ol = s_klo[j];
+                    lt += (oh < mh) | ((oh == mh) & (ol < ml));
+                    eq += (oh == mh) & (ol == ml) & (j < r);
+                }
+            } else {
+                for (int j = gs; j < r; ++j) {
+                    const uint64_t o = s_khi[j];
+                    lt += o < mh;
+                    eq += o == mh;
+                }
+                for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
+            }
+            const int p = gs + lt + eq;
+            if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+            s_sa[c ^ 1][p] = s_sa[c][r];
+            s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+            if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+            list[i] = (uint16_t)p;       // where this suffix went
+        }
+        __syncwarp();
+        // classify: resolved suffixes go home now; the rest stay on the list (compacted in place: an entry
+        // is written at or before the position it was read from, and a warp reads 32 entries before it writes)
+        d += KW * P::SPW;
+        int next = 0;
+        for (int i = lane; (i & ~31) < cnt; i += 32) {
+            bool again = false;
+            int p = 0;
+            if (i < cnt) {
+                p = list[i];
+                const bool h0 = (s_hb[p >> 5] >> (p & 31)) & 1u;
+                const bool h1 = (s_hb[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u;
+                again = !(h0 && h1);
+                if (!again) {
+                    sa[win + p] = s_sa[c ^ 1][p];
+                    if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
+                    if (WIDE) sa_hi[win + p] = s_hi[c ^ 1][p];
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, again);
+            if (again) list[next + __popc(m & lanemask_lt())] = (uint16_t)p;
+            next += __popc(m);
+        }
+        __syncwarp();
+        // next keys of the survivors
+        for (int i0 = lane; (i0 & ~31) < next; i0 += 128) {
+            uint64_t pos[4];
+            int slot[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32;
+                slot[u] = -1;
+                pos[u] = 0;
+                if (i < next) {
+                    const int p = list[i];
+                    slot[u] = p;
+                    pos[u] = WIDE ? (((uint64_t)s_hi[c ^ 1][p] << lo_bits) | s_sa[c ^ 1][p]) : (uint64_t)s_sa[c ^ 1][p];
+                }
+            }
+            fetch4(pos, slot, d);
+        }
+        // publish the new heads of this range (bits only ever get set; neighbours' bits are left alone)
+        for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) {
+            const int lo = ws > (i << 5) ? ws - (i << 5) : 0, hi = (we - 1) - (i << 5) < 31 ? (we - 1) - (i << 5) : 31;
+            const uint32_t mask = (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
+            const uint32_t add = s_hb[i] & mask & ~s_ha[i];
+            if (add) atomicOr(&s_ha[i], add);
+        }
+        c ^= 1;
+        cnt = next;
+        __syncwarp();
+    }
+
+    for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) {
+        const uint32_t fresh = s_hb[i] & ~head_cur[w0 + i];
+        if (fresh) atomicOr(&head_next[w0 + i], fresh);
+    }
+    if (lane == 0 && fetched) atomicAdd(&remaining[64 + ((wid + warp) & 63)], fetched);
+}
+
 // ---------------------------------------------------------------------------
 // large-group path
 // ---------------------------------------------------------------------------
@@ -1564,6 +1857,42 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
     }
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
+    // default schedule: multi-step with the text of the unresolved suffixes resident in shared memory
+    static const int variant = [] {
+        const char *e = std::getenv("DSMFM_REFINE_VARIANT"); // 0: CTA-wide steps (refine_kernel), 2: independent warps
+        return e ? std::atoi(e) : 2;
+    }();
+    if (multi_step && variant == 2) {
+        static bool attr3_set = false;
+        if (!attr3_set) {
+#define SET3(B, K)                                                                                               \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)sizeof(RwSmem<K, false>)));                                               \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)sizeof(RwSmem<K, true>)))
+            SET3(3, 1); SET3(4, 1); SET3(8, 1); SET3(3, 2); SET3(4, 2); SET3(8, 2);
+#undef SET3
+            attr3_set = true;
+        }
+#define RW(B, K, W)                                                                                               \
+    refine_warps_kernel<B, K, W><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                                \
+        packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \
+        win_next, win_next_count, bwt, sa_hi, lo_bits)
+#define CALL3(B)                                                                                                  \
+    do {                                                                                                          \
+        if (key_words == 2) {                                                                                     \
+            if (sa_hi) RW(B, 2, true); else RW(B, 2, false);                                                      \
+        } else {                                                                                                  \
+            if (sa_hi) RW(B, 1, true); else RW(B, 1, false);                                                      \
+        }                                                                                                         \
+    } while (0)
+        DISPATCH_BITS(bits, CALL3);
+#undef CALL3
+#undef RW
+        DSM_LAUNCH_CHECK();
+        if (launches) ++*launches;
+        return;
+    }
 #define REFINE(B, K, W)                                                                                             \
     refine_kernel<B, K, W><<<grid, kRefThreads, sizeof(RefSmem<K, W>), st>>>(                                       \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,   \

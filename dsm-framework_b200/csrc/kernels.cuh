@@ -65,6 +65,7 @@ constexpr int kRefThreads = 256;
 constexpr int kRefWindow = 1024;   // group heads owned by one CTA lie in a window of this many slots
 constexpr int kRefGroupMax = 1024; // larger groups go through the global path
 constexpr int kRefCap = kRefWindow + kRefGroupMax;
+constexpr int kRefGroupMaxWarps = 768; // the same limit in the default (independent-warps) schedule
 
 inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32 + 8; }
 
