@@ -5,6 +5,7 @@
 // <=256-entry Huffman code table and the tree shape, and writes files.
 #include "../../include/dsmfm.h"
 #include "kernels.cuh"
+#include "fasta.cuh"
 #include "radix_sort.cuh"
 
 #include <algorithm>
@@ -525,10 +526,89 @@ struct dsmfm_builder {
         wt.release(stream);
     }
 
+    uint32_t pre_launches = 0; // kernels launched before build() (the FASTA front end)
+    void append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info *info);
     void build();
     void fetch();
     void make_sa_image();
 };
+
+// ---------------------------------------------------------------------------
+// FASTA front end (fasta.cu): `m` bytes of whole lines -> documents appended to the collection
+// ---------------------------------------------------------------------------
+void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info *info)
+{
+    cudaStream_t st = stream;
+    uint32_t *L = &pre_launches;
+    uint8_t *d_text = static_cast<uint8_t *>(dmalloc(m + 64));
+    DSM_CUDA(cudaMemcpyAsync(d_text, text, m, cudaMemcpyHostToDevice, st));
+    const uint64_t ntiles = fasta_tiles(m);
+    long long *d_last = static_cast<long long *>(dmalloc(ntiles * 8));
+    long long *d_entry = static_cast<long long *>(dmalloc(ntiles * 8));
+    uint32_t *d_cs = static_cast<uint32_t *>(dmalloc(ntiles * 4));
+    uint32_t *d_ch = static_cast<uint32_t *>(dmalloc(ntiles * 4));
+    uint64_t *d_os = static_cast<uint64_t *>(dmalloc(ntiles * 8));
+    uint64_t *d_oh = static_cast<uint64_t *>(dmalloc(ntiles * 8));
+    uint64_t *d_tot = static_cast<uint64_t *>(dmalloc(4 * 8));
+    unsigned long long *d_cnt = static_cast<unsigned long long *>(dmalloc(4 * 8));
+    launch_fasta_scan_lines(st, d_text, m, d_last, d_entry, d_cs, d_ch, d_os, d_oh, d_tot, L);
+    uint64_t tot[2] = {0, 0};
+    DSM_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    dfree(d_last);
+    dfree(d_cs);
+    dfree(d_ch);
+    const uint64_t nseq = tot[0], nhdr = tot[1], nrec = nhdr + 1;
+
+    uint64_t *d_B = static_cast<uint64_t *>(dmalloc((nrec + 1) * 8));
+    uint64_t *d_O = static_cast<uint64_t *>(dmalloc(nrec * 8));
+    const uint64_t rtiles = fasta_rec_tiles(nrec);
+    uint32_t *d_rc = static_cast<uint32_t *>(dmalloc(rtiles * 4));
+    uint64_t *d_ro = static_cast<uint64_t *>(dmalloc(rtiles * 8));
+    const unsigned long long cnt0[4] = {0, 0, ~0ull, 0};
+    const uint64_t zero = 0;
+    DSM_CUDA(cudaMemcpyAsync(d_cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));
+    DSM_CUDA(cudaMemcpyAsync(d_B, &zero, 8, cudaMemcpyHostToDevice, st));
+    DSM_CUDA(cudaMemcpyAsync(d_B + nrec, &nseq, 8, cudaMemcpyHostToDevice, st));
+    launch_fasta_records(st, d_text, m, d_entry, d_os, d_oh, nrec, d_B, d_O, d_rc, d_ro, d_tot, d_cnt, L);
+    DSM_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    dfree(d_rc);
+    dfree(d_ro);
+    const uint64_t ndocs = tot[0], doc_bytes = 2 * nseq + 2 * ndocs;
+
+    unsigned long long cnt[4] = {0, 0, ~0ull, 0};
+    if (doc_bytes) {
+        uint8_t *d_out = static_cast<uint8_t *>(dmalloc(doc_bytes + 64));
+        const size_t bm_bytes = (size_t)div_up(nrec, 32) * 4;
+        uint32_t *d_bm = static_cast<uint32_t *>(dmalloc(bm_bytes));
+        DSM_CUDA(cudaMemsetAsync(d_bm, 0, bm_bytes, st));
+        launch_fasta_emit(st, d_text, m, d_entry, d_os, d_oh, d_B, d_O, d_out, d_bm, d_cnt, L);
+        DSM_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        dfree(d_bm);
+        chunks.push_back(Chunk{d_out, (size_t)doc_bytes + 64, (size_t)doc_bytes});
+        n += doc_bytes;
+    } else {
+        DSM_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+    }
+    dfree(d_text);
+    dfree(d_entry);
+    dfree(d_os);
+    dfree(d_oh);
+    dfree(d_tot);
+    dfree(d_cnt);
+    dfree(d_B);
+    dfree(d_O);
+    info->records = nhdr;
+    info->documents = ndocs;
+    info->bases = nseq;
+    info->doc_bytes = doc_bytes;
+    info->bad_headers = cnt[0];
+    info->invalid_records = cnt[1];
+    info->first_invalid_offset = cnt[2];
+}
 
 // ---------------------------------------------------------------------------
 // the device build
@@ -1023,6 +1103,7 @@ void dsmfm_builder::build()
     for (auto &e : ev) cudaEventDestroy(e);
     cudaEventDestroy(ev_pass0);
     cudaEventDestroy(ev_pass1);
+    stats.kernel_launches += pre_launches;
     built = true;
 }
 
@@ -1289,6 +1370,62 @@ DSMFM_API int dsmfm_append_batch_device(dsmfm_builder *b, const void *docs_dev, 
 {
     API_GUARD(b);
     return append_bulk(b, docs_dev, bytes, cudaMemcpyDeviceToDevice);
+}
+
+DSMFM_API int dsmfm_append_fasta(dsmfm_builder *b, const uint8_t *text, size_t len, int final, dsmfm_fasta_info *info)
+{
+    API_GUARD(b);
+    if (!info) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: null info");
+    std::memset(info, 0, sizeof *info);
+    info->first_invalid_offset = ~0ull;
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: new text can not be inserted after dsmfm_finish");
+    if (!text && len) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: null text");
+    size_t use = 0;
+    if (final) {
+        // `getline(...).good()`: a last line without '\n' is dropped (builder.cpp:211)
+        const void *p = len ? memrchr(text, '\n', len) : nullptr;
+        use = p ? (size_t)(static_cast<const uint8_t *>(p) - text) + 1 : 0;
+        info->consumed = len;
+    } else {
+        // everything in front of the last header line: the record it opens may continue in the next call
+        size_t i = len;
+        while (i > 0) {
+            const void *p = memrchr(text, '>', i);
+            if (!p) break;
+            const size_t q = (size_t)(static_cast<const uint8_t *>(p) - text);
+            if (q == 0 || text[q - 1] == '\n') {
+                use = q;
+                break;
+            }
+            i = q;
+        }
+        info->consumed = use;
+    }
+    if (use == 0) return DSMFM_OK;
+    try {
+        b->flush_stage();
+        b->append_fasta(text, use, info);
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API void *dsmfm_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+DSMFM_API void dsmfm_free_pinned(void *p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 DSMFM_API int dsmfm_build_device(dsmfm_builder *b)

@@ -62,6 +62,15 @@ class Stats(C.Structure):
         return d
 
 
+class FastaInfo(C.Structure):
+    _fields_ = [("consumed", C.c_uint64), ("records", C.c_uint64), ("documents", C.c_uint64), ("bases", C.c_uint64),
+                ("doc_bytes", C.c_uint64), ("invalid_records", C.c_uint64), ("first_invalid_offset", C.c_uint64),
+                ("bad_headers", C.c_uint64)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 class DsmfmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("dsmfm error %d: %s" % (code, msg))
@@ -86,6 +95,7 @@ def lib():
     L.dsmfm_append.argtypes = [B, C.c_void_p, C.c_size_t]
     L.dsmfm_append_batch.argtypes = [B, C.c_void_p, C.c_size_t]
     L.dsmfm_append_batch_device.argtypes = [B, C.c_void_p, C.c_size_t]
+    L.dsmfm_append_fasta.argtypes = [B, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(FastaInfo)]
     L.dsmfm_finish.argtypes = [B, C.POINTER(Index)]
     L.dsmfm_build_device.argtypes = [B]
     L.dsmfm_fetch.argtypes = [B, C.POINTER(Index)]
@@ -180,6 +190,14 @@ class Builder:
         addr, n, keep = _ptr(tensor)
         self._keep.append(keep)
         self._check(self._L.dsmfm_append_batch_device(self._h, addr, n))
+
+    def append_fasta(self, text, final=True):
+        """FASTA bytes (host memory) -> documents, parsed and transformed on the GPU (the reference CLI's record
+        loop, builder.cpp:203-262).  Returns the dsmfm_fasta_info fields as a dict."""
+        addr, n, keep = _ptr(text)
+        info = FastaInfo()
+        self._check(self._L.dsmfm_append_fasta(self._h, addr, n, 1 if final else 0, C.byref(info)))
+        return info.as_dict()
 
     def build_device(self):
         self._check(self._L.dsmfm_build_device(self._h))

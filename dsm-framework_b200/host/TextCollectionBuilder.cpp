@@ -14,6 +14,7 @@ struct TCBuilderRep
     unsigned numberOfTexts;
     ulong maxTextLength;
     bool insertAllowed;
+    bool lengthsCounted; // false once InsertFasta was used: the longest document is then only known to the device
     std::vector<std::string> name; // accepted and ignored by the index, as in the reference (FMIndex.cpp:100-116)
 };
 
@@ -26,6 +27,7 @@ TextCollectionBuilder::TextCollectionBuilder(unsigned samplerate, ulong estimate
     p_->numberOfTexts = 0;
     p_->maxTextLength = 0;
     p_->insertAllowed = true;
+    p_->lengthsCounted = true;
     p_->gpu = 0;
 
     dsmfm_options opt;
@@ -80,6 +82,34 @@ void TextCollectionBuilder::InsertText(uchar const *text, std::string const &nam
     InsertText(text);
 }
 
+void TextCollectionBuilder::InsertFasta(uchar const *text, ulong length, bool final, FastaReport &report)
+{
+    if (!p_->insertAllowed)
+    {
+        std::cerr << "TextCollectionBuilder::InsertFasta() error: new text can not be inserted after InitTextCollection() call!" << std::endl;
+        std::exit(1);
+    }
+    dsmfm_fasta_info info;
+    if (dsmfm_append_fasta(p_->gpu, text, length, final ? 1 : 0, &info) != DSMFM_OK)
+    {
+        std::cerr << "TextCollectionBuilder::InsertFasta() error: " << dsmfm_last_error(p_->gpu) << std::endl;
+        std::exit(1);
+    }
+    p_->n += info.doc_bytes;
+    p_->numberOfTexts += (unsigned)info.documents;
+    p_->lengthsCounted = false;
+    report.consumed = info.consumed;
+    report.records = info.records;
+    report.documents = info.documents;
+    report.bases = info.bases;
+    report.invalidRecords = info.invalid_records;
+    report.firstInvalidOffset = info.first_invalid_offset;
+    report.badHeaders = info.bad_headers;
+}
+
+void *TextCollectionBuilder::AllocPinned(ulong bytes) { return dsmfm_alloc_pinned(bytes); }
+void TextCollectionBuilder::FreePinned(void *p) { dsmfm_free_pinned(p); }
+
 TextCollection *TextCollectionBuilder::InitTextCollection(bool storePlainText, bool color, unsigned rotationLength)
 {
     p_->insertAllowed = false;
@@ -97,7 +127,8 @@ TextCollection *TextCollectionBuilder::InitTextCollection(bool storePlainText, b
         // what the device found must be what InsertText counted (the reference asserts length == n,
         // TextCollectionBuilder.cpp:128)
         if (p_->numberOfTexts != 0 &&
-            (idx.n != p_->n || idx.number_of_texts != p_->numberOfTexts || idx.max_text_length != p_->maxTextLength))
+            (idx.n != p_->n || idx.number_of_texts != p_->numberOfTexts ||
+             (p_->lengthsCounted && idx.max_text_length != p_->maxTextLength)))
         {
             std::cerr << "TextCollectionBuilder::InitTextCollection() error: device/host document accounting mismatch" << std::endl;
             std::exit(1);

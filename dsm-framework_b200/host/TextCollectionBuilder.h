@@ -33,6 +33,21 @@ public:
     void InsertText(uchar const *);
     void InsertText(uchar const *, std::string const &);
 
+    // Extension (no counterpart in the reference class): the record loop of the reference CLI -- rows, '>' headers,
+    // normalize() and transform(), builder.cpp:60-104, 183-262 -- run on the GPU over `length` bytes of FASTA text.
+    // Every record with a non-empty sequence becomes one document, exactly as if the CLI had called InsertText
+    // for it.  final = false (streaming): only the bytes in front of the last header line are consumed
+    // (report.consumed); present the rest again followed by more input.
+    struct FastaReport
+    {
+        ulong consumed, records, documents, bases, invalidRecords, firstInvalidOffset, badHeaders;
+    };
+    void InsertFasta(uchar const *text, ulong length, bool final, FastaReport &report);
+
+    // Page-locked host memory for InsertFasta / InsertText input (faster host-to-device copies).
+    static void *AllocPinned(ulong bytes);
+    static void FreePinned(void *);
+
     // Build the static index on the GPU.  The caller deletes the result.
     TextCollection *InitTextCollection(bool storePlainText = false, bool color = false, unsigned rotationLength = 0);
 

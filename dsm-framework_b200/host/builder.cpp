@@ -7,17 +7,21 @@
 #include "TextCollectionBuilder.h"
 
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <getopt.h>
 #include <iostream>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 
 namespace {
 
 bool g_verbose = false;
 bool g_samples = false; // --samples: also write <output>.sa (the reference's dormant FMIndex::saveSamples)
+bool g_host_parse = false; // --host-parse: the reference's per-read loop on the host instead of the GPU front end
 
 struct Clock
 {
@@ -82,7 +86,9 @@ void help(char const *name)
               << " -h, --help                    Display command line options." << std::endl
               << " -v, --verbose                 Print progress information." << std::endl
               << "     --samples                 Also write <output>.sa, the suffix array samples of" << std::endl
-              << "                               FMIndex::saveSamples (extension; off in the reference)." << std::endl;
+              << "                               FMIndex::saveSamples (extension; off in the reference)." << std::endl
+              << "     --host-parse              Parse and transform the reads on the host, one InsertText" << std::endl
+              << "                               per read as the reference does (default: on the GPU)." << std::endl;
 }
 
 int parse_int_at_least(char const *value, int min, char const *parameter, char const *name)
@@ -99,6 +105,112 @@ int parse_int_at_least(char const *value, int min, char const *parameter, char c
         std::exit(1);
     }
     return i;
+}
+
+// After the GPU front end reported symbols that normalize() turns into N: print the reference's warning
+// (builder.cpp:94-103) for the first such record, found by re-reading the rows around `offset` on the host.
+void warn_invalid(unsigned char const *text, size_t length, size_t offset, unsigned long records)
+{
+    size_t h = offset; // the header line of the record: the last line start at or before `offset` holding '>'
+    std::string name = "undef";
+    size_t body = 0;
+    while (true)
+    {
+        size_t ls = h;
+        while (ls > 0 && text[ls - 1] != '\n') --ls;
+        if (text[ls] == '>')
+        {
+            size_t e = ls;
+            while (e < length && text[e] != '\n') ++e;
+            std::string row((char const *)text + ls, e - ls);
+            row = row.substr(row.find_first_not_of(" \t", 1));
+            name = row.substr(0, row.find_first_of(" \t"));
+            body = e + 1;
+            break;
+        }
+        if (ls == 0) break;
+        h = ls - 1;
+    }
+    std::string offending;
+    for (size_t i = body; i < length; ++i)
+    {
+        if (text[i] == '>' && (i == 0 || text[i - 1] == '\n')) break;
+        if (text[i] == '\n') continue;
+        if (!kSym.valid[text[i]] && offending.find((char)text[i]) == std::string::npos) offending += (char)text[i];
+    }
+    std::cerr << "Warning: sequence " << name << " contains invalid symbol(s): " << offending << std::endl;
+    if (records > 1)
+        std::cerr << "Warning: " << records - 1 << " more sequence(s) in this part of the input contain invalid symbols"
+                  << " (all turned into N)" << std::endl;
+}
+
+// The record loop of build() below, run on the GPU: the file goes to the device in large pieces cut at header
+// lines, and TextCollectionBuilder::InsertFasta turns every record into its document there.
+void build_gpu_front_end(FILE *in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
+{
+    TextCollectionBuilder *tcb = new TextCollectionBuilder(samplerate, 1);
+    size_t cap = (size_t)512 << 20;
+    if (const char *e = std::getenv("DSMFM_FASTA_CHUNK_MB")) cap = std::max<size_t>(1, (size_t)std::atol(e)) << 20;
+    unsigned char *buf = (unsigned char *)TextCollectionBuilder::AllocPinned(cap);
+    if (!buf)
+    {
+        std::cerr << "builder: unable to allocate the input buffer" << std::endl;
+        std::exit(1);
+    }
+    size_t have = 0;
+    unsigned long bases = 0, records = 0;
+    bool eof = false;
+    while (!eof)
+    {
+        const size_t got = std::fread(buf + have, 1, cap - have, in);
+        have += got;
+        eof = got == 0 || std::feof(in);
+        TextCollectionBuilder::FastaReport r;
+        tcb->InsertFasta(buf, have, eof, r);
+        if (r.badHeaders) // row.substr(npos) in the reference's loop (builder.cpp:215)
+            throw std::out_of_range("basic_string::substr: header line without a name");
+        if (r.invalidRecords) warn_invalid(buf, eof ? have : r.consumed, r.firstInvalidOffset, r.invalidRecords);
+        bases += r.bases;
+        records += r.records;
+        if (g_verbose)
+            std::cerr << "Inserting: " << records << " sequences so far (" << bases / (1024 * 1024) << " MB, elapsed "
+                      << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)" << std::endl;
+        if (eof) break;
+        if (r.consumed == 0 && have == cap)
+        {
+            // one record larger than the buffer: grow it
+            unsigned char *bigger = (unsigned char *)TextCollectionBuilder::AllocPinned(cap * 2);
+            if (!bigger)
+            {
+                std::cerr << "builder: unable to grow the input buffer" << std::endl;
+                std::exit(1);
+            }
+            std::memcpy(bigger, buf, have);
+            TextCollectionBuilder::FreePinned(buf);
+            buf = bigger;
+            cap *= 2;
+            continue;
+        }
+        std::memmove(buf, buf + r.consumed, have - r.consumed);
+        have -= r.consumed;
+    }
+    TextCollectionBuilder::FreePinned(buf);
+
+    std::cerr << "Warning: not thread-safe" << std::endl;
+    if (g_verbose)
+        std::cerr << "Creating new index with " << records << " sequences, total " << bases << " bytes, "
+                  << bases / 1024 << " kb (elapsed " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)"
+                  << std::endl;
+    TextCollection *tc = tcb->InitTextCollection(false, false, 0);
+    delete tcb;
+    if (g_verbose)
+        std::cerr << tc->buildReport() << std::endl
+                  << "Saving to file " << outputfile << std::endl
+                  << "(total wall-clock time " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)"
+                  << std::endl;
+    tc->save(outputfile);
+    if (g_samples) tc->saveSamples(outputfile);
+    delete tc;
 }
 
 void build(std::istream &in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
@@ -180,6 +292,7 @@ int main(int argc, char **argv)
                                            {"help", no_argument, 0, 'h'},
                                            {"verbose", no_argument, 0, 'v'},
                                            {"samples", no_argument, 0, 1000},
+                                           {"host-parse", no_argument, 0, 1001},
                                            {0, 0, 0, 0}};
     int option_index = 0, c;
     // same option string as the reference (builder.cpp:353): -c, -R and -F are accepted by getopt
@@ -195,6 +308,7 @@ int main(int argc, char **argv)
             g_samples = true;
             setenv("DSMFM_KEEP_SA", "1", 1);
             break;
+        case 1001: g_host_parse = true; break;
         case '?': usage(argv[0]); return 1;
         default: usage(argv[0]); std::abort();
         }
@@ -214,14 +328,21 @@ int main(int argc, char **argv)
     const std::string inputfile = argv[optind++];
     std::string outputfile = optind != argc ? std::string(argv[optind++]) : inputfile; // ".fmi" is added by save()
 
+    if (std::getenv("DSMFM_HOST_PARSE")) g_host_parse = true;
     std::ifstream file;
     std::istream *in = &std::cin;
+    FILE *fin = stdin;
     if (inputfile != "-")
     {
-        file.open(inputfile.c_str());
-        in = &file;
+        if (g_host_parse)
+        {
+            file.open(inputfile.c_str());
+            in = &file;
+        }
+        else
+            fin = std::fopen(inputfile.c_str(), "rb");
     }
-    if (!in->good())
+    if (g_host_parse ? !in->good() : fin == 0)
     {
         std::cerr << "builder: unable to read input file " << inputfile << std::endl;
         return 1;
@@ -231,7 +352,10 @@ int main(int argc, char **argv)
     std::cerr.precision(2);
     Clock wall;
     if (g_verbose) std::cerr << "Building the forward index:" << std::endl;
-    build(*in, outputfile, samplerate, wall);
+    if (g_host_parse)
+        build(*in, outputfile, samplerate, wall);
+    else
+        build_gpu_front_end(fin, outputfile, samplerate, wall);
     if (g_verbose)
         std::cerr << "Skipping reverse indexing. Save complete. (total wall-clock time " << wall.seconds() << " s, "
                   << wall.seconds() / 3600 << " hours)" << std::endl;

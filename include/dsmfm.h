@@ -158,6 +158,29 @@ DSMFM_API int dsmfm_append_batch(dsmfm_builder *b, const uint8_t *docs, size_t b
  * resident in HBM); copied device-to-device on the builder's stream. */
 DSMFM_API int dsmfm_append_batch_device(dsmfm_builder *b, const void *docs_dev, size_t bytes);
 
+/* Replaces: the record loop and per-read transform of the reference CLI, build() in builder.cpp:203-262
+ * with normalize() (60-104) and transform() (183-201) -- SURVEY 8(f) row 3, the step in front of InsertText.
+ * `text` holds `len` bytes of a FASTA file (host memory).  On the device, every record with a non-empty
+ * sequence s becomes the document complement(s) + '-' + reverse(s) + '\0' and is appended to the
+ * collection in file order, exactly the bytes the reference's loop hands to InsertText: rows are split
+ * at '\n' only ('\r' stays in the sequence and is normalised to N like any other foreign symbol), rows
+ * in front of the first header form a record of their own, records without sequence are skipped.
+ * final != 0: everything is parsed; a last row without '\n' is dropped, as `getline(...).good()` drops it
+ * (builder.cpp:211).  final == 0 (streaming): only the bytes in front of the last header line are parsed,
+ * info->consumed says how many; present the rest again, followed by more input. */
+typedef struct dsmfm_fasta_info {
+    uint64_t consumed;             /* bytes of `text` this call has dealt with                            */
+    uint64_t records;              /* header lines seen                                                   */
+    uint64_t documents;            /* documents appended (records with a non-empty sequence)              */
+    uint64_t bases;                /* sequence symbols                                                    */
+    uint64_t doc_bytes;            /* bytes appended to the collection (documents incl. terminators)      */
+    uint64_t invalid_records;      /* records holding symbols outside ACGTNacgtn0123. (they become N)      */
+    uint64_t first_invalid_offset; /* offset in `text` of the first such symbol, ~0 if none               */
+    uint64_t bad_headers;          /* header lines with nothing but blanks after '>': the reference throws */
+                                   /* std::out_of_range on them (builder.cpp:215)                          */
+} dsmfm_fasta_info;
+DSMFM_API int dsmfm_append_fasta(dsmfm_builder *b, const uint8_t *text, size_t len, int final, dsmfm_fasta_info *info);
+
 /* Replaces: TextCollectionBuilder::InitTextCollection -> RLCSABuilder::getBWT
  * -> FMIndex::FMIndex -> makewavelet -> HuffWT::makeHuffWT -> BitRank::BuildRank
  * (TextCollectionBuilder.cpp:100-152; rlcsa_builder.cpp:166-179; FMIndex.cpp:92-123,
@@ -245,6 +268,11 @@ DSMFM_API int dsmfm_version(void);
  * same size allocates nothing).  This returns the cached memory of `device`
  * (-1 = all devices) to the system. */
 DSMFM_API int dsmfm_release_cached(int device);
+
+/* Page-locked host memory (cudaHostAlloc) for the buffers handed to dsmfm_append_batch / dsmfm_append_fasta:
+ * host-to-device copies from it run at the full PCIe rate.  NULL on failure. */
+DSMFM_API void *dsmfm_alloc_pinned(size_t bytes);
+DSMFM_API void dsmfm_free_pinned(void *p);
 
 /* ---- kernel-level entry points used by the unit tests (host buffers in/out) ---- */
 

@@ -39,9 +39,10 @@ def test_struct_layouts_match_the_header(tmp_path):
 #include <stddef.h>
 #include "dsmfm.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dsmfm_options), sizeof(dsmfm_code), sizeof(dsmfm_node),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dsmfm_options), sizeof(dsmfm_code), sizeof(dsmfm_node),
          sizeof(dsmfm_index), sizeof(dsmfm_stats), offsetof(dsmfm_index, codetable), offsetof(dsmfm_index, nodes),
-         offsetof(dsmfm_stats, ms_total), offsetof(dsmfm_stats, sort_pass_bytes));
+         offsetof(dsmfm_stats, ms_total), offsetof(dsmfm_stats, sort_pass_bytes), sizeof(dsmfm_fasta_info),
+         offsetof(dsmfm_fasta_info, bad_headers));
   return 0; }
 '''
     src = tmp_path / "layout.c"
@@ -51,7 +52,8 @@ int main(void) {
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(dsmfm.Options), C.sizeof(dsmfm.Code), C.sizeof(dsmfm.Node), C.sizeof(dsmfm.Index),
             C.sizeof(dsmfm.Stats), dsmfm.Index.codetable.offset, dsmfm.Index.nodes.offset,
-            dsmfm.Stats.ms_total.offset, dsmfm.Stats.sort_pass_bytes.offset]
+            dsmfm.Stats.ms_total.offset, dsmfm.Stats.sort_pass_bytes.offset, C.sizeof(dsmfm.FastaInfo),
+            dsmfm.FastaInfo.bad_headers.offset]
     assert got == want
 
 

@@ -244,6 +244,28 @@ def test_builder_cli_writes_the_reference_bytes(name, tmp_path):
     r = subprocess.run([exe, "-", str(tmp_path / "out")], input=_golden(name, ".fasta"), capture_output=True)
     assert r.returncode == 0, r.stderr
     assert open(str(tmp_path / "out.fmi"), "rb").read() == _golden(name, ".fmi")
+    # the reference's per-read loop on the host (one InsertText per read) instead of the GPU front end
+    r = subprocess.run([exe, "--host-parse", str(fa), str(tmp_path / "hp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(str(tmp_path / "hp.fmi"), "rb").read() == _golden(name, ".fmi")
+    if name in ("crlf", "multiline_and_blank"):
+        assert "contains invalid symbol(s)" in r.stderr
+
+
+def test_builder_cli_streams_the_input_in_pieces(tmp_path):
+    """A 1 MB input buffer (DSMFM_FASTA_CHUNK_MB) makes the CLI hand the file to the GPU front end in pieces cut at
+    header lines; the index must not depend on it."""
+    import dsmfm
+    import dsmgen
+    exe = os.path.join(ROOT, "dsm-framework_b200", "builder")
+    kw = dict(seed=5, pool_seed=5, pool_size=2, n_genomes=2, genome_len=20000, n_reads=40000, read_len=100, sub=0.005, pn=0.001)
+    fa = tmp_path / "s.fasta"
+    dsmgen.fasta(**kw).tofile(str(fa))
+    env = dict(os.environ, DSMFM_FASTA_CHUNK_MB="1")
+    r = subprocess.run([exe, "-v", str(fa)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stderr.count("Inserting:") >= 4
+    assert open(str(fa) + ".fmi", "rb").read() == dsmfm.build_fmi(dsmgen.docs(**kw))
 
 
 def test_builder_cli_samplerate(tmp_path):
