@@ -5,6 +5,7 @@
 // <=256-entry Huffman code table and the tree shape, and writes files.
 #include "../../include/dsmfm.h"
 #include "kernels.cuh"
+#include <thread>
 #include "fasta.cuh"
 #include "radix_sort.cuh"
 
@@ -38,6 +39,19 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 thread_local double g_alloc_ms = 0.0;
+
+// DSMFM_TRACE=1: wall-clock milestones of a process on stderr (cold-start costs -- context creation, first
+// device allocations, pinned buffers -- are invisible to the CUDA-event timers in dsmfm_stats)
+void trace(const char *what)
+{
+    static const bool on = std::getenv("DSMFM_TRACE") != nullptr;
+    if (!on) return;
+    static const double t0 = now_ms();
+    static double last = t0;
+    const double t = now_ms();
+    std::fprintf(stderr, "[dsmfm %9.1f ms +%8.1f] %s\n", t - t0, t - last, what);
+    last = t;
+}
 
 void *dev_alloc(size_t bytes, cudaStream_t st)
 {
@@ -375,11 +389,12 @@ PiecePlan plan_pieces(const WtShape &shape, const uint64_t *hist_all, uint32_t w
     return p;
 }
 
-void wavelet_fetch(cudaStream_t st, WaveletResult &r)
+// `ready`: a page-locked buffer of at least section_bytes acquired ahead of time (or nullptr)
+void wavelet_fetch(cudaStream_t st, WaveletResult &r, uint8_t *ready = nullptr)
 {
     const int m = r.shape.n_internal;
     if (m > 0) {
-        r.h_sections = static_cast<uint8_t *>(g_pinned.get(r.section_bytes));
+        r.h_sections = ready ? ready : static_cast<uint8_t *>(g_pinned.get(r.section_bytes));
         r.h_ch.resize(m);
         DSM_CUDA(cudaMemcpyAsync(r.h_sections, r.d_sections, r.section_bytes, cudaMemcpyDeviceToHost, st));
         DSM_CUDA(cudaMemcpyAsync(r.h_ch.data(), r.d_ch, (size_t)m, cudaMemcpyDeviceToHost, st));
@@ -514,6 +529,11 @@ struct dsmfm_builder {
 
     void release_device()
     {
+        if (host_prefetch.joinable()) {
+            host_prefetch.join();
+            g_pinned.put(host_ready);
+            host_ready = nullptr;
+        }
         for (auto &a : allocs) dev_free(a.first, stream);
         allocs.clear();
         chunks.clear();
@@ -527,6 +547,11 @@ struct dsmfm_builder {
     }
 
     uint32_t pre_launches = 0; // kernels launched before build() (the FASTA front end)
+    // Page-locking the host buffer of the sections costs ~0.4 s per GB the first time (later builds find it in
+    // the pool): a helper thread does it while the GPU sorts, as soon as the histogram fixes the size.
+    std::thread host_prefetch;
+    uint8_t *host_ready = nullptr;
+    size_t host_ready_bytes = 0;
     void append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info *info);
     void build();
     void fetch();
@@ -540,6 +565,7 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
 {
     cudaStream_t st = stream;
     uint32_t *L = &pre_launches;
+    trace("append_fasta: begin");
     uint8_t *d_text = static_cast<uint8_t *>(dmalloc(m + 64));
     DSM_CUDA(cudaMemcpyAsync(d_text, text, m, cudaMemcpyHostToDevice, st));
     const uint64_t ntiles = fasta_tiles(m);
@@ -559,6 +585,7 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     dfree(d_cs);
     dfree(d_ch);
     const uint64_t nseq = tot[0], nhdr = tot[1], nrec = nhdr + 1;
+    trace("append_fasta: text on the device, lines scanned");
 
     uint64_t *d_B = static_cast<uint64_t *>(dmalloc((nrec + 1) * 8));
     uint64_t *d_O = static_cast<uint64_t *>(dmalloc(nrec * 8));
@@ -601,6 +628,7 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     dfree(d_cnt);
     dfree(d_B);
     dfree(d_O);
+    trace("append_fasta: documents written");
     info->records = nhdr;
     info->documents = ndocs;
     info->bases = nseq;
@@ -624,6 +652,7 @@ void dsmfm_builder::build()
     DSM_CUDA(cudaEventCreate(&ev_pass0));
     DSM_CUDA(cudaEventCreate(&ev_pass1));
 
+    trace("build: begin");
     flush_stage();
     bool empty_collection = false;
     if (n == 0) { // TextCollectionBuilder.cpp:111-119: one empty text
@@ -733,6 +762,27 @@ void dsmfm_builder::build()
     for (int c = 1; c < 256; ++c)
         if (code_map[c]) inv_map[code_map[c]] = (uint8_t)c;
 
+    if (!sharded && !host_prefetch.joinable()) {
+        dsmfm_code tab[256];
+        WaveletResult probe;
+        if (build_codetable(counts, tab) <= 31) {
+            wavelet_prepare(tab, probe);
+            if (probe.shape.n_internal > 0) {
+                const size_t want = probe.section_bytes;
+                const int dev = device;
+                host_ready_bytes = want;
+                host_prefetch = std::thread([this, want, dev] {
+                    cudaSetDevice(dev);
+                    try {
+                        host_ready = static_cast<uint8_t *>(g_pinned.get(want));
+                    } catch (...) {
+                        host_ready = nullptr;
+                        host_ready_bytes = 0;
+                    }
+                });
+            }
+        }
+    }
     index.n = n;
     index.samplerate = samplerate;
     index.number_of_texts = (uint32_t)counts[0];
@@ -761,6 +811,7 @@ void dsmfm_builder::build()
     chunks.clear();
     d_raw = nullptr;
     DSM_CUDA(cudaEventRecord(ev[1], st));
+    trace("build: statistics done, pack launched");
 
     // ---- which suffixes this builder sorts ------------------------------------------------
     // Unsharded: all n, in one go.  Sharded: the collection is cut into `shard_count` key ranges of
@@ -825,6 +876,7 @@ void dsmfm_builder::build()
     uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(m_max * 8));
     uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
     uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
+    trace("build: sort buffers allocated");
     RadixWorkspace ws; // buffers owned by the builder's allocation list
     ws.status_tiles = div_up(m_max < kSweepPortion ? m_max : kSweepPortion, kSweepTile);
     ws.hist = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * kMaxPasses * kRadix));
@@ -921,6 +973,7 @@ void dsmfm_builder::build()
             return t;
         };
         uint64_t remaining = read_remaining();
+        trace("build: initial sort done");
 
         // ---- refinement rounds ------------------------------------------------------------
         // Suffixes that still agree on their first `depth` symbols are re-sorted by the next
@@ -1030,6 +1083,7 @@ void dsmfm_builder::build()
         if (d_sa_all) DSM_CUDA(cudaMemcpyAsync(d_sa_all + off, d_sorted_vals, m * 4, cudaMemcpyDeviceToDevice, st));
         DSM_CUDA(cudaEventRecord(evr[2], st));
         DSM_CUDA(cudaStreamSynchronize(st));
+        trace("build: refinement done");
         float ms;
         cudaEventElapsedTime(&ms, evr[0], evr[1]); ms_sort += ms;
         cudaEventElapsedTime(&ms, evr[1], evr[2]); ms_refine += ms;
@@ -1062,6 +1116,7 @@ void dsmfm_builder::build()
     }
     DSM_CUDA(cudaEventRecord(ev[5], st));
     DSM_CUDA(cudaStreamSynchronize(st));
+    trace("build: wavelet tree done");
 
     // ---- release what the sections do not need ---------------------------------------
     dfree(d_map);
@@ -1112,8 +1167,17 @@ void dsmfm_builder::fetch()
     cudaEvent_t e0, e1;
     DSM_CUDA(cudaEventCreate(&e0));
     DSM_CUDA(cudaEventCreate(&e1));
+    trace("fetch: begin");
     DSM_CUDA(cudaEventRecord(e0, stream));
-    wavelet_fetch(stream, wt);
+    uint8_t *ready = nullptr;
+    if (host_prefetch.joinable()) {
+        host_prefetch.join();
+        if (host_ready_bytes >= wt.section_bytes && wt.shape.n_internal > 0) ready = host_ready;
+        else g_pinned.put(host_ready);
+        host_ready = nullptr;
+    }
+    wavelet_fetch(stream, wt, ready);
+    trace("fetch: sections in host memory");
     if ((flags & DSMFM_FLAG_KEEP_BWT) && shard_count <= 1) {
         h_bwt = static_cast<uint8_t *>(g_pinned.get(index.n));
         DSM_CUDA(cudaMemcpyAsync(h_bwt, d_bwt, index.n, cudaMemcpyDeviceToHost, stream));
@@ -1254,6 +1318,7 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
 {
     if (!out) return DSMFM_EINVAL;
     *out = nullptr;
+    trace("dsmfm_create");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -1310,6 +1375,7 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
         delete b;
         return DSMFM_ECUDA;
     }
+    trace("dsmfm_create: device, pool and stream ready");
     *out = b;
     return DSMFM_OK;
 }
@@ -1765,6 +1831,7 @@ DSMFM_API int dsmfm_release_cached(int device)
 DSMFM_API void dsmfm_destroy(dsmfm_builder *b)
 {
     if (!b) return;
+    trace("destroy: begin");
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     b->release_device();
@@ -1775,6 +1842,7 @@ DSMFM_API void dsmfm_destroy(dsmfm_builder *b)
     }
     if (b->own_stream) cudaStreamDestroy(b->stream);
     delete b;
+    trace("destroy: done");
 }
 
 // ---- serialisation: FMIndex::save, FMIndex.cpp:155-217 ---------------------------------------
@@ -1860,11 +1928,13 @@ DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix)
     if (!idx || !path_prefix) return DSMFM_EINVAL;
     const std::string name = std::string(path_prefix) + ".fmi"; // TextCollection::FMINDEX_EXTENSION
     Sink s;
+    trace("write_fmi: begin");
     s.f = std::fopen(name.c_str(), "wb");
     if (!s.f) return DSMFM_EIO;
     serialize(idx, s);
     if (std::fflush(s.f) != 0) s.ok = false;
     std::fclose(s.f);
+    trace("write_fmi: file written");
     return s.ok ? DSMFM_OK : DSMFM_EIO;
 }
 

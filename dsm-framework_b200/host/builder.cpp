@@ -13,14 +13,18 @@
 #include <fstream>
 #include <getopt.h>
 #include <iostream>
+#include <condition_variable>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace {
 
 bool g_verbose = false;
 bool g_samples = false; // --samples: also write <output>.sa (the reference's dormant FMIndex::saveSamples)
+bool g_fast_exit = true;   // leave through _Exit once the files are written (DSMFM_ORDERLY_EXIT=1: normal teardown)
 bool g_host_parse = false; // --host-parse: the reference's per-read loop on the host instead of the GPU front end
 
 struct Clock
@@ -145,56 +149,157 @@ void warn_invalid(unsigned char const *text, size_t length, size_t offset, unsig
 }
 
 // The record loop of build() below, run on the GPU: the file goes to the device in large pieces cut at header
-// lines, and TextCollectionBuilder::InsertFasta turns every record into its document there.
+// lines, and TextCollectionBuilder::InsertFasta turns every record into its document there.  A reader thread
+// fills one buffer while the GPU works on the other -- and while the CUDA context comes up, which alone takes
+// longer than reading a gigabyte.
+struct Piece
+{
+    unsigned char *buf = 0;
+    size_t cap = 0, have = 0, use = 0; // bytes held / bytes in front of the last header line (all of them at eof)
+    bool eof = false;
+};
+
+class PieceReader
+{
+public:
+    PieceReader(FILE *in, size_t cap) : in_(in)
+    {
+        for (int i = 0; i < 2; ++i)
+        {
+            piece_[i].buf = (unsigned char *)std::malloc(cap);
+            piece_[i].cap = cap;
+            if (!piece_[i].buf)
+            {
+                std::cerr << "builder: unable to allocate the input buffer" << std::endl;
+                std::exit(1);
+            }
+        }
+        thread_ = std::thread([this] { run(); });
+    }
+    ~PieceReader()
+    {
+        thread_.join();
+        std::free(piece_[0].buf);
+        std::free(piece_[1].buf);
+    }
+    // the next piece, or 0 after the last one; the previous piece is released by this call
+    Piece *next()
+    {
+        std::unique_lock<std::mutex> lock(mu_);
+        if (taken_ >= 0)
+        {
+            busy_[taken_] = false;
+            taken_ = -1;
+            cv_.notify_all();
+        }
+        cv_.wait(lock, [this] { return ready_ >= 0 || done_; });
+        if (ready_ < 0) return 0;
+        taken_ = ready_;
+        ready_ = -1;
+        return &piece_[taken_];
+    }
+
+private:
+    void run()
+    {
+        int i = 0;
+        size_t carry = 0;
+        while (true)
+        {
+            Piece &p = piece_[i];
+            p.have = carry;
+            while (true)
+            {
+                const size_t got = std::fread(p.buf + p.have, 1, p.cap - p.have, in_);
+                p.have += got;
+                p.eof = got == 0 || std::feof(in_);
+                p.use = p.have;
+                if (p.eof) break;
+                // cut in front of the last header line: the record it opens may continue in the next piece
+                p.use = 0;
+                for (size_t k = p.have; k > 0;)
+                {
+                    const void *q = memrchr(p.buf, '>', k);
+                    if (!q) break;
+                    const size_t at = (size_t)((unsigned char const *)q - p.buf);
+                    if (at == 0 || p.buf[at - 1] == '\n')
+                    {
+                        p.use = at;
+                        break;
+                    }
+                    k = at;
+                }
+                if (p.use > 0) break;
+                // one record larger than the buffer: grow it and keep reading
+                unsigned char *bigger = (unsigned char *)std::realloc(p.buf, p.cap * 2);
+                if (!bigger)
+                {
+                    std::cerr << "builder: unable to grow the input buffer" << std::endl;
+                    std::exit(1);
+                }
+                p.buf = bigger;
+                p.cap *= 2;
+            }
+            carry = p.have - p.use;
+            Piece &other = piece_[i ^ 1];
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [&] { return !busy_[i ^ 1]; }); // the GPU is done with the other buffer
+            }
+            if (carry)
+            {
+                if (other.cap < carry + (p.cap >> 1))
+                {
+                    std::free(other.buf);
+                    other.cap = p.cap;
+                    other.buf = (unsigned char *)std::malloc(other.cap);
+                    if (!other.buf) std::exit(1);
+                }
+                std::memcpy(other.buf, p.buf + p.use, carry);
+            }
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [this] { return ready_ < 0; });
+                busy_[i] = true;
+                ready_ = i;
+                if (p.eof) done_ = true;
+                cv_.notify_all();
+                if (p.eof) return;
+            }
+            i ^= 1;
+        }
+    }
+
+    FILE *in_;
+    Piece piece_[2];
+    bool busy_[2] = {false, false};
+    int ready_ = -1, taken_ = -1;
+    bool done_ = false;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread thread_;
+};
+
 void build_gpu_front_end(FILE *in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
 {
-    TextCollectionBuilder *tcb = new TextCollectionBuilder(samplerate, 1);
-    size_t cap = (size_t)512 << 20;
+    size_t cap = (size_t)4 << 30; // virtual: only the pages a piece really fills are ever touched
     if (const char *e = std::getenv("DSMFM_FASTA_CHUNK_MB")) cap = std::max<size_t>(1, (size_t)std::atol(e)) << 20;
-    unsigned char *buf = (unsigned char *)TextCollectionBuilder::AllocPinned(cap);
-    if (!buf)
-    {
-        std::cerr << "builder: unable to allocate the input buffer" << std::endl;
-        std::exit(1);
-    }
-    size_t have = 0;
+    PieceReader reader(in, cap); // starts reading now, while the device context is created
+    TextCollectionBuilder *tcb = new TextCollectionBuilder(samplerate, 1);
     unsigned long bases = 0, records = 0;
-    bool eof = false;
-    while (!eof)
+    while (Piece *p = reader.next())
     {
-        const size_t got = std::fread(buf + have, 1, cap - have, in);
-        have += got;
-        eof = got == 0 || std::feof(in);
         TextCollectionBuilder::FastaReport r;
-        tcb->InsertFasta(buf, have, eof, r);
+        tcb->InsertFasta(p->buf, p->use, true, r); // a piece holds whole lines (except, at eof, the dropped last one)
         if (r.badHeaders) // row.substr(npos) in the reference's loop (builder.cpp:215)
             throw std::out_of_range("basic_string::substr: header line without a name");
-        if (r.invalidRecords) warn_invalid(buf, eof ? have : r.consumed, r.firstInvalidOffset, r.invalidRecords);
+        if (r.invalidRecords) warn_invalid(p->buf, p->use, r.firstInvalidOffset, r.invalidRecords);
         bases += r.bases;
         records += r.records;
         if (g_verbose)
             std::cerr << "Inserting: " << records << " sequences so far (" << bases / (1024 * 1024) << " MB, elapsed "
                       << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)" << std::endl;
-        if (eof) break;
-        if (r.consumed == 0 && have == cap)
-        {
-            // one record larger than the buffer: grow it
-            unsigned char *bigger = (unsigned char *)TextCollectionBuilder::AllocPinned(cap * 2);
-            if (!bigger)
-            {
-                std::cerr << "builder: unable to grow the input buffer" << std::endl;
-                std::exit(1);
-            }
-            std::memcpy(bigger, buf, have);
-            TextCollectionBuilder::FreePinned(buf);
-            buf = bigger;
-            cap *= 2;
-            continue;
-        }
-        std::memmove(buf, buf + r.consumed, have - r.consumed);
-        have -= r.consumed;
     }
-    TextCollectionBuilder::FreePinned(buf);
 
     std::cerr << "Warning: not thread-safe" << std::endl;
     if (g_verbose)
@@ -210,6 +315,7 @@ void build_gpu_front_end(FILE *in, std::string const &outputfile, unsigned sampl
                   << std::endl;
     tc->save(outputfile);
     if (g_samples) tc->saveSamples(outputfile);
+    if (g_fast_exit) return; // the process is about to end: tearing the index down would only cost time
     delete tc;
 }
 
@@ -329,6 +435,7 @@ int main(int argc, char **argv)
     std::string outputfile = optind != argc ? std::string(argv[optind++]) : inputfile; // ".fmi" is added by save()
 
     if (std::getenv("DSMFM_HOST_PARSE")) g_host_parse = true;
+    if (std::getenv("DSMFM_ORDERLY_EXIT")) g_fast_exit = false;
     std::ifstream file;
     std::istream *in = &std::cin;
     FILE *fin = stdin;
@@ -359,5 +466,13 @@ int main(int argc, char **argv)
     if (g_verbose)
         std::cerr << "Skipping reverse indexing. Save complete. (total wall-clock time " << wall.seconds() << " s, "
                   << wall.seconds() / 3600 << " hours)" << std::endl;
+    if (g_fast_exit)
+    {
+        // Everything is on disk (save() closed its files).  Unwinding the CUDA context -- tens of gigabytes of
+        // pooled device memory -- takes longer than the whole build; the OS reclaims it just the same.
+        std::cerr.flush();
+        std::fflush(0);
+        std::_Exit(0);
+    }
     return 0;
 }
