@@ -17,6 +17,9 @@
 //   ref_driver bwt  <docs> <out.bwt>      [threads] [buffer_bytes]
 //   ref_driver fmi  <docs> <out_prefix>   [threads] [buffer_bytes] [samplerate]
 //   ref_driver sa   <index.fmi> <out_prefix>
+//   ref_driver query <index.fmi> <queries.txt> <answers.txt>
+//        one query per line: "L <symbol code> <i>" -> TextCollection::LF(c, i)  (FMIndex.h:84-90)
+//                            "G <i>"               -> TextCollection::getL(i)   (FMIndex.h:99-102)
 // Timings go to stdout as one line "seconds_total=... seconds_bwt=...".
 #include "rlcsa_builder.h"
 #include "TextCollection.h"
@@ -110,6 +113,34 @@ int main(int argc, char **argv)
         tc->saveSamples(argv[3]);
         delete tc;
         std::printf("seconds_total=%.3f\n", now() - t0);
+        return 0;
+    }
+    if (mode == "query")
+    {
+        if (argc < 5) { std::fprintf(stderr, "query needs <index.fmi> <queries> <answers>\n"); return 2; }
+        TextCollection *tc = TextCollection::load(argv[2]);
+        FILE *q = std::fopen(argv[3], "r"), *a = std::fopen(argv[4], "w");
+        if (!q || !a) { std::perror("query files"); return 2; }
+        char op;
+        while (std::fscanf(q, " %c", &op) == 1)
+        {
+            unsigned long c = 0, i = 0;
+            if (op == 'L')
+            {
+                if (std::fscanf(q, "%lu %lu", &c, &i) != 2) return 2;
+                std::fprintf(a, "%lu\n", (unsigned long)tc->LF((uchar)c, (ulong)i));
+            }
+            else if (op == 'G')
+            {
+                if (std::fscanf(q, "%lu", &i) != 1) return 2;
+                std::fprintf(a, "%u\n", (unsigned)tc->getL((ulong)i));
+            }
+            else
+                return 2;
+        }
+        std::fclose(q);
+        std::fclose(a);
+        delete tc;
         return 0;
     }
     std::fprintf(stderr, "unknown mode %s\n", mode.c_str());

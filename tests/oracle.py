@@ -37,6 +37,18 @@ def lib():
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.dsm_oracle_free.argtypes = [C.c_void_p]
         L.dsm_oracle_free.restype = None
+        L.dsm_oracle_index_open.argtypes = [C.c_void_p, C.c_size_t]
+        L.dsm_oracle_index_open.restype = C.c_void_p
+        L.dsm_oracle_index_close.argtypes = [C.c_void_p]
+        L.dsm_oracle_index_close.restype = None
+        L.dsm_oracle_index_length.argtypes = [C.c_void_p]
+        L.dsm_oracle_index_length.restype = C.c_uint64
+        L.dsm_oracle_rank.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64]
+        L.dsm_oracle_rank.restype = C.c_uint64
+        L.dsm_oracle_lf.argtypes = [C.c_void_p, C.c_uint8, C.c_uint64]
+        L.dsm_oracle_lf.restype = C.c_uint64
+        L.dsm_oracle_access.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.dsm_oracle_access.restype = C.c_uint8
         _lib = L
     return _lib
 
@@ -59,6 +71,35 @@ def fasta_to_docs(fasta):
     rc = lib().dsm_oracle_fasta_to_docs(fasta, len(fasta), C.byref(out), C.byref(n), C.byref(nd))
     assert rc == 0
     return _take(out, n), nd.value
+
+
+class Index:
+    """The query side of a loaded .fmi as the consumers see it: FMIndex::LF / getL over HuffWT::rank / access."""
+
+    def __init__(self, fmi):
+        self._fmi = bytes(fmi)
+        self._h = lib().dsm_oracle_index_open(self._fmi, len(self._fmi))
+        assert self._h, "not an .fmi image"
+        self.n = lib().dsm_oracle_index_length(self._h)
+
+    def rank(self, c, i):
+        return lib().dsm_oracle_rank(self._h, c, i % 2**64)
+
+    def lf(self, c, i):
+        return lib().dsm_oracle_lf(self._h, c, i % 2**64)
+
+    def access(self, i):
+        r = C.c_uint64()
+        c = lib().dsm_oracle_access(self._h, i, C.byref(r))
+        return c, r.value
+
+    def close(self):
+        if self._h:
+            lib().dsm_oracle_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def bwt(text, want_sa=False):

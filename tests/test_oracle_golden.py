@@ -117,3 +117,61 @@ def test_oracle_sa_file_matches_live_reference(tmp_path):
     docs, _ = oracle.fasta_to_docs(fa)
     for rate in (6, 31):
         assert oracle.sa_file_from_docs(docs, rate) == oracle.reference_sa(fa, tmp_path, samplerate=rate)
+
+
+# ---- the query side: FMIndex::LF / getL as the mining client calls them ----------------
+
+QUERIES = json.load(open(os.path.join(GOLDEN, "queries.json")))
+
+
+@pytest.mark.parametrize("name", sorted(QUERIES["cases"]))
+def test_oracle_queries_match_the_reference(name):
+    """dsm_oracle_lf / dsm_oracle_access against the answers of the unmodified reference (tests/golden/queries.json,
+    made by tests/golden/make_query_golden.py through TextCollection::load + LF / getL)."""
+    q = QUERIES["cases"][name]
+    x = oracle.Index(_golden(name, ".fmi"))
+    assert x.n == q["n"]
+    for c, i, want in q["lf"]:
+        assert x.lf(c, i) == want, (c, i)
+    for i, want in q["getl"]:
+        assert x.access(i)[0] == want, i
+    x.close()
+
+
+@pytest.mark.parametrize("name", ["small_random", "mixed_alphabet", "poly_a", "duplicates"])
+def test_oracle_queries_match_plain_counting_over_the_bwt(name):
+    """rank(c, i) is the number of c in BWT[0..i]; access(i) is BWT[i] together with its rank."""
+    docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+    bwt = oracle.bwt(docs)
+    x = oracle.Index(_golden(name, ".fmi"))
+    assert x.n == len(bwt)
+    seen = {}
+    for i, c in enumerate(bwt):
+        seen[c] = seen.get(c, 0) + 1
+        assert x.access(i) == (c, seen[c])
+        if i % 7 == 0 or i + 1 == len(bwt):
+            for s in set(bwt):
+                assert x.rank(s, i) == seen.get(s, 0)
+    for s in set(bwt):
+        assert x.rank(s, -1) == 0
+    x.close()
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not present")
+def test_oracle_queries_match_live_reference(tmp_path):
+    import random
+    import subprocess
+    fasta = cases.rnd_fasta(77, 300, 80)
+    fmi = oracle.build(fasta)
+    (tmp_path / "x.fmi").write_bytes(fmi)
+    x = oracle.Index(fmi)
+    rng = random.Random(5)
+    qs = [("L", rng.choice(b"\0-ACGNT"), rng.randrange(x.n)) for _ in range(400)] + [("G", 0, rng.randrange(x.n)) for _ in range(200)]
+    (tmp_path / "q.txt").write_text("".join("L %d %d\n" % (c, i) if op == "L" else "G %d\n" % i for op, c, i in qs))
+    exe = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ref_driver")
+    subprocess.run([exe, "query", str(tmp_path / "x.fmi"), str(tmp_path / "q.txt"), str(tmp_path / "a.txt")], check=True,
+                   capture_output=True)
+    ans = [int(v) for v in (tmp_path / "a.txt").read_text().split()]
+    for (op, c, i), a in zip(qs, ans):
+        assert (x.lf(c, i) if op == "L" else x.access(i)[0]) == a
+    x.close()
