@@ -1,0 +1,525 @@
+// search.cu -- the query half of the index on the GPU (sm_100a): what the mining client asks of an .fmi.
+//
+// Replaces, for batches of queries, FMIndex::LF / getL (FMIndex.h:84-102) over HuffWT::rank / access
+// (HuffWT.h:66-83, 125-157) and BitRank::rank (BitRank.cpp:191-195) -- the only index operations
+// EnumerateQuery performs while it walks the suffix trie (Query.h:37-45, EnumerateQuery.cpp:39-58, 105-149).
+// The wavelet tree is used in the layout the builder writes and the reference loads (per internal node: bit
+// words, Rs per 256 bits, Rb per 64 bits), resident in HBM; one thread answers one query by walking the
+// Huffman code of its symbol from the root, three small reads per level.  Indices wrap like the reference's
+// unsigned longs: a rank "up to position -1" is 0 because BitRank::rank pre-increments its argument.
+#include "common.cuh"
+#include "../../include/dsmfm.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace dsmfm {
+
+namespace {
+
+struct QNode {
+    const uint64_t *data; // BitRank::data
+    const uint64_t *Rs;   // ones in front of every 256-bit superblock
+    const uint8_t *Rb;    // ones in front of every word inside its superblock
+    int32_t left, right;  // children in the node table
+    uint8_t leaf, ch;
+    uint8_t pad[6];
+};
+
+struct QIndex {
+    uint64_t n;
+    uint64_t C[257];     // C[256] = n: the reference reads C[c+1] (FMIndex.h:86)
+    uint32_t code[256];  // Huffman code of a symbol, first branch in bit 0
+    uint8_t present[256];
+    QNode nodes[512];
+};
+
+// ones among the first `cnt` bits = BitRank::rank(cnt - 1)
+__device__ __forceinline__ uint64_t ones_before(const QNode &nd, uint64_t cnt)
+{
+    return __ldg(nd.Rs + (cnt >> 8)) + __ldg(nd.Rb + (cnt >> 6)) +
+           (uint64_t)__popcll(__ldg(nd.data + (cnt >> 6)) & ((1ull << (cnt & 63)) - 1));
+}
+
+// HuffWT::rank(c, i): occurrences of c in [0, i]
+__device__ __forceinline__ uint64_t wt_rank(const QIndex *__restrict__ x, uint32_t c, uint64_t i)
+{
+    if (!x->present[c]) return 0;
+    uint64_t cnt = i + 1; // positions considered; 0 for i = (ulong)-1
+    uint32_t code = x->code[c];
+    const QNode *t = &x->nodes[0];
+    while (!t->leaf) {
+        const uint64_t r1 = ones_before(*t, cnt);
+        if (code & 1u) {
+            cnt = r1;
+            t = &x->nodes[t->right];
+        } else {
+            cnt -= r1;
+            t = &x->nodes[t->left];
+        }
+        code >>= 1;
+    }
+    return cnt;
+}
+
+// FMIndex::LF(c, i) = C[c] + rank_c(L, i)
+__device__ __forceinline__ uint64_t fm_lf(const QIndex *__restrict__ x, uint32_t c, uint64_t i)
+{
+    const uint64_t base = x->C[c];
+    if (x->C[c + 1] == base) return base;
+    return base + wt_rank(x, c, i);
+}
+
+__global__ void __launch_bounds__(256) search_rank_kernel(const QIndex *__restrict__ x, const uint8_t *__restrict__ c,
+                                                          const uint64_t *__restrict__ i, uint64_t *__restrict__ out,
+                                                          uint64_t count, int lf)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= count) return;
+    out[q] = lf ? fm_lf(x, c[q], i[q]) : wt_rank(x, c[q], i[q]);
+}
+
+// HuffWT::access(i, rank): the symbol at position i and the number of its occurrences in [0, i]
+__global__ void __launch_bounds__(256) search_access_kernel(const QIndex *__restrict__ x, const uint64_t *__restrict__ i,
+                                                            uint8_t *__restrict__ sym, uint64_t *__restrict__ rank,
+                                                            uint64_t count)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= count) return;
+    uint64_t p = i[q];
+    const QNode *t = &x->nodes[0];
+    while (!t->leaf) {
+        const bool bit = (__ldg(t->data + (p >> 6)) >> (p & 63)) & 1u;
+        const uint64_t r1 = ones_before(*t, p + 1);
+        if (bit) {
+            p = r1 - 1;
+            t = &x->nodes[t->right];
+        } else {
+            p = p - r1;
+            t = &x->nodes[t->left];
+        }
+    }
+    sym[q] = t->ch;
+    if (rank) rank[q] = p + 1;
+}
+
+// Query::pushChar for every symbol of a small alphabet at once (Query.h:37-45; EnumerateQuery.cpp:45-55):
+// [sp, ep] -> [LF(c, sp-1), LF(c, ep)-1]; an empty interval (sp > ep) is passed through unchanged.
+__global__ void __launch_bounds__(256) search_extend_kernel(const QIndex *__restrict__ x, const uint64_t *__restrict__ sp,
+                                                            const uint64_t *__restrict__ ep, uint64_t count,
+                                                            const uint8_t *__restrict__ symbols, uint32_t nsym,
+                                                            uint64_t *__restrict__ sp_out, uint64_t *__restrict__ ep_out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= count * nsym) return;
+    const uint64_t q = t / nsym;
+    const uint32_t c = symbols[t - q * nsym];
+    uint64_t lo = sp[q], hi = ep[q];
+    if (lo <= hi) {
+        lo = fm_lf(x, c, lo - 1);
+        hi = fm_lf(x, c, hi) - 1;
+    }
+    sp_out[t] = lo;
+    ep_out[t] = hi;
+}
+
+// backward search of whole patterns, last symbol first, from the interval of all suffixes
+__global__ void __launch_bounds__(256) search_count_kernel(const QIndex *__restrict__ x, const uint8_t *__restrict__ patterns,
+                                                           const uint64_t *__restrict__ offsets, uint64_t count,
+                                                           uint64_t *__restrict__ sp_out, uint64_t *__restrict__ ep_out)
+{
+    const uint64_t q = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (q >= count) return;
+    uint64_t lo = 0, hi = x->n - 1;
+    for (uint64_t k = offsets[q + 1]; k > offsets[q] && lo <= hi;) {
+        const uint32_t c = patterns[--k];
+        lo = fm_lf(x, c, lo - 1);
+        hi = fm_lf(x, c, hi) - 1;
+    }
+    sp_out[q] = lo;
+    ep_out[q] = hi;
+}
+
+std::string g_search_create_error;
+
+} // namespace
+} // namespace dsmfm
+
+using namespace dsmfm;
+
+struct dsmfm_searcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    QIndex *d_index = nullptr;
+    uint8_t *d_blob = nullptr;
+    size_t blob_bytes = 0;
+    uint64_t n = 0;
+    // staging for the host-pointer entry points, grown on demand
+    uint8_t *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    std::string err;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    uint8_t *stage(size_t bytes)
+    {
+        if (bytes > stage_bytes) {
+            if (d_stage) cudaFree(d_stage);
+            d_stage = nullptr;
+            stage_bytes = 0;
+            DSM_CUDA(cudaMalloc(&d_stage, bytes));
+            stage_bytes = bytes;
+        }
+        return d_stage;
+    }
+};
+
+namespace {
+
+size_t up8(size_t x) { return (x + 7) & ~(size_t)7; }
+
+// children of the pre-order node list
+int link_nodes(const dsmfm_node *nodes, uint32_t n_nodes, uint32_t &next, QIndex &q)
+{
+    if (next >= n_nodes || next >= 512) return -1;
+    const int me = (int)next++;
+    q.nodes[me].leaf = nodes[me].leaf;
+    q.nodes[me].ch = nodes[me].ch;
+    q.nodes[me].left = q.nodes[me].right = -1;
+    if (!nodes[me].leaf) {
+        const int l = link_nodes(nodes, n_nodes, next, q);
+        const int r = link_nodes(nodes, n_nodes, next, q);
+        if (l < 0 || r < 0) return -1;
+        q.nodes[me].left = l;
+        q.nodes[me].right = r;
+    }
+    return me;
+}
+
+int searcher_from_index(int device, const dsmfm_index *idx, dsmfm_searcher **out)
+{
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_search_create_error = "no CUDA device available (this library has no CPU fallback)";
+        return DSMFM_ECUDA;
+    }
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev) {
+        g_search_create_error = "device ordinal out of range";
+        return DSMFM_EINVAL;
+    }
+    if (!idx || !idx->nodes || idx->n_nodes == 0 || idx->n_nodes > 512) {
+        g_search_create_error = "index without a wavelet tree (or with more than 512 nodes)";
+        return DSMFM_EINVAL;
+    }
+    dsmfm_searcher *s = new (std::nothrow) dsmfm_searcher();
+    QIndex *q = new (std::nothrow) QIndex();
+    if (!s || !q) {
+        delete s;
+        delete q;
+        return DSMFM_ENOMEM;
+    }
+    std::memset(q, 0, sizeof *q);
+    s->device = device;
+    s->n = idx->n;
+    q->n = idx->n;
+    std::memcpy(q->C, idx->C, sizeof idx->C);
+    q->C[256] = idx->n;
+    for (int c = 0; c < 256; ++c) {
+        q->code[c] = idx->codetable[c].code;
+        q->present[c] = idx->codetable[c].count != 0;
+    }
+    uint32_t next = 0;
+    if (link_nodes(idx->nodes, idx->n_nodes, next, *q) < 0 || next != idx->n_nodes) {
+        g_search_create_error = "malformed wavelet tree";
+        delete s;
+        delete q;
+        return DSMFM_EINVAL;
+    }
+    size_t total = 0;
+    for (uint32_t i = 0; i < idx->n_nodes; ++i) {
+        const dsmfm_node &nd = idx->nodes[i];
+        if (nd.leaf) continue;
+        total += up8(8 * nd.integers) + up8(8 * (nd.nbits / 256 + 1)) + up8(nd.nbits / 64 + 1);
+    }
+    try {
+        DSM_CUDA(cudaSetDevice(device));
+        DSM_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        DSM_CUDA(cudaMalloc(&s->d_blob, total ? total : 8));
+        s->blob_bytes = total;
+        size_t off = 0;
+        for (uint32_t i = 0; i < idx->n_nodes; ++i) {
+            const dsmfm_node &nd = idx->nodes[i];
+            if (nd.leaf) continue;
+            const size_t b_data = 8 * nd.integers, b_rs = 8 * (nd.nbits / 256 + 1), b_rb = nd.nbits / 64 + 1;
+            DSM_CUDA(cudaMemcpyAsync(s->d_blob + off, nd.data, b_data, cudaMemcpyHostToDevice, s->stream));
+            q->nodes[i].data = reinterpret_cast<const uint64_t *>(s->d_blob + off);
+            off += up8(b_data);
+            DSM_CUDA(cudaMemcpyAsync(s->d_blob + off, nd.Rs, b_rs, cudaMemcpyHostToDevice, s->stream));
+            q->nodes[i].Rs = reinterpret_cast<const uint64_t *>(s->d_blob + off);
+            off += up8(b_rs);
+            DSM_CUDA(cudaMemcpyAsync(s->d_blob + off, nd.Rb, b_rb, cudaMemcpyHostToDevice, s->stream));
+            q->nodes[i].Rb = s->d_blob + off;
+            off += up8(b_rb);
+        }
+        DSM_CUDA(cudaMalloc(&s->d_index, sizeof(QIndex)));
+        DSM_CUDA(cudaMemcpyAsync(s->d_index, q, sizeof(QIndex), cudaMemcpyHostToDevice, s->stream));
+        DSM_CUDA(cudaStreamSynchronize(s->stream));
+    } catch (const CudaError &e) {
+        g_search_create_error = std::string("CUDA error: ") + cudaGetErrorString(e.code);
+        if (s->d_blob) cudaFree(s->d_blob);
+        if (s->d_index) cudaFree(s->d_index);
+        if (s->stream) cudaStreamDestroy(s->stream);
+        delete s;
+        delete q;
+        return e.code == cudaErrorMemoryAllocation ? DSMFM_ENOMEM : DSMFM_ECUDA;
+    }
+    delete q;
+    *out = s;
+    return DSMFM_OK;
+}
+
+unsigned grid_of(uint64_t threads) { return (unsigned)((threads + 255) / 256); }
+
+#define SEARCH_GUARD(s)                                       \
+    if (!(s)) return DSMFM_EINVAL;                            \
+    if (cudaSetDevice((s)->device) != cudaSuccess) return (s)->fail(DSMFM_ECUDA, "cudaSetDevice failed")
+
+} // namespace
+
+extern "C" {
+
+DSMFM_API int dsmfm_searcher_create(int device, const dsmfm_index *idx, dsmfm_searcher **out)
+{
+    if (!out) return DSMFM_EINVAL;
+    return searcher_from_index(device, idx, out);
+}
+
+// FMIndex::FMIndex(FILE *) (FMIndex.cpp:245-357), HuffWT::load (HuffWT.cpp:57-71, 201-207), BitRank::BitRank(FILE *)
+// (BitRank.cpp:111-132): only what the queries need -- n, C, the code table and the tree.
+DSMFM_API int dsmfm_searcher_open(int device, const char *fmi_path, dsmfm_searcher **out)
+{
+    if (!out || !fmi_path) return DSMFM_EINVAL;
+    *out = nullptr;
+    FILE *f = std::fopen(fmi_path, "rb");
+    if (!f) {
+        g_search_create_error = std::string("unable to open ") + fmi_path;
+        return DSMFM_EIO;
+    }
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> img((size_t)(sz > 0 ? sz : 0));
+    const bool ok = sz > 0 && std::fread(img.data(), 1, (size_t)sz, f) == (size_t)sz;
+    std::fclose(f);
+    const size_t head = 1 + 8 + 4 + 2048 + 8 + 4096;
+    if (!ok || img.size() < head + 2 || img[0] != 17) {
+        g_search_create_error = "not a version-17 .fmi file";
+        return DSMFM_EINVAL;
+    }
+    dsmfm_index idx;
+    std::memset(&idx, 0, sizeof idx);
+    size_t pos = 1;
+    std::memcpy(&idx.n, &img[pos], 8); pos += 8;
+    std::memcpy(&idx.samplerate, &img[pos], 4); pos += 4;
+    std::memcpy(idx.C, &img[pos], 2048); pos += 2048 + 8;
+    for (int c = 0; c < 256; ++c) {
+        std::memcpy(&idx.codetable[c].count, &img[pos], 8);
+        std::memcpy(&idx.codetable[c].bits, &img[pos + 8], 4);
+        std::memcpy(&idx.codetable[c].code, &img[pos + 12], 4);
+        pos += 16;
+    }
+    // the arrays sit at odd offsets in the file: aligned copies
+    std::vector<dsmfm_node> nodes;
+    std::vector<std::vector<uint64_t>> keep;
+    int open_children = 1;
+    while (open_children > 0) {
+        if (pos + 2 > img.size() || nodes.size() >= 512) {
+            g_search_create_error = "truncated .fmi file";
+            return DSMFM_EINVAL;
+        }
+        dsmfm_node nd;
+        std::memset(&nd, 0, sizeof nd);
+        nd.leaf = img[pos++] != 0;
+        nd.ch = img[pos++];
+        --open_children;
+        if (!nd.leaf) {
+            uint32_t b = 0, sf = 0;
+            if (pos + 24 > img.size()) return DSMFM_EINVAL;
+            std::memcpy(&nd.nbits, &img[pos], 8);
+            std::memcpy(&nd.integers, &img[pos + 8], 8);
+            std::memcpy(&b, &img[pos + 16], 4);
+            std::memcpy(&sf, &img[pos + 20], 4);
+            pos += 24;
+            const size_t b_data = 8 * nd.integers, b_rs = 8 * (nd.nbits / 256 + 1), b_rb = nd.nbits / 64 + 1;
+            if (b != 64 || sf != 256 || pos + b_data + b_rs + b_rb > img.size()) {
+                g_search_create_error = "malformed BitRank in the .fmi file";
+                return DSMFM_EINVAL;
+            }
+            for (size_t bytes : {b_data, b_rs, b_rb}) {
+                keep.emplace_back((bytes + 7) / 8 + 1);
+                std::memcpy(keep.back().data(), &img[pos], bytes);
+                pos += bytes;
+            }
+            nd.data = keep[keep.size() - 3].data();
+            nd.Rs = keep[keep.size() - 2].data();
+            nd.Rb = reinterpret_cast<const uint8_t *>(keep[keep.size() - 1].data());
+            open_children += 2;
+        }
+        nodes.push_back(nd);
+    }
+    idx.n_nodes = (uint32_t)nodes.size();
+    idx.nodes = nodes.data();
+    return searcher_from_index(device, &idx, out);
+}
+
+DSMFM_API uint64_t dsmfm_searcher_length(const dsmfm_searcher *s) { return s ? s->n : 0; }
+
+static int rank_or_lf(dsmfm_searcher *s, const uint8_t *c, const uint64_t *i, uint64_t *out, uint64_t count, int lf,
+                      bool on_device)
+{
+    SEARCH_GUARD(s);
+    if (count == 0) return DSMFM_OK;
+    if (!c || !i || !out) return s->fail(DSMFM_EINVAL, "null argument");
+    try {
+        if (on_device) {
+            search_rank_kernel<<<grid_of(count), 256, 0, s->stream>>>(s->d_index, c, i, out, count, lf);
+            DSM_LAUNCH_CHECK();
+            DSM_CUDA(cudaStreamSynchronize(s->stream));
+            return DSMFM_OK;
+        }
+        uint8_t *st = s->stage(count * 17 + 64);
+        uint64_t *d_i = reinterpret_cast<uint64_t *>(st), *d_o = d_i + count;
+        uint8_t *d_c = reinterpret_cast<uint8_t *>(d_o + count);
+        DSM_CUDA(cudaMemcpyAsync(d_i, i, count * 8, cudaMemcpyHostToDevice, s->stream));
+        DSM_CUDA(cudaMemcpyAsync(d_c, c, count, cudaMemcpyHostToDevice, s->stream));
+        search_rank_kernel<<<grid_of(count), 256, 0, s->stream>>>(s->d_index, d_c, d_i, d_o, count, lf);
+        DSM_LAUNCH_CHECK();
+        DSM_CUDA(cudaMemcpyAsync(out, d_o, count * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaStreamSynchronize(s->stream));
+    } catch (const CudaError &e) {
+        return s->fail(DSMFM_ECUDA, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_searcher_rank(dsmfm_searcher *s, const uint8_t *c, const uint64_t *i, uint64_t *out, uint64_t count)
+{
+    return rank_or_lf(s, c, i, out, count, 0, false);
+}
+
+DSMFM_API int dsmfm_searcher_lf(dsmfm_searcher *s, const uint8_t *c, const uint64_t *i, uint64_t *out, uint64_t count)
+{
+    return rank_or_lf(s, c, i, out, count, 1, false);
+}
+
+DSMFM_API int dsmfm_searcher_lf_device(dsmfm_searcher *s, const void *c_dev, const void *i_dev, void *out_dev, uint64_t count)
+{
+    return rank_or_lf(s, static_cast<const uint8_t *>(c_dev), static_cast<const uint64_t *>(i_dev),
+                      static_cast<uint64_t *>(out_dev), count, 1, true);
+}
+
+DSMFM_API int dsmfm_searcher_access(dsmfm_searcher *s, const uint64_t *i, uint8_t *sym, uint64_t *rank, uint64_t count)
+{
+    SEARCH_GUARD(s);
+    if (count == 0) return DSMFM_OK;
+    if (!i || !sym) return s->fail(DSMFM_EINVAL, "null argument");
+    for (uint64_t k = 0; k < count; ++k)
+        if (i[k] >= s->n) return s->fail(DSMFM_EINVAL, "position %llu is outside the index", (unsigned long long)i[k]);
+    try {
+        uint8_t *st = s->stage(count * 17 + 64);
+        uint64_t *d_i = reinterpret_cast<uint64_t *>(st), *d_r = d_i + count;
+        uint8_t *d_s = reinterpret_cast<uint8_t *>(d_r + count);
+        DSM_CUDA(cudaMemcpyAsync(d_i, i, count * 8, cudaMemcpyHostToDevice, s->stream));
+        search_access_kernel<<<grid_of(count), 256, 0, s->stream>>>(s->d_index, d_i, d_s, d_r, count);
+        DSM_LAUNCH_CHECK();
+        DSM_CUDA(cudaMemcpyAsync(sym, d_s, count, cudaMemcpyDeviceToHost, s->stream));
+        if (rank) DSM_CUDA(cudaMemcpyAsync(rank, d_r, count * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaStreamSynchronize(s->stream));
+    } catch (const CudaError &e) {
+        return s->fail(DSMFM_ECUDA, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_searcher_extend(dsmfm_searcher *s, const uint64_t *sp, const uint64_t *ep, uint64_t count,
+                                    const uint8_t *symbols, uint32_t nsym, uint64_t *sp_out, uint64_t *ep_out)
+{
+    SEARCH_GUARD(s);
+    if (count == 0 || nsym == 0) return DSMFM_OK;
+    if (!sp || !ep || !symbols || !sp_out || !ep_out) return s->fail(DSMFM_EINVAL, "null argument");
+    if (nsym > 256) return s->fail(DSMFM_EINVAL, "more than 256 symbols");
+    try {
+        const uint64_t total = count * nsym;
+        uint8_t *st = s->stage(16 * count + 16 * total + 256 + 64);
+        uint64_t *d_sp = reinterpret_cast<uint64_t *>(st), *d_ep = d_sp + count, *d_so = d_ep + count, *d_eo = d_so + total;
+        uint8_t *d_sym = reinterpret_cast<uint8_t *>(d_eo + total);
+        DSM_CUDA(cudaMemcpyAsync(d_sp, sp, count * 8, cudaMemcpyHostToDevice, s->stream));
+        DSM_CUDA(cudaMemcpyAsync(d_ep, ep, count * 8, cudaMemcpyHostToDevice, s->stream));
+        DSM_CUDA(cudaMemcpyAsync(d_sym, symbols, nsym, cudaMemcpyHostToDevice, s->stream));
+        search_extend_kernel<<<grid_of(total), 256, 0, s->stream>>>(s->d_index, d_sp, d_ep, count, d_sym, nsym, d_so, d_eo);
+        DSM_LAUNCH_CHECK();
+        DSM_CUDA(cudaMemcpyAsync(sp_out, d_so, total * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaMemcpyAsync(ep_out, d_eo, total * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaStreamSynchronize(s->stream));
+    } catch (const CudaError &e) {
+        return s->fail(DSMFM_ECUDA, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_searcher_count(dsmfm_searcher *s, const uint8_t *patterns, const uint64_t *offsets, uint64_t count,
+                                   uint64_t *sp_out, uint64_t *ep_out)
+{
+    SEARCH_GUARD(s);
+    if (count == 0) return DSMFM_OK;
+    if (!patterns || !offsets || !sp_out || !ep_out) return s->fail(DSMFM_EINVAL, "null argument");
+    try {
+        const uint64_t bytes = offsets[count];
+        uint8_t *st = s->stage(8 * (count + 1) + 16 * count + bytes + 64);
+        uint64_t *d_off = reinterpret_cast<uint64_t *>(st), *d_so = d_off + count + 1, *d_eo = d_so + count;
+        uint8_t *d_pat = reinterpret_cast<uint8_t *>(d_eo + count);
+        DSM_CUDA(cudaMemcpyAsync(d_off, offsets, (count + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        if (bytes) DSM_CUDA(cudaMemcpyAsync(d_pat, patterns, bytes, cudaMemcpyHostToDevice, s->stream));
+        search_count_kernel<<<grid_of(count), 256, 0, s->stream>>>(s->d_index, d_pat, d_off, count, d_so, d_eo);
+        DSM_LAUNCH_CHECK();
+        DSM_CUDA(cudaMemcpyAsync(sp_out, d_so, count * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaMemcpyAsync(ep_out, d_eo, count * 8, cudaMemcpyDeviceToHost, s->stream));
+        DSM_CUDA(cudaStreamSynchronize(s->stream));
+    } catch (const CudaError &e) {
+        return s->fail(DSMFM_ECUDA, "CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API const char *dsmfm_searcher_last_error(const dsmfm_searcher *s)
+{
+    return s ? s->err.c_str() : g_search_create_error.c_str();
+}
+
+DSMFM_API void dsmfm_searcher_destroy(dsmfm_searcher *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->d_stage) cudaFree(s->d_stage);
+    if (s->d_blob) cudaFree(s->d_blob);
+    if (s->d_index) cudaFree(s->d_index);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+} // extern "C"

@@ -122,6 +122,21 @@ def lib():
     L.dsmfm_pieces_bytes.restype = C.c_uint64
     L.dsmfm_build_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.dsmfm_assemble_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_void_p]
+    S = C.c_void_p
+    L.dsmfm_searcher_create.argtypes = [C.c_int, C.POINTER(Index), C.POINTER(S)]
+    L.dsmfm_searcher_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(S)]
+    L.dsmfm_searcher_length.argtypes = [S]
+    L.dsmfm_searcher_length.restype = C.c_uint64
+    L.dsmfm_searcher_rank.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.dsmfm_searcher_lf.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.dsmfm_searcher_lf_device.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.dsmfm_searcher_access.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.dsmfm_searcher_extend.argtypes = [S, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.dsmfm_searcher_count.argtypes = [S, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.dsmfm_searcher_last_error.argtypes = [S]
+    L.dsmfm_searcher_last_error.restype = C.c_char_p
+    L.dsmfm_searcher_destroy.argtypes = [S]
+    L.dsmfm_searcher_destroy.restype = None
     L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
     L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]
@@ -307,6 +322,93 @@ class Builder:
             self._L.dsmfm_destroy(self._h)
             self._h = C.c_void_p()
             self.index = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Searcher:
+    """The query half of an index on the GPU: batched FMIndex::LF / getL / interval extension (include/dsmfm.h)."""
+
+    def __init__(self, source, device=0):
+        """source: path of an .fmi file, or a Builder that has finished (its sections are uploaded)."""
+        import numpy as np
+        self._np = np
+        self._L = lib()
+        self._h = C.c_void_p()
+        if isinstance(source, (str, bytes, os.PathLike)):
+            rc = self._L.dsmfm_searcher_open(device, os.fsencode(source), C.byref(self._h))
+        else:
+            rc = self._L.dsmfm_searcher_create(device, C.byref(source.index), C.byref(self._h))
+        if rc != OK:
+            raise DsmfmError(rc, (self._L.dsmfm_searcher_last_error(None) or b"").decode())
+        self.n = self._L.dsmfm_searcher_length(self._h)
+
+    def _check(self, rc):
+        if rc != OK:
+            raise DsmfmError(rc, (self._L.dsmfm_searcher_last_error(self._h) or b"").decode())
+
+    def _ci(self, c, i):
+        np = self._np
+        i = np.ascontiguousarray(np.asarray(i, dtype=np.uint64))
+        c = np.ascontiguousarray(np.broadcast_to(np.asarray(c, dtype=np.uint8), i.shape))
+        return c, i, np.empty(i.shape, dtype=np.uint64)
+
+    def rank(self, c, i):
+        c, i, out = self._ci(c, i)
+        self._check(self._L.dsmfm_searcher_rank(self._h, c.ctypes.data, i.ctypes.data, out.ctypes.data, i.size))
+        return out
+
+    def lf(self, c, i):
+        c, i, out = self._ci(c, i)
+        self._check(self._L.dsmfm_searcher_lf(self._h, c.ctypes.data, i.ctypes.data, out.ctypes.data, i.size))
+        return out
+
+    def lf_device(self, c, i, out):
+        """torch tensors on the searcher's device: uint8 [count], int64/uint64 [count], int64/uint64 [count]"""
+        self._check(self._L.dsmfm_searcher_lf_device(self._h, c.data_ptr(), i.data_ptr(), out.data_ptr(), i.numel()))
+
+    def access(self, i):
+        np = self._np
+        i = np.ascontiguousarray(np.asarray(i, dtype=np.uint64))
+        sym, rank = np.empty(i.shape, dtype=np.uint8), np.empty(i.shape, dtype=np.uint64)
+        self._check(self._L.dsmfm_searcher_access(self._h, i.ctypes.data, sym.ctypes.data, rank.ctypes.data, i.size))
+        return sym, rank
+
+    def extend(self, sp, ep, symbols=b"ACGT"):
+        np = self._np
+        sp = np.ascontiguousarray(np.asarray(sp, dtype=np.uint64))
+        ep = np.ascontiguousarray(np.asarray(ep, dtype=np.uint64))
+        sym = np.frombuffer(bytes(symbols), dtype=np.uint8)
+        so, eo = np.empty((sp.size, sym.size), dtype=np.uint64), np.empty((sp.size, sym.size), dtype=np.uint64)
+        self._check(self._L.dsmfm_searcher_extend(self._h, sp.ctypes.data, ep.ctypes.data, sp.size, sym.ctypes.data,
+                                                  sym.size, so.ctypes.data, eo.ctypes.data))
+        return so, eo
+
+    def count(self, patterns):
+        """patterns: list of bytes -> (sp, ep) arrays; the pattern occurs ep - sp + 1 times if sp <= ep"""
+        np = self._np
+        off = np.zeros(len(patterns) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(p) for p in patterns])
+        blob = np.frombuffer(b"".join(patterns) + b"\0", dtype=np.uint8)
+        sp, ep = np.empty(len(patterns), dtype=np.uint64), np.empty(len(patterns), dtype=np.uint64)
+        self._check(self._L.dsmfm_searcher_count(self._h, blob.ctypes.data, off.ctypes.data, len(patterns),
+                                                 sp.ctypes.data, ep.ctypes.data))
+        return sp, ep
+
+    def close(self):
+        if self._h:
+            self._L.dsmfm_searcher_destroy(self._h)
+            self._h = C.c_void_p()
 
     def __enter__(self):
         return self

@@ -269,6 +269,38 @@ DSMFM_API int dsmfm_version(void);
  * (-1 = all devices) to the system. */
 DSMFM_API int dsmfm_release_cached(int device);
 
+/* ---- the query half of the index on the GPU -------------------------------------------
+ * Replaces, for batches of queries, what the mining client (metaenumerate, EnumerateQuery.cpp:39-58, 105-149;
+ * Query.h:37-45) asks of a loaded index: FMIndex::LF and getL (FMIndex.h:84-102) over HuffWT::rank / access
+ * (HuffWT.h:66-83, 125-157) and BitRank::rank (BitRank.cpp:191-195).  The wavelet tree stays in HBM in the
+ * layout of the .fmi file.  All arrays are HOST memory of `count` entries unless stated otherwise; positions
+ * wrap like the reference's unsigned longs (rank / LF at i = (uint64_t)-1 count nothing). */
+typedef struct dsmfm_searcher dsmfm_searcher;
+/* from the sections dsmfm_finish / dsmfm_fetch returned (uploads them) */
+DSMFM_API int dsmfm_searcher_create(int device, const dsmfm_index *idx, dsmfm_searcher **out);
+/* Replaces: TextCollection::load -> FMIndex::FMIndex(FILE *) (TextCollection.cpp:27-62; FMIndex.cpp:245-357;
+ * HuffWT.cpp:57-71, 201-207; BitRank.cpp:111-132) for what the queries need: n, C, code table, tree. */
+DSMFM_API int dsmfm_searcher_open(int device, const char *fmi_path, dsmfm_searcher **out);
+DSMFM_API uint64_t dsmfm_searcher_length(const dsmfm_searcher *s);
+/* out[k] = HuffWT::rank(c[k], i[k]): occurrences of c[k] in BWT[0 .. i[k]] */
+DSMFM_API int dsmfm_searcher_rank(dsmfm_searcher *s, const uint8_t *c, const uint64_t *i, uint64_t *out, uint64_t count);
+/* out[k] = FMIndex::LF(c[k], i[k]) = C[c] + rank_c(i) */
+DSMFM_API int dsmfm_searcher_lf(dsmfm_searcher *s, const uint8_t *c, const uint64_t *i, uint64_t *out, uint64_t count);
+/* the same with DEVICE arrays on the searcher's device (no copies; for measuring the kernel) */
+DSMFM_API int dsmfm_searcher_lf_device(dsmfm_searcher *s, const void *c_dev, const void *i_dev, void *out_dev, uint64_t count);
+/* sym[k] = FMIndex::getL(i[k]); rank[k] (may be NULL) = its rank, as HuffWT::access(i, rank) returns it */
+DSMFM_API int dsmfm_searcher_access(dsmfm_searcher *s, const uint64_t *i, uint8_t *sym, uint64_t *rank, uint64_t count);
+/* Query::pushChar for every symbol of `symbols` at once: interval k extended to the left by symbols[j] is
+ * [sp_out, ep_out][k * nsym + j] = [LF(c, sp-1), LF(c, ep)-1]; empty intervals (sp > ep) pass through. */
+DSMFM_API int dsmfm_searcher_extend(dsmfm_searcher *s, const uint64_t *sp, const uint64_t *ep, uint64_t count,
+                                    const uint8_t *symbols, uint32_t nsym, uint64_t *sp_out, uint64_t *ep_out);
+/* backward search of whole patterns (pattern k = patterns[offsets[k] .. offsets[k+1])), last symbol first, from
+ * the interval of all suffixes: [sp, ep] of its occurrences, sp > ep if there are none */
+DSMFM_API int dsmfm_searcher_count(dsmfm_searcher *s, const uint8_t *patterns, const uint64_t *offsets, uint64_t count,
+                                   uint64_t *sp_out, uint64_t *ep_out);
+DSMFM_API const char *dsmfm_searcher_last_error(const dsmfm_searcher *s);
+DSMFM_API void dsmfm_searcher_destroy(dsmfm_searcher *s);
+
 /* Page-locked host memory (cudaHostAlloc) for the buffers handed to dsmfm_append_batch / dsmfm_append_fasta:
  * host-to-device copies from it run at the full PCIe rate.  NULL on failure. */
 DSMFM_API void *dsmfm_alloc_pinned(size_t bytes);
