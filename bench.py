@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the FASTA front-end and query-side measurements (N=1)")
     ap.add_argument("--ranges-per-gpu", type=int, default=1, help="N>1: key ranges sorted one after the other per GPU")
     return ap.parse_args()
 
@@ -180,6 +181,73 @@ def run_reference(args):
             "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+def fasta_front_end(args, kw, local, stream, torch, dsmfm, dsmgen):
+    """The path of the drop-in CLI: FASTA bytes in pinned host memory -> dsmfm_append_fasta (record loop, normalize and
+    transform on the GPU) -> dsmfm_finish (sections in host memory).  Same workload, same metric."""
+    import numpy as np
+    fa = dsmgen.fasta(**kw)
+    host = torch.empty(fa.size, dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:] = fa
+    del fa
+    bases = kw["n_reads"] * kw["read_len"]
+
+    def step():
+        b = dsmfm.Builder(device=local, stream=stream.cuda_stream)
+        info = b.append_fasta(host)
+        b.finish()
+        s = b.stats()
+        b.close()
+        return info, s
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    steps = max(2, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        info, s = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(bases / dt / 1e6, 2), "unit": "Mbp/s", "ms_per_step": round(1000 * dt, 2),
+            "fasta_bytes_per_step": int(host.numel()), "documents": int(info["documents"]),
+            "api": "dsmfm_create / dsmfm_append_fasta (pinned host buffer, parsed on the GPU) / dsmfm_finish / dsmfm_destroy",
+            "gpu_launches_per_step": int(s.kernel_launches), "build_device_ms": round(s.ms_total, 2),
+            "build_wall_ms": round(s.ms_wall_build, 2), "alloc_wall_ms": round(s.ms_wall_alloc, 2),
+            "fetch_wall_ms": round(s.ms_wall_fetch, 2)}
+
+
+def query_side(host_docs, local, stream, torch, dsmfm):
+    """dsmfm_searcher_lf_device on the index of the workload: random (symbol, position) LF queries, device arrays,
+    CUDA events.  Every query walks the Huffman code of its symbol: per level one 8-byte Rs, one 1-byte Rb and one
+    8-byte bit word, each a random access to HBM."""
+    b = dsmfm.Builder(device=local, stream=stream.cuda_stream)
+    b.append_batch(host_docs)
+    b.finish()
+    s = dsmfm.Searcher(b, device=local)
+    n = s.n
+    b.close()
+    m = 1 << 26
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    qi = torch.randint(0, n, (m,), dtype=torch.int64, device="cuda", generator=g)
+    qc = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")[torch.randint(0, 4, (m,), device="cuda", generator=g)]
+    out = torch.empty(m, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        s.lf_device(qc, qi, out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        s.lf_device(qc, qi, out)  # runs on the searcher's stream and waits for it
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    s.close()
+    return {"value": round(m / ms / 1e6, 3), "unit": "G LF queries/s", "queries_per_launch": m, "ms_per_launch": round(ms, 3),
+            "index_symbols": int(n), "api": "dsmfm_searcher_lf_device (FMIndex::LF over HuffWT::rank, one thread per query)"}
 
 
 def main():
@@ -390,13 +458,17 @@ def main():
     ref_ms = sum(s.ms_refine for s in stats) / len(stats)
     ref_ach = ref_bytes / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else 0.0
     line["roofline_refine"] = {
-        "bound": "hbm", "kernel": "refine_kernel (%d launch(es) per build; all tie groups resolved in shared memory, keys "
-                                  "gathered from the packed text)" % s0.refine_launches,
+        "bound": "hbm", "kernel": "refine_warps_kernel (%d launch(es) per build; every warp resolves the tie groups of its part "
+                                  "of a 1024-slot window in shared memory, keys gathered from the packed text)" % s0.refine_launches,
         "achieved": round(ref_ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ref_ach / peak, 4),
         "algorithmic_bytes_per_launch": ref_bytes // max(1, s0.refine_launches),
         "ms_per_launch": round(ref_ms / max(1, s0.refine_launches), 3),
         "keys_gathered": s0.refine_key_fetches, "traffic": profile.get("refine_dram_bytes_per_launch"),
         "traffic_note": profile.get("refine_note")}
+
+    if world == 1 and not args.no_extras:
+        line["fasta_e2e"] = fasta_front_end(args, kw, local, stream, torch, dsmfm, dsmgen)
+        line["search"] = query_side(host_docs, local, stream, torch, dsmfm)
 
     if world == 1 and not args.no_cpu_baseline:
         import tempfile
