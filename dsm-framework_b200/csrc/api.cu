@@ -888,6 +888,7 @@ void dsmfm_builder::build()
     uint32_t *d_head[2];
     d_head[0] = static_cast<uint32_t *>(dmalloc(hwords * 4));
     d_head[1] = static_cast<uint32_t *>(dmalloc(hwords * 4));
+    uint32_t *d_diff = static_cast<uint32_t *>(dmalloc(hwords * 4)); // see launch_heads
     // [0,64): suffixes left in groups of >= 2; [64,128): keys the refinement gathered from the text
     unsigned long long *d_remaining = static_cast<unsigned long long *>(dmalloc(128 * 8));
     const uint32_t big_cap = (uint32_t)(m_max / kRefGroupMaxWarps + 2);
@@ -913,6 +914,10 @@ void dsmfm_builder::build()
     // the one-depth-per-launch schedule, used by the tests to exercise the worklist path)
     bool multi_step = true;
     if (const char *e = std::getenv("DSMFM_REFINE_SINGLE_STEP")) multi_step = std::atoi(e) == 0;
+    // The index needs the BWT, not the suffix array: tie groups whose members share one BWT symbol stay unsorted
+    // unless the suffix array itself is wanted (DSMFM_FLAG_KEEP_SA; DSMFM_REFINE_FULL_ORDER=1 forces it).
+    bool full_order = keep_sa;
+    if (const char *e = std::getenv("DSMFM_REFINE_FULL_ORDER")) full_order = full_order || std::atoi(e) != 0;
     int key_words = 1; // symbols compared per step = key_words * SPW (DSMFM_REFINE_KEY_WORDS=2: 128-bit keys)
     if (const char *e = std::getenv("DSMFM_REFINE_KEY_WORDS")) key_words = std::atoi(e) == 2 ? 2 : 1;
 
@@ -959,8 +964,9 @@ void dsmfm_builder::build()
 
         DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 128 * 8, st));
         const uint64_t hw = head_words_for(m);
+        const bool use_diff = carry_bwt && !full_order;
         launch_heads(st, bits, d_sorted_keys, m, d_head[0], hw, d_remaining, key_bits, d_inv,
-                     carry_bwt ? bwt_out : nullptr, hi_out, hi_shift, L);
+                     carry_bwt ? bwt_out : nullptr, hi_out, hi_shift, use_diff ? d_diff : nullptr, L);
         DSM_CUDA(cudaEventRecord(evr[1], st));
 
         auto read_remaining = [&]() -> uint64_t {
@@ -1004,7 +1010,8 @@ void dsmfm_builder::build()
             ++stats.refine_launches;
             launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
                           d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                          carry_bwt ? bwt_out : nullptr, multi_step, key_words, hi_out, lo_bits, L);
+                          carry_bwt ? bwt_out : nullptr, multi_step, key_words, hi_out, lo_bits, full_order,
+                          (use_diff && round == 1) ? d_diff : nullptr, L);
             uint32_t nbig = 0;
             DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
             remaining = read_remaining();
@@ -1126,6 +1133,7 @@ void dsmfm_builder::build()
     dfree(d_keys_b);
     dfree(d_head[0]);
     dfree(d_head[1]);
+    dfree(d_diff);
     dfree(d_remaining);
     dfree(d_big_heads);
     dfree(d_big_len);

@@ -574,7 +574,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
                                                     uint32_t *__restrict__ head, uint64_t head_words,
                                                     unsigned long long *__restrict__ remaining, int key_bits,
                                                     const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt,
-                                                    uint8_t *__restrict__ pos_hi, int hi_shift)
+                                                    uint8_t *__restrict__ pos_hi, int hi_shift,
+                                                    uint32_t *__restrict__ diff)
 {
     __shared__ unsigned long long s_cnt[8];
     __shared__ uint8_t s_inv[256];
@@ -584,28 +585,53 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t warps_total = (uint64_t)gridDim.x * 8;
     unsigned long long active = 0;
-    for (uint64_t w = (uint64_t)blockIdx.x * 8 + warp; w < head_words; w += warps_total) {
-        const uint64_t i = w * 32 + lane;
-        bool h = true, act = false;
-        if (i < n) {
-            const uint64_t kraw = keys[i];
-            const uint64_t k = kraw & kmask;
-            h = (i == 0) || key_terminated<BITS>(k) || (keys[i - 1] & kmask) != k;
-            bool hn = true;
-            if (i + 1 < n) {
-                const uint64_t kn = keys[i + 1] & kmask;
-                hn = key_terminated<BITS>(kn) || kn != k;
-            }
-            act = !(h && hn);
-            // the symbol before suffix i rode along above the sorted bits (make_keys_kernel)
-            if (bwt) bwt[i] = s_inv[(kraw >> key_bits) & Pack<BITS>::FIELD];
-            if (pos_hi) pos_hi[i] = (uint8_t)(kraw >> hi_shift); // high part of the text position (wide builds)
+    // four head words (128 keys) per warp and iteration: the twelve loads of a lane are issued back to back
+    constexpr int U = 4;
+    for (uint64_t w0 = ((uint64_t)blockIdx.x * 8 + warp) * U; w0 < head_words; w0 += warps_total * U) {
+        uint64_t kraw[U], kprev[U], knext[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = (w0 + u) * 32 + lane;
+            kraw[u] = i < n ? keys[i] : 0ull;
+            // neighbours come from the neighbouring lanes; only the two ends of the warp's 32 keys load them
+            kprev[u] = (lane == 0 && i > 0 && i < n) ? keys[i - 1] : 0ull;
+            knext[u] = (lane == 31 && i + 1 < n) ? keys[i + 1] : 0ull;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, h);
-        const uint32_t aw = __ballot_sync(0xffffffffu, act);
-        if (lane == 0) {
-            head[w] = word;
-            active += __popc(aw);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t up = __shfl_up_sync(0xffffffffu, kraw[u], 1), dn = __shfl_down_sync(0xffffffffu, kraw[u], 1);
+            if (lane != 0) kprev[u] = up;
+            if (lane != 31) knext[u] = dn;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t w = w0 + u;
+            if (w >= head_words) break; // warp-uniform
+            const uint64_t i = w * 32 + lane;
+            bool h = true, act = false, df = false;
+            if (i < n) {
+                const uint64_t k = kraw[u] & kmask;
+                h = (i == 0) || key_terminated<BITS>(k) || (kprev[u] & kmask) != k;
+                // inside a group: does the symbol in front of this suffix differ from its predecessor's?
+                df = !h && (((kraw[u] ^ kprev[u]) >> key_bits) & Pack<BITS>::FIELD) != 0;
+                bool hn = true;
+                if (i + 1 < n) {
+                    const uint64_t kn = knext[u] & kmask;
+                    hn = key_terminated<BITS>(kn) || kn != k;
+                }
+                act = !(h && hn);
+                // the symbol before suffix i rode along above the sorted bits (make_keys_kernel)
+                if (bwt) bwt[i] = s_inv[(kraw[u] >> key_bits) & Pack<BITS>::FIELD];
+                if (pos_hi) pos_hi[i] = (uint8_t)(kraw[u] >> hi_shift); // high part of the text position (wide builds)
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, h);
+            const uint32_t aw = __ballot_sync(0xffffffffu, act);
+            const uint32_t dw = diff ? __ballot_sync(0xffffffffu, df) : 0u;
+            if (lane == 0) {
+                head[w] = word;
+                if (diff) diff[w] = dw;
+                active += __popc(aw);
+            }
         }
     }
     if (lane == 0) s_cnt[warp] = active;
@@ -926,17 +952,26 @@ template <int KW, bool WIDE> struct RwSmem {
     uint8_t hi[2][WIDE ? kRwCap : 1];  // wide builds: text position = hi << lo_bits | sa
     uint32_t head_a[kRwCap / 32 + 2];
     uint32_t head_b[kRwCap / 32 + 2];
+    uint32_t mix[kRwCap / 32 + 2];     // per group head: the group's members carry different BWT symbols
+    uint32_t df[kRwCap / 32 + 2];      // per slot: BWT symbol differs from the predecessor's inside a group
+    uint32_t act[kRwCap / 32 + 2];     // per slot: member of a group that has to be sorted
     int range[2];
 };
 
-template <int BITS, int KW, bool WIDE>
+// ORDER = false: only the BWT is wanted, not the suffix array.  Then a tie group whose members all carry the
+// same BWT symbol needs no sorting at all -- whatever their order, the BWT bytes of its slots are that symbol --
+// and such groups are the rule in read collections: suffixes that agree on their next 16+ symbols mostly come
+// from reads overlapping the same stretch of a genome, and they agree on the symbol in front of it too.  Only
+// groups with mixed symbols are loaded and refined, and a group that becomes uniform after a split is dropped
+// at once.  (ORDER = true, DSMFM_FLAG_KEEP_SA: the full order, as needed for the .sa samples.)
+template <int BITS, int KW, bool WIDE, bool ORDER>
 __global__ void __launch_bounds__(kRefThreads, 4)
 refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
                     uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
                     uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
                     unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
                     uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint8_t *__restrict__ bwt,
-                    uint8_t *__restrict__ sa_hi, int lo_bits)
+                    uint8_t *__restrict__ sa_hi, int lo_bits, const uint32_t *__restrict__ diff_bits)
 {
     using P = Pack<BITS>;
     constexpr int HW = kRwCap / 32 + 2;
@@ -951,7 +986,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
     uint32_t(*s_sa)[kRwCap] = S.sa;
     uint8_t(*s_bw)[kRwCap] = S.bw;
     uint8_t(*s_hi)[WIDE ? kRwCap : 1] = S.hi;
-    uint32_t *s_ha = S.head_a, *s_hb = S.head_b;
+    uint32_t *s_ha = S.head_a, *s_hb = S.head_b, *s_mix = S.mix, *s_df = S.df, *s_act = S.act;
     int *s_range = S.range;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -962,6 +997,11 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         const uint32_t h = head_cur[w0 + i];
         s_ha[i] = h;
         s_hb[i] = h;
+        s_mix[i] = 0;
+        if (!ORDER) {
+            s_act[i] = 0;
+            s_df[i] = diff_bits ? diff_bits[w0 + i] : 0u;
+        }
     }
     __syncthreads();
 
@@ -1044,7 +1084,60 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         }
     };
 
-    // load the suffixes (and their BWT bytes) that sit in groups of >= 2, and their first keys
+    // bits of this warp's range in head word i
+    auto range_mask = [&](int i) -> uint32_t {
+        const int lo = ws > (i << 5) ? ws - (i << 5) : 0, hi = (we - 1) - (i << 5) < 31 ? (we - 1) - (i << 5) : 31;
+        return (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
+    };
+    auto mixed = [&](int g) -> bool { return (s_mix[g >> 5] >> (g & 31)) & 1u; };
+
+    if (!ORDER) {
+        // Which groups hold more than one BWT symbol.  After the initial sort the answer is in diff_bits (one
+        // bit per slot whose symbol differs from its predecessor's in the same group, written by heads_kernel
+        // while the symbols were in registers); later launches compare the bytes.
+        if (diff_bits) {
+            for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) {
+                uint32_t dw = s_df[i] & range_mask(i);
+                while (dw) {
+                    const int g = prev_set_le(s_ha, (i << 5) + __ffs(dw) - 1);
+                    dw &= dw - 1;
+                    atomicOr(&s_mix[g >> 5], 1u << (g & 31));
+                }
+            }
+        } else {
+            for (int r = ws + lane; r < we; r += 32) {
+                const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
+                const bool h1 = (s_ha[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+                if (!(h0 && h1)) s_bw[0][r] = bwt[win + r];
+            }
+            __syncwarp();
+            for (int r = ws + lane; r < we; r += 32) {
+                const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
+                const bool h1 = (s_ha[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
+                if (!(h0 && h1) && !h0) { // a member behind its group's head
+                    const int g = prev_set_le(s_ha, r);
+                    if (s_bw[0][r] != s_bw[0][g]) atomicOr(&s_mix[g >> 5], 1u << (g & 31));
+                }
+            }
+        }
+        __syncwarp();
+        // the slots of those groups
+        for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) {
+            uint32_t mw = s_mix[i] & range_mask(i);
+            while (mw) {
+                const int g = (i << 5) + __ffs(mw) - 1;
+                mw &= mw - 1;
+                const int e = next_set_gt(s_ha, g); // one behind the group's last slot
+                for (int w = g >> 5; w <= (e - 1) >> 5; ++w) {
+                    const int lo = g > (w << 5) ? g - (w << 5) : 0, hi = (e - 1) - (w << 5) < 31 ? (e - 1) - (w << 5) : 31;
+                    atomicOr(&s_act[w], (0xffffffffu << lo) & (0xffffffffu >> (31 - hi)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // load the suffixes (and their BWT bytes) that sit in groups that have to be sorted, and their first keys
     uint32_t d = depth;
     int cnt = 0;
     for (int b0 = ws; b0 < we; b0 += 128) {
@@ -1059,7 +1152,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
             if (r < we) {
                 const bool h0 = (s_ha[r >> 5] >> (r & 31)) & 1u;
                 const bool h1 = (s_ha[(r + 1) >> 5] >> ((r + 1) & 31)) & 1u;
-                act = !(h0 && h1);
+                act = ORDER ? !(h0 && h1) : ((s_act[r >> 5] >> (r & 31)) & 1u);
             }
             slot[u] = act ? r : -1;
             sv[u] = 0;
@@ -1125,6 +1218,17 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
             list[i] = (uint16_t)p;       // where this suffix went
         }
         __syncwarp();
+        if (!ORDER) {
+            // which of the new groups still hold more than one BWT symbol
+            for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) atomicAnd(&s_mix[i], ~range_mask(i));
+            __syncwarp();
+            for (int i = lane; i < cnt; i += 32) {
+                const int p = list[i];
+                const int g = prev_set_le(s_hb, p);
+                if (g != p && s_bw[c ^ 1][p] != s_bw[c ^ 1][g]) atomicOr(&s_mix[g >> 5], 1u << (g & 31));
+            }
+            __syncwarp();
+        }
         // classify: resolved suffixes go home now; the rest stay on the list (compacted in place: an entry
         // is written at or before the position it was read from, and a warp reads 32 entries before it writes)
         d += KW * P::SPW;
@@ -1137,6 +1241,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 const bool h0 = (s_hb[p >> 5] >> (p & 31)) & 1u;
                 const bool h1 = (s_hb[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u;
                 again = !(h0 && h1);
+                if (!ORDER && again) again = mixed(prev_set_le(s_hb, p));
                 if (!again) {
                     sa[win + p] = s_sa[c ^ 1][p];
                     if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
@@ -1167,9 +1272,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         }
         // publish the new heads of this range (bits only ever get set; neighbours' bits are left alone)
         for (int i = (ws >> 5) + lane; i <= ((we - 1) >> 5); i += 32) {
-            const int lo = ws > (i << 5) ? ws - (i << 5) : 0, hi = (we - 1) - (i << 5) < 31 ? (we - 1) - (i << 5) : 31;
-            const uint32_t mask = (0xffffffffu << lo) & (0xffffffffu >> (31 - hi));
-            const uint32_t add = s_hb[i] & mask & ~s_ha[i];
+            const uint32_t add = s_hb[i] & range_mask(i) & ~s_ha[i];
             if (add) atomicOr(&s_ha[i], add);
         }
         c ^= 1;
@@ -1825,11 +1928,11 @@ void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n
 
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
                   uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
-                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *launches)
+                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *diff, uint32_t *launches)
 {
 #define CALL(B)                                                                                                 \
     heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
-                                                                  key_bits, inv_map, bwt, pos_hi, hi_shift)
+                                                                  key_bits, inv_map, bwt, pos_hi, hi_shift, diff)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
@@ -1840,7 +1943,8 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   int key_words, uint8_t *sa_hi, int lo_bits, uint32_t *launches)
+                   int key_words, uint8_t *sa_hi, int lo_bits, bool full_order, const uint32_t *diff_bits,
+                   uint32_t *launches)
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
     const int max_steps = multi_step ? (1 << 30) : 1;
@@ -1865,19 +1969,27 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
     if (multi_step && variant == 2) {
         static bool attr3_set = false;
         if (!attr3_set) {
-#define SET3(B, K)                                                                                               \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)sizeof(RwSmem<K, false>)));                                               \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+#define SET3(B, K)                                                                                                      \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)sizeof(RwSmem<K, false>)));                                                      \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)sizeof(RwSmem<K, true>)));                                                       \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)sizeof(RwSmem<K, false>)));                                                      \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                   (int)sizeof(RwSmem<K, true>)))
             SET3(3, 1); SET3(4, 1); SET3(8, 1); SET3(3, 2); SET3(4, 2); SET3(8, 2);
 #undef SET3
             attr3_set = true;
         }
-#define RW(B, K, W)                                                                                               \
-    refine_warps_kernel<B, K, W><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                                \
+#define RW2(B, K, W, O)                                                                                           \
+    refine_warps_kernel<B, K, W, O><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                             \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \
-        win_next, win_next_count, bwt, sa_hi, lo_bits)
+        win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits)
+#define RW(B, K, W)                                                                                               \
+    do {                                                                                                          \
+        if (full_order || !bwt) RW2(B, K, W, true); else RW2(B, K, W, false);                                     \
+    } while (0)
 #define CALL3(B)                                                                                                  \
     do {                                                                                                          \
         if (key_words == 2) {                                                                                     \
@@ -1889,6 +2001,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
         DISPATCH_BITS(bits, CALL3);
 #undef CALL3
 #undef RW
+#undef RW2
         DSM_LAUNCH_CHECK();
         if (launches) ++*launches;
         return;

@@ -56,10 +56,11 @@ void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n
 // array through the refinement, like the BWT bytes do.
 
 // Only the low key_bits of a key are compared.  If bwt != nullptr, bwt[i] = inv_map[code carried above
-// the key bits] is written for every rank i.
+// the key bits] is written for every rank i.  diff (optional, head_words words): bit i = suffix i is not a
+// group head and the carried symbol differs from that of suffix i-1, i.e. its group holds mixed BWT symbols.
 void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64_t n, uint32_t *head,
                   uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
-                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *launches);
+                  uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *diff, uint32_t *launches);
 
 constexpr int kRefThreads = 256;
 constexpr int kRefWindow = 1024;   // group heads owned by one CTA lie in a window of this many slots
@@ -79,12 +80,16 @@ inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32
 // (one per rank) are permuted together with the suffix array.  With multi_step a CTA keeps
 // extending the keys (depth += SPW) until every group it owns is resolved, so that one launch
 // finishes everything except the groups that do not fit a CTA.  key_words = 1 or 2: a step compares
-// SPW or 2*SPW symbols (64- or 128-bit keys).
+// SPW or 2*SPW symbols (64- or 128-bit keys).  full_order = false (default schedule, needs bwt): groups whose
+// members all carry the same BWT symbol are left as they are -- their order cannot change the BWT -- so the
+// suffix array is then only sorted as far as the BWT needs it.  diff_bits: launch_heads' bitmap while it is
+// still valid (first launch after the initial sort), nullptr afterwards (the kernel then compares the bytes).
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
-                   int key_words, uint8_t *sa_hi, int lo_bits, uint32_t *launches);
+                   int key_words, uint8_t *sa_hi, int lo_bits, bool full_order, const uint32_t *diff_bits,
+                   uint32_t *launches);
 
 // Large-group path, step 1: length of each listed group (distance to the next head).
 void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,

@@ -53,6 +53,32 @@ def test_radix_sort_matches_stable_numpy_sort(n, bits):
     assert np.array_equal(k, keys[order])
 
 
+@pytest.mark.parametrize("bits", [(0, 48), (0, 24), (0, 60), (3, 39), (12, 48)])
+@pytest.mark.parametrize("n,dna", [(1, True), (4097, True), (1_000_003, True), (600_000, False)])
+def test_radix_sort_key_widths_of_the_build(n, dna, bits):
+    """The key widths the build uses (48 bits = 16 three-bit symbols, and the other multiples of a symbol), on
+    DNA-like keys (few digit values, long runs) and on random keys."""
+    import dsmfm
+    rng = np.random.default_rng(n + bits[1])
+    if dna:
+        sym = rng.choice(np.array([0, 1, 2, 3, 4, 5, 6], dtype=np.uint64), size=(n, 21), p=[.02, .02, .235, .235, .235, .02, .235])
+        keys = np.zeros(n, dtype=np.uint64)
+        for j in range(21):
+            keys = (keys << np.uint64(3)) | sym[:, j]
+    else:
+        keys = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    if n > 1000:
+        keys[: n // 4] = keys[0]
+    vals = np.arange(n, dtype=np.uint32)
+    lo, hi = bits
+    mask = np.uint64(((1 << (hi - lo)) - 1) << lo)
+    order = np.argsort(keys & mask, kind="stable")
+    k, v = keys.copy(), vals.copy()
+    dsmfm.radix_sort(k, v, lo, hi)
+    assert np.array_equal(v, vals[order])
+    assert np.array_equal(k, keys[order])
+
+
 def test_radix_sort_dna_like_keys():
     """3-bit symbols, only 5 of 8 codes in use: the skewed digit histograms of the real workload."""
     import dsmfm
