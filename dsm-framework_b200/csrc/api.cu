@@ -981,6 +981,78 @@ void dsmfm_builder::build()
         uint64_t remaining = read_remaining();
         trace("build: initial sort done");
 
+        // What the refinement works on: the suffix array itself or, in BWT-only builds, dense copies of the groups
+        // whose members carry different BWT symbols (kernels.cu, "compaction of the groups that have to be sorted").
+        uint32_t *r_sa = d_sorted_vals;
+        uint32_t *r_head[2] = {d_head[0], d_head[1]};
+        uint8_t *r_bwt = carry_bwt ? bwt_out : nullptr;
+        uint8_t *r_hi = hi_out;
+        uint64_t r_m = m, r_hw = hw;
+        const uint32_t *r_diff = use_diff ? d_diff : nullptr;
+        uint32_t *c_sa = nullptr, *c_orig = nullptr, *c_head[2] = {nullptr, nullptr};
+        uint8_t *c_bw = nullptr, *c_hi = nullptr;
+        uint64_t m_act = 0;
+        static const bool compact_off = [] {
+            const char *e = std::getenv("DSMFM_REFINE_COMPACT");
+            return e && std::atoi(e) == 0;
+        }();
+        const bool compact = use_diff && multi_step && !compact_off && remaining > 0;
+        bool c_owned = false; // the dense arrays are allocations of their own (else: carved out of a key buffer)
+        if (compact) {
+            // scratch of the compaction: the key buffers of the initial sort are free from here on (the large-group
+            // path, their only other user, starts later and never needs more than 8 bytes per dense entry)
+            const uint64_t ntile = active_tiles(div_up(m, 32));
+            uint32_t *d_act = reinterpret_cast<uint32_t *>(d_keys_a);
+            uint64_t *d_tile = reinterpret_cast<uint64_t *>(d_keys_a) + (hw + 1) / 2;
+            const bool scratch_fits = (hw + 1) / 2 + ntile + 1 <= m_max;
+            if (!scratch_fits) {
+                d_act = static_cast<uint32_t *>(dmalloc(hw * 4));
+                d_tile = static_cast<uint64_t *>(dmalloc((ntile + 1) * 8));
+            }
+            DSM_CUDA(cudaMemsetAsync(d_act, 0, hw * 4, st));
+            launch_mark_active(st, d_head[0], d_diff, m, d_act, d_tile, L);
+            DSM_CUDA(cudaMemcpyAsync(&m_act, d_tile + ntile, 8, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            stats.refine_members += m_act;
+            if (m_act == 0) {
+                remaining = 0; // every tie group carries a single BWT symbol
+            } else if (m_act * 2 > remaining) {
+                m_act = 0; // most members have to be sorted anyway (high repetition): refine in place
+            } else {
+                r_m = m_act;
+                r_hw = head_words_for(m_act);
+                auto up16 = [](uint64_t x) { return (x + 15) & ~(uint64_t)15; };
+                const uint64_t b_sa = up16(m_act * 4 + 16), b_bw = up16(m_act + 16), b_hi = wide ? up16(m_act + 16) : 0,
+                               b_head = up16(r_hw * 4);
+                const uint64_t need = 2 * b_sa + b_bw + b_hi + 2 * b_head;
+                // the upper part of the second key buffer, above what the large-group path can touch
+                uint8_t *base = reinterpret_cast<uint8_t *>(d_keys_b) + up16(m_act * 8);
+                c_owned = up16(m_act * 8) + need > m_max * 8;
+                if (c_owned) base = static_cast<uint8_t *>(dmalloc(need));
+                c_sa = reinterpret_cast<uint32_t *>(base);
+                c_orig = reinterpret_cast<uint32_t *>(base + b_sa);
+                c_bw = base + 2 * b_sa;
+                c_hi = wide ? base + 2 * b_sa + b_bw : nullptr;
+                c_head[0] = reinterpret_cast<uint32_t *>(base + 2 * b_sa + b_bw + b_hi);
+                c_head[1] = reinterpret_cast<uint32_t *>(base + 2 * b_sa + b_bw + b_hi + b_head);
+                DSM_CUDA(cudaMemsetAsync(c_head[0], 0, r_hw * 4, st));
+                launch_compact_active(st, d_act, d_head[0], m, d_tile, d_sorted_vals, bwt_out, hi_out, m_act, c_sa, c_bw,
+                                      c_hi, c_orig, c_head[0], r_hw, L);
+                r_sa = c_sa;
+                r_head[0] = c_head[0];
+                r_head[1] = c_head[1];
+                r_bwt = c_bw;
+                r_hi = c_hi;
+                r_diff = nullptr;
+            }
+            if (!scratch_fits) {
+                dfree(d_act);
+                dfree(d_tile);
+            }
+        } else if (remaining > 0) {
+            stats.refine_members += remaining;
+        }
+
         // ---- refinement rounds ------------------------------------------------------------
         // Suffixes that still agree on their first `depth` symbols are re-sorted by the next
         // SPW symbols taken straight from the packed text.  (The reference re-keys with the
@@ -992,7 +1064,7 @@ void dsmfm_builder::build()
         uint32_t depth_next = (uint32_t)first_syms; // symbols every unresolved group is known to agree on
         const uint32_t max_rounds = (uint32_t)(maxgap / spw + 4);
         // windows that still own unresolved groups: all of them in the first round, a compact list afterwards
-        const uint32_t nwin = (uint32_t)div_up(m, kRefWindow);
+        const uint32_t nwin = (uint32_t)div_up(r_m, kRefWindow);
         const uint32_t *win_list = nullptr;
         uint32_t n_list = nwin;
         int wl = 0;
@@ -1002,23 +1074,22 @@ void dsmfm_builder::build()
             if (round < 32) stats.active[round] += remaining;
             ++round;
             const uint32_t depth = depth_next;
-            DSM_CUDA(cudaMemcpyAsync(d_head[cur ^ 1], d_head[cur], hw * 4, cudaMemcpyDeviceToDevice, st));
+            DSM_CUDA(cudaMemcpyAsync(r_head[cur ^ 1], r_head[cur], r_hw * 4, cudaMemcpyDeviceToDevice, st));
             DSM_CUDA(cudaMemsetAsync(d_remaining, 0, 128 * 8, st));
             DSM_CUDA(cudaMemsetAsync(d_big_count, 0, 4, st));
             DSM_CUDA(cudaMemsetAsync(d_win_flag, 0, (size_t)nwin * 4, st));
             DSM_CUDA(cudaMemsetAsync(d_win_count, 0, 4, st));
             ++stats.refine_launches;
-            launch_refine(st, bits, d_packed, d_sorted_vals, d_head[cur], d_head[cur ^ 1], m, depth, win_list, n_list,
+            launch_refine(st, bits, d_packed, r_sa, r_head[cur], r_head[cur ^ 1], r_m, depth, win_list, n_list,
                           d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                          carry_bwt ? bwt_out : nullptr, multi_step, key_words, hi_out, lo_bits, full_order,
-                          (use_diff && round == 1) ? d_diff : nullptr, L);
+                          r_bwt, multi_step, key_words, r_hi, lo_bits, full_order, round == 1 ? r_diff : nullptr, L);
             uint32_t nbig = 0;
             DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
             remaining = read_remaining();
             if (nbig > 0) {
                 // groups too large for one CTA: one global (group, key) radix sort over all of them
                 if (nbig > big_cap) throw CudaError{cudaErrorUnknown, "large-group list overflow", __FILE__, __LINE__};
-                launch_big_extent(st, d_head[cur], m, d_big_heads, nbig, d_big_len, L);
+                launch_big_extent(st, r_head[cur], r_m, d_big_heads, nbig, d_big_len, L);
                 std::vector<uint32_t> heads(nbig), lens(nbig);
                 DSM_CUDA(cudaMemcpyAsync(heads.data(), d_big_heads, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
                 DSM_CUDA(cudaMemcpyAsync(lens.data(), d_big_len, (size_t)nbig * 4, cudaMemcpyDeviceToHost, st));
@@ -1044,8 +1115,8 @@ void dsmfm_builder::build()
                 uint8_t *d_bhi = wide ? static_cast<uint8_t *>(dmalloc(total + 16)) : nullptr;
                 DSM_CUDA(cudaMemcpyAsync(d_big_heads, sheads.data(), (size_t)nbig * 4, cudaMemcpyHostToDevice, st));
                 DSM_CUDA(cudaMemcpyAsync(d_off, offs.data(), (size_t)(nbig + 1) * 8, cudaMemcpyHostToDevice, st));
-                launch_big_gather(st, bits, d_packed, d_sorted_vals, depth, d_big_heads, d_off, nbig, total, d_bsa,
-                                  d_bkey, d_bgid, hi_out, d_bhi, lo_bits, L);
+                launch_big_gather(st, bits, d_packed, r_sa, depth, d_big_heads, d_off, nbig, total, d_bsa,
+                                  d_bkey, d_bgid, r_hi, d_bhi, lo_bits, L);
                 // the key buffers of the initial sort are free by now
                 DSM_CUDA(cudaMemcpyAsync(d_keys_a, d_bkey, total * 8, cudaMemcpyDeviceToDevice, st));
                 int p1 = radix_sort_pairs(st, ws, d_keys_a, d_other_vals, d_keys_b, d_perm, total, 0, full_key_bits, true, L);
@@ -1061,9 +1132,9 @@ void dsmfm_builder::build()
                     int p2 = radix_sort_pairs(st, ws, k2a, pres, k2b, pfree, total, 0, gbits, false, L);
                     if (p2 & 1) std::swap(pres, pfree);
                 }
-                launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, d_sorted_vals,
-                                   d_head[cur ^ 1], d_win_flag, d_win_list[wl], d_win_count, d_packed, d_inv,
-                                   carry_bwt ? bwt_out : nullptr, d_bhi, hi_out, lo_bits, L);
+                launch_big_scatter(st, bits, pres, d_bsa, d_bkey, d_bgid, d_big_heads, d_off, total, r_sa,
+                                   r_head[cur ^ 1], d_win_flag, d_win_list[wl], d_win_count, d_packed, d_inv,
+                                   r_bwt, d_bhi, r_hi, lo_bits, L);
                 DSM_CUDA(cudaStreamSynchronize(st)); // sheads / offs are host vectors
                 dfree(d_off);
                 dfree(d_bsa);
@@ -1083,6 +1154,10 @@ void dsmfm_builder::build()
             cur ^= 1;
             if (remaining > 0 && n_list == 0)
                 throw CudaError{cudaErrorUnknown, "unresolved groups without an owning window (internal error)", __FILE__, __LINE__};
+        }
+        if (compact && m_act) { // the BWT bytes of the sorted groups go back to their slots
+            launch_scatter_bwt(st, c_orig, c_bw, m_act, bwt_out, L);
+            if (c_owned) dfree(c_sa);
         }
         rounds_max = std::max(rounds_max, round);
         // ---- BWT when it could not ride along (64-bit first keys, unsharded only) -----------

@@ -1288,6 +1288,148 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------
+// compaction of the groups that have to be sorted
+// ---------------------------------------------------------------------------
+// When only the BWT is wanted, most tie groups need no sorting (see refine_warps_kernel, ORDER = false) and
+// a refinement that visits every window of the suffix array spends its time finding out that there is
+// little to do.  The groups with mixed BWT symbols are therefore copied out first, in order, into dense
+// arrays (suffix, BWT byte, high position byte, original slot, group heads); the refinement runs on those
+// as on a much shorter suffix array, and only the BWT bytes are copied back to their slots afterwards.
+constexpr int kActTileWords = 256; // head words per CTA in the compaction passes (8192 slots)
+
+// act bit i = slot i belongs to a group holding a diff bit; act is zeroed by the caller.
+__global__ void __launch_bounds__(256) mark_active_kernel(const uint32_t *__restrict__ head, const uint32_t *__restrict__ diff,
+                                                          uint64_t nwords, uint32_t *__restrict__ act)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= nwords) return;
+    uint32_t dw = diff[t];
+    uint64_t done_to = 0; // slots below this are already marked by this thread
+    while (dw) {
+        const int b = __ffs(dw) - 1;
+        dw &= dw - 1;
+        const uint64_t slot = t * 32 + b;
+        if (slot < done_to) continue; // same group as the previous diff bit
+        // group head: last head bit at or before slot (a diff bit is never a head itself)
+        uint64_t w = t;
+        uint32_t m = head[w] & (0xffffffffu >> (31 - b));
+        while (m == 0) m = head[--w];
+        const uint64_t g = w * 32 + (31 - __clz(m));
+        // one behind its last slot: first head bit after slot
+        w = t;
+        m = b == 31 ? 0u : (head[w] & (0xffffffffu << (b + 1)));
+        while (m == 0) m = head[++w];
+        const uint64_t e = w * 32 + (__ffs(m) - 1);
+        for (uint64_t x = g >> 5; x <= (e - 1) >> 5; ++x) {
+            const int lo = g > (x << 5) ? (int)(g - (x << 5)) : 0;
+            const int hi = (e - 1) - (x << 5) < 31 ? (int)((e - 1) - (x << 5)) : 31;
+            atomicOr(&act[x], (0xffffffffu << lo) & (0xffffffffu >> (31 - hi)));
+        }
+        done_to = e;
+    }
+}
+
+__global__ void __launch_bounds__(256) count_active_kernel(const uint32_t *__restrict__ act, uint64_t nwords,
+                                                           uint64_t *__restrict__ tile_count)
+{
+    __shared__ uint32_t s_w[8];
+    const uint64_t t = (uint64_t)blockIdx.x * kActTileWords + threadIdx.x;
+    uint32_t c = t < nwords ? __popc(act[t]) : 0u;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < 8; ++k) tot += s_w[k];
+        tile_count[blockIdx.x] = tot;
+    }
+}
+
+// exclusive scan of u64 counts in place, total behind the last entry; one block
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t *__restrict__ v, uint64_t n)
+{
+    __shared__ uint64_t scratch[33];
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t x = i < n ? v[i] : 0;
+        uint64_t total;
+        const uint64_t e = block_excl_sum(x, scratch, &total);
+        if (i < n) v[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) v[n] = carry;
+}
+
+// The active slots, in order, into dense arrays.  chead must be zeroed; its bit j is set iff compact entry j
+// starts a group, and every bit from m_act on is set (what heads_kernel does behind the last suffix).
+__global__ void __launch_bounds__(256)
+compact_active_kernel(const uint32_t *__restrict__ act, const uint32_t *__restrict__ head, uint64_t nwords,
+                      const uint64_t *__restrict__ tile_off, const uint32_t *__restrict__ sa, const uint8_t *__restrict__ bwt,
+                      const uint8_t *__restrict__ sa_hi, uint32_t *__restrict__ csa, uint8_t *__restrict__ cbw,
+                      uint8_t *__restrict__ chi, uint32_t *__restrict__ corig, uint32_t *__restrict__ chead)
+{
+    __shared__ uint32_t scratch[9];
+    const uint64_t t = (uint64_t)blockIdx.x * kActTileWords + threadIdx.x;
+    uint32_t a = t < nwords ? act[t] : 0u;
+    const uint32_t hd = t < nwords ? head[t] : 0u;
+    const uint32_t c = __popc(a);
+    uint32_t total;
+    const uint32_t e = block_excl_sum(c, scratch, &total);
+    if (c == 0) return;
+    uint64_t j = tile_off[blockIdx.x] + e;
+    // head bits of the active slots, compressed, at bit offset j of chead
+    uint64_t hb = 0;
+    {
+        uint32_t aa = a;
+        int out = 0;
+        while (aa) {
+            const int b = __ffs(aa) - 1;
+            aa &= aa - 1;
+            hb |= (uint64_t)((hd >> b) & 1u) << out;
+            ++out;
+        }
+    }
+    if (hb) {
+        const int sh = (int)(j & 31);
+        const uint64_t lo = hb << sh;
+        atomicOr(&chead[j >> 5], (uint32_t)lo);
+        if (lo >> 32) atomicOr(&chead[(j >> 5) + 1], (uint32_t)(lo >> 32));
+        if (sh && (hb >> (64 - sh))) atomicOr(&chead[(j >> 5) + 2], (uint32_t)(hb >> (64 - sh)));
+    }
+    while (a) {
+        const int b = __ffs(a) - 1;
+        a &= a - 1;
+        const uint64_t slot = t * 32 + b;
+        csa[j] = sa[slot];
+        cbw[j] = bwt[slot];
+        if (chi) chi[j] = sa_hi[slot];
+        corig[j] = (uint32_t)slot;
+        ++j;
+    }
+}
+
+// bits m_act.. of the compact head bitmap (head_words words)
+__global__ void __launch_bounds__(256) pad_heads_kernel(uint32_t *__restrict__ chead, uint64_t m_act, uint64_t head_words)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t w = (m_act >> 5) + (uint64_t)blockIdx.x * 256 + threadIdx.x; w < head_words; w += stride) {
+        if (w == (m_act >> 5))
+            atomicOr(&chead[w], 0xffffffffu << (m_act & 31));
+        else
+            chead[w] = 0xffffffffu;
+    }
+}
+
+// BWT bytes of the compact entries back to their slots
+__global__ void __launch_bounds__(256) scatter_bwt_kernel(const uint32_t *__restrict__ corig, const uint8_t *__restrict__ cbw,
+                                                          uint64_t m_act, uint8_t *__restrict__ bwt)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t j = (uint64_t)blockIdx.x * 256 + threadIdx.x; j < m_act; j += stride) bwt[corig[j]] = cbw[j];
+}
+
+// ---------------------------------------------------------------------------
 // large-group path
 // ---------------------------------------------------------------------------
 // One warp per listed group: distance from its head to the next head.
@@ -2021,6 +2163,41 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
     DISPATCH_BITS(bits, CALL);
 #undef CALL
 #undef REFINE
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+uint64_t active_tiles(uint64_t head_words) { return div_up(head_words, kActTileWords); }
+
+void launch_mark_active(cudaStream_t st, const uint32_t *head, const uint32_t *diff, uint64_t n, uint32_t *act,
+                        uint64_t *tile_off, uint32_t *launches)
+{
+    const uint64_t nwords = div_up(n, 32);
+    const unsigned tiles = (unsigned)active_tiles(nwords);
+    mark_active_kernel<<<(unsigned)div_up(nwords, 256), 256, 0, st>>>(head, diff, nwords, act);
+    count_active_kernel<<<tiles, 256, 0, st>>>(act, nwords, tile_off);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_off, tiles);
+    DSM_LAUNCH_CHECK();
+    if (launches) *launches += 3;
+}
+
+void launch_compact_active(cudaStream_t st, const uint32_t *act, const uint32_t *head, uint64_t n, const uint64_t *tile_off,
+                           const uint32_t *sa, const uint8_t *bwt, const uint8_t *sa_hi, uint64_t m_act, uint32_t *csa,
+                           uint8_t *cbw, uint8_t *chi, uint32_t *corig, uint32_t *chead, uint64_t chead_words,
+                           uint32_t *launches)
+{
+    const uint64_t nwords = div_up(n, 32);
+    compact_active_kernel<<<(unsigned)active_tiles(nwords), 256, 0, st>>>(act, head, nwords, tile_off, sa, bwt, sa_hi, csa,
+                                                                          cbw, chi, corig, chead);
+    pad_heads_kernel<<<grid_for(chead_words - (m_act >> 5), 256), 256, 0, st>>>(chead, m_act, chead_words);
+    DSM_LAUNCH_CHECK();
+    if (launches) *launches += 2;
+}
+
+void launch_scatter_bwt(cudaStream_t st, const uint32_t *corig, const uint8_t *cbw, uint64_t m_act, uint8_t *bwt,
+                        uint32_t *launches)
+{
+    scatter_bwt_kernel<<<grid_for(m_act, 256 * 8), 256, 0, st>>>(corig, cbw, m_act, bwt);
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

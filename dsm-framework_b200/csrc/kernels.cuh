@@ -91,6 +91,22 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    int key_words, uint8_t *sa_hi, int lo_bits, bool full_order, const uint32_t *diff_bits,
                    uint32_t *launches);
 
+// BWT-only builds: the groups with mixed BWT symbols, copied out in order so that the refinement works on dense
+// arrays.  launch_mark_active: act (zeroed, head_words words) gets the slots of those groups, tile_off
+// (active_tiles(words of n) + 1 entries) their running counts per tile, the total behind the last entry.
+// launch_compact_active: fills the dense arrays (m_act entries; chi/sa_hi may be nullptr) and the compact
+// head bitmap chead (zeroed by the caller, chead_words words, bits from m_act on set).
+// launch_scatter_bwt: bwt[corig[j]] = cbw[j].
+uint64_t active_tiles(uint64_t head_words);
+void launch_mark_active(cudaStream_t st, const uint32_t *head, const uint32_t *diff, uint64_t n, uint32_t *act,
+                        uint64_t *tile_off, uint32_t *launches);
+void launch_compact_active(cudaStream_t st, const uint32_t *act, const uint32_t *head, uint64_t n, const uint64_t *tile_off,
+                           const uint32_t *sa, const uint8_t *bwt, const uint8_t *sa_hi, uint64_t m_act, uint32_t *csa,
+                           uint8_t *cbw, uint8_t *chi, uint32_t *corig, uint32_t *chead, uint64_t chead_words,
+                           uint32_t *launches);
+void launch_scatter_bwt(cudaStream_t st, const uint32_t *corig, const uint8_t *cbw, uint64_t m_act, uint8_t *bwt,
+                        uint32_t *launches);
+
 // Large-group path, step 1: length of each listed group (distance to the next head).
 void launch_big_extent(cudaStream_t st, const uint32_t *head_cur, uint64_t n, const uint32_t *big_heads,
                        uint32_t nbig, uint32_t *big_len, uint32_t *launches);

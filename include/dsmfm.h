@@ -136,6 +136,8 @@ typedef struct dsmfm_stats {
     float reserved2;
     uint64_t refine_key_fetches; /* 8-byte keys the refinement kernel gathered from the text */
     uint64_t refine_launches;    /* refine_kernel launches                                  */
+    uint64_t refine_members;     /* suffixes in the tie groups that had to be sorted: all of them when the */
+                                 /* suffix array is kept, else those of groups with mixed BWT symbols       */
 } dsmfm_stats;
 
 /* Replaces: TextCollectionBuilder::TextCollectionBuilder (TextCollectionBuilder.cpp:32-57). */

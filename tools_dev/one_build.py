@@ -19,7 +19,7 @@ for it in range(reps):
     b.append_batch_device(d)
     b.build_device()
     s = b.stats()
-    print("n=%d pack %.1f sort %.1f (pass %.2f) refine %.1f wt %.1f total %.1f launches %d active %s" % (
+    print("n=%d pack %.1f sort %.1f (pass %.2f) refine %.1f wt %.1f total %.1f launches %d active %s members %.3f fetches %.3f" % (
         s.n, s.ms_pack, s.ms_sort, s.ms_sort_pass, s.ms_refine, s.ms_wt, s.ms_total, s.kernel_launches,
-        [round(s.active[r] / s.n, 3) for r in range(s.rounds)]))
+        [round(s.active[r] / s.n, 3) for r in range(s.rounds)], s.refine_members / s.n, s.refine_key_fetches / s.n))
     b.close()
