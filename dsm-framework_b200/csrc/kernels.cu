@@ -569,6 +569,11 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nw
 // ---------------------------------------------------------------------------
 // group heads after the initial sort
 // ---------------------------------------------------------------------------
+// One warp per chunk of U head words (32*U consecutive ranks).  Everything a rank needs comes from its own key
+// and its predecessor's (one 64-bit shuffle; the first lane of a word reads it): with x = key ^ previous key,
+// the sorted bits of x tell whether the rank opens a group and the carried bits whether its BWT symbol
+// differs.  "Next rank opens a group" is the head bit of the next rank, so the count of suffixes left in
+// groups of >= 2 falls out of the head words themselves.
 template <int BITS>
 __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
@@ -577,60 +582,89 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
                                                     uint8_t *__restrict__ pos_hi, int hi_shift,
                                                     uint32_t *__restrict__ diff)
 {
+    constexpr int U = 4;
     __shared__ unsigned long long s_cnt[8];
     __shared__ uint8_t s_inv[256];
     if (bwt) s_inv[threadIdx.x] = inv_map[threadIdx.x];
     __syncthreads();
     const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t nchunks = (head_words + U - 1) / U;
     const uint64_t warps_total = (uint64_t)gridDim.x * 8;
+    const uint64_t nfull = n / 32; // head words whose 32 ranks all exist
+    // BITS = 3: the code -> byte table fits a register
+    uint64_t inv_reg = 0;
+    if (BITS == 3 && bwt)
+        for (int c = 0; c < 8; ++c) inv_reg |= (uint64_t)s_inv[c] << (8 * c);
     unsigned long long active = 0;
-    // four head words (128 keys) per warp and iteration: the twelve loads of a lane are issued back to back
-    constexpr int U = 4;
-    for (uint64_t w0 = ((uint64_t)blockIdx.x * 8 + warp) * U; w0 < head_words; w0 += warps_total * U) {
-        uint64_t kraw[U], kprev[U], knext[U];
+    for (uint64_t ch = (uint64_t)blockIdx.x * 8 + warp; ch < nchunks; ch += warps_total) {
+        const uint64_t w0 = ch * U;
+        const uint64_t base = w0 * 32; // rank of lane 0 in the chunk's first word
+        // U+1 words' worth of head bits: the last one only provides "the next rank opens a group" for rank 32U-1
+        uint64_t kraw[U];
+        uint64_t kcarry; // key in front of the chunk
+        uint64_t kafter = 0; // key behind the chunk (one rank)
+        const bool full = w0 + U <= nfull && base + 32 * U < n;
+        if (full) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t i = (w0 + u) * 32 + lane;
-            kraw[u] = i < n ? keys[i] : 0ull;
-            // neighbours come from the neighbouring lanes; only the two ends of the warp's 32 keys load them
-            kprev[u] = (lane == 0 && i > 0 && i < n) ? keys[i - 1] : 0ull;
-            knext[u] = (lane == 31 && i + 1 < n) ? keys[i + 1] : 0ull;
+            for (int u = 0; u < U; ++u) kraw[u] = keys[base + 32 * u + lane];
+            kcarry = base ? keys[base - 1] : 0ull;
+            kafter = keys[base + 32 * U];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = base + 32 * u + lane;
+                kraw[u] = i < n ? keys[i] : 0ull;
+            }
+            kcarry = (base && base - 1 < n) ? keys[base - 1] : 0ull;
+            kafter = base + 32 * U < n ? keys[base + 32 * U] : 0ull;
         }
+        uint32_t hw[U + 1];
+        uint64_t prev_last = kcarry; // key of the rank in front of the current word
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint64_t up = __shfl_up_sync(0xffffffffu, kraw[u], 1), dn = __shfl_down_sync(0xffffffffu, kraw[u], 1);
-            if (lane != 0) kprev[u] = up;
-            if (lane != 31) knext[u] = dn;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t w = w0 + u;
-            if (w >= head_words) break; // warp-uniform
-            const uint64_t i = w * 32 + lane;
-            bool h = true, act = false, df = false;
-            if (i < n) {
-                const uint64_t k = kraw[u] & kmask;
-                h = (i == 0) || key_terminated<BITS>(k) || (kprev[u] & kmask) != k;
-                // inside a group: does the symbol in front of this suffix differ from its predecessor's?
-                df = !h && (((kraw[u] ^ kprev[u]) >> key_bits) & Pack<BITS>::FIELD) != 0;
-                bool hn = true;
-                if (i + 1 < n) {
-                    const uint64_t kn = knext[u] & kmask;
-                    hn = key_terminated<BITS>(kn) || kn != k;
+            uint64_t kp = __shfl_up_sync(0xffffffffu, kraw[u], 1);
+            if (lane == 0) kp = prev_last;
+            prev_last = __shfl_sync(0xffffffffu, kraw[u], 31);
+            const uint64_t x = kraw[u] ^ kp;
+            const uint64_t i = base + 32 * u + lane;
+            bool h = (x & kmask) != 0 || key_terminated<BITS>(kraw[u] & kmask) || i == 0;
+            bool df = !h && ((x >> key_bits) & Pack<BITS>::FIELD) != 0;
+            if (!full) {
+                h = h || i >= n; // ranks behind the last suffix count as heads
+                df = df && i < n;
+            }
+            hw[u] = __ballot_sync(0xffffffffu, h);
+            if (diff) {
+                const uint32_t dw = __ballot_sync(0xffffffffu, df);
+                if (lane == 0 && w0 + u < head_words) diff[w0 + u] = dw;
+            }
+            if (full || i < n) {
+                if (bwt) {
+                    const uint32_t code = (uint32_t)(kraw[u] >> key_bits) & (uint32_t)Pack<BITS>::FIELD;
+                    bwt[i] = BITS == 3 ? (uint8_t)(inv_reg >> (8 * code)) : s_inv[code];
                 }
-                act = !(h && hn);
-                // the symbol before suffix i rode along above the sorted bits (make_keys_kernel)
-                if (bwt) bwt[i] = s_inv[(kraw[u] >> key_bits) & Pack<BITS>::FIELD];
                 if (pos_hi) pos_hi[i] = (uint8_t)(kraw[u] >> hi_shift); // high part of the text position (wide builds)
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, h);
-            const uint32_t aw = __ballot_sync(0xffffffffu, act);
-            const uint32_t dw = diff ? __ballot_sync(0xffffffffu, df) : 0u;
-            if (lane == 0) {
-                head[w] = word;
-                if (diff) diff[w] = dw;
-                active += __popc(aw);
+        }
+        {
+            // head bit of the rank right behind the chunk
+            const uint64_t i = base + 32 * U;
+            const uint64_t x = kafter ^ prev_last;
+            hw[U] = (i >= n || (x & kmask) != 0 || key_terminated<BITS>(kafter & kmask)) ? 1u : 0u;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (w0 + u < head_words) {
+                    head[w0 + u] = hw[u];
+                    // in a group of >= 2: not (head and next rank is a head)
+                    const uint32_t next = (hw[u] >> 1) | (hw[u + 1] << 31);
+                    uint32_t in_group = ~(hw[u] & next);
+                    const uint64_t first = (w0 + u) * 32;
+                    if (first + 32 > n) in_group &= first >= n ? 0u : ((1u << (n - first)) - 1u);
+                    active += __popc(in_group);
+                }
             }
         }
     }
@@ -1742,23 +1776,88 @@ __device__ __forceinline__ uint32_t wt_valid_mask(uint64_t n, uint64_t p0)
     return left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
 }
 
+// Trees with at most 8 internal nodes (reads: 6): one table lookup per symbol yields its membership and branch
+// bit for every node at once (low byte: member of node v, high byte: branch taken there); four symbols are
+// packed into one word per byte lane, and a multiply gathers one node's four bits -- instead of one lookup
+// per (symbol, node).
+constexpr int kWtSmallNodes = 8;
+
+__device__ __forceinline__ void wt_small_table(const uint8_t *__restrict__ node_info, int n_internal, uint16_t *lut16)
+{
+    uint32_t e = 0;
+    for (int v = 0; v < n_internal; ++v) {
+        const uint32_t x = node_info[v * 256 + threadIdx.x];
+        e |= (x & 1u) << v;
+        e |= ((x >> 1) & 1u) << (8 + v);
+    }
+    lut16[threadIdx.x] = (uint16_t)e;
+}
+
+__device__ __forceinline__ void wt_masks_small(const uint16_t *lut16, const uint32_t (&w)[8], uint32_t valid, int n_internal,
+                                               uint32_t (&m)[kWtSmallNodes], uint32_t (&b)[kWtSmallNodes])
+{
+#pragma unroll
+    for (int v = 0; v < kWtSmallNodes; ++v) m[v] = b[v] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t e0 = lut16[w[i] & 0xff], e1 = lut16[(w[i] >> 8) & 0xff], e2 = lut16[(w[i] >> 16) & 0xff],
+                       e3 = lut16[w[i] >> 24];
+        const uint32_t lo = e0 | (e1 << 16), hi = e2 | (e3 << 16); // [mem0 br0 mem1 br1], [mem2 br2 mem3 br3]
+        const uint32_t M4 = __byte_perm(lo, hi, 0x6420), B4 = __byte_perm(lo, hi, 0x7531);
+#pragma unroll
+        for (int v = 0; v < kWtSmallNodes; ++v) {
+            if (v < n_internal) {
+                m[v] |= ((((M4 >> v) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
+                b[v] |= ((((B4 >> v) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < kWtSmallNodes; ++v) {
+        m[v] &= valid;
+        b[v] &= valid;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 wt_count_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
                 uint64_t ntiles, uint64_t *__restrict__ tile_count)
 {
     extern __shared__ uint8_t s_info[];
     __shared__ uint32_t s_sum[8];
+    __shared__ uint16_t s_lut16[256];
+    __shared__ uint32_t s_part[kWtSmallNodes][8];
+    const uint64_t tile = blockIdx.x;
+    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
+    uint32_t w[8];
+    wt_load32(seq, n, p0, w);
+    const uint32_t valid = wt_valid_mask(n, p0);
+    if (n_internal <= kWtSmallNodes) {
+        wt_small_table(node_info, n_internal, s_lut16);
+        __syncthreads();
+        uint32_t m[kWtSmallNodes], b[kWtSmallNodes];
+        wt_masks_small(s_lut16, w, valid, n_internal, m, b);
+#pragma unroll
+        for (int v = 0; v < kWtSmallNodes; ++v) {
+            if (v < n_internal) {
+                const uint32_t c = warp_sum((uint32_t)__popc(m[v]));
+                if ((threadIdx.x & 31) == 0) s_part[v][threadIdx.x >> 5] = c;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < n_internal) {
+            uint32_t t = 0;
+            for (int k = 0; k < 8; ++k) t += s_part[threadIdx.x][k];
+            tile_count[(uint64_t)threadIdx.x * ntiles + tile] = t;
+        }
+        return;
+    }
     const bool staged = n_internal <= kWtInfoSmemNodes;
     if (staged) {
         for (int i = threadIdx.x; i < n_internal * 256; i += 256) s_info[i] = node_info[i];
         __syncthreads();
     }
     const uint8_t *info = staged ? s_info : node_info;
-    const uint64_t tile = blockIdx.x;
-    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
-    uint32_t w[8];
-    wt_load32(seq, n, p0, w);
-    const uint32_t valid = wt_valid_mask(n, p0);
     for (int v = 0; v < n_internal; ++v) {
         uint32_t m, b;
         wt_masks(info + v * 256, w, valid, m, b);
@@ -1789,6 +1888,32 @@ __global__ void __launch_bounds__(1024) wt_scan_kernel(uint64_t *__restrict__ ti
     }
 }
 
+// the bits of one node contributed by one thread: software pext of the branch bits over the member mask, OR-ed
+// into the node's bit array at the thread's global bit offset
+__device__ __forceinline__ void wt_emit(uint32_t m, uint32_t b, uint32_t c, uint64_t local, int v, const uint32_t (&w)[8],
+                                        uint64_t *const *__restrict__ node_data, uint8_t *__restrict__ node_ch,
+                                        const uint64_t *__restrict__ bit_base)
+{
+    uint64_t bits = 0;
+    uint32_t mm = m;
+    int out = 0;
+    while (mm) {
+        const int j = __ffs(mm) - 1;
+        bits |= (uint64_t)((b >> j) & 1u) << out;
+        ++out;
+        mm &= mm - 1;
+    }
+    const uint64_t o = local + (bit_base ? bit_base[v] : 0ull); // bit offset in the node's array
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]);
+    const int sh = (int)(o & 63);
+    if (bits << sh) atomicOr(d + (o >> 6), (unsigned long long)(bits << sh));
+    if (sh + (int)c > 64 && (bits >> (64 - sh))) atomicOr(d + (o >> 6) + 1, (unsigned long long)(bits >> (64 - sh)));
+    if (local == 0) { // first symbol of the node's subsequence (HuffWT.cpp:8)
+        const int j = __ffs(m) - 1;
+        node_ch[v] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
                uint64_t ntiles, const uint64_t *__restrict__ tile_off, uint64_t *const *__restrict__ node_data,
@@ -1796,45 +1921,54 @@ wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__res
 {
     extern __shared__ uint8_t s_info[];
     __shared__ uint32_t scratch[9];
+    __shared__ uint16_t s_lut16[256];
+    __shared__ uint32_t s_part[kWtSmallNodes][8];
+    const uint64_t tile = blockIdx.x;
+    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
+    uint32_t w[8];
+    wt_load32(seq, n, p0, w);
+    const uint32_t valid = wt_valid_mask(n, p0);
+    if (n_internal <= kWtSmallNodes) {
+        wt_small_table(node_info, n_internal, s_lut16);
+        __syncthreads();
+        uint32_t m[kWtSmallNodes], b[kWtSmallNodes], incl[kWtSmallNodes];
+        wt_masks_small(s_lut16, w, valid, n_internal, m, b);
+        // exclusive prefix of every node's member count over the threads of the tile: one barrier for all nodes
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int v = 0; v < kWtSmallNodes; ++v) {
+            if (v < n_internal) {
+                incl[v] = warp_incl_sum((uint32_t)__popc(m[v]));
+                if (lane == 31) s_part[v][warp] = incl[v];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < kWtSmallNodes; ++v) {
+            if (v < n_internal) {
+                const uint32_t c = __popc(m[v]);
+                if (c) {
+                    uint32_t before = incl[v] - c;
+                    for (int k = 0; k < warp; ++k) before += s_part[v][k];
+                    wt_emit(m[v], b[v], c, tile_off[(uint64_t)v * ntiles + tile] + before, v, w, node_data, node_ch, bit_base);
+                }
+            }
+        }
+        return;
+    }
     const bool staged = n_internal <= kWtInfoSmemNodes;
     if (staged) {
         for (int i = threadIdx.x; i < n_internal * 256; i += 256) s_info[i] = node_info[i];
         __syncthreads();
     }
     const uint8_t *info = staged ? s_info : node_info;
-    const uint64_t tile = blockIdx.x;
-    const uint64_t p0 = tile * kWtTile + (uint64_t)threadIdx.x * 32;
-    uint32_t w[8];
-    wt_load32(seq, n, p0, w);
-    const uint32_t valid = wt_valid_mask(n, p0);
     for (int v = 0; v < n_internal; ++v) {
         uint32_t m, b;
         wt_masks(info + v * 256, w, valid, m, b);
         const uint32_t c = __popc(m);
         uint32_t total;
         const uint32_t e = block_excl_sum(c, scratch, &total);
-        if (c) {
-            // compress the branch bits of the members (software pext)
-            uint64_t bits = 0;
-            uint32_t mm = m;
-            int out = 0;
-            while (mm) {
-                const int j = __ffs(mm) - 1;
-                bits |= (uint64_t)((b >> j) & 1u) << out;
-                ++out;
-                mm &= mm - 1;
-            }
-            const uint64_t local = tile_off[(uint64_t)v * ntiles + tile] + e; // rank among the node's members
-            const uint64_t o = local + (bit_base ? bit_base[v] : 0ull);        // bit offset in the node's array
-            unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]);
-            const int sh = (int)(o & 63);
-            if (bits << sh) atomicOr(d + (o >> 6), (unsigned long long)(bits << sh));
-            if (sh + (int)c > 64 && (bits >> (64 - sh))) atomicOr(d + (o >> 6) + 1, (unsigned long long)(bits >> (64 - sh)));
-            if (local == 0) { // first symbol of the node's subsequence (HuffWT.cpp:8)
-                const int j = __ffs(m) - 1;
-                node_ch[v] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 0xff);
-            }
-        }
+        if (c) wt_emit(m, b, c, tile_off[(uint64_t)v * ntiles + tile] + e, v, w, node_data, node_ch, bit_base);
     }
 }
 
