@@ -270,7 +270,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keeps NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner / debug lines off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -450,21 +450,24 @@ def main():
         },
     }
 
-    # The kernel with the largest share of the step is the refinement (one launch, random 8-byte gathers from the
-    # packed text); its algorithmic bytes: per suffix in a tie group 4+1 B read and 4+1 B written (suffix, BWT
-    # symbol), 8 B per key gathered, n/4 B of group-head bitmaps.
-    act = sum(s0.active[r] for r in range(min(s0.rounds, 32)))
-    ref_bytes = 10 * act + 8 * s0.refine_key_fetches + s0.n // 4
+    # Second kernel of the step: the refinement.  Only the tie groups whose members carry different BWT symbols are
+    # sorted (BWT-only build); its algorithmic bytes: per member 4+1 B read and 1 B written back (suffix, BWT symbol),
+    # 8 B per key gathered from the packed text, and the two bitmaps (group heads, symbol differences) of n/8 B each.
+    members = s0.refine_members
+    ref_bytes = 6 * members + 8 * s0.refine_key_fetches + s0.n // 4
     ref_ms = sum(s.ms_refine for s in stats) / len(stats)
     ref_ach = ref_bytes / (ref_ms * 1e-3) / 1e9 if ref_ms > 0 else 0.0
     line["roofline_refine"] = {
-        "bound": "hbm", "kernel": "refine_warps_kernel (%d launch(es) per build; every warp resolves the tie groups of its part "
-                                  "of a 1024-slot window in shared memory, keys gathered from the packed text)" % s0.refine_launches,
+        "bound": "hbm", "kernel": "refinement phase: mark/count/compact the groups with mixed BWT symbols, refine_warps_kernel "
+                                  "(%d launch(es); every warp resolves the groups of its part of a 1024-slot window in shared "
+                                  "memory, keys gathered from the packed text), scatter the BWT bytes back" % s0.refine_launches,
         "achieved": round(ref_ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ref_ach / peak, 4),
-        "algorithmic_bytes_per_launch": ref_bytes // max(1, s0.refine_launches),
-        "ms_per_launch": round(ref_ms / max(1, s0.refine_launches), 3),
+        "algorithmic_bytes": ref_bytes, "ms": round(ref_ms, 3),
+        "tie_group_members": int(sum(s0.active[r] for r in range(min(s0.rounds, 1)))), "members_sorted": int(members),
         "keys_gathered": s0.refine_key_fetches, "traffic": profile.get("refine_dram_bytes_per_launch"),
-        "traffic_note": profile.get("refine_note")}
+        "traffic_note": profile.get("refine_note"),
+        "note": "random 16-byte gathers: the bound is DRAM row activations (about 56 G accesses/s measured, "
+                "tools_dev/gather_bench.cu), not bytes"}
 
     if world == 1 and not args.no_extras:
         line["fasta_e2e"] = fasta_front_end(args, kw, local, stream, torch, dsmfm, dsmgen)
