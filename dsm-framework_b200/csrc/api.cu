@@ -992,10 +992,8 @@ void dsmfm_builder::build()
         uint32_t *c_sa = nullptr, *c_orig = nullptr, *c_head[2] = {nullptr, nullptr};
         uint8_t *c_bw = nullptr, *c_hi = nullptr;
         uint64_t m_act = 0;
-        static const bool compact_off = [] {
-            const char *e = std::getenv("DSMFM_REFINE_COMPACT");
-            return e && std::atoi(e) == 0;
-        }();
+        const char *compact_env = std::getenv("DSMFM_REFINE_COMPACT"); // 0: refine in place (tests)
+        const bool compact_off = compact_env && std::atoi(compact_env) == 0;
         const bool compact = use_diff && multi_step && !compact_off && remaining > 0;
         bool c_owned = false; // the dense arrays are allocations of their own (else: carved out of a key buffer)
         if (compact) {

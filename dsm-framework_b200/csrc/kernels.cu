@@ -2238,10 +2238,8 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
     // default schedule: multi-step with the text of the unresolved suffixes resident in shared memory
-    static const int variant = [] {
-        const char *e = std::getenv("DSMFM_REFINE_VARIANT"); // 0: CTA-wide steps (refine_kernel), 2: independent warps
-        return e ? std::atoi(e) : 2;
-    }();
+    const char *variant_env = std::getenv("DSMFM_REFINE_VARIANT"); // 0: CTA-wide steps (refine_kernel), 2: independent warps
+    const int variant = variant_env ? std::atoi(variant_env) : 2;
     if (multi_step && variant == 2) {
         static bool attr3_set = false;
         if (!attr3_set) {

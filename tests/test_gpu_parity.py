@@ -186,6 +186,43 @@ def test_single_step_refinement_schedule(monkeypatch, key_words):
     assert hashlib.sha256(_build(docs)).hexdigest() == MANIFEST["digests"]["high_coverage"]["fmi_sha256"]
 
 
+@pytest.mark.parametrize("env", [{"DSMFM_REFINE_COMPACT": "0"}, {"DSMFM_REFINE_FULL_ORDER": "1"}, {"DSMFM_REFINE_VARIANT": "0"},
+                                 {"DSMFM_REFINE_VARIANT": "0", "DSMFM_REFINE_FULL_ORDER": "1"},
+                                 {"DSMFM_REFINE_COMPACT": "0", "DSMFM_REFINE_KEY_WORDS": "2"}])
+def test_refinement_schedules_give_the_same_index(monkeypatch, env):
+    """BWT-only refinement on dense copies of the mixed groups (default), in place with the difference bitmap, the
+    full suffix order, and the schedule with CTA-wide steps: one index."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("reads100", "duplicates", "poly_a", "mixed_alphabet", "one_base_reads"):
+        docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+        _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
+    for name in ("high_coverage", "ragged_2k"):
+        docs, _ = oracle.fasta_to_docs(cases.digest_cases()[name])
+        got = _build(docs)
+        assert hashlib.sha256(got).hexdigest() == MANIFEST["digests"][name]["fmi_sha256"]
+
+
+def test_bwt_only_build_sorts_fewer_suffixes():
+    """The statistics tell the two refinements apart: members sorted vs members of tie groups."""
+    import dsmfm
+    import dsmgen
+    docs = dsmgen.docs(**MANIFEST["generated"]["gen_20k"]["params"])
+    with dsmfm.Builder(device=0) as b:
+        b.append_batch(docs)
+        b.finish()
+        lean = b.stats()
+        fmi = b.fmi()
+    with dsmfm.Builder(device=0, flags=dsmfm.FLAG_KEEP_SA) as b:
+        b.append_batch(docs)
+        b.finish()
+        full = b.stats()
+        assert b.fmi() == fmi
+    assert full.refine_members == full.active[0] > 0
+    assert 0 < lean.refine_members < full.refine_members // 2
+    assert lean.refine_key_fetches < full.refine_key_fetches
+
+
 def test_128_bit_refinement_keys(monkeypatch):
     monkeypatch.setenv("DSMFM_REFINE_KEY_WORDS", "2")
     for name in ["reads100", "poly_a", "colour_space", "duplicates"]:
