@@ -106,6 +106,44 @@ struct PinnedPool {
 };
 PinnedPool g_pinned;
 
+// Scratch of the FASTA front end: one device buffer per device that only grows and is shared by all builders
+// of the process (a call holds the lock and ends with a stream synchronize, so the buffer is idle in between).
+// The stream-ordered pool is fast when the sizes of a build repeat; the front end's sizes follow the input
+// file, and carving them out of pooled blocks of other sizes stalled for 100+ ms per call.
+struct ScratchArena {
+    static constexpr int kMaxDev = 64;
+    std::mutex mu;
+    void *ptr[kMaxDev] = {};
+    size_t cap[kMaxDev] = {};
+    size_t hint[kMaxDev] = {}; // what the last call on the device would have liked to find
+    void *reserve(int dev, size_t bytes)
+    {
+        if (dev < 0 || dev >= kMaxDev) throw CudaError{cudaErrorInvalidDevice, "scratch arena", __FILE__, __LINE__};
+        if (cap[dev] >= bytes) return ptr[dev];
+        if (ptr[dev]) cudaFree(ptr[dev]);
+        ptr[dev] = nullptr;
+        cap[dev] = 0;
+        const size_t want = bytes + bytes / 8;
+        const double t0 = now_ms();
+        DSM_CUDA(cudaMalloc(&ptr[dev], want));
+        g_alloc_ms += now_ms() - t0;
+        cap[dev] = want;
+        return ptr[dev];
+    }
+    void trim(int dev)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (int d = 0; d < kMaxDev; ++d) {
+            if ((dev >= 0 && d != dev) || !ptr[d]) continue;
+            cudaSetDevice(d);
+            cudaFree(ptr[d]);
+            ptr[d] = nullptr;
+            cap[d] = hint[d] = 0;
+        }
+    }
+};
+ScratchArena g_fasta_arena;
+
 // ---------------------------------------------------------------------------
 // Huffman code table -- node::makecodetable / maketable, HuffWT.cpp:133-184.
 // Same container (std::priority_queue over std::vector with std::greater),
@@ -566,32 +604,40 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     cudaStream_t st = stream;
     uint32_t *L = &pre_launches;
     trace("append_fasta: begin");
-    uint8_t *d_text = static_cast<uint8_t *>(dmalloc(m + 64));
-    DSM_CUDA(cudaMemcpyAsync(d_text, text, m, cudaMemcpyHostToDevice, st));
+    std::lock_guard<std::mutex> arena_lock(g_fasta_arena.mu);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    // part 1 (sizes follow the text), part 2 (sizes follow the number of records, known after the first pass)
     const uint64_t ntiles = fasta_tiles(m);
-    long long *d_last = static_cast<long long *>(dmalloc(ntiles * 8));
-    long long *d_entry = static_cast<long long *>(dmalloc(ntiles * 8));
-    uint32_t *d_cs = static_cast<uint32_t *>(dmalloc(ntiles * 4));
-    uint32_t *d_ch = static_cast<uint32_t *>(dmalloc(ntiles * 4));
-    uint64_t *d_os = static_cast<uint64_t *>(dmalloc(ntiles * 8));
-    uint64_t *d_oh = static_cast<uint64_t *>(dmalloc(ntiles * 8));
-    uint64_t *d_tot = static_cast<uint64_t *>(dmalloc(4 * 8));
-    unsigned long long *d_cnt = static_cast<unsigned long long *>(dmalloc(4 * 8));
+    const size_t o_text = 0, o_last = o_text + up(m + 64), o_entry = o_last + up(ntiles * 8), o_cs = o_entry + up(ntiles * 8),
+                 o_ch = o_cs + up(ntiles * 4), o_os = o_ch + up(ntiles * 4), o_oh = o_os + up(ntiles * 8),
+                 o_tot = o_oh + up(ntiles * 8), o_cnt = o_tot + 256, part1 = o_cnt + 256;
+    uint8_t *base = static_cast<uint8_t *>(g_fasta_arena.reserve(device, std::max(part1, g_fasta_arena.hint[device])));
+    uint8_t *d_text = base + o_text;
+    long long *d_last = reinterpret_cast<long long *>(base + o_last), *d_entry = reinterpret_cast<long long *>(base + o_entry);
+    uint32_t *d_cs = reinterpret_cast<uint32_t *>(base + o_cs), *d_ch = reinterpret_cast<uint32_t *>(base + o_ch);
+    uint64_t *d_os = reinterpret_cast<uint64_t *>(base + o_os), *d_oh = reinterpret_cast<uint64_t *>(base + o_oh);
+    uint64_t *d_tot = reinterpret_cast<uint64_t *>(base + o_tot);
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(base + o_cnt);
+    DSM_CUDA(cudaMemcpyAsync(d_text, text, m, cudaMemcpyHostToDevice, st));
     launch_fasta_scan_lines(st, d_text, m, d_last, d_entry, d_cs, d_ch, d_os, d_oh, d_tot, L);
     uint64_t tot[2] = {0, 0};
     DSM_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
     DSM_CUDA(cudaStreamSynchronize(st));
-    dfree(d_last);
-    dfree(d_cs);
-    dfree(d_ch);
     const uint64_t nseq = tot[0], nhdr = tot[1], nrec = nhdr + 1;
     trace("append_fasta: text on the device, lines scanned");
 
-    uint64_t *d_B = static_cast<uint64_t *>(dmalloc((nrec + 1) * 8));
-    uint64_t *d_O = static_cast<uint64_t *>(dmalloc(nrec * 8));
     const uint64_t rtiles = fasta_rec_tiles(nrec);
-    uint32_t *d_rc = static_cast<uint32_t *>(dmalloc(rtiles * 4));
-    uint64_t *d_ro = static_cast<uint64_t *>(dmalloc(rtiles * 8));
+    const size_t bm_bytes = (size_t)div_up(nrec, 32) * 4;
+    const size_t o_B = 0, o_O = o_B + up((nrec + 1) * 8), o_rc = o_O + up(nrec * 8), o_ro = o_rc + up(rtiles * 4),
+                 o_bm = o_ro + up(rtiles * 8), part2 = o_bm + up(bm_bytes);
+    g_fasta_arena.hint[device] = part1 + part2;
+    uint8_t *base2 = base + part1;
+    void *own2 = nullptr; // the arena was sized for another input: part 2 gets an allocation of its own this time
+    if (g_fasta_arena.cap[device] < part1 + part2) base2 = static_cast<uint8_t *>(own2 = dmalloc(part2));
+    uint64_t *d_B = reinterpret_cast<uint64_t *>(base2 + o_B), *d_O = reinterpret_cast<uint64_t *>(base2 + o_O);
+    uint32_t *d_rc = reinterpret_cast<uint32_t *>(base2 + o_rc);
+    uint64_t *d_ro = reinterpret_cast<uint64_t *>(base2 + o_ro);
+    uint32_t *d_bm = reinterpret_cast<uint32_t *>(base2 + o_bm);
     const unsigned long long cnt0[4] = {0, 0, ~0ull, 0};
     const uint64_t zero = 0;
     DSM_CUDA(cudaMemcpyAsync(d_cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));
@@ -600,34 +646,19 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     launch_fasta_records(st, d_text, m, d_entry, d_os, d_oh, nrec, d_B, d_O, d_rc, d_ro, d_tot, d_cnt, L);
     DSM_CUDA(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, st));
     DSM_CUDA(cudaStreamSynchronize(st));
-    dfree(d_rc);
-    dfree(d_ro);
     const uint64_t ndocs = tot[0], doc_bytes = 2 * nseq + 2 * ndocs;
 
     unsigned long long cnt[4] = {0, 0, ~0ull, 0};
     if (doc_bytes) {
         uint8_t *d_out = static_cast<uint8_t *>(dmalloc(doc_bytes + 64));
-        const size_t bm_bytes = (size_t)div_up(nrec, 32) * 4;
-        uint32_t *d_bm = static_cast<uint32_t *>(dmalloc(bm_bytes));
         DSM_CUDA(cudaMemsetAsync(d_bm, 0, bm_bytes, st));
         launch_fasta_emit(st, d_text, m, d_entry, d_os, d_oh, d_B, d_O, d_out, d_bm, d_cnt, L);
-        DSM_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-        DSM_CUDA(cudaStreamSynchronize(st));
-        dfree(d_bm);
         chunks.push_back(Chunk{d_out, (size_t)doc_bytes + 64, (size_t)doc_bytes});
         n += doc_bytes;
-    } else {
-        DSM_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-        DSM_CUDA(cudaStreamSynchronize(st));
     }
-    dfree(d_text);
-    dfree(d_entry);
-    dfree(d_os);
-    dfree(d_oh);
-    dfree(d_tot);
-    dfree(d_cnt);
-    dfree(d_B);
-    dfree(d_O);
+    DSM_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st)); // the arena is idle again
+    dfree(own2);
     trace("append_fasta: documents written");
     info->records = nhdr;
     info->documents = ndocs;
@@ -1895,6 +1926,7 @@ DSMFM_API const char *dsmfm_last_error(const dsmfm_builder *b)
 DSMFM_API int dsmfm_release_cached(int device)
 {
     g_pinned.trim();
+    g_fasta_arena.trim(device);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) return DSMFM_ECUDA;
     for (int d = 0; d < ndev; ++d) {
