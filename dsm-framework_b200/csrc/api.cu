@@ -53,17 +53,111 @@ void trace(const char *what)
     last = t;
 }
 
+// Large device blocks (>= 32 MB) are kept in a process-wide cache keyed by their exact size: a build of the same
+// shape finds every one of its buffers again without a driver call.  (The stream-ordered pool alone is not
+// enough: when the sizes free at the moment do not match a request it carves up or remaps a larger block, and
+// an 8 GB request then takes anything from 5 to 800 ms -- measured in the multi-GPU bench.)  A block is handed
+// out again only after an event recorded at its release, so different streams may share the cache.  Smaller
+// allocations stay in the stream-ordered pool.
+struct BlockCache {
+    static constexpr size_t kMinBytes = (size_t)32 << 20;
+    struct Blk { void *p; size_t bytes; int dev; cudaEvent_t ready; };
+    std::mutex mu;
+    std::vector<Blk> free_;
+    std::vector<Blk> live_; // blocks handed out (ready unused)
+    size_t free_bytes = 0;
+
+    void drop(size_t i)
+    {
+        Blk b = free_[i];
+        free_.erase(free_.begin() + i);
+        free_bytes -= b.bytes;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != b.dev) cudaSetDevice(b.dev);
+        cudaEventSynchronize(b.ready);
+        cudaEventDestroy(b.ready);
+        cudaFree(b.p);
+        if (cur != b.dev) cudaSetDevice(cur);
+    }
+    void *get(size_t bytes, cudaStream_t st)
+    {
+        int dev = 0;
+        DSM_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = free_.size(); i-- > 0;) {
+            if (free_[i].dev != dev || free_[i].bytes != bytes) continue;
+            Blk b = free_[i];
+            free_.erase(free_.begin() + i);
+            free_bytes -= b.bytes;
+            DSM_CUDA(cudaStreamWaitEvent(st, b.ready, 0));
+            cudaEventDestroy(b.ready);
+            b.ready = nullptr;
+            live_.push_back(b);
+            return b.p;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation) { // give back what is cached and try once more
+            cudaGetLastError();
+            while (!free_.empty()) drop(free_.size() - 1);
+            e = cudaMalloc(&p, bytes);
+        }
+        if (e != cudaSuccess) throw CudaError{e, "cudaMalloc (device block cache)", __FILE__, __LINE__};
+        live_.push_back(Blk{p, bytes, dev, nullptr});
+        return p;
+    }
+    // true if p was one of ours
+    bool put(void *p, cudaStream_t st)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < live_.size(); ++i) {
+            if (live_[i].p != p) continue;
+            Blk b = live_[i];
+            live_.erase(live_.begin() + i);
+            if (cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventRecord(b.ready, st) != cudaSuccess) {
+                cudaStreamSynchronize(st);
+                cudaFree(b.p);
+                return true;
+            }
+            free_.push_back(b);
+            free_bytes += b.bytes;
+            // blocks of shapes that do not come back must not pile up next to other users of the device (the caller's
+            // own cudaMalloc, torch's allocator): at most 64 GB idle, oldest go first.  (No driver query here: on a
+            // box where other processes allocate, cudaMemGetInfo stalled this path for up to 200 ms.)
+            while (free_bytes > ((size_t)64 << 30) && free_.size() > 1) drop(0);
+            return true;
+        }
+        return false;
+    }
+    void trim(int dev)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = free_.size(); i-- > 0;)
+            if (dev < 0 || free_[i].dev == dev) drop(i);
+    }
+};
+BlockCache g_blocks;
+
 void *dev_alloc(size_t bytes, cudaStream_t st)
 {
     void *p = nullptr;
     const double t0 = now_ms();
-    DSM_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
-    g_alloc_ms += now_ms() - t0;
+    if (bytes >= BlockCache::kMinBytes)
+        p = g_blocks.get(bytes, st);
+    else
+        DSM_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, st));
+    const double dt = now_ms() - t0;
+    g_alloc_ms += dt;
+    static const bool loud = std::getenv("DSMFM_TRACE_ALLOC") != nullptr;
+    if (loud && dt > 1.0) std::fprintf(stderr, "[dsmfm alloc] %zu bytes took %.1f ms\n", bytes, dt);
     return p;
 }
 void dev_free(void *p, cudaStream_t st)
 {
-    if (p) cudaFreeAsync(p, st);
+    if (!p) return;
+    if (!g_blocks.put(p, st)) cudaFreeAsync(p, st);
 }
 
 struct PinnedPool {
@@ -1927,6 +2021,7 @@ DSMFM_API int dsmfm_release_cached(int device)
 {
     g_pinned.trim();
     g_fasta_arena.trim(device);
+    g_blocks.trim(device);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess) return DSMFM_ECUDA;
     for (int d = 0; d < ndev; ++d) {
