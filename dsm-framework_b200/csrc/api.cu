@@ -124,9 +124,9 @@ struct BlockCache {
             free_.push_back(b);
             free_bytes += b.bytes;
             // blocks of shapes that do not come back must not pile up next to other users of the device (the caller's
-            // own cudaMalloc, torch's allocator): at most 64 GB idle, oldest go first.  (No driver query here: on a
+            // own cudaMalloc, torch's allocator): at most 128 GB idle (a 16 Gbp 8-GPU build holds 77 GB), oldest go first.  (No driver query here: on a
             // box where other processes allocate, cudaMemGetInfo stalled this path for up to 200 ms.)
-            while (free_bytes > ((size_t)64 << 30) && free_.size() > 1) drop(0);
+            while (free_bytes > ((size_t)128 << 30) && free_.size() > 1) drop(0);
             return true;
         }
         return false;
