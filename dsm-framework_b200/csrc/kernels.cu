@@ -570,10 +570,11 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nw
 // group heads after the initial sort
 // ---------------------------------------------------------------------------
 // One warp per chunk of U head words (32*U consecutive ranks).  Everything a rank needs comes from its own key
-// and its predecessor's (one 64-bit shuffle; the first lane of a word reads it): with x = key ^ previous key,
-// the sorted bits of x tell whether the rank opens a group and the carried bits whether its BWT symbol
-// differs.  "Next rank opens a group" is the head bit of the next rank, so the count of suffixes left in
-// groups of >= 2 falls out of the head words themselves.
+// and its predecessor's (one 64-bit shuffle; the first lane of a word takes the last key of the word before):
+// with x = key ^ previous key, the sorted bits of x tell whether the rank opens a group and the carried bits
+// whether its BWT symbol differs.  "Next rank opens a group" is the head bit of the next rank, so the count of
+// suffixes left in groups of >= 2 falls out of the head words themselves.  Chunks that lie entirely inside
+// the array take a path without bounds checks and with 32-bit offsets from the chunk's base pointers.
 template <int BITS>
 __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
                                                     uint32_t *__restrict__ diff)
 {
     constexpr int U = 4;
+    constexpr uint64_t FIELD = Pack<BITS>::FIELD;
     __shared__ unsigned long long s_cnt[8];
     __shared__ uint8_t s_inv[256];
     if (bwt) s_inv[threadIdx.x] = inv_map[threadIdx.x];
@@ -591,57 +593,93 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t nchunks = (head_words + U - 1) / U;
     const uint64_t warps_total = (uint64_t)gridDim.x * 8;
-    const uint64_t nfull = n / 32; // head words whose 32 ranks all exist
     // BITS = 3: the code -> byte table fits a register
     uint64_t inv_reg = 0;
     if (BITS == 3 && bwt)
         for (int c = 0; c < 8; ++c) inv_reg |= (uint64_t)s_inv[c] << (8 * c);
-    unsigned long long active = 0;
+    uint32_t active = 0; // per lane, summed at the end (fast path) / lane 0 (slow path)
     for (uint64_t ch = (uint64_t)blockIdx.x * 8 + warp; ch < nchunks; ch += warps_total) {
         const uint64_t w0 = ch * U;
         const uint64_t base = w0 * 32; // rank of lane 0 in the chunk's first word
-        // U+1 words' worth of head bits: the last one only provides "the next rank opens a group" for rank 32U-1
-        uint64_t kraw[U];
-        uint64_t kcarry; // key in front of the chunk
-        uint64_t kafter = 0; // key behind the chunk (one rank)
-        const bool full = w0 + U <= nfull && base + 32 * U < n;
-        if (full) {
+        if (base > 0 && base + 32 * U < n && w0 + U <= head_words) {
+            // ---- all 32U ranks, the one before and the one behind exist ----
+            const uint64_t *kp = keys + base;
+            uint64_t k[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) kraw[u] = keys[base + 32 * u + lane];
-            kcarry = base ? keys[base - 1] : 0ull;
-            kafter = keys[base + 32 * U];
-        } else {
+            for (int u = 0; u < U; ++u) k[u] = kp[32 * u + lane];
+            uint64_t edge = 0; // lane 0: key in front of the chunk; lane 31: key behind it
+            if (lane == 0) edge = kp[-1];
+            if (lane == 31) edge = kp[32 * U];
+            uint32_t hw[U + 1], dw[U];
+            uint64_t prev_last = __shfl_sync(0xffffffffu, edge, 0);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint64_t i = base + 32 * u + lane;
-                kraw[u] = i < n ? keys[i] : 0ull;
+                uint64_t kprev = __shfl_up_sync(0xffffffffu, k[u], 1);
+                if (lane == 0) kprev = prev_last;
+                prev_last = __shfl_sync(0xffffffffu, k[u], 31);
+                const uint64_t x = k[u] ^ kprev;
+                const bool h = ((x & kmask) != 0) | ((k[u] & FIELD) == 0);
+                const bool df = !h & (((x >> key_bits) & FIELD) != 0);
+                hw[u] = __ballot_sync(0xffffffffu, h);
+                dw[u] = diff ? __ballot_sync(0xffffffffu, df) : 0u;
+                if (bwt) {
+                    const uint32_t code = (uint32_t)(k[u] >> key_bits) & (uint32_t)FIELD;
+                    bwt[base + 32 * u + lane] = BITS == 3 ? (uint8_t)(inv_reg >> (8 * code)) : s_inv[code];
+                }
+                if (pos_hi) pos_hi[base + 32 * u + lane] = (uint8_t)(k[u] >> hi_shift);
             }
-            kcarry = (base && base - 1 < n) ? keys[base - 1] : 0ull;
-            kafter = base + 32 * U < n ? keys[base + 32 * U] : 0ull;
+            {
+                const uint64_t kafter = __shfl_sync(0xffffffffu, edge, 31);
+                const uint64_t x = kafter ^ prev_last;
+                hw[U] = (((x & kmask) != 0) | ((kafter & FIELD) == 0)) ? 1u : 0u;
+            }
+            // lane u stores word u; every lane counts the suffixes in groups of >= 2 of "its" word
+            uint32_t myh = 0, myd = 0, mynext = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (lane == u) {
+                    myh = hw[u];
+                    myd = dw[u];
+                    mynext = (hw[u] >> 1) | (hw[u + 1] << 31);
+                }
+            }
+            if (lane < U) {
+                head[w0 + lane] = myh;
+                if (diff) diff[w0 + lane] = myd;
+                active += __popc(~(myh & mynext));
+            }
+            continue;
         }
+        // ---- first chunk and the chunks around the end of the array ----
+        uint64_t kraw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = base + 32 * u + lane;
+            kraw[u] = i < n ? keys[i] : 0ull;
+        }
+        const uint64_t kcarry = (base && base - 1 < n) ? keys[base - 1] : 0ull;
+        const uint64_t kafter = base + 32 * U < n ? keys[base + 32 * U] : 0ull;
         uint32_t hw[U + 1];
         uint64_t prev_last = kcarry; // key of the rank in front of the current word
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            uint64_t kp = __shfl_up_sync(0xffffffffu, kraw[u], 1);
-            if (lane == 0) kp = prev_last;
+            uint64_t kprev = __shfl_up_sync(0xffffffffu, kraw[u], 1);
+            if (lane == 0) kprev = prev_last;
             prev_last = __shfl_sync(0xffffffffu, kraw[u], 31);
-            const uint64_t x = kraw[u] ^ kp;
+            const uint64_t x = kraw[u] ^ kprev;
             const uint64_t i = base + 32 * u + lane;
             bool h = (x & kmask) != 0 || key_terminated<BITS>(kraw[u] & kmask) || i == 0;
-            bool df = !h && ((x >> key_bits) & Pack<BITS>::FIELD) != 0;
-            if (!full) {
-                h = h || i >= n; // ranks behind the last suffix count as heads
-                df = df && i < n;
-            }
+            bool df = !h && ((x >> key_bits) & FIELD) != 0;
+            h = h || i >= n; // ranks behind the last suffix count as heads
+            df = df && i < n;
             hw[u] = __ballot_sync(0xffffffffu, h);
             if (diff) {
                 const uint32_t dw = __ballot_sync(0xffffffffu, df);
                 if (lane == 0 && w0 + u < head_words) diff[w0 + u] = dw;
             }
-            if (full || i < n) {
+            if (i < n) {
                 if (bwt) {
-                    const uint32_t code = (uint32_t)(kraw[u] >> key_bits) & (uint32_t)Pack<BITS>::FIELD;
+                    const uint32_t code = (uint32_t)(kraw[u] >> key_bits) & (uint32_t)FIELD;
                     bwt[i] = BITS == 3 ? (uint8_t)(inv_reg >> (8 * code)) : s_inv[code];
                 }
                 if (pos_hi) pos_hi[i] = (uint8_t)(kraw[u] >> hi_shift); // high part of the text position (wide builds)
@@ -668,7 +706,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
             }
         }
     }
-    if (lane == 0) s_cnt[warp] = active;
+    const unsigned long long mine = warp_sum((unsigned long long)active);
+    if (lane == 0) s_cnt[warp] = mine;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
