@@ -234,16 +234,32 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 constexpr int kKeyTileThreads = 128; // one packed word per thread and tile
 constexpr int kMaxKeyPasses = 8;     // 64 key bits / 8-bit digits
 
-template <int BITS>
+// cut_at_terminator without the early exit (same result; the keys of a whole word are cut back to back)
+template <int BITS> __device__ __forceinline__ uint64_t cut_at_terminator_nb(uint64_t x)
+{
+    using P = Pack<BITS>;
+    uint64_t nz = x;
+#pragma unroll
+    for (int i = 1; i < BITS; ++i) nz |= x >> i;
+    const uint64_t z = ~nz & P::LSB;                 // bit 0 of each zero field
+    const int top = 64 - __clzll((long long)z) + BITS - 1; // one past the most significant zero field (BITS - 1 if none)
+    const uint64_t keep = z == 0 ? ~0ull : (top >= 64 ? 0ull : ~((1ull << top) - 1));
+    return x & keep;
+}
+
+// NP: number of 8-bit digits counted, fixed at compile time (6 for the 48-bit first key), or -1: `npass` at run time
+template <int BITS, int NP>
 __global__ void __launch_bounds__(kKeyTileThreads)
 make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, uint64_t *__restrict__ keys,
-                      int key_bits, bool carry_prev, int npass, uint64_t *__restrict__ ghist)
+                      int key_bits, bool carry_prev, int npass_rt, uint64_t *__restrict__ ghist)
 {
     using P = Pack<BITS>;
     constexpr int CAP = kKeyTileThreads * P::SPW;
+    constexpr int HP = NP < 0 ? kMaxKeyPasses : (NP == 0 ? 1 : NP);
+    const int npass = NP < 0 ? npass_rt : NP;
     __shared__ uint64_t s_key[CAP];
-    __shared__ uint32_t s_hist[kMaxKeyPasses][256];
-    for (int i = threadIdx.x; i < kMaxKeyPasses * 256; i += kKeyTileThreads) (&s_hist[0][0])[i] = 0;
+    __shared__ uint32_t s_hist[HP][256];
+    for (int i = threadIdx.x; i < HP * 256; i += kKeyTileThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
     const uint64_t ntiles = (nwords + kKeyTileThreads - 1) / kKeyTileThreads;
@@ -257,21 +273,23 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
                 x1 <<= 2;
             }
             const uint64_t p0 = w * P::SPW;
+            const int have = p0 + P::SPW <= n ? P::SPW : (int)(n - p0); // positions of this word inside the text
 #pragma unroll
             for (int j = 0; j < P::SPW; ++j) {
-                if (p0 + j >= n) break; // positions behind the text (last word only)
-                const int b = BITS * j;
-                const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0; // stream from symbol j on
-                uint64_t k = (v >> (64 - key_bits)) | ~kmask;                // ones above: only real fields can be zero
-                k = cut_at_terminator<BITS>(k) & kmask;
+                if (j < have) {
+                    const int b = BITS * j;
+                    const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0; // stream from symbol j on
+                    uint64_t k = (v >> (64 - key_bits)) | ~kmask;                // ones above: only real fields can be zero
+                    k = cut_at_terminator_nb<BITS>(k) & kmask;
 #pragma unroll
-                for (int q = 0; q < kMaxKeyPasses; ++q)
-                    if (q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu], 1u);
-                if (carry_prev) {
-                    const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
-                    k |= (uint64_t)prev << key_bits;
+                    for (int q = 0; q < HP; ++q)
+                        if (NP > 0 || q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu], 1u);
+                    if (carry_prev) {
+                        const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
+                        k |= (uint64_t)prev << key_bits;
+                    }
+                    s_key[threadIdx.x * P::SPW + j] = k;
                 }
-                s_key[threadIdx.x * P::SPW + j] = k;
             }
         }
         __syncthreads();
@@ -2171,8 +2189,15 @@ void launch_make_keys_hist(cudaStream_t st, int bits, const uint64_t *packed, ui
     const int npass = (key_bits + 7) / 8;
     const uint64_t nwords = div_up(n, 64 / bits);
     const int grid = grid_for(nwords, kKeyTileThreads, 16);
-#define CALL(B) \
-    make_keys_hist_kernel<B><<<grid, kKeyTileThreads, 0, st>>>(packed, n, nwords, keys, key_bits, carry_prev, npass, ghist)
+#define CALL(B)                                                                                                       \
+    do {                                                                                                              \
+        if (npass == 6)                                                                                               \
+            make_keys_hist_kernel<B, 6><<<grid, kKeyTileThreads, 0, st>>>(packed, n, nwords, keys, key_bits, carry_prev, \
+                                                                          npass, ghist);                              \
+        else                                                                                                          \
+            make_keys_hist_kernel<B, -1><<<grid, kKeyTileThreads, 0, st>>>(packed, n, nwords, keys, key_bits,          \
+                                                                           carry_prev, npass, ghist);                 \
+    } while (0)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();
