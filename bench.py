@@ -21,6 +21,10 @@ roofline: the dominant kernel is the one-sweep LSD radix pass (6 passes, each on
           library around the passes of every timed step, divided by the number of launches).
 cpu_baseline: the UNMODIFIED reference `builder` (oracle/_ref/builder, single-threaded as shipped)
           on a bounded toydata-shaped sample, on this box's host cores, rank 0 at N=1 only.
+fasta_e2e (N=1): the path of the drop-in CLI -- FASTA bytes in pinned host memory, parsed and transformed on the GPU
+          (dsmfm_append_fasta), sections copied back; same workload, same unit.
+search (N=1): dsmfm_searcher_lf_device on the index of the workload, G LF queries/s (the query half of the index).
+roofline_refine: the refinement phase (second largest share of the step) against the same HBM peak.
 """
 import argparse
 import json
