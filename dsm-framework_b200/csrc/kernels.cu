@@ -1951,14 +1951,17 @@ __device__ __forceinline__ void wt_emit(uint32_t m, uint32_t b, uint32_t c, uint
                                         uint64_t *const *__restrict__ node_data, uint8_t *__restrict__ node_ch,
                                         const uint64_t *__restrict__ bit_base)
 {
-    uint64_t bits = 0;
-    uint32_t mm = m;
-    int out = 0;
-    while (mm) {
-        const int j = __ffs(mm) - 1;
-        bits |= (uint64_t)((b >> j) & 1u) << out;
-        ++out;
-        mm &= mm - 1;
+    uint64_t bits = b; // all 32 symbols are members (always so at the root): nothing to compress
+    if (m != 0xffffffffu) {
+        bits = 0;
+        uint32_t mm = m;
+        int out = 0;
+        while (mm) {
+            const int j = __ffs(mm) - 1;
+            bits |= (uint64_t)((b >> j) & 1u) << out;
+            ++out;
+            mm &= mm - 1;
+        }
     }
     const uint64_t o = local + (bit_base ? bit_base[v] : 0ull); // bit offset in the node's array
     unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]);
