@@ -858,8 +858,16 @@ void dsmfm_builder::build()
     // The initial radix sort orders suffixes by their first `first_syms` symbols only (48 key bits = 6
     // LSD passes instead of 8); the refinement rounds extend from there.  For DNA reads 16 symbols
     // already separate everything that is not a genuine repeat, so the two saved passes cost almost
-    // no extra refinement work.  DSMFM_FIRST_KEY_BITS overrides (multiple of 8 and of bits/symbol).
+    // no extra refinement work.  That stops being true when the collection is large: with L distinct loci the
+    // chance that a 16-mer also occurs at an unrelated locus is about L / 4^16, and unrelated loci in one tie
+    // group carry different BWT symbols, so the group has to be refined (8 GPUs x 1 Gbp: 3.2 G loci, 75 %;
+    // the refinement took 75 ms per GPU instead of 24).  Collections beyond 2^32 symbols therefore sort 18
+    // symbols (54 bits, a seventh pass of 6 bits): 16x fewer chance matches for about 13 ms of sorting.
+    // DSMFM_FIRST_KEY_BITS overrides (any multiple of bits/symbol); DSMFM_LONG_KEY_ABOVE moves the threshold (tests).
+    uint64_t long_key_above = 1ull << 32;
+    if (const char *e = std::getenv("DSMFM_LONG_KEY_ABOVE")) long_key_above = std::strtoull(e, nullptr, 10);
     int first_key_bits = 48;
+    if (n > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);
     if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
     if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
     int first_syms = std::max(1, first_key_bits / bits);

@@ -164,6 +164,27 @@ def test_suffix_array_bwt_and_index_match_oracle(seed, kw):
         _assert_same_fmi(b.fmi(), oracle.fmi_from_docs(docs))
 
 
+def test_long_first_key_of_large_collections(monkeypatch):
+    """Collections beyond 2^32 symbols sort 18 symbols (54 bits, 7 passes) instead of 16; with the threshold moved
+    down the same schedule runs on small inputs, unsharded and as key-range shards with wide positions."""
+    import dsmfm
+    monkeypatch.setenv("DSMFM_LONG_KEY_ABOVE", "1000")
+    for name in ["reads100", "poly_a", "duplicates", "mixed_alphabet"]:
+        docs, _ = oracle.fasta_to_docs(_golden(name, ".fasta"))
+        _assert_same_fmi(_build(docs), _golden(name, ".fmi"))
+    docs, _ = oracle.fasta_to_docs(cases.digest_cases()["reads100_3k"])
+    with dsmfm.Builder(device=0) as b:
+        b.append_batch(docs)
+        b.finish()
+        assert b.stats().sort_passes == 7
+        assert hashlib.sha256(b.fmi()).hexdigest() == MANIFEST["digests"]["reads100_3k"]["fmi_sha256"]
+    monkeypatch.setenv("DSMFM_POS_LO_BITS", "12")
+    want_bwt, want_sa = oracle.bwt(docs, want_sa=True)
+    fmi, bwt, sa = _sharded_build(docs, 3)
+    assert bwt == want_bwt and np.array_equal(sa.astype(np.uint64), want_sa)
+    assert hashlib.sha256(fmi).hexdigest() == MANIFEST["digests"]["reads100_3k"]["fmi_sha256"]
+
+
 @pytest.mark.parametrize("first_key_bits", ["63", "24", "9"])
 def test_first_key_width_does_not_change_the_result(first_key_bits, monkeypatch):
     """The initial sort may use fewer symbols (more refinement) or all 21 (BWT gathered instead of
