@@ -21,6 +21,35 @@ def rnd_fasta(seed, nreads, maxlen, alpha="ACGT", dup=0.2, pn=0.02, genome=2000,
     return "".join(out).encode()
 
 
+NASTY_CASES = [(1, 5, 10), (2, 40, 30), (3, 300, 90), (4, 2000, 200), (5, 50, 9000)]  # seed, rows, longest row
+
+
+def nasty_fasta(seed, nlines, maxlen):
+    """Everything the record loop has an opinion about: rows in front of the first header, empty rows, runs of
+    headers, CRLF, lower case, foreign symbols, '>' inside a row, long rows, blank-padded names."""
+    rng = random.Random(seed)
+    out = []
+    if rng.random() < 0.5:
+        out.append("ACGTTGCA"[: rng.randint(0, 8)] + "\n")
+    for i in range(nlines):
+        r = rng.random()
+        if r < 0.25:
+            out.append(">%sr%d%s\n" % (" \t"[rng.randint(0, 1)] * rng.randint(0, 2), i, rng.choice(["", " desc", "\tx y"])))
+        elif r < 0.30:
+            out.append("\n")
+        else:
+            ln = rng.randint(1, maxlen)
+            alpha = rng.choice(["ACGT", "ACGTN", "acgtn", "ACGTacgtRYKM", "ACGT>", "AC GT"])
+            row = "".join(rng.choice(alpha) for _ in range(ln))
+            if row[0] == ">":
+                row = "A" + row[1:]
+            out.append(row + rng.choice(["\n", "\n", "\n", "\r\n"]))
+    s = "".join(out)
+    if rng.random() < 0.3:
+        s += "ACGTAC"  # unterminated last row: dropped
+    return s.encode()
+
+
 # name -> FASTA bytes.  Small enough for the plain-C oracle and for committing the reference's output.
 def golden_cases():
     c = {}

@@ -1,5 +1,6 @@
 """GPU suite: the FASTA front end on the device (dsmfm_append_fasta) against the oracle's restatement of the
 reference CLI's record loop (builder.cpp:203-262) and against the golden files of the unmodified reference."""
+import hashlib
 import json
 import os
 import random
@@ -15,6 +16,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 MANIFEST = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+NASTY = json.load(open(os.path.join(GOLDEN, "nasty.json")))
 
 
 def _golden(name, ext):
@@ -55,30 +57,7 @@ def _assert_same_fmi(got, want):
     assert got == want
 
 
-def nasty_fasta(seed, nlines, maxlen):
-    """Everything the record loop has an opinion about: rows in front of the first header, empty rows, runs of
-    headers, CRLF, lower case, foreign symbols, '>' inside a row, long rows, blank-padded names."""
-    rng = random.Random(seed)
-    out = []
-    if rng.random() < 0.5:
-        out.append("ACGTTGCA"[: rng.randint(0, 8)] + "\n")
-    for i in range(nlines):
-        r = rng.random()
-        if r < 0.25:
-            out.append(">%sr%d%s\n" % (" \t"[rng.randint(0, 1)] * rng.randint(0, 2), i, rng.choice(["", " desc", "\tx y"])))
-        elif r < 0.30:
-            out.append("\n")
-        else:
-            ln = rng.randint(1, maxlen)
-            alpha = rng.choice(["ACGT", "ACGTN", "acgtn", "ACGTacgtRYKM", "ACGT>", "AC GT"])
-            row = "".join(rng.choice(alpha) for _ in range(ln))
-            if row[0] == ">":
-                row = "A" + row[1:]
-            out.append(row + rng.choice(["\n", "\n", "\n", "\r\n"]))
-    s = "".join(out)
-    if rng.random() < 0.3:
-        s += "ACGTAC"  # unterminated last row: dropped
-    return s.encode()
+nasty_fasta = cases.nasty_fasta
 
 
 @pytest.mark.parametrize("name", sorted(MANIFEST["files"]))
@@ -103,6 +82,9 @@ def test_nasty_fasta_matches_the_oracle(seed, nlines, maxlen):
     assert i["records"] == sum(1 for row in fasta.split(b"\n")[:-1] if row[:1] == b">")
     assert i["bad_headers"] == 0
     _assert_same_fmi(got, want)
+    pinned = NASTY["cases"].get("nasty_%d" % seed)  # what the unmodified reference wrote for this input
+    if pinned and (seed, nlines, maxlen) in cases.NASTY_CASES:
+        assert hashlib.sha256(got).hexdigest() == pinned["fmi_sha256"]
 
 
 @pytest.mark.parametrize("seed,chunk", [(3, 7), (3, 100), (4, 4096), (6, 5000), (7, 65536), (8, 1 << 20)])

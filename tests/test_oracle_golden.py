@@ -175,3 +175,25 @@ def test_oracle_queries_match_live_reference(tmp_path):
     for (op, c, i), a in zip(qs, ans):
         assert (x.lf(c, i) if op == "L" else x.access(i)[0]) == a
     x.close()
+
+
+# ---- the record loop on adversarial FASTA (rows before the first header, runs of headers, CRLF, '>' inside a row ...) ----
+
+NASTY = json.load(open(os.path.join(GOLDEN, "nasty.json")))
+
+
+@pytest.mark.parametrize("seed,rows,longest", cases.NASTY_CASES)
+def test_oracle_front_end_matches_the_reference_on_adversarial_fasta(seed, rows, longest):
+    """tests/golden/nasty.json: digests of what the unmodified reference builder wrote for cases.nasty_fasta."""
+    e = NASTY["cases"]["nasty_%d" % seed]
+    fasta = cases.nasty_fasta(seed, rows, longest)
+    assert hashlib.sha256(fasta).hexdigest() == e["fasta_sha256"], "tests/cases.py drifted from the committed digest"
+    got = oracle.build(fasta)
+    assert len(got) == e["fmi_bytes"] and hashlib.sha256(got).hexdigest() == e["fmi_sha256"]
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not present")
+def test_oracle_front_end_matches_live_reference_on_adversarial_fasta(tmp_path):
+    for seed in (11, 12, 13):
+        fasta = cases.nasty_fasta(seed, 200, 150)
+        assert oracle.build(fasta) == oracle.reference_build(fasta, tmp_path)
