@@ -126,6 +126,27 @@ def section_bytes(idx):
     return total
 
 
+def fmi_sha256(index, dsmfm):
+    """SHA-256 of the `.fmi` bytes FMIndex::save would write for these sections (dsmfm_fmi_serialize)."""
+    import hashlib
+    blob = dsmfm.fmi_bytes(index)
+    return hashlib.sha256(blob).hexdigest(), len(blob)
+
+
+def reference_digest(workload, kw):
+    """Digest of the `.fmi` the UNMODIFIED reference wrote for exactly these generator parameters
+    (tests/golden/fullsize.json, made by tests/golden/make_fullsize_golden.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize.json")) as f:
+            table = json.load(f)
+    except Exception:
+        return None
+    for name, rec in table.items():
+        if all(rec["params"].get(k) == v for k, v in kw.items()) and len(rec["params"]) == len(kw):
+            return dict(rec, name=name)
+    return None
+
+
 def cpu_reference_run(threads, params, tmpdir):
     """Times the reference's own CPU implementation on a bounded sample.  threads == 1: the stock
     `builder` binary; threads > 1: oracle/_ref/ref_driver, which drives the same reference classes
@@ -173,7 +194,9 @@ def run_reference(args):
     value = bases * len(times) / total / 1e6
     sample = ("%d x %d-bp reads (%.0f Mbp, 10x coverage, sub 0.005, N 0.001) per step; the reference classes "
               "(RLCSABuilder -> FMIndex -> HuffWT) driven by oracle/ref_driver.cpp with incbwt's OpenMP sort on "
-              "%d threads" % (CPU_SAMPLE["n_reads"], CPU_SAMPLE["read_len"], bases / 1e6, threads))
+              "%d threads; the documents are handed over ready-made (FASTA parsing and transform() are NOT timed, "
+              "which favours the CPU arm; a single 512 MiB batch, so incbwt's merge by backward search never runs)"
+              % (CPU_SAMPLE["n_reads"], CPU_SAMPLE["read_len"], bases / 1e6, threads))
     line = {"impl": "reference", "metric": "fm_index_build_throughput", "value": round(value, 4), "unit": "Mbp/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1000 * total / len(times), 2), "higher_is_better": True, "scaling": "weak",
@@ -409,7 +432,10 @@ def main():
         "dtype": "u64",
         "data": "synthetic",
         "config": {
-            "workload": "%s: %d x %d-bp ACGTN reads per GPU (%.2f Gbp, n = %d indexed symbols), SA + BWT + HuffWT + BitRank"
+            "workload": "%s: %d x %d-bp ACGTN reads per GPU (%.2f Gbp, n = %d indexed symbols): every section of the .fmi "
+                        "(suffix sort -> BWT -> C[] -> HuffWT -> BitRank).  The headline build sorts the suffixes only as far "
+                        "as the BWT needs (tie groups whose members share one BWT symbol stay unsorted: the .fmi holds no "
+                        "suffix array); the build that finishes the whole suffix array is `with_suffix_array`"
                         % (args.workload, n_reads, L, bases / 1e9, nbytes),
             "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs build ONE index of %.2f Gbp: NCCL all-gather of the raw text, key-range sharded suffix "
@@ -473,6 +499,39 @@ def main():
         "note": "random 16-byte gathers: the bound is DRAM row activations (about 56 G accesses/s measured, "
                 "tools_dev/gather_bench.cu), not bytes"}
 
+    if world == 1:
+        # the same workload with the WHOLE suffix array finished (DSMFM_FLAG_KEEP_SA: what BASELINE.json's "SA" and the
+        # .sa sampling need); device-resident inputs, CUDA events on the build stream like `value`
+        sa_steps = max(2, min(args.steps, 3))
+        sa_stats = []
+        for i in range(1 + sa_steps):
+            b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=dsmfm.FLAG_KEEP_SA)
+            b.append_batch_device(dev_docs)
+            b.build_device()
+            if i:
+                sa_stats.append(b.stats())
+            b.close()
+        sa_ms = sum(x.ms_total for x in sa_stats) / len(sa_stats)
+        line["with_suffix_array"] = {
+            "value": round(bases / (sa_ms * 1e-3) / 1e6, 2), "unit": "Mbp/s", "ms_per_step": round(sa_ms, 3), "steps": sa_steps,
+            "phase_ms": {"pack": round(sa_stats[-1].ms_pack, 2), "sort": round(sa_stats[-1].ms_sort, 2),
+                         "refine": round(sa_stats[-1].ms_refine, 2), "wavelet": round(sa_stats[-1].ms_wt, 2)},
+            "members_sorted": int(sa_stats[-1].refine_members),
+            "note": "DSMFM_FLAG_KEEP_SA: every tie group sorted to the end; device time of dsmfm_build_device (events inside the library)"}
+
+        # parity of what was timed: one more default-flags build through the host-buffer API, serialised and hashed, against
+        # the digest of the .fmi the unmodified reference wrote for the same documents (tests/golden/fullsize.json)
+        b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
+        b.append_batch(host_docs)
+        sha, size = fmi_sha256(b.finish(), dsmfm)
+        b.close()
+        want = reference_digest(args.workload, kw)
+        line["parity"] = {"sha256": sha, "fmi_bytes": size,
+                          "matches": None if want is None else bool(want["fmi_sha256"] == sha and want["fmi_bytes"] == size),
+                          "against": None if want is None else
+                          "tests/golden/fullsize.json[%s]: %s" % (want["name"], want["reference"]),
+                          "flags": flags}
+
     if world == 1 and not args.no_extras:
         line["fasta_e2e"] = fasta_front_end(args, kw, local, stream, torch, dsmfm, dsmgen)
         line["search"] = query_side(host_docs, local, stream, torch, dsmfm)
@@ -502,6 +561,9 @@ def main():
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    if line.get("parity", {}).get("matches") is False:
+        print("bench.py: the index that was timed differs from the reference's", file=sys.stderr)
+        return 3
     return 0
 
 

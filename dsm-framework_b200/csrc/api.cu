@@ -787,17 +787,19 @@ void dsmfm_builder::build()
         empty_collection = true;
     }
 
-    // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the
-    // default 64-byte L2 fetch granularity every miss drags in a second, unused sector.
-    size_t old_gran = 0;
-    cudaDeviceGetLimit(&old_gran, cudaLimitMaxL2FetchGranularity);
-    size_t want_gran = 32;
-    if (const char *e = std::getenv("DSMFM_L2_FETCH")) want_gran = (size_t)std::atoi(e);
-    if (want_gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want_gran);
-    struct RestoreGran {
-        size_t v;
-        ~RestoreGran() { if (v) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, v); }
-    } restore_gran{old_gran};
+    // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the default
+    // 64-byte L2 fetch granularity every miss drags in a second, unused sector.  The limit is a property of the
+    // device context, so it is set ONCE per device by the first build of the process (not per build, and not
+    // restored: toggling it around every build would change device-global state under other streams' feet).
+    // DSMFM_L2_FETCH=0 leaves the limit alone, any other value overrides the 32 bytes.
+    {
+        static DeviceOnce gran_once;
+        gran_once.run([] {
+            size_t want_gran = 32;
+            if (const char *e = std::getenv("DSMFM_L2_FETCH")) want_gran = (size_t)std::atoi(e);
+            if (want_gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want_gran);
+        });
+    }
 
     DSM_CUDA(cudaEventRecord(ev[0], st));
     // contiguous text
@@ -1580,7 +1582,9 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
             uint64_t keep = ~0ull;
             DSM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
-        if (!b->stream) {
+        // opts->stream == NULL means "a stream of the builder's own" unless the caller states that it really
+        // wants the legacy default stream (handle 0), e.g. because its own work is queued there
+        if (!b->stream && !(b->flags & DSMFM_FLAG_DEFAULT_STREAM)) {
             DSM_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
             b->own_stream = true;
         }
@@ -1942,6 +1946,8 @@ DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out)
         b->stats.ms_wall_fetch = (float)(now_ms() - t0);
     } catch (const CudaError &e) {
         return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
     }
     if (out) *out = b->index;
     return DSMFM_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 
 namespace dsmfm {
@@ -24,6 +25,25 @@ struct CudaError {
 #define DSM_LAUNCH_CHECK() DSM_CUDA(cudaGetLastError())
 
 static inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// Function attributes (dynamic shared memory above 48 KB, carve-out) are per DEVICE: a process that builds on
+// several GPUs (dsmfm_options.device; the multi-GPU host runs one thread per device) must set them once on each.
+// run(f) calls f the first time it is reached on the current device; callers on other threads wait for it.
+struct DeviceOnce {
+    std::mutex mu;
+    uint64_t done[4] = {0, 0, 0, 0}; // up to 256 device ordinals
+    template <typename F> void run(F &&f)
+    {
+        int dev = 0;
+        DSM_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> g(mu);
+        const uint64_t bit = 1ull << (dev & 63);
+        uint64_t &word = done[(dev >> 6) & 3];
+        if (word & bit) return;
+        f();
+        word |= bit;
+    }
+};
 
 // Number of SMs on B200; grids for grid-stride kernels are sized in multiples of it.
 constexpr int kNumSMs = 148;

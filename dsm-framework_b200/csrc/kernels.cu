@@ -2291,8 +2291,8 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
     const int max_steps = multi_step ? (1 << 30) : 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    attr_once.run([] {
 #define SET(B, K)                                                                                             \
     DSM_CUDA(cudaFuncSetAttribute(refine_kernel<B, K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)sizeof(RefSmem<K, false>)));                                           \
@@ -2300,16 +2300,15 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                                   (int)sizeof(RefSmem<K, true>)))
         SET(3, 1); SET(4, 1); SET(8, 1); SET(3, 2); SET(4, 2); SET(8, 2);
 #undef SET
-        attr_set = true;
-    }
+    });
     const unsigned grid = win_list ? n_list : nwin;
     if (grid == 0) return;
     // default schedule: multi-step with the text of the unresolved suffixes resident in shared memory
     const char *variant_env = std::getenv("DSMFM_REFINE_VARIANT"); // 0: CTA-wide steps (refine_kernel), 2: independent warps
     const int variant = variant_env ? std::atoi(variant_env) : 2;
     if (multi_step && variant == 2) {
-        static bool attr3_set = false;
-        if (!attr3_set) {
+        static DeviceOnce attr3_once;
+        attr3_once.run([] {
 #define SET3(B, K)                                                                                                      \
     DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)sizeof(RwSmem<K, false>)));                                                      \
@@ -2321,8 +2320,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                                   (int)sizeof(RwSmem<K, true>)))
             SET3(3, 1); SET3(4, 1); SET3(8, 1); SET3(3, 2); SET3(4, 2); SET3(8, 2);
 #undef SET3
-            attr3_set = true;
-        }
+        });
 #define RW2(B, K, W, O)                                                                                           \
     refine_warps_kernel<B, K, W, O><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                             \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \

@@ -272,9 +272,12 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
     if (div_up(n < kSweepPortion ? n : kSweepPortion, kSweepTile) > ws.status_tiles)
         throw CudaError{cudaErrorInvalidValue, "radix_sort_pairs: workspace too small", __FILE__, __LINE__};
 
-    static bool attr_set = false;
-    static bool hw_match = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    static const bool hw_match = [] { // experiment: match.any instead of the ballot rounds
+        const char *e = getenv("DSMFM_SWEEP_MATCH");
+        return e && atoi(e) != 0;
+    }();
+    attr_once.run([] {
         const int sm = (int)sizeof(SweepSmem);
         DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -284,9 +287,7 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        if (const char *e = getenv("DSMFM_SWEEP_MATCH")) hw_match = atoi(e) != 0; // experiment: match.any vs ballots
-        attr_set = true;
-    }
+    });
 
     if (!hist_ready) {
         DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * npass * kRadix, stream));

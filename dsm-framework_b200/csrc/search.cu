@@ -25,6 +25,7 @@ struct QNode {
     const uint64_t *data; // BitRank::data
     const uint64_t *Rs;   // ones in front of every 256-bit superblock
     const uint8_t *Rb;    // ones in front of every word inside its superblock
+    uint64_t nbits;       // length of the node's bit vector: every position handed to it is clamped to this
     int32_t left, right;  // children in the node table
     uint8_t leaf, ch;
     uint8_t pad[6];
@@ -53,6 +54,9 @@ __device__ __forceinline__ uint64_t wt_rank(const QIndex *__restrict__ x, uint32
     uint32_t code = x->code[c];
     const QNode *t = &x->nodes[0];
     while (!t->leaf) {
+        // positions behind the node's last bit count as its last one (i >= n, or directories of a damaged file
+        // that promise more ones than the child holds): no read ever leaves the node's arrays
+        cnt = cnt < t->nbits ? cnt : t->nbits;
         const uint64_t r1 = ones_before(*t, cnt);
         if (code & 1u) {
             cnt = r1;
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(256) search_access_kernel(const QIndex *__rest
     uint64_t p = i[q];
     const QNode *t = &x->nodes[0];
     while (!t->leaf) {
+        if (p >= t->nbits) p = t->nbits ? t->nbits - 1 : 0; // never outside the node (see wt_rank)
         const bool bit = (__ldg(t->data + (p >> 6)) >> (p & 63)) & 1u;
         const uint64_t r1 = ones_before(*t, p + 1);
         if (bit) {
@@ -198,7 +203,10 @@ int link_nodes(const dsmfm_node *nodes, uint32_t n_nodes, uint32_t &next, QIndex
     q.nodes[me].leaf = nodes[me].leaf;
     q.nodes[me].ch = nodes[me].ch;
     q.nodes[me].left = q.nodes[me].right = -1;
+    q.nodes[me].nbits = nodes[me].leaf ? 0 : nodes[me].nbits;
     if (!nodes[me].leaf) {
+        // BitRank.cpp:97-101: integers = ceil((n+1)/64); the kernels index data/Rs/Rb by positions <= nbits
+        if (nodes[me].integers != nodes[me].nbits / 64 + 1 || !nodes[me].data || !nodes[me].Rs || !nodes[me].Rb) return -1;
         const int l = link_nodes(nodes, n_nodes, next, q);
         const int r = link_nodes(nodes, n_nodes, next, q);
         if (l < 0 || r < 0) return -1;
@@ -243,7 +251,8 @@ int searcher_from_index(int device, const dsmfm_index *idx, dsmfm_searcher **out
         q->present[c] = idx->codetable[c].count != 0;
     }
     uint32_t next = 0;
-    if (link_nodes(idx->nodes, idx->n_nodes, next, *q) < 0 || next != idx->n_nodes) {
+    if (link_nodes(idx->nodes, idx->n_nodes, next, *q) < 0 || next != idx->n_nodes ||
+        (!idx->nodes[0].leaf && idx->nodes[0].nbits != idx->n)) {
         g_search_create_error = "malformed wavelet tree";
         delete s;
         delete q;
@@ -305,8 +314,15 @@ extern "C" {
 DSMFM_API int dsmfm_searcher_create(int device, const dsmfm_index *idx, dsmfm_searcher **out)
 {
     if (!out) return DSMFM_EINVAL;
-    return searcher_from_index(device, idx, out);
+    try {
+        return searcher_from_index(device, idx, out);
+    } catch (const std::bad_alloc &) {
+        g_search_create_error = "host allocation failed";
+        return DSMFM_ENOMEM;
+    }
 }
+
+static int searcher_open_impl(int device, const char *fmi_path, dsmfm_searcher **out);
 
 // FMIndex::FMIndex(FILE *) (FMIndex.cpp:245-357), HuffWT::load (HuffWT.cpp:57-71, 201-207), BitRank::BitRank(FILE *)
 // (BitRank.cpp:111-132): only what the queries need -- n, C, the code table and the tree.
@@ -314,6 +330,16 @@ DSMFM_API int dsmfm_searcher_open(int device, const char *fmi_path, dsmfm_search
 {
     if (!out || !fmi_path) return DSMFM_EINVAL;
     *out = nullptr;
+    try {
+        return searcher_open_impl(device, fmi_path, out);
+    } catch (const std::bad_alloc &) { // the whole file and aligned copies of its arrays live in host vectors
+        g_search_create_error = "host allocation failed while loading the .fmi file";
+        return DSMFM_ENOMEM;
+    }
+}
+
+static int searcher_open_impl(int device, const char *fmi_path, dsmfm_searcher **out)
+{
     FILE *f = std::fopen(fmi_path, "rb");
     if (!f) {
         g_search_create_error = std::string("unable to open ") + fmi_path;
@@ -364,8 +390,13 @@ DSMFM_API int dsmfm_searcher_open(int device, const char *fmi_path, dsmfm_search
             std::memcpy(&b, &img[pos + 16], 4);
             std::memcpy(&sf, &img[pos + 20], 4);
             pos += 24;
-            const size_t b_data = 8 * nd.integers, b_rs = 8 * (nd.nbits / 256 + 1), b_rb = nd.nbits / 64 + 1;
-            if (b != 64 || sf != 256 || pos + b_data + b_rs + b_rb > img.size()) {
+            // sizes come from the file: bound them by the file before any arithmetic can wrap
+            const size_t left = img.size() - pos;
+            const bool sane = b == 64 && sf == 256 && nd.nbits / 8 <= left && nd.integers == nd.nbits / 64 + 1 &&
+                              (nodes.empty() ? nd.nbits == idx.n : nd.nbits <= idx.n);
+            const size_t b_data = sane ? 8 * nd.integers : 0, b_rs = sane ? 8 * (nd.nbits / 256 + 1) : 0,
+                         b_rb = sane ? nd.nbits / 64 + 1 : 0;
+            if (!sane || b_data > left || b_rs > left - b_data || b_rb > left - b_data - b_rs) {
                 g_search_create_error = "malformed BitRank in the .fmi file";
                 return DSMFM_EINVAL;
             }

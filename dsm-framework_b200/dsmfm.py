@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdsmfm.so")
 
 OK, EINVAL, ECUDA, ENOMEM, EEMPTY, ELIMIT, EIO = 0, -1, -2, -3, -4, -5, -6
-FLAG_KEEP_BWT, FLAG_KEEP_SA = 1, 2
+FLAG_KEEP_BWT, FLAG_KEEP_SA, FLAG_DEFAULT_STREAM = 1, 2, 4
 
 
 class Options(C.Structure):
@@ -217,6 +217,7 @@ class Builder:
 
     def build_device(self):
         self._check(self._L.dsmfm_build_device(self._h))
+        self._keep = []  # the build has synchronised its stream: the appended buffers have been consumed
 
     def shard_info(self):
         sh = Shard()

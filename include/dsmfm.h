@@ -51,7 +51,12 @@ typedef struct dsmfm_options {
     int32_t device;          /* CUDA device ordinal; -1 = current device                         */
     uint32_t samplerate;     /* 0 -> 124, as TextCollectionBuilder.cpp:37-39                      */
     uint64_t expected_bytes; /* hint: total bytes of documents incl. terminators (0 = unknown)    */
-    void *stream;            /* cudaStream_t to run on; NULL = the builder creates its own        */
+    void *stream;            /* cudaStream_t to run on; NULL = the builder creates a non-blocking  */
+                             /* stream of its own (NULL + DSMFM_FLAG_DEFAULT_STREAM: the legacy    */
+                             /* default stream).  Everything the builder does is ordered on this   */
+                             /* stream ONLY: device buffers handed to dsmfm_append_batch_device /   */
+                             /* dsmfm_build_packed must be complete on it, i.e. produced on it or   */
+                             /* synchronised with it by the caller before the call                  */
     uint32_t flags;          /* DSMFM_FLAG_*                                                      */
     uint32_t reserved;
     /* Key-range sharding of ONE collection over several GPUs (one builder per GPU, every builder is
@@ -70,6 +75,7 @@ typedef struct dsmfm_options {
 
 #define DSMFM_FLAG_KEEP_BWT 1u /* keep the plain BWT in host memory after finish (dsmfm_index.bwt)   */
 #define DSMFM_FLAG_KEEP_SA 2u  /* keep suffix array, BWT and document boundaries on the device (dsmfm_write_sa) */
+#define DSMFM_FLAG_DEFAULT_STREAM 4u /* opts->stream == NULL names the legacy default stream, not "create one" */
 
 /* One Huffman code-table entry: HuffWT::TCodeEntry, HuffWT.h:13-19. */
 typedef struct dsmfm_code {
@@ -153,11 +159,15 @@ DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len);
 /* Bulk form of dsmfm_append: `bytes` bytes holding documents each followed by
  * one '\0' (the layout RLCSABuilder keeps in its buffer, rlcsa_builder.cpp:54-60).
  * The last byte must be '\0'.  Document count and longest length are taken on
- * the device. */
+ * the device.  The host-to-device copy is asynchronous when `docs` is page-locked: the buffer must stay
+ * unchanged until the build has synchronised (dsmfm_build_device / dsmfm_finish return). */
 DSMFM_API int dsmfm_append_batch(dsmfm_builder *b, const uint8_t *docs, size_t bytes);
 
 /* Same, but `docs` is DEVICE memory on the builder's device (inputs already
- * resident in HBM); copied device-to-device on the builder's stream. */
+ * resident in HBM); copied device-to-device on the builder's stream.  The copy is ordered after earlier
+ * work of THAT stream only: a buffer filled on another stream (a collective, another library) must be
+ * complete -- synchronise, or make the builder's stream wait on an event -- before this call.  The buffer
+ * may be released once the builder's stream has consumed the copy (dsmfm_build_device synchronises it). */
 DSMFM_API int dsmfm_append_batch_device(dsmfm_builder *b, const void *docs_dev, size_t bytes);
 
 /* Replaces: the record loop and per-read transform of the reference CLI, build() in builder.cpp:203-262

@@ -1,12 +1,47 @@
 """GPU suite at BASELINE.json's sizes, where neither the oracle nor the reference finishes in test
 time: size-independent properties of the result (sortedness of sampled suffix-array windows under the
 reference's comparison rule, BWT/text consistency, rank-directory self-consistency)."""
+import hashlib
+import json
 import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _fullsize_digests():
+    with open(os.path.join(HERE, "golden", "fullsize.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("config", ["C1", "C4s", "C5s", "C3"])
+def test_full_size_fmi_equals_the_reference_digest(config):
+    """The BENCHMARKED code path at the benchmarked size against the reference itself: tests/golden/fullsize.json
+    holds size and SHA-256 of the `.fmi` the unmodified reference classes wrote for the documents of the
+    configuration (tests/golden/make_fullsize_golden.py; C3 = the 1 Gbp workload bench.py times, four incbwt
+    batches merged by backward search).  The default build (flags = 0: BWT-only refinement on the compacted
+    groups, what bench.py runs) and the build that keeps the whole suffix array must both reproduce it."""
+    import dsmfm
+    import dsmgen
+    want = _fullsize_digests()[config]
+    kw = want["params"]
+    if os.environ.get("DSMFM_TEST_SMALL") and config == "C3":
+        pytest.skip("C3 digest needs the full 1 Gbp sample")
+    docs = dsmgen.docs(**kw)
+    assert docs.nbytes == want["docs_bytes"]
+    if config != "C3":  # (hashing 2 GB of input as well is not worth the test time)
+        assert hashlib.sha256(docs).hexdigest() == want["docs_sha256"]
+    for flags in (0, dsmfm.FLAG_KEEP_SA):
+        with dsmfm.Builder(flags=flags, expected_bytes=docs.size) as b:
+            b.append_batch(docs)
+            b.finish()
+            got = b.fmi()
+        assert len(got) == want["fmi_bytes"]
+        assert hashlib.sha256(got).hexdigest() == want["fmi_sha256"], "flags=%d: .fmi differs from the reference's" % flags
+        del got
 
 
 def _suffix_less_equal(text, a, b):
