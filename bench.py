@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the FASTA front-end and query-side measurements (N=1)")
     ap.add_argument("--ranges-per-gpu", type=int, default=1, help="N>1: key ranges sorted one after the other per GPU")
+    ap.add_argument("--no-full-parity", action="store_true", help="N>1: skip the one-GPU rebuild of the full collection (parity)")
     return ap.parse_args()
 
 
@@ -145,6 +146,93 @@ def reference_digest(workload, kw):
         if all(rec["params"].get(k) == v for k, v in kw.items()) and len(rec["params"]) == len(kw):
             return dict(rec, name=name)
     return None
+
+
+def sha256_file(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        while True:
+            blk = f.read(1 << 24)
+            if not blk:
+                break
+            h.update(blk)
+    return h.hexdigest(), os.path.getsize(path)
+
+
+def multi_gpu_parity(args, dist, torch, dsmfm, dsmgen, multigpu, engine, host_docs, kw, rank, world, local):
+    """Parity of the N-GPU build (outside the timed regions).
+    (1) preflight at reduced size: 100k reads per rank built by the N ranks, every rank writing its share of the
+        file, against the SAME documents built unsharded on one GPU (the path pinned to the reference's digests);
+    (2) full size: the index of the workload just timed, written by the N ranks, against a one-GPU build of the
+        same N x 1 Gbp collection on rank 0 (key ranges sorted one after the other; --no-full-parity skips it)."""
+    import shutil
+    import tempfile
+    import traceback
+    box = [tempfile.mkdtemp(prefix="dsmfm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tmp = box[0]
+    out = {"world": world}
+    try:
+        # ---- (1) reduced size ----
+        small = dict(kw, n_reads=100_000, genome_len=max(10_000, kw["genome_len"] // 100))
+        kws = [dict(small, seed=small["seed"] - 1000 * rank + 1000 * r, pool_seed=small["pool_seed"] - 1000 * rank + 1000 * r)
+               for r in range(world)]
+        mine = torch.from_numpy(dsmgen.docs(**kws[rank])).pin_memory()
+        sb = multigpu.build_sharded(dist, mine, engine, ranges_per_gpu=args.ranges_per_gpu)
+        sb.write(os.path.join(tmp, "small"))
+        sb.close()
+        dist.barrier()
+        if rank == 0:
+            got, size = sha256_file(os.path.join(tmp, "small.fmi"))
+            with dsmfm.Builder(device=local) as b1:
+                for r in range(world):
+                    b1.append_batch(dsmgen.docs(**kws[r]))
+                want, wsize = fmi_sha256(b1.finish(), dsmfm)
+            out["preflight"] = {"reads_per_rank": small["n_reads"], "sha256": got, "fmi_bytes": size,
+                                "matches": bool(got == want and size == wsize),
+                                "against": "the same documents built unsharded on one GPU (dsmfm_finish)"}
+        # ---- (2) the workload itself ----
+        sb = multigpu.build_sharded(dist, host_docs, engine, ranges_per_gpu=args.ranges_per_gpu)
+        sb.write(os.path.join(tmp, "full"))
+        sb.close()
+        dist.barrier()
+        if rank == 0:
+            got, size = sha256_file(os.path.join(tmp, "full.fmi"))
+            out.update({"sha256": got, "fmi_bytes": size, "matches": None, "against": None})
+            os.remove(os.path.join(tmp, "full.fmi"))
+            if not args.no_full_parity:
+                try:
+                    dsmfm.lib().dsmfm_release_cached(local)
+                    torch.cuda.empty_cache()
+                    k = max(2, world)
+                    with dsmfm.Builder(device=local, shard_index=0, shard_count=k, shard_span=k) as b1:
+                        for r in range(world):
+                            kr = dict(kw, seed=kw["seed"] - 1000 * rank + 1000 * r, pool_seed=kw["pool_seed"] - 1000 * rank + 1000 * r)
+                            b1.append_batch(host_docs if r == rank else dsmgen.docs(**kr))
+                        b1.build_device()
+                        info = b1.shard_info()
+                        b1.assemble(int(info.bwt_dev), int(info.n_total))
+                        want, wsize = fmi_sha256(b1.fetch(), dsmfm)
+                    out["matches"] = bool(got == want and size == wsize)
+                    out["against"] = ("the same %d x %.2f Gbp collection built on ONE GPU (rank 0: %d key ranges sorted one after "
+                                      "the other, wavelet tree over the whole BWT), itself pinned to the reference by the C3 digest "
+                                      "at N=1" % (world, kw["n_reads"] * kw["read_len"] / 1e9, k))
+                except Exception as e:  # (e.g. not enough memory for the one-GPU build): the preflight still stands
+                    out["full_size_error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
+                    traceback.print_exc(file=sys.stderr)
+                    out["matches"] = out.get("preflight", {}).get("matches")
+                    out["against"] = "preflight only (the one-GPU build of the full collection failed, see full_size_error)"
+            else:
+                out["matches"] = out.get("preflight", {}).get("matches")
+                out["against"] = "preflight only (--no-full-parity)"
+            if out.get("preflight", {}).get("matches") is False:
+                out["matches"] = False
+        dist.barrier()
+    finally:
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out if rank == 0 else None
 
 
 def cpu_reference_run(threads, params, tmpdir):
@@ -322,25 +410,21 @@ def main():
 
     if world > 1:
         import multigpu
-        engine = multigpu.CudaEngine(local, stream=stream.cuda_stream, flags=flags)
+        engine = multigpu.CudaEngine(local, flags=flags)
         launches = [0]
 
-        def sharded(docs, fetch):
-            handle, info = multigpu.build_sharded(dist, docs, engine, ranges_per_gpu=args.ranges_per_gpu)
-            s, out_bytes = info["stats"], 0
-            if handle is not None:
-                if fetch:
-                    out_bytes = section_bytes(handle.fetch())
-                s = handle.stats()
-                handle.close()
+        def sharded(docs):
+            sb = multigpu.build_sharded(dist, docs, engine, ranges_per_gpu=args.ranges_per_gpu)
+            s, out_bytes = sb.build_stats(), sb.section_bytes
+            sb.close()
             launches[0] += s.kernel_launches
             return s, out_bytes
 
         def device_step():
-            return sharded(dev_docs, False)[0]
+            return sharded(dev_docs)[0]
 
         def e2e_step():
-            return sharded(host_docs, True)
+            return sharded(host_docs)
     else:
         def device_step():
             b = dsmfm.Builder(device=local, stream=stream.cuda_stream, expected_bytes=nbytes, flags=flags)
@@ -392,10 +476,11 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     barrier()
     t_e2e = float(t_e2e.item())
-    n_launch = torch.tensor([sum(s.kernel_launches for s in stats)], dtype=torch.int64, device="cuda")
+    n_launch = torch.tensor([sum(s.kernel_launches for s in stats), e2e_out[-1][1]], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(n_launch)
-    n_launch = int(n_launch.item())
+    n_launch, d2h_bytes = int(n_launch[0].item()), int(n_launch[1].item())
+    parity = multi_gpu_parity(args, dist, torch, dsmfm, dsmgen, multigpu, engine, host_docs, kw, rank, world, local) if world > 1 else None
 
     if rank != 0:
         if dist is not None:
@@ -438,8 +523,10 @@ def main():
                         "suffix array); the build that finishes the whole suffix array is `with_suffix_array`"
                         % (args.workload, n_reads, L, bases / 1e9, nbytes),
             "parallelism": "1 GPU" if world == 1 else
-                           "%d GPUs build ONE index of %.2f Gbp: NCCL all-gather of the raw text, key-range sharded suffix "
-                           "sort (%d range(s) per GPU), BWT slices gathered on rank 0 for the wavelet tree"
+                           "%d GPUs build ONE index of %.2f Gbp: every rank packs its block, NCCL all-gather of the PACKED slots "
+                           "(3 bits per symbol), key-range sharded suffix sort from the replicated packed text (%d range(s) per "
+                           "GPU, no exchange during the sort), every rank builds its share of the wavelet tree and BitRank "
+                           "directories on its own GPU and copies it to its own host (no funnel through one GPU)"
                            % (world, world * bases / 1e9, args.ranges_per_gpu),
             "cache": "inputs (%.2f GB) and sort buffers are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
             "bits_per_symbol": s0.bits_per_symbol,
@@ -458,9 +545,12 @@ def main():
             "value": round(world * bases * args.steps / t_e2e / 1e6, 2),
             "unit": "Mbp/s",
             "h2d_bytes_per_step": world * nbytes,
-            "d2h_bytes_per_step": e2e_out[-1][1],
+            "d2h_bytes_per_step": d2h_bytes,
             "ms_per_step": round(1000 * t_e2e / args.steps, 2),
-            "api": "dsmfm_create / dsmfm_append_batch (pinned host buffer) / dsmfm_finish / dsmfm_destroy",
+            "api": "dsmfm_create / dsmfm_append_batch (pinned host buffer) / dsmfm_finish / dsmfm_destroy" if world == 1 else
+                   "per rank: dsmfm_create / dsmfm_append_batch (pinned host buffer) / dsmfm_block_stats / dsmfm_block_pack / "
+                   "NCCL all-gather of the packed slots / dsmfm_build_packed / dsmfm_pieces_build (the rank's share of the sections "
+                   "copied to ITS host memory) / dsmfm_pieces_merge / dsmfm_destroy",
         },
         "gpu_launches": n_launch,
         "roofline": {
@@ -499,6 +589,8 @@ def main():
         "note": "random 16-byte gathers: the bound is DRAM row activations (about 56 G accesses/s measured, "
                 "tools_dev/gather_bench.cu), not bytes"}
 
+    if parity is not None:
+        line["parity"] = parity
     if world == 1:
         # the same workload with the WHOLE suffix array finished (DSMFM_FLAG_KEEP_SA: what BASELINE.json's "SA" and the
         # .sa sampling need); device-resident inputs, CUDA events on the build stream like `value`

@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <fcntl.h>
+#include <unistd.h>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -573,6 +575,7 @@ struct dsmfm_builder {
     uint64_t n = 0;
 
     bool finished = false, built = false, fetched = false;
+    bool sealed = false; // dsmfm_block_stats has been taken: no more appends
 
     // device state of the build
     uint8_t *d_raw = nullptr;
@@ -669,6 +672,10 @@ struct dsmfm_builder {
         for (auto &a : allocs) dev_free(a.first, stream);
         allocs.clear();
         chunks.clear();
+        g_pinned.put(ph.h_blob);
+        ph.h_blob = nullptr;
+        delete ext;
+        ext = nullptr;
         d_raw = nullptr;
         d_sa = nullptr;
         d_sa_hi = nullptr;
@@ -678,6 +685,34 @@ struct dsmfm_builder {
         wt.release(stream);
     }
 
+    // ---- one collection over several builders, packed-text exchange (dsmfm_block_* / dsmfm_build_packed) ----
+    // `ext` set: the text to index is a caller-owned row of packed slots (one per block of documents, every
+    // builder holds the whole row); this builder's own raw block has been packed into it and released.
+    struct PackedText {
+        const uint64_t *text = nullptr; // device: world * slot_words (+ 8 zero) words
+        SelGeom geom;                   // slot_words, world, symbols per block
+        uint64_t n_real = 0;            // symbols of the collection
+        uint64_t words = 0;             // world * slot_words
+        uint64_t documents = 0, maxlen = 0;
+        std::vector<unsigned long long> top; // 4096 bins: top 12 key bits of every suffix of the collection
+    };
+    PackedText *ext = nullptr;
+    bool block_stats_done = false;
+    dsmfm_block_info block_info;
+    // pieces of the wavelet tree owned by this builder (dsmfm_pieces_build): host copies and their description
+    struct PieceHost {
+        std::vector<dsmfm_piece> piece;
+        std::vector<dsmfm_piece_edge> edge;
+        std::vector<uint64_t> bit_off, bit_count; // per internal node
+        uint8_t *h_blob = nullptr;                // pinned
+        size_t h_bytes = 0;
+        uint32_t world = 0, rank = 0;
+        bool merged = false;
+        WtShape shape;
+        std::vector<uint64_t> file_off_data, file_off_rs, file_off_rb, file_off_node; // per internal node / per node
+        uint64_t file_bytes = 0;
+    } ph;
+
     uint32_t pre_launches = 0; // kernels launched before build() (the FASTA front end)
     // Page-locking the host buffer of the sections costs ~0.4 s per GB the first time (later builds find it in
     // the pool): a helper thread does it while the GPU sorts, as soon as the histogram fixes the size.
@@ -685,6 +720,8 @@ struct dsmfm_builder {
     uint8_t *host_ready = nullptr;
     size_t host_ready_bytes = 0;
     void append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info *info);
+    void gather_raw();
+    void block_stats(uint32_t *L);
     void build();
     void fetch();
     void make_sa_image();
@@ -764,62 +801,38 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
 }
 
 // ---------------------------------------------------------------------------
-// the device build
+// the raw text in one piece; its statistics
 // ---------------------------------------------------------------------------
-void dsmfm_builder::build()
+void dsmfm_builder::gather_raw()
 {
+    if (d_raw) return;
     cudaStream_t st = stream;
-    uint32_t *L = &stats.kernel_launches;
-    std::memset(&stats, 0, sizeof stats);
-    cudaEvent_t ev[8];
-    for (auto &e : ev) DSM_CUDA(cudaEventCreate(&e));
-    cudaEvent_t ev_pass0, ev_pass1;
-    DSM_CUDA(cudaEventCreate(&ev_pass0));
-    DSM_CUDA(cudaEventCreate(&ev_pass1));
-
-    trace("build: begin");
-    flush_stage();
-    bool empty_collection = false;
-    if (n == 0) { // TextCollectionBuilder.cpp:111-119: one empty text
-        const uint8_t z = 0;
-        push_device(&z, 1, cudaMemcpyHostToDevice);
-        DSM_CUDA(cudaStreamSynchronize(st));
-        empty_collection = true;
-    }
-
-    // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the default
-    // 64-byte L2 fetch granularity every miss drags in a second, unused sector.  The limit is a property of the
-    // device context, so it is set ONCE per device by the first build of the process (not per build, and not
-    // restored: toggling it around every build would change device-global state under other streams' feet).
-    // DSMFM_L2_FETCH=0 leaves the limit alone, any other value overrides the 32 bytes.
-    {
-        static DeviceOnce gran_once;
-        gran_once.run([] {
-            size_t want_gran = 32;
-            if (const char *e = std::getenv("DSMFM_L2_FETCH")) want_gran = (size_t)std::atoi(e);
-            if (want_gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want_gran);
-        });
-    }
-
-    DSM_CUDA(cudaEventRecord(ev[0], st));
-    // contiguous text
     if (chunks.size() == 1) {
         d_raw = chunks[0].d;
         raw_is_chunk = true;
-    } else {
-        d_raw = static_cast<uint8_t *>(dmalloc(n + 64));
-        raw_is_chunk = false;
-        size_t o = 0;
-        for (auto &c : chunks) {
-            DSM_CUDA(cudaMemcpyAsync(d_raw + o, c.d, c.used, cudaMemcpyDeviceToDevice, st));
-            o += c.used;
-        }
-        DSM_CUDA(cudaStreamSynchronize(st));
-        for (auto &c : chunks) dfree(c.d);
-        chunks.clear();
+        return;
     }
+    d_raw = static_cast<uint8_t *>(dmalloc(n + 64));
+    raw_is_chunk = false;
+    size_t o = 0;
+    for (auto &c : chunks) {
+        DSM_CUDA(cudaMemcpyAsync(d_raw + o, c.d, c.used, cudaMemcpyDeviceToDevice, st));
+        o += c.used;
+    }
+    DSM_CUDA(cudaStreamSynchronize(st));
+    for (auto &c : chunks) dfree(c.d);
+    chunks.clear();
+}
 
-    // ---- histogram, document statistics, alphabet --------------------------------
+// 256-bin histogram (= the BWT's counts: C[] and the Huffman weights), number of documents, longest document
+// incl. its terminator (TextCollectionBuilder.cpp:73-81), empty-document detection.  Synchronises the stream.
+void dsmfm_builder::block_stats(uint32_t *L)
+{
+    cudaStream_t st = stream;
+    std::memset(&block_info, 0, sizeof block_info);
+    block_info.bytes = n;
+    block_stats_done = true;
+    if (n == 0) return;
     uint64_t *d_counts = static_cast<uint64_t *>(dmalloc(256 * 8));
     const uint64_t nstat = div_up(n, kStatChunk);
     ChunkStat *d_stat = static_cast<ChunkStat *>(dmalloc(nstat * sizeof(ChunkStat)));
@@ -827,7 +840,7 @@ void dsmfm_builder::build()
     launch_byte_hist(st, d_raw, n, d_counts, L);
     launch_doc_stats(st, d_raw, n, d_stat, L);
     std::vector<ChunkStat> hstat(nstat);
-    DSM_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(block_info.counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
     DSM_CUDA(cudaMemcpyAsync(hstat.data(), d_stat, nstat * sizeof(ChunkStat), cudaMemcpyDeviceToHost, st));
     DSM_CUDA(cudaStreamSynchronize(st));
     dfree(d_counts);
@@ -847,8 +860,66 @@ void dsmfm_builder::build()
     }
     if (lastz != (int64_t)n - 1)
         throw CudaError{cudaErrorInvalidValue, "text does not end with a document terminator", __FILE__, __LINE__};
-    if (mingap == 1 && !empty_collection)
-        throw CudaError{cudaErrorInvalidValue, "EMPTY", __FILE__, __LINE__};
+    block_info.documents = block_info.counts[0];
+    block_info.max_text_length = maxgap;
+    block_info.empty_document = mingap == 1 ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------
+// the device build
+// ---------------------------------------------------------------------------
+void dsmfm_builder::build()
+{
+    cudaStream_t st = stream;
+    uint32_t *L = &stats.kernel_launches;
+    std::memset(&stats, 0, sizeof stats);
+    cudaEvent_t ev[8];
+    for (auto &e : ev) DSM_CUDA(cudaEventCreate(&e));
+    cudaEvent_t ev_pass0, ev_pass1;
+    DSM_CUDA(cudaEventCreate(&ev_pass0));
+    DSM_CUDA(cudaEventCreate(&ev_pass1));
+
+    trace("build: begin");
+    const bool packed_in = ext != nullptr;
+    bool empty_collection = false;
+    uint64_t maxgap = 0;
+    if (!packed_in) {
+        flush_stage();
+        if (n == 0) { // TextCollectionBuilder.cpp:111-119: one empty text
+            const uint8_t z = 0;
+            push_device(&z, 1, cudaMemcpyHostToDevice);
+            DSM_CUDA(cudaStreamSynchronize(st));
+            empty_collection = true;
+        }
+    }
+
+    // Random 16-byte gathers from the packed text dominate the refinement's DRAM traffic; with the default
+    // 64-byte L2 fetch granularity every miss drags in a second, unused sector.  The limit is a property of the
+    // device context, so it is set ONCE per device by the first build of the process (not per build, and not
+    // restored: toggling it around every build would change device-global state under other streams' feet).
+    // DSMFM_L2_FETCH=0 leaves the limit alone, any other value overrides the 32 bytes.
+    {
+        static DeviceOnce gran_once;
+        gran_once.run([] {
+            size_t want_gran = 32;
+            if (const char *e = std::getenv("DSMFM_L2_FETCH")) want_gran = (size_t)std::atoi(e);
+            if (want_gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want_gran);
+        });
+    }
+
+    DSM_CUDA(cudaEventRecord(ev[0], st));
+    if (!packed_in) {
+        // ---- contiguous text, histogram, document statistics ----------------------------------
+        gather_raw();
+        if (!block_stats_done) block_stats(L);
+        std::memcpy(counts, block_info.counts, sizeof counts);
+        maxgap = block_info.max_text_length;
+        if (block_info.empty_document && !empty_collection)
+            throw CudaError{cudaErrorInvalidValue, "EMPTY", __FILE__, __LINE__};
+    } else {
+        maxgap = ext->maxlen;
+    }
+    const uint64_t n_idx = packed_in ? ext->n_real : n;                                // symbols of the index
 
     uint8_t code_map[256];
     std::memset(code_map, 0, sizeof code_map);
@@ -857,6 +928,9 @@ void dsmfm_builder::build()
         if (counts[c]) code_map[c] = (uint8_t)++sigma;
     const int bits = sigma <= 7 ? 3 : (sigma <= 15 ? 4 : 8);
     const int spw = 64 / bits;
+    // positions are positions in the text as it lies in HBM: the packed slots with their padding when the text
+    // came in packed (one slot per block), the plain text otherwise
+    const uint64_t n_text = packed_in ? ext->words * (uint64_t)spw : n;
     // The initial radix sort orders suffixes by their first `first_syms` symbols only (48 key bits = 6
     // LSD passes instead of 8); the refinement rounds extend from there.  For DNA reads 16 symbols
     // already separate everything that is not a genuine repeat, so the two saved passes cost almost
@@ -869,18 +943,19 @@ void dsmfm_builder::build()
     uint64_t long_key_above = 1ull << 32;
     if (const char *e = std::getenv("DSMFM_LONG_KEY_ABOVE")) long_key_above = std::strtoull(e, nullptr, 10);
     int first_key_bits = 48;
-    if (n > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);
+    if (n_idx > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);
     if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
     if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
     int first_syms = std::max(1, first_key_bits / bits);
     // Text positions: the u32 value of the sort holds the low `lo_bits` bits (32; fewer only in tests, which
     // thereby exercise the wide path on small inputs), anything above rides in the key's spare top bits.
-    const bool sharded = shard_count > 1;
+    // A packed-text build always takes the key-range path (its padding positions must not be sorted).
+    const bool sharded = shard_count > 1 || packed_in;
     int lo_bits = 32;
     if (const char *e = std::getenv("DSMFM_POS_LO_BITS")) lo_bits = std::min(32, std::max(4, std::atoi(e)));
     if (!sharded) lo_bits = 32;
     int hi_bits = 0;
-    while (lo_bits + hi_bits < 64 && ((n - 1) >> (lo_bits + hi_bits))) ++hi_bits;
+    while (lo_bits + hi_bits < 64 && ((n_text - 1) >> (lo_bits + hi_bits))) ++hi_bits;
     const bool wide = hi_bits > 0;
     if (wide && !sharded)
         throw CudaError{cudaErrorInvalidValue, "more than 2^32 symbols in one unsharded build (set shard_count / shard_span)", __FILE__, __LINE__};
@@ -918,33 +993,39 @@ void dsmfm_builder::build()
             }
         }
     }
-    index.n = n;
+    index.n = n_idx;
     index.samplerate = samplerate;
     index.number_of_texts = (uint32_t)counts[0];
     index.max_text_length = maxgap;
-    stats.n = n;
-    stats.bases = n - counts[0];
+    stats.n = n_idx;
+    stats.bases = n_idx - counts[0];
     stats.bits_per_symbol = bits;
     stats.sigma = sigma;
 
     // ---- pack -----------------------------------------------------------------------
-    const uint64_t nwords = div_up(n, spw) + 8; // zero words behind the text: refinement rows read up to 5 words ahead
+    // zero words behind the text: refinement rows read up to 5 words ahead
+    const uint64_t nwords = packed_in ? ext->words + 8 : div_up(n, spw) + 8;
     uint8_t *d_map = static_cast<uint8_t *>(dmalloc(256));
     uint8_t *d_inv = static_cast<uint8_t *>(dmalloc(256));
     DSM_CUDA(cudaMemcpyAsync(d_inv, inv_map, 256, cudaMemcpyHostToDevice, st));
-    uint64_t *d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
     DSM_CUDA(cudaMemcpyAsync(d_map, code_map, 256, cudaMemcpyHostToDevice, st));
-    launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
-    if ((flags & DSMFM_FLAG_KEEP_SA) && shard_count <= 1) { // the .sa writer needs the document boundaries
-        d_doc_end = static_cast<uint32_t *>(dmalloc((size_t)counts[0] * 4 + 16));
-        uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(term_tiles(n) * 8));
-        launch_term_positions(st, d_raw, n, d_tile, d_doc_end, L);
-        dfree(d_tile);
+    uint64_t *d_packed = nullptr;
+    if (packed_in) {
+        d_packed = const_cast<uint64_t *>(ext->text);
+    } else {
+        d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
+        launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
+        if ((flags & DSMFM_FLAG_KEEP_SA) && shard_count <= 1) { // the .sa writer needs the document boundaries
+            d_doc_end = static_cast<uint32_t *>(dmalloc((size_t)counts[0] * 4 + 16));
+            uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(term_tiles(n) * 8));
+            launch_term_positions(st, d_raw, n, d_tile, d_doc_end, L);
+            dfree(d_tile);
+        }
+        // the raw text is not looked at again: everything downstream reads the packed text (3/8 of its size)
+        dfree(d_raw);
+        chunks.clear();
+        d_raw = nullptr;
     }
-    // the raw text is not looked at again: everything downstream reads the packed text (3/8 of its size)
-    dfree(d_raw);
-    chunks.clear();
-    d_raw = nullptr;
     DSM_CUDA(cudaEventRecord(ev[1], st));
     trace("build: statistics done, pack launched");
 
@@ -964,13 +1045,20 @@ void dsmfm_builder::build()
         ranges.push_back(Range{0, 0, n, 0});
     } else {
         const int nbins = 1 << top_bits;
-        unsigned long long *d_top = static_cast<unsigned long long *>(dmalloc(4096 * 8));
-        DSM_CUDA(cudaMemsetAsync(d_top, 0, 4096 * 8, st));
-        launch_key_top_hist(st, bits, d_packed, n, first_syms, top_bits, d_top, L);
-        std::vector<unsigned long long> top(4096);
-        DSM_CUDA(cudaMemcpyAsync(top.data(), d_top, 4096 * 8, cudaMemcpyDeviceToHost, st));
-        DSM_CUDA(cudaStreamSynchronize(st));
-        dfree(d_top);
+        std::vector<unsigned long long> top(4096, 0ull);
+        if (packed_in) {
+            // every builder counted the suffixes of its own block while packing it; the sum came in with the text
+            if (top_bits != 12)
+                throw CudaError{cudaErrorInvalidValue, "packed-text builds need a first key of >= 12 bits", __FILE__, __LINE__};
+            top = ext->top;
+        } else {
+            unsigned long long *d_top = static_cast<unsigned long long *>(dmalloc(4096 * 8));
+            DSM_CUDA(cudaMemsetAsync(d_top, 0, 4096 * 8, st));
+            launch_key_top_hist(st, bits, d_packed, n, first_syms, top_bits, d_top, L);
+            DSM_CUDA(cudaMemcpyAsync(top.data(), d_top, 4096 * 8, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            dfree(d_top);
+        }
         // range s takes the bins whose running count first reaches s*n/G ... (s+1)*n/G
         std::vector<int> cut(shard_count + 1, nbins);
         cut[0] = 0;
@@ -979,7 +1067,7 @@ void dsmfm_builder::build()
         for (int bin = 0; bin < nbins && next < shard_count; ++bin) {
             run += top[bin];
             while (next < shard_count &&
-                   run >= (n / shard_count) * next + (n % shard_count) * next / shard_count) {
+                   run >= (n_idx / shard_count) * next + (n_idx % shard_count) * next / shard_count) {
                 cut[next++] = bin + 1;
             }
         }
@@ -1018,6 +1106,16 @@ void dsmfm_builder::build()
     ws.carry = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * 2 * kRadix));
     ws.status = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t) * ws.status_tiles * kRadix));
     ws.counter = static_cast<uint32_t *>(dmalloc(sizeof(uint32_t)));
+    SelGeom sel_geom;
+    std::memset(&sel_geom, 0, sizeof sel_geom);
+    if (packed_in) {
+        sel_geom = ext->geom;
+    } else {
+        sel_geom.slot_words = nwords - 8;
+        sel_geom.world = 1;
+        sel_geom.bytes[0] = n;
+    }
+    uint32_t *d_sel_lut = sharded ? static_cast<uint32_t *>(dmalloc(sizeof(uint32_t) * kSelLutWords)) : nullptr;
     const int full_key_bits = spw * bits; // sorted bits of a refinement key (large-group path)
     const uint64_t hwords = head_words_for(m_max);
     uint32_t *d_head[2];
@@ -1080,10 +1178,11 @@ void dsmfm_builder::build()
             launch_make_keys_hist(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, ws.hist, L);
             hist_ready = true;
         } else {
-            const uint64_t ntile = select_tiles(n, bits, first_syms, top_bits);
+            const uint64_t twords = nwords - 8; // words that hold text
+            const uint64_t ntile = select_tiles(twords, bits, first_syms, top_bits);
             uint64_t *d_tile = static_cast<uint64_t *>(dmalloc(ntile * 8));
-            launch_select(st, bits, d_packed, n, first_syms, top_bits, carry_bwt, rg.key_lo, rg.key_hi, d_tile,
-                          ws.counter, d_keys_a, d_vals_a, lo_bits, hi_shift, L);
+            launch_select(st, bits, d_packed, twords, first_syms, top_bits, carry_bwt, rg.key_lo, rg.key_hi, d_tile,
+                          ws.counter, d_keys_a, d_vals_a, lo_bits, hi_shift, sel_geom, d_sel_lut, L);
             dfree(d_tile);
         }
         const int passes = radix_sort_pairs(st, ws, d_keys_a, d_vals_a, d_keys_b, d_vals_b, m, 0, key_bits, !sharded, L,
@@ -1336,7 +1435,8 @@ void dsmfm_builder::build()
     // ---- release what the sections do not need ---------------------------------------
     dfree(d_map);
     dfree(d_inv);
-    dfree(d_packed);
+    dfree(d_sel_lut);
+    if (!packed_in) dfree(d_packed);
     dfree(d_keys_a);
     dfree(d_keys_b);
     dfree(d_head[0]);
@@ -1601,7 +1701,7 @@ DSMFM_API int dsmfm_create(const dsmfm_options *opts, dsmfm_builder **out)
 DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len)
 {
     API_GUARD(b);
-    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_append: new text can not be inserted after dsmfm_finish");
+    if (b->finished || b->sealed) return b->fail(DSMFM_EINVAL, "dsmfm_append: new text can not be inserted after dsmfm_finish");
     if (!doc) return b->fail(DSMFM_EINVAL, "dsmfm_append: null document");
     if (len == 0) return b->fail(DSMFM_EEMPTY, "dsmfm_append: can not index empty texts");
     try {
@@ -1631,7 +1731,7 @@ DSMFM_API int dsmfm_append(dsmfm_builder *b, const uint8_t *doc, size_t len)
 
 static int append_bulk(dsmfm_builder *b, const void *src, size_t bytes, cudaMemcpyKind kind)
 {
-    if (b->finished) return b->fail(DSMFM_EINVAL, "append: new text can not be inserted after dsmfm_finish");
+    if (b->finished || b->sealed) return b->fail(DSMFM_EINVAL, "append: new text can not be inserted after dsmfm_finish");
     if (!src || bytes == 0) return b->fail(DSMFM_EINVAL, "append: empty batch");
     try {
         b->flush_stage();
@@ -1662,7 +1762,7 @@ DSMFM_API int dsmfm_append_fasta(dsmfm_builder *b, const uint8_t *text, size_t l
     if (!info) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: null info");
     std::memset(info, 0, sizeof *info);
     info->first_invalid_offset = ~0ull;
-    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: new text can not be inserted after dsmfm_finish");
+    if (b->finished || b->sealed) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: new text can not be inserted after dsmfm_finish");
     if (!text && len) return b->fail(DSMFM_EINVAL, "dsmfm_append_fasta: null text");
     size_t use = 0;
     if (final) {
@@ -1712,10 +1812,8 @@ DSMFM_API void dsmfm_free_pinned(void *p)
     if (p) cudaFreeHost(p);
 }
 
-DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
+static int run_build(dsmfm_builder *b)
 {
-    API_GUARD(b);
-    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_build_device: already built");
     b->finished = true;
     const double t0 = now_ms();
     g_alloc_ms = 0.0;
@@ -1737,6 +1835,136 @@ DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
         return b->fail(DSMFM_ENOMEM, "host allocation failed");
     }
     return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_build_device(dsmfm_builder *b)
+{
+    API_GUARD(b);
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_build_device: already built");
+    if (b->sealed) return b->fail(DSMFM_EINVAL, "dsmfm_build_device: the block belongs to a packed-text build (dsmfm_build_packed)");
+    return run_build(b);
+}
+
+// ---- one collection over several builders: packed-text exchange ---------------------------------
+
+DSMFM_API int dsmfm_block_stats(dsmfm_builder *b, dsmfm_block_info *out)
+{
+    API_GUARD(b);
+    if (!out) return DSMFM_EINVAL;
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_block_stats: already built");
+    try {
+        b->flush_stage();
+        if (b->n == 0) {
+            std::memset(&b->block_info, 0, sizeof b->block_info);
+            b->block_stats_done = true;
+        } else {
+            b->gather_raw();
+            if (!b->block_stats_done) b->block_stats(&b->pre_launches);
+        }
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    b->sealed = true;
+    *out = b->block_info;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_text_plan_make(const dsmfm_block_info *all, uint32_t world, dsmfm_text_plan *out)
+{
+    if (!all || !out || world == 0 || world > DSMFM_MAX_BLOCKS) return DSMFM_EINVAL;
+    std::memset(out, 0, sizeof *out);
+    out->world = world;
+    for (uint32_t r = 0; r < world; ++r) {
+        if (all[r].empty_document) return DSMFM_EEMPTY;
+        for (int c = 0; c < 256; ++c) out->counts[c] += all[r].counts[c];
+        out->n += all[r].bytes;
+        out->documents += all[r].documents;
+        out->max_text_length = std::max(out->max_text_length, all[r].max_text_length);
+        out->block_bytes[r] = all[r].bytes;
+    }
+    uint32_t sigma = 0;
+    for (int c = 1; c < 256; ++c) sigma += out->counts[c] != 0;
+    out->bits = sigma <= 7 ? 3 : (sigma <= 15 ? 4 : 8);
+    const uint64_t spw = 64 / out->bits;
+    uint64_t slot = 1;
+    for (uint32_t r = 0; r < world; ++r) slot = std::max(slot, div_up(all[r].bytes, spw));
+    out->slot_words = (slot + 15) & ~(uint64_t)15; // whole 128-byte lines per slot
+    out->text_bytes = (out->slot_words * world + 8) * 8;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_block_pack(dsmfm_builder *b, const dsmfm_text_plan *plan, uint32_t rank, void *text_dev,
+                               uint64_t *top_hist4096)
+{
+    API_GUARD(b);
+    if (!plan || !text_dev || !top_hist4096 || rank >= plan->world || plan->world > DSMFM_MAX_BLOCKS)
+        return b->fail(DSMFM_EINVAL, "dsmfm_block_pack: bad arguments");
+    if (!b->sealed || b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_block_pack: call dsmfm_block_stats first");
+    if (plan->block_bytes[rank] != b->n) return b->fail(DSMFM_EINVAL, "dsmfm_block_pack: block %u of the plan is not this builder's", rank);
+    try {
+        cudaStream_t st = b->stream;
+        uint32_t *L = &b->pre_launches;
+        uint8_t code_map[256];
+        std::memset(code_map, 0, sizeof code_map);
+        uint32_t sigma = 0;
+        for (int c = 1; c < 256; ++c)
+            if (plan->counts[c]) code_map[c] = (uint8_t)++sigma;
+        const int bits = (int)plan->bits, spw = 64 / bits;
+        uint64_t *slot = static_cast<uint64_t *>(text_dev) + (uint64_t)rank * plan->slot_words;
+        uint8_t *d_map = static_cast<uint8_t *>(b->dmalloc(256));
+        unsigned long long *d_top = static_cast<unsigned long long *>(b->dmalloc(4096 * 8));
+        DSM_CUDA(cudaMemcpyAsync(d_map, code_map, 256, cudaMemcpyHostToDevice, st));
+        DSM_CUDA(cudaMemsetAsync(d_top, 0, 4096 * 8, st));
+        // the slot: the block's symbols, then zeros; 8 zero words behind the last slot of this device's copy
+        launch_pack(st, bits, b->d_raw, b->n, d_map, slot, plan->slot_words, L);
+        DSM_CUDA(cudaMemsetAsync(static_cast<uint64_t *>(text_dev) + (uint64_t)plan->world * plan->slot_words, 0, 64, st));
+        if (b->n) launch_key_top_hist(st, bits, slot, b->n, spw, 12, d_top, L);
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "histogram words");
+        DSM_CUDA(cudaMemcpyAsync(top_hist4096, d_top, 4096 * 8, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        b->dfree(d_map);
+        b->dfree(d_top);
+        if (b->d_raw) b->dfree(b->d_raw);
+        b->chunks.clear();
+        b->d_raw = nullptr;
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_build_packed(dsmfm_builder *b, const dsmfm_text_plan *plan, const void *text_dev,
+                                 const uint64_t *top_hist4096)
+{
+    API_GUARD(b);
+    if (!plan || !text_dev || !top_hist4096 || plan->world == 0 || plan->world > DSMFM_MAX_BLOCKS)
+        return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: bad arguments");
+    if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: already built");
+    if (!b->sealed || b->d_raw) return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: call dsmfm_block_stats and dsmfm_block_pack first");
+    if (b->flags & DSMFM_FLAG_KEEP_SA)
+        return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: DSMFM_FLAG_KEEP_SA is not supported (positions are positions in the padded text)");
+    if (plan->n == 0) return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: empty collection (build it with dsmfm_finish on one builder)");
+    uint64_t total = 0;
+    for (int i = 0; i < 4096; ++i) total += top_hist4096[i];
+    if (total != plan->n) return b->fail(DSMFM_EINVAL, "dsmfm_build_packed: the key histogram does not add up to the collection");
+    auto *ext = new (std::nothrow) dsmfm_builder::PackedText();
+    if (!ext) return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    ext->text = static_cast<const uint64_t *>(text_dev);
+    std::memset(&ext->geom, 0, sizeof ext->geom);
+    ext->geom.slot_words = plan->slot_words;
+    ext->geom.world = plan->world;
+    for (uint32_t r = 0; r < plan->world; ++r) ext->geom.bytes[r] = plan->block_bytes[r];
+    ext->n_real = plan->n;
+    ext->words = plan->slot_words * plan->world;
+    ext->documents = plan->documents;
+    ext->maxlen = plan->max_text_length;
+    ext->top.assign(top_hist4096, top_hist4096 + 4096);
+    delete b->ext;
+    b->ext = ext;
+    std::memcpy(b->counts, plan->counts, sizeof b->counts);
+    return run_build(b);
 }
 
 DSMFM_API int dsmfm_shard_info(dsmfm_builder *b, dsmfm_shard *out)
@@ -1932,6 +2160,361 @@ DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, 
     }
     b->assembled = true;
     return DSMFM_OK;
+}
+
+// ---- wavelet tree and BitRank directories built where the BWT slices are --------------------------
+// Slice r's members of node v occupy the bits [o, o + c) of the node's vector (o, c from the slices' byte
+// histograms).  Builder r OWNS the data words whose first bit lies in that range -- [ceil(o/64), ceil((o+c)/64)) --
+// with their Rb entries, and the Rs entries of the superblocks that start in it; the last slice with members also
+// owns what lies behind the last bit (BitRank.cpp:97-101: integers = n/64 + 1).  Everything owned follows from the
+// slice's own bits plus B = the ones of the slices in front of it (histograms again), except next to a boundary:
+// the last owned word may hold bits of later slices, and the Rb entries of a superblock that starts in front of
+// the slice need the ones of earlier slices inside that superblock.  Those few words travel as dsmfm_piece_edge.
+namespace {
+uint64_t ones_of_slice(const WtShape &shape, int v, const uint64_t *hist_row)
+{
+    uint64_t c = 0;
+    for (int s = 0; s < 256; ++s)
+        if (shape.info[(size_t)v * 256 + s] == 3u) c += hist_row[s];
+    return c;
+}
+
+// offsets of every section of the .fmi file (FMIndex::save, FMIndex.cpp:155-217)
+void fmi_layout(const WtShape &shape, std::vector<uint64_t> &node_off, std::vector<uint64_t> &data_off,
+                std::vector<uint64_t> &rs_off, std::vector<uint64_t> &rb_off, uint64_t &tail_off, uint64_t &total)
+{
+    uint64_t pos = 1 + 8 + 4 + 2048 + 8 + 256 * 16;
+    node_off.assign(shape.nodes.size(), 0);
+    data_off.assign(shape.n_internal, 0);
+    rs_off.assign(shape.n_internal, 0);
+    rb_off.assign(shape.n_internal, 0);
+    for (size_t i = 0; i < shape.nodes.size(); ++i) {
+        node_off[i] = pos;
+        pos += 2;
+        const int v = shape.internal_of_node[i];
+        if (v < 0) continue;
+        const dsmfm_node &nd = shape.nodes[i];
+        pos += 8 + 8 + 4 + 4;
+        data_off[v] = pos;
+        pos += nd.integers * 8;
+        rs_off[v] = pos;
+        pos += (nd.nbits / 256 + 1) * 8;
+        rb_off[v] = pos;
+        pos += nd.nbits / 64 + 1;
+    }
+    tail_off = pos;
+    total = pos + 4 + 8 + 1 + 1 + 1 + 4;
+}
+
+bool pwrite_all(int fd, const void *p, size_t n, uint64_t off)
+{
+    const uint8_t *q = static_cast<const uint8_t *>(p);
+    while (n) {
+        const ssize_t w = ::pwrite(fd, q, n, (off_t)off);
+        if (w <= 0) return false;
+        q += w;
+        n -= (size_t)w;
+        off += (uint64_t)w;
+    }
+    return true;
+}
+} // namespace
+
+DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, dsmfm_pieces *out)
+{
+    API_GUARD(b);
+    if (!out || !hist_all || world == 0 || rank >= world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: bad arguments");
+    if (!b->built || !b->d_bwt) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: nothing built (or already fetched)");
+    if (b->ph.h_blob) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: already built");
+    for (int c = 0; c < 256; ++c) { // the slices together must hold exactly the symbols of the collection
+        uint64_t t = 0;
+        for (uint32_t r = 0; r < world; ++r) t += hist_all[(size_t)r * 256 + c];
+        if (t != b->counts[c]) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: slice histograms do not add up to the collection's");
+    }
+    uint64_t mine = 0;
+    for (int c = 0; c < 256; ++c) mine += hist_all[(size_t)rank * 256 + c];
+    const uint64_t slice_m = b->shard_count > 1 || b->ext ? b->shard_m : b->index.n;
+    if (mine != slice_m) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: histogram row %u is not this slice's", rank);
+    try {
+        cudaStream_t st = b->stream;
+        uint32_t *L = &b->stats.kernel_launches;
+        cudaEvent_t e0, e1;
+        DSM_CUDA(cudaEventCreate(&e0));
+        DSM_CUDA(cudaEventCreate(&e1));
+        DSM_CUDA(cudaEventRecord(e0, st));
+        auto &ph = b->ph;
+        WaveletResult tmp;
+        wavelet_prepare(b->index.codetable, tmp);
+        ph.shape = tmp.shape;
+        ph.world = world;
+        ph.rank = rank;
+        const int m = ph.shape.n_internal;
+        const PiecePlan pp = plan_pieces(ph.shape, hist_all, world);
+        std::vector<uint64_t> nbits_of(m, 0);
+        std::vector<uint32_t> node_of(m, 0);
+        for (size_t i = 0; i < ph.shape.nodes.size(); ++i) {
+            const int v = ph.shape.internal_of_node[i];
+            if (v >= 0) { nbits_of[v] = ph.shape.nodes[i].nbits; node_of[v] = (uint32_t)i; }
+        }
+        ph.piece.assign(m, dsmfm_piece());
+        ph.edge.assign(m, dsmfm_piece_edge());
+        ph.bit_off.assign(m, 0);
+        ph.bit_count.assign(m, 0);
+        // layout of the device pieces: node v's bits start at local bit `base` of an array that begins at the
+        // superblock holding bit o (word G0 = 4 * (o / 256)), so that local superblocks are global superblocks
+        struct Loc { uint64_t G0, base, nb, words, nsb, nrb, off_data, off_rs, off_rb, B; bool last; };
+        std::vector<Loc> loc(m);
+        size_t blob = 0;
+        for (int v = 0; v < m; ++v) {
+            const uint64_t o = pp.bit_off[(size_t)rank * m + v], c = pp.count[(size_t)rank * m + v];
+            ph.bit_off[v] = o;
+            ph.bit_count[v] = c;
+            Loc &l = loc[v];
+            l.G0 = 4 * (o / 256);
+            l.base = o - 64 * l.G0;
+            l.nb = l.base + c;
+            l.words = l.nb / 64 + 1;
+            l.nsb = l.nb / 256 + 1;
+            l.nrb = l.nb / 64 + 1;
+            l.B = 0;
+            for (uint32_t q = 0; q < rank; ++q) l.B += ones_of_slice(ph.shape, v, hist_all + (size_t)q * 256);
+            l.last = c > 0;
+            for (uint32_t q = rank + 1; q < world; ++q)
+                if (pp.count[(size_t)q * m + v]) l.last = false;
+            l.off_data = blob; blob += l.words * 8;
+            l.off_rs = blob;   blob += l.nsb * 8;
+            l.off_rb = blob;   blob += align8(l.nrb);
+        }
+        const size_t blob_bytes = blob + align8((size_t)(m ? m : 1));
+        uint8_t *d_blob = static_cast<uint8_t *>(b->dmalloc(blob_bytes));
+        DSM_CUDA(cudaMemsetAsync(d_blob, 0, blob_bytes, st));
+        uint8_t *d_ch = d_blob + blob;
+        std::vector<uint64_t *> ptrs(m);
+        std::vector<uint64_t> base(m);
+        uint64_t max_sb = 1;
+        for (int v = 0; v < m; ++v) {
+            ptrs[v] = reinterpret_cast<uint64_t *>(d_blob + loc[v].off_data);
+            base[v] = loc[v].base;
+            max_sb = std::max(max_sb, loc[v].nsb);
+        }
+        wavelet_fill_bits(st, b->d_bwt, slice_m, ph.shape, ptrs, base, d_ch, L);
+        uint64_t *d_scratch = static_cast<uint64_t *>(b->dmalloc(sizeof(uint64_t) * (div_up(max_sb, kRankChunk) + 1)));
+        for (int v = 0; v < m; ++v)
+            if (ph.bit_count[v])
+                launch_bitrank(st, ptrs[v], loc[v].nb, reinterpret_cast<uint64_t *>(d_blob + loc[v].off_rs),
+                               d_blob + loc[v].off_rb, d_scratch, L, loc[v].B);
+        DSM_CUDA(cudaEventRecord(e1, st));
+        ph.h_blob = static_cast<uint8_t *>(g_pinned.get(blob_bytes));
+        ph.h_bytes = blob_bytes;
+        DSM_CUDA(cudaMemcpyAsync(ph.h_blob, d_blob, blob_bytes, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        b->stats.ms_wt = ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        b->dfree(d_scratch);
+        b->dfree(d_blob);
+        b->dfree(b->d_bwt);
+        b->d_bwt = nullptr;
+
+        uint64_t held = 0;
+        for (int v = 0; v < m; ++v) {
+            const Loc &l = loc[v];
+            const uint64_t o = ph.bit_off[v], c = ph.bit_count[v], nbits = nbits_of[v];
+            dsmfm_piece &pc = ph.piece[v];
+            dsmfm_piece_edge &ed = ph.edge[v];
+            pc.node = node_of[v];
+            uint64_t *h_data = reinterpret_cast<uint64_t *>(ph.h_blob + l.off_data);
+            uint64_t *h_rs = reinterpret_cast<uint64_t *>(ph.h_blob + l.off_rs);
+            uint8_t *h_rb = ph.h_blob + l.off_rb;
+            if (c) {
+                pc.word_first = div_up(o, 64);
+                const uint64_t w_end = l.last ? nbits / 64 + 1 : div_up(o + c, 64);
+                pc.word_count = w_end > pc.word_first ? w_end - pc.word_first : 0;
+                pc.rb_first = pc.word_first;
+                pc.rb_count = pc.word_count;
+                pc.rs_first = div_up(o, 256);
+                const uint64_t s_end = l.last ? nbits / 256 + 1 : div_up(o + c, 256);
+                pc.rs_count = s_end > pc.rs_first ? s_end - pc.rs_first : 0;
+                pc.data = h_data + (pc.word_first - l.G0);
+                pc.Rb = h_rb + (pc.word_first - l.G0);
+                pc.Rs = h_rs + (pc.rs_first - l.G0 / 4);
+                ed.count = c;
+                ed.first_word = o / 64;
+                ed.last_word = (o + c - 1) / 64;
+                for (int t = 0; t < 4; ++t) {
+                    const uint64_t fi = ed.first_word - l.G0 + t;
+                    ed.first[t] = fi < l.words ? h_data[fi] : 0ull;
+                    const int64_t li = (int64_t)(ed.last_word - l.G0) - 3 + t;
+                    ed.last[t] = li >= 0 && (uint64_t)li < l.words ? h_data[li] : 0ull;
+                }
+                ed.ch = ph.h_blob[blob + v];
+                held += pc.word_count * 8 + pc.rs_count * 8 + pc.rb_count;
+            }
+        }
+        ph.merged = false;
+        out->n_internal = (uint32_t)m;
+        out->world = world;
+        out->rank = rank;
+        out->reserved = 0;
+        out->bytes = held;
+        out->piece = ph.piece.data();
+        out->edge = ph.edge.data();
+        b->stats.ms_d2h = 0.f;
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_pieces_merge(dsmfm_builder *b, const dsmfm_piece_edge *edges_all, uint32_t world)
+{
+    if (!b || !edges_all) return DSMFM_EINVAL;
+    auto &ph = b->ph;
+    if (!ph.h_blob || world != ph.world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_merge: call dsmfm_pieces_build first (same world)");
+    if (ph.merged) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_merge: already merged");
+    const int m = ph.shape.n_internal;
+    const uint32_t rank = ph.rank;
+    for (int v = 0; v < m; ++v) {
+        // what any builder contributes to data word w of node v (first / last windows of its record)
+        auto contribution = [&](uint32_t q, uint64_t w) -> uint64_t {
+            const dsmfm_piece_edge &e = edges_all[(size_t)q * m + v];
+            if (!e.count) return 0ull;
+            uint64_t x = 0;
+            if (w >= e.first_word && w < e.first_word + 4) x |= e.first[w - e.first_word];
+            if (w + 3 >= e.last_word && w <= e.last_word) x |= e.last[w + 3 - e.last_word];
+            return x;
+        };
+        dsmfm_piece &pc = ph.piece[v];
+        if (!ph.bit_count[v]) continue;
+        // (a) bits of later slices in the last owned word (and, for tiny slices, in any owned word)
+        for (uint32_t q = 0; q < world; ++q) {
+            if (q == rank) continue;
+            const dsmfm_piece_edge &e = edges_all[(size_t)q * m + v];
+            if (!e.count) continue;
+            for (int t = 0; t < 4; ++t) {
+                const uint64_t wf = e.first_word + t;
+                if (wf >= pc.word_first && wf < pc.word_first + pc.word_count) pc.data[wf - pc.word_first] |= e.first[t];
+                if (e.last_word + t >= 3) {
+                    const uint64_t wl = e.last_word - 3 + t;
+                    if (wl >= pc.word_first && wl < pc.word_first + pc.word_count) pc.data[wl - pc.word_first] |= e.last[t];
+                }
+            }
+        }
+        // (b) Rb of the owned words whose superblock starts in front of the slice
+        const uint64_t o = ph.bit_off[v];
+        const uint64_t first_full = 4 * div_up(o, 256); // first word of the first superblock that starts inside the slice
+        for (uint64_t k = pc.rb_first; k < pc.rb_first + pc.rb_count && k < first_full; ++k) {
+            uint32_t sum = 0;
+            for (uint64_t w = 4 * (k / 4); w < k; ++w) {
+                uint64_t x = 0;
+                if (w >= pc.word_first && w < pc.word_first + pc.word_count) {
+                    x = pc.data[w - pc.word_first];
+                } else {
+                    for (uint32_t q = 0; q < world; ++q) x |= contribution(q, w);
+                }
+                sum += (uint32_t)__builtin_popcountll(x);
+            }
+            pc.Rb[k - pc.rb_first] = (uint8_t)sum;
+        }
+    }
+    // node symbols (every builder fills the whole table: the one that writes the header needs it)
+    for (size_t i = 0; i < ph.shape.nodes.size(); ++i) {
+        const int v = ph.shape.internal_of_node[i];
+        if (v < 0) continue;
+        for (uint32_t q = 0; q < world; ++q) {
+            const dsmfm_piece_edge &e = edges_all[(size_t)q * m + v];
+            if (e.count) {
+                ph.shape.nodes[i].ch = (uint8_t)e.ch;
+                break;
+            }
+        }
+    }
+    ph.merged = true;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_pieces_index(dsmfm_builder *b, dsmfm_index *out)
+{
+    if (!b || !out) return DSMFM_EINVAL;
+    if (!b->ph.merged) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_index: call dsmfm_pieces_merge first");
+    *out = b->index;
+    out->n_nodes = (uint32_t)b->ph.shape.nodes.size();
+    out->nodes = b->ph.shape.nodes.data();
+    out->bwt = nullptr;
+    return DSMFM_OK;
+}
+
+DSMFM_API int dsmfm_pieces_write(dsmfm_builder *b, const char *path_prefix, int header)
+{
+    if (!b || !path_prefix) return DSMFM_EINVAL;
+    auto &ph = b->ph;
+    if (!ph.merged) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_write: call dsmfm_pieces_merge first");
+    const std::string name = std::string(path_prefix) + ".fmi"; // TextCollection::FMINDEX_EXTENSION
+    const int fd = ::open(name.c_str(), O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) return b->fail(DSMFM_EIO, "dsmfm_pieces_write: can not open %s", name.c_str());
+    std::vector<uint64_t> node_off, data_off, rs_off, rb_off;
+    uint64_t tail_off = 0, total = 0;
+    fmi_layout(ph.shape, node_off, data_off, rs_off, rb_off, tail_off, total);
+    bool ok = true;
+    const int m = ph.shape.n_internal;
+    for (int v = 0; v < m && ok; ++v) {
+        const dsmfm_piece &pc = ph.piece[v];
+        if (!ph.bit_count[v]) continue;
+        ok = ok && pwrite_all(fd, pc.data, pc.word_count * 8, data_off[v] + pc.word_first * 8);
+        ok = ok && pwrite_all(fd, pc.Rs, pc.rs_count * 8, rs_off[v] + pc.rs_first * 8);
+        ok = ok && pwrite_all(fd, pc.Rb, pc.rb_count, rb_off[v] + pc.rb_first);
+    }
+    if (header && ok) {
+        std::vector<uint8_t> h;
+        auto put = [&h](const void *p, size_t n) {
+            const uint8_t *q = static_cast<const uint8_t *>(p);
+            h.insert(h.end(), q, q + n);
+        };
+        const uint8_t version = 17; // FMIndex.cpp:51
+        const uint64_t bwt_end_pos = 0;
+        put(&version, 1);
+        put(&b->index.n, 8);
+        put(&b->index.samplerate, 4);
+        put(b->index.C, sizeof b->index.C);
+        put(&bwt_end_pos, 8);
+        for (int i = 0; i < 256; ++i) {
+            put(&b->index.codetable[i].count, 8);
+            put(&b->index.codetable[i].bits, 4);
+            put(&b->index.codetable[i].code, 4);
+        }
+        ok = ok && pwrite_all(fd, h.data(), h.size(), 0);
+        const uint32_t b64 = 64, s256 = 256;
+        for (size_t i = 0; i < ph.shape.nodes.size() && ok; ++i) {
+            const dsmfm_node &nd = ph.shape.nodes[i];
+            h.clear();
+            put(&nd.leaf, 1);
+            put(&nd.ch, 1);
+            if (!nd.leaf) {
+                put(&nd.nbits, 8);
+                put(&nd.integers, 8);
+                put(&b64, 4);
+                put(&s256, 4);
+            }
+            ok = ok && pwrite_all(fd, h.data(), h.size(), node_off[i]);
+        }
+        h.clear();
+        const uint8_t z8 = 0;
+        const uint32_t z32 = 0;
+        put(&b->index.number_of_texts, 4);
+        put(&b->index.max_text_length, 8);
+        put(&z8, 1);
+        put(&z8, 1);
+        put(&z8, 1);
+        put(&z32, 4);
+        ok = ok && pwrite_all(fd, h.data(), h.size(), tail_off);
+        ok = ok && ::ftruncate(fd, (off_t)total) == 0;
+    }
+    ok = (::close(fd) == 0) && ok;
+    return ok ? DSMFM_OK : b->fail(DSMFM_EIO, "dsmfm_pieces_write: write error on %s", name.c_str());
 }
 
 DSMFM_API int dsmfm_fetch(dsmfm_builder *b, dsmfm_index *out)

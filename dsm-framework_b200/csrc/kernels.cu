@@ -3,6 +3,7 @@
 // and BitRank directories.  All integer / byte work, HBM-bound; no tensor cores.
 #include "kernels.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace dsmfm {
 
@@ -444,24 +445,25 @@ template <int BITS> __device__ __forceinline__ void load_stream(const uint64_t *
 }
 
 
-// selection mask of the SPW suffixes starting in word w: bit j set iff suffix w*SPW+j exists and its bin is in range
+// Selection mask of the SPW suffixes starting in a packed word: bit j set iff the bin of suffix j lies in the
+// range.  The decision is read from a bitmap indexed by the RAW leading bits of the suffix (TopBits::RAW: the
+// uncut first symbols), which the host fills for the range at hand -- cut at the terminator included -- so a
+// suffix costs a funnel shift, a shared-memory load and a bit test instead of the whole top_bin arithmetic.
+// `valid` = number of leading positions of the word that are suffixes of the collection (the rest is padding).
 template <int BITS>
-__device__ __forceinline__ uint32_t select_mask(const uint64_t *__restrict__ packed, uint64_t w, uint64_t nwords,
-                                                uint64_t n, uint32_t bin_lo, uint32_t bin_hi)
+__device__ __forceinline__ uint32_t select_mask_lut(const uint32_t *s_lut, const uint32_t (&s)[4], int valid)
 {
     using P = Pack<BITS>;
-    if (w >= nwords) return 0u;
-    uint32_t s[4];
-    load_stream<BITS>(packed, w, nwords, s);
+    using T = TopBits<BITS>;
     uint32_t sel = 0;
 #pragma unroll
     for (int j = 0; j < P::SPW; ++j) {
-        const uint32_t bin = top_bin<BITS>(s, j);
-        sel |= (uint32_t)(bin >= bin_lo && bin < bin_hi) << j;
+        const int b = BITS * j, q = b >> 5, r = b & 31;
+        const uint32_t top32 = __funnelshift_l(s[q + 1 < 4 ? q + 1 : 3], s[q], r);
+        const uint32_t raw = top32 >> (32 - T::RAW);
+        sel |= ((s_lut[raw >> 5] >> (raw & 31)) & 1u) << j;
     }
-    const uint64_t p0 = w * P::SPW;
-    if (p0 + P::SPW > n) sel &= p0 >= n ? 0u : ((1u << (n - p0)) - 1u);
-    return sel;
+    return valid >= P::SPW ? sel : (sel & ((1u << valid) - 1u));
 }
 
 template <int BITS>
@@ -501,24 +503,41 @@ constexpr unsigned long long kSelFlagAgg = 1ull << 62, kSelFlagPrefix = 2ull << 
 
 template <int BITS>
 __global__ void __launch_bounds__(kSweepSelThreads)
-select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t nwords, int drop_bits, int key_bits,
-                    uint32_t bin_lo, uint32_t bin_hi, volatile unsigned long long *status, uint32_t *counter,
+select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int key_bits, const uint32_t *__restrict__ lut,
+                    const SelGeom geom, volatile unsigned long long *status, uint32_t *counter,
                     uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int lo_bits, int hi_shift)
 {
     using P = Pack<BITS>;
+    using T = TopBits<BITS>;
     constexpr int CAP = kSweepSelWords * P::SPW; // suffixes per tile
+    constexpr int LUT_WORDS = (1 << T::RAW) / 32;
     __shared__ uint64_t s_key[CAP];
     __shared__ uint32_t s_val[CAP];
+    __shared__ uint32_t s_lut[LUT_WORDS];
     __shared__ uint32_t scratch[kSweepSelThreads / 32 + 1];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    for (int i = tid; i < LUT_WORDS; i += kSweepSelThreads) s_lut[i] = __ldg(lut + i);
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
     const uint64_t w = (uint64_t)tile * kSweepSelWords + tid;
-    uint32_t sel = select_mask<BITS>(packed, w, nwords, n, bin_lo, bin_hi);
+    // the word's block (slot) and how many of its positions are suffixes of that block
+    int valid = 0;
+    if (w < nwords) {
+        const uint64_t slot = w / geom.slot_words;
+        const uint64_t first = (w - slot * geom.slot_words) * P::SPW; // position of the word inside its block
+        const uint64_t have = slot < geom.world ? geom.bytes[slot] : 0ull;
+        valid = have > first ? (have - first >= (uint64_t)P::SPW ? P::SPW : (int)(have - first)) : 0;
+    }
+    uint32_t sel = 0;
+    if (valid) {
+        uint32_t st[4];
+        load_stream<BITS>(packed, w, nwords, st);
+        sel = select_mask_lut<BITS>(s_lut, st, valid);
+    }
     uint32_t total;
     uint32_t o = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
     if (tid == 0) status[tile] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
@@ -2088,7 +2107,8 @@ __global__ void __launch_bounds__(1024) rank_chunk_scan_kernel(uint64_t *__restr
 
 __global__ void __launch_bounds__(256)
 rank_write_kernel(const uint64_t *__restrict__ data, uint64_t integers, uint64_t nbits,
-                  const uint64_t *__restrict__ chunk_base, uint64_t *__restrict__ Rs, uint8_t *__restrict__ Rb)
+                  const uint64_t *__restrict__ chunk_base, uint64_t *__restrict__ Rs, uint8_t *__restrict__ Rb,
+                  uint64_t base)
 {
     constexpr int SB_PER_THREAD = kRankChunk / 256; // 8
     __shared__ uint64_t scratch[9];
@@ -2110,7 +2130,7 @@ rank_write_kernel(const uint64_t *__restrict__ data, uint64_t integers, uint64_t
         mine += run;
     }
     uint64_t total;
-    uint64_t e = block_excl_sum(mine, scratch, &total) + chunk_base[blockIdx.x];
+    uint64_t e = block_excl_sum(mine, scratch, &total) + chunk_base[blockIdx.x] + base;
 #pragma unroll
     for (int q = 0; q < SB_PER_THREAD; ++q) {
         const uint64_t j = sb0 + q;
@@ -2226,35 +2246,60 @@ void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint
     if (launches) ++*launches;
 }
 
-uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits)
+uint64_t select_tiles(uint64_t nwords, int bits, int first_syms, int top_bits)
 {
-    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(div_up(n, 64 / bits), kSweepSelWords);
-    return div_up(n, kSelTile);
+    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(nwords, kSweepSelWords);
+    return div_up(nwords * (uint64_t)(64 / bits), kSelTile);
 }
 
-void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+// top 12 key bits of a suffix from the raw (uncut) leading bits: the host mirror of top_bin()
+static uint32_t host_top_bin(int bits, uint32_t raw)
+{
+    const int syms = bits == 8 ? 2 : 12 / bits, rawbits = syms * bits;
+    uint32_t x = 0;
+    for (int i = 0; i < syms; ++i) { // fields from the most significant on; everything after the first zero field is cut
+        const uint32_t f = (raw >> (rawbits - bits * (i + 1))) & ((1u << bits) - 1u);
+        if (!f) break;
+        x |= f << (rawbits - bits * (i + 1));
+    }
+    return x >> (rawbits - 12);
+}
+
+void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t nwords, int first_syms, int top_bits,
                    bool carry_prev, uint64_t key_lo, uint64_t key_hi, uint64_t *tile_scratch, uint32_t *counter,
-                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches)
+                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, const SelGeom &geom, uint32_t *lut_scratch,
+                   uint32_t *launches)
 {
     const int drop_bits = (64 / bits - first_syms) * bits;
     const int key_bits = first_syms * bits;
-    const unsigned tiles = (unsigned)select_tiles(n, bits, first_syms, top_bits);
+    const unsigned tiles = (unsigned)select_tiles(nwords, bits, first_syms, top_bits);
     if (select_fast_ok(bits, first_syms, top_bits) && carry_prev) {
         const int sh = key_bits - 12;
-        const uint64_t nwords = div_up(n, 64 / bits);
+        const uint32_t bin_lo = (uint32_t)(key_lo >> sh), bin_hi = (uint32_t)(key_hi >> sh);
+        const int rawbits = (bits == 8 ? 2 : 12 / bits) * bits;
+        std::vector<uint32_t> lut((size_t)1 << (rawbits - 5), 0u);
+        for (uint32_t raw = 0; raw < (1u << rawbits); ++raw) {
+            const uint32_t bin = host_top_bin(bits, raw);
+            if (bin >= bin_lo && bin < bin_hi) lut[raw >> 5] |= 1u << (raw & 31);
+        }
+        // (pageable source: the copy has left the vector when the call returns)
+        DSM_CUDA(cudaMemcpyAsync(lut_scratch, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st));
         DSM_CUDA(cudaMemsetAsync(tile_scratch, 0, (size_t)tiles * 8, st));
         DSM_CUDA(cudaMemsetAsync(counter, 0, 4, st));
 #define CALL(B)                                                                                                        \
     select_sweep_kernel<B><<<tiles, kSweepSelThreads, 0, st>>>(                                                        \
-        packed, n, nwords, drop_bits, key_bits, (uint32_t)(key_lo >> sh), (uint32_t)(key_hi >> sh),                    \
-        reinterpret_cast<volatile unsigned long long *>(tile_scratch), counter, keys, vals, lo_bits, hi_shift)
+        packed, nwords, key_bits, lut_scratch, geom, reinterpret_cast<volatile unsigned long long *>(tile_scratch),     \
+        counter, keys, vals, lo_bits, hi_shift)
         DISPATCH_BITS(bits, CALL);
 #undef CALL
         DSM_LAUNCH_CHECK();
         if (launches) ++*launches;
         return;
     }
-    // generic path (first keys shorter than 12 bits: only under DSMFM_FIRST_KEY_BITS experiments)
+    // generic path (first keys shorter than 12 bits: only under DSMFM_FIRST_KEY_BITS experiments, one block only)
+    if (geom.world != 1)
+        throw CudaError{cudaErrorInvalidValue, "key-range selection over several blocks needs a first key of >= 12 bits", __FILE__, __LINE__};
+    const uint64_t n = geom.bytes[0];
 #define CALL(B) select_count_kernel<B><<<tiles, 256, 0, st>>>(packed, n, drop_bits, key_lo, key_hi, tile_scratch)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
@@ -2541,7 +2586,7 @@ void launch_wt_merge_pieces(cudaStream_t st, const uint64_t *src, const WtPiece 
 }
 
 void launch_bitrank(cudaStream_t st, const uint64_t *data, uint64_t nbits, uint64_t *Rs, uint8_t *Rb, uint64_t *scratch,
-                    uint32_t *launches)
+                    uint32_t *launches, uint64_t base)
 {
     const uint64_t integers = nbits / 64 + 1;
     const uint64_t nsb = nbits / 256 + 1; // superblock entries 0..nbits/256
@@ -2550,7 +2595,7 @@ void launch_bitrank(cudaStream_t st, const uint64_t *data, uint64_t nbits, uint6
     DSM_LAUNCH_CHECK();
     rank_chunk_scan_kernel<<<1, 1024, 0, st>>>(scratch, nchunks);
     DSM_LAUNCH_CHECK();
-    rank_write_kernel<<<nchunks, 256, 0, st>>>(data, integers, nbits, scratch, Rs, Rb);
+    rank_write_kernel<<<nchunks, 256, 0, st>>>(data, integers, nbits, scratch, Rs, Rb, base);
     DSM_LAUNCH_CHECK();
     if (launches) *launches += 3;
 }

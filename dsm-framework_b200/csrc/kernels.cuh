@@ -45,11 +45,24 @@ void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint
                          unsigned long long *hist, uint32_t *launches);
 // (key, position) pairs of the suffixes whose first key lies in [key_lo, key_hi), in text order.  The bounds
 // are multiples of 2^(key_bits - top_bits) (bin boundaries of the histogram above).  tile_scratch holds
-// select_tiles(...) u64, counter one u32.
-uint64_t select_tiles(uint64_t n, int bits, int first_syms, int top_bits);
-void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, int first_syms, int top_bits,
+// select_tiles(...) u64, counter one u32, lut_scratch kSelLutWords u32 (device).
+// The packed text may be a row of equally sized SLOTS, one per block of documents (the blocks of the GPUs of a
+// multi-GPU build, packed where they lived and exchanged as words): slot s holds geom.bytes[s] symbols from its
+// first word on, zero padding behind them.  Positions are positions in this padded ("virtual") text; padding
+// positions are never selected.  One block: world = 1, slot_words = all words, bytes[0] = n.
+constexpr int kMaxBlocks = 64;
+constexpr int kSelLutWords = 2048;
+struct SelGeom {
+    uint64_t slot_words;
+    uint32_t world;
+    uint32_t reserved;
+    uint64_t bytes[kMaxBlocks];
+};
+uint64_t select_tiles(uint64_t nwords, int bits, int first_syms, int top_bits);
+void launch_select(cudaStream_t st, int bits, const uint64_t *packed, uint64_t nwords, int first_syms, int top_bits,
                    bool carry_prev, uint64_t key_lo, uint64_t key_hi, uint64_t *tile_scratch, uint32_t *counter,
-                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, uint32_t *launches);
+                   uint64_t *keys, uint32_t *vals, int lo_bits, int hi_shift, const SelGeom &geom, uint32_t *lut_scratch,
+                   uint32_t *launches);
 // Wide builds (more than 2^lo_bits symbols in the collection): a text position is hi << lo_bits | lo with
 // lo in the u32 value of the sort and hi (<= 8 bits) riding in the key bits from hi_shift upwards
 // (hi_shift = 0: not wide); launch_heads then unloads hi into a byte array that travels with the suffix
@@ -180,7 +193,8 @@ void launch_wt_merge_pieces(cudaStream_t st, const uint64_t *src, const WtPiece 
 // words [0,4j), j <= nbits/256; Rb[k] = ones in words [4*(k/4), k), k <= nbits/64.
 // `scratch` holds ceil((nbits/256+1)/kRankChunk)+1 u64.
 constexpr int kRankChunk = 2048; // superblocks per CTA
+// `base` is added to every Rs entry (ones in front of the array when it is a piece of a longer bit vector).
 void launch_bitrank(cudaStream_t st, const uint64_t *data, uint64_t nbits, uint64_t *Rs, uint8_t *Rb,
-                    uint64_t *scratch, uint32_t *launches);
+                    uint64_t *scratch, uint32_t *launches, uint64_t base = 0);
 
 } // namespace dsmfm

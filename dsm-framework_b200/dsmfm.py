@@ -27,6 +27,36 @@ class Shard(C.Structure):
                 ("bwt_dev", C.c_void_p), ("sa_dev", C.c_void_p)]
 
 
+MAX_BLOCKS = 64
+
+
+class BlockInfo(C.Structure):
+    _fields_ = [("counts", C.c_uint64 * 256), ("bytes", C.c_uint64), ("documents", C.c_uint64),
+                ("max_text_length", C.c_uint64), ("empty_document", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class TextPlan(C.Structure):
+    _fields_ = [("world", C.c_uint32), ("bits", C.c_uint32), ("n", C.c_uint64), ("documents", C.c_uint64),
+                ("max_text_length", C.c_uint64), ("slot_words", C.c_uint64), ("text_bytes", C.c_uint64),
+                ("counts", C.c_uint64 * 256), ("block_bytes", C.c_uint64 * MAX_BLOCKS)]
+
+
+class PieceEdge(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("first_word", C.c_uint64), ("first", C.c_uint64 * 4), ("last_word", C.c_uint64),
+                ("last", C.c_uint64 * 4), ("ch", C.c_uint64)]
+
+
+class Piece(C.Structure):
+    _fields_ = [("node", C.c_uint32), ("reserved", C.c_uint32), ("word_first", C.c_uint64), ("word_count", C.c_uint64),
+                ("rs_first", C.c_uint64), ("rs_count", C.c_uint64), ("rb_first", C.c_uint64), ("rb_count", C.c_uint64),
+                ("data", C.POINTER(C.c_uint64)), ("Rs", C.POINTER(C.c_uint64)), ("Rb", C.POINTER(C.c_uint8))]
+
+
+class Pieces(C.Structure):
+    _fields_ = [("n_internal", C.c_uint32), ("world", C.c_uint32), ("rank", C.c_uint32), ("reserved", C.c_uint32),
+                ("bytes", C.c_uint64), ("piece", C.POINTER(Piece)), ("edge", C.POINTER(PieceEdge))]
+
+
 class Code(C.Structure):
     _fields_ = [("count", C.c_uint64), ("bits", C.c_uint32), ("code", C.c_uint32)]
 
@@ -123,6 +153,14 @@ def lib():
     L.dsmfm_pieces_bytes.restype = C.c_uint64
     L.dsmfm_build_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.dsmfm_assemble_pieces.argtypes = [B, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.dsmfm_block_stats.argtypes = [B, C.POINTER(BlockInfo)]
+    L.dsmfm_text_plan_make.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(TextPlan)]
+    L.dsmfm_block_pack.argtypes = [B, C.POINTER(TextPlan), C.c_uint32, C.c_void_p, C.c_void_p]
+    L.dsmfm_build_packed.argtypes = [B, C.POINTER(TextPlan), C.c_void_p, C.c_void_p]
+    L.dsmfm_pieces_build.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Pieces)]
+    L.dsmfm_pieces_merge.argtypes = [B, C.c_void_p, C.c_uint32]
+    L.dsmfm_pieces_index.argtypes = [B, C.POINTER(Index)]
+    L.dsmfm_pieces_write.argtypes = [B, C.c_char_p, C.c_int]
     S = C.c_void_p
     L.dsmfm_searcher_create.argtypes = [C.c_int, C.POINTER(Index), C.POINTER(S)]
     L.dsmfm_searcher_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(S)]
@@ -257,6 +295,48 @@ class Builder:
         h = self._hist_table(hist_all)
         self._keep.append(pieces)
         self._check(self._L.dsmfm_assemble_pieces(self._h, h.ctypes.data, h.shape[0], pieces.data_ptr()))
+
+    # ---- packed-text exchange between builders (include/dsmfm.h, "one collection over several GPUs") ----
+    def block_stats(self):
+        """Statistics of this builder's block of documents as bytes (a dsmfm_block_info record, to be all-gathered)."""
+        info = BlockInfo()
+        self._check(self._L.dsmfm_block_stats(self._h, C.byref(info)))
+        self._keep = []  # the stream has been synchronised: appended buffers are consumed
+        return bytes(info)
+
+    def block_pack(self, plan, rank, text):
+        """Packs the block into slot `rank` of `text` (uint8 CUDA tensor of plan.text_bytes); returns the block's
+        histogram of the top 12 key bits (numpy uint64[4096])."""
+        import numpy as np
+        top = np.zeros(4096, dtype=np.uint64)
+        self._check(self._L.dsmfm_block_pack(self._h, C.byref(plan), rank, text.data_ptr(), top.ctypes.data))
+        return top
+
+    def build_packed(self, plan, text, top_sum):
+        import numpy as np
+        top = np.ascontiguousarray(top_sum, dtype=np.uint64)
+        self._check(self._L.dsmfm_build_packed(self._h, C.byref(plan), text.data_ptr(), top.ctypes.data))
+
+    def pieces_build(self, hist_all, rank):
+        """Returns (Pieces, edges) -- edges: this builder's dsmfm_piece_edge records as bytes."""
+        h = self._hist_table(hist_all)
+        out = Pieces()
+        self._check(self._L.dsmfm_pieces_build(self._h, h.ctypes.data, h.shape[0], rank, C.byref(out)))
+        self.pieces = out
+        return out, C.string_at(out.edge, C.sizeof(PieceEdge) * out.n_internal)
+
+    def pieces_merge(self, edges_all, world):
+        """edges_all: the records of every builder in slice order, back to back (bytes)."""
+        buf = C.create_string_buffer(bytes(edges_all), len(edges_all))
+        self._check(self._L.dsmfm_pieces_merge(self._h, buf, world))
+
+    def pieces_index(self):
+        idx = Index()
+        self._check(self._L.dsmfm_pieces_index(self._h, C.byref(idx)))
+        return idx
+
+    def pieces_write(self, prefix, header):
+        self._check(self._L.dsmfm_pieces_write(self._h, os.fsencode(prefix), 1 if header else 0))
 
     def assemble(self, bwt_dev, n_total):
         """bwt_dev: device address (int) or torch CUDA tensor holding the concatenated BWT."""
@@ -423,6 +503,19 @@ class Searcher:
             self.close()
         except Exception:
             pass
+
+
+def text_plan(infos):
+    """infos: list of dsmfm_block_info records (bytes) in block order -> dsmfm_text_plan (host arithmetic only)."""
+    blob = b"".join(infos)
+    world = len(infos)
+    assert len(blob) == world * C.sizeof(BlockInfo)
+    buf = C.create_string_buffer(blob, len(blob))
+    plan = TextPlan()
+    rc = lib().dsmfm_text_plan_make(buf, world, C.byref(plan))
+    if rc != OK:
+        raise DsmfmError(rc, "dsmfm_text_plan_make failed" + (" (a block holds an empty document)" if rc == EEMPTY else ""))
+    return plan
 
 
 def build_fmi(docs, **kw):

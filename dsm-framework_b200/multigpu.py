@@ -1,103 +1,108 @@
 """One FM-index over reads held by several GPUs of one box (BASELINE.json configs[3]).
 
-One process per GPU (torchrun).  Rank r holds a contiguous block of the documents (document ids are
-global: all documents of rank r precede those of rank r+1, exactly as if they had been inserted one after
-the other into one TextCollectionBuilder).  The build:
+One process per GPU (torchrun).  Rank r holds a contiguous block of the documents (document ids are global:
+all documents of rank r precede those of rank r+1, exactly as if they had been inserted one after the other
+into one TextCollectionBuilder).  What replaces incbwt's batch merge by backward search
+(incbwt/rlcsa_builder.cpp:245-318) is that the merged order is a property of the text alone:
 
-  1. the raw blocks are all-gathered over NVLink (NCCL), so every GPU holds the whole text (1 byte per
-     symbol; 180 GB of HBM holds the 32 GB of the 16 Gbp configuration many times over);
-  2. every GPU packs the text and suffix-sorts ITS key ranges (dsmfm_options.shard_*): the suffixes are cut
-     by their first 16 symbols into world x ranges_per_gpu ranges of equal population, which every GPU
-     derives from the same histogram without talking to the others.  The refinement keys come from the
-     replicated text, so no rank exchange is needed -- this replaces incbwt's merge by backward search
-     (rlcsa_builder.cpp:245-318) and yields the same order, because the order is a property of the text;
-  3. the BWT slices are contiguous pieces of the global BWT, in rank order.  Every GPU turns its slice into
-     the bits it contributes to each node of the Huffman-shaped wavelet tree, already shifted to their
-     global bit offset (known from an all-gather of the slices' 256-bin histograms), and sends these
-     pieces (0.28 bytes per symbol) to rank 0 (NCCL point-to-point), which copies them into place, builds
-     the BitRank directories and owns the finished index.  (Engines without piece support -- and
-     wavelet="root" -- ship the BWT slices themselves and rank 0 builds the whole tree, dsmfm_assemble.)
+  1. every rank takes the statistics of its block (histogram, documents, longest document); the records are
+     all-gathered (2 KB each) and every rank derives the same plan: alphabet, bits per symbol, slot size;
+  2. every rank packs ITS block (3 bits per symbol for reads) into its slot of the packed text and counts the
+     top 12 key bits of its suffixes; the slots are all-gathered over NVLink (NCCL, in place: 0.375 bytes per
+     symbol instead of the raw text's 1), the 4096-bin histograms are summed;
+  3. every rank suffix-sorts ITS key ranges of the global suffix order (dsmfm_options.shard_*), selecting the
+     suffixes from the replicated packed text -- the refinement keys come from the same text, so the sort
+     needs no exchange at all -- and ends up with a contiguous slice of the global BWT;
+  4. the slices' byte histograms are all-gathered (2 KB each): they fix, for every node of the Huffman-shaped
+     wavelet tree, which bits of the node every slice contributes and how many ones precede them.  Every rank
+     builds its share of every node -- bit words, Rs and Rb directories -- on its own GPU, copies it to its
+     own host memory, and after an exchange of the few words next to the slice boundaries (96 bytes per node
+     and rank) writes it straight into the `.fmi` file at the offsets of FMIndex::save's layout.
 
-torch.distributed is plumbing only.  `engine` abstracts the device work so that the host logic (block
-offsets, uneven sizes, slice order) is testable with the gloo backend on CPU tensors.
+No rank ever holds the whole index and nothing funnels through one GPU.  torch.distributed is plumbing only:
+the phases below are explicit so that the same host logic runs (a) one rank per process over NCCL or gloo and
+(b) all ranks in one process, one after the other, on a single GPU (tests on a one-GPU box).  `engine`
+abstracts the device work; tests/cpu_engine.py is a numpy model of it for the gloo tests.
 """
 import os
 import time
 
+import numpy as np
 import torch
 
 
 class CudaEngine:
-    """The device work through the C ABI (libdsmfm.so)."""
+    """The device work through the C ABI (libdsmfm.so), on an explicit stream: torch's collectives are issued
+    with that stream current, so everything a rank does is ordered on ONE stream."""
 
-    def __init__(self, device, stream=None, flags=0, samplerate=0):
+    def __init__(self, device, flags=0, samplerate=0):
         import dsmfm
         self._dsmfm = dsmfm
         self.device = device
-        self.stream = stream
         self.flags = flags
         self.samplerate = samplerate
+        with torch.cuda.device(device):
+            self.stream = torch.cuda.Stream()
 
     def tensor_device(self):
         return torch.device("cuda", self.device)
 
-    def open(self, text, shard_index, shard_count, shard_span):
-        """text: uint8 CUDA tensor with the whole collection; it is copied into the builder (the caller may drop
-        its tensor afterwards, which matters when the collection is tens of GB)."""
-        b = self._dsmfm.Builder(device=self.device, stream=self.stream, expected_bytes=text.numel(), flags=self.flags,
-                                samplerate=self.samplerate, shard_index=shard_index, shard_count=shard_count,
-                                shard_span=shard_span)
+    def stream_context(self):
+        return torch.cuda.stream(self.stream)
+
+    def open(self, local_docs, rank, world, ranges_per_gpu):
+        k = max(1, int(ranges_per_gpu))
+        b = self._dsmfm.Builder(device=self.device, stream=self.stream.cuda_stream, expected_bytes=local_docs.numel(),
+                                flags=self.flags, samplerate=self.samplerate, shard_index=rank * k, shard_count=world * k,
+                                shard_span=k)
         try:
-            t0 = time.perf_counter()
-            b.append_batch_device(text)
-            torch.cuda.current_stream().synchronize()
-            self._t_append = 1000 * (time.perf_counter() - t0)
+            if local_docs.numel():
+                if local_docs.is_cuda:
+                    self.stream.wait_stream(torch.cuda.current_stream(local_docs.device))  # whoever produced it
+                    b.append_batch_device(local_docs)
+                else:
+                    b.append_batch(local_docs)
         except Exception:
             b.close()
             raise
         return b
 
-    def sort(self, b):
-        """Returns (handle, rank_begin, count) of this builder's slice of the global suffix order."""
-        try:
-            t1 = time.perf_counter()
-            b.build_device()
-            t2 = time.perf_counter()
-            info = b.shard_info()
-        except Exception:
-            b.close()
-            raise
-        self.last_walls = (self._t_append, 1000 * (t2 - t1))  # append, build (host wall, for DSMFM_MG_TRACE)
-        return b, info.rank_begin, info.count
+    def block_stats(self, b):
+        return b.block_stats()
 
-    def sort_slice(self, text, shard_index, shard_count, shard_span):
-        return self.sort(self.open(text, shard_index, shard_count, shard_span))
+    def plan(self, infos):
+        p = self._dsmfm.text_plan(infos)
+        return p, int(p.text_bytes), int(p.slot_words) * 8
 
-    def export_bwt(self, handle, out):
-        handle.shard_export(bwt_dst=out)
+    def new_text(self, text_bytes):
+        return torch.empty(text_bytes, dtype=torch.uint8, device=self.tensor_device())
 
-    def assemble(self, handle, bwt, n_total):
-        handle.assemble(bwt, n_total)
-        return handle
+    def block_pack(self, b, plan, rank, text):
+        return b.block_pack(plan, rank, text)
 
-    def slice_hist(self, handle):
-        return handle.slice_hist()
+    def build_packed(self, b, plan, text, top_sum):
+        b.build_packed(plan, text, top_sum)
+        info = b.shard_info()
+        return int(info.rank_begin), int(info.count)
 
-    def pieces_bytes(self, handle, hist_all, rank):
-        return handle.pieces_bytes(hist_all, rank)
+    def slice_hist(self, b):
+        return b.slice_hist()
 
-    def build_pieces(self, handle, hist_all, rank, out):
-        handle.build_pieces(hist_all, rank, out)
+    def pieces_build(self, b, hist_all, rank):
+        pieces, edges = b.pieces_build(hist_all, rank)
+        return edges, int(pieces.bytes)
 
-    def assemble_pieces(self, handle, hist_all, pieces):
-        handle.assemble_pieces(hist_all, pieces)
-        return handle
+    def pieces_merge(self, b, edges_all, world):
+        b.pieces_merge(edges_all, world)
 
-    def stats(self, handle):
-        return handle.stats()
+    def pieces_write(self, b, prefix, header):
+        b.pieces_write(prefix, header)
 
-    def close(self, handle):
-        handle.close()
+    def stats(self, b):
+        return b.stats()
+
+    def close(self, b):
+        b.close()
 
 
 def block_of(n_items, rank, world):
@@ -107,171 +112,186 @@ def block_of(n_items, rank, world):
     return begin, begin + q + (1 if rank < r else 0)
 
 
-def _all_gather_sizes(dist, value, device):
-    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
-    out = torch.empty(dist.get_world_size(), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(out, t)
-    return [int(x) for x in out.cpu()]
-
-
-def gather_text(dist, local, device):
-    """All-gathers the ranks' raw blocks (uint8, possibly of different sizes) into the whole text."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    sizes = _all_gather_sizes(dist, local.numel(), device)
-    n = sum(sizes)
-    offs = [0]
-    for s in sizes:
-        offs.append(offs[-1] + s)
-    full = torch.empty(n, dtype=torch.uint8, device=device)
-    mine = full[offs[rank]:offs[rank + 1]]
-    mine.copy_(local, non_blocking=True)  # host->device for a pinned host block, device->device otherwise
-    if world > 1:
-        if len(set(sizes)) == 1:
-            dist.all_gather_into_tensor(full, mine)
-        else:
-            for r in range(world):
-                if sizes[r]:
-                    dist.broadcast(full[offs[r]:offs[r + 1]], src=r)
-    return full, sizes
-
-
-def check_tiling(dist, rank_begin, count, n_total, device):
+def check_tiling(begins, counts, n_total):
     """The ranks' slices must tile the suffix order [0, n_total) in rank order, without gaps."""
-    counts = _all_gather_sizes(dist, count, device)
-    begins = _all_gather_sizes(dist, rank_begin, device)
     pos = 0
-    for r in range(dist.get_world_size()):
-        if counts[r] and begins[r] != pos:
-            raise RuntimeError("BWT slices do not tile the suffix order: rank %d begins at %d, expected %d"
-                               % (r, begins[r], pos))
-        pos += counts[r]
+    for r, (b, c) in enumerate(zip(begins, counts)):
+        if c and b != pos:
+            raise RuntimeError("BWT slices do not tile the suffix order: rank %d begins at %d, expected %d" % (r, b, pos))
+        pos += c
     if pos != n_total:
         raise RuntimeError("BWT slices cover %d of %d suffixes" % (pos, n_total))
-    return counts
 
 
-def gather_to_root(dist, piece, sizes, device, root=0):
-    """Concatenates the ranks' uint8 buffers (sizes[r] bytes each) on `root` in rank order; None elsewhere."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    assert piece.numel() == sizes[rank]
-    offs = [0]
-    for s in sizes:
-        offs.append(offs[-1] + s)
-    if rank == root:
-        full = torch.empty(offs[-1], dtype=torch.uint8, device=device)
-        full[offs[rank]:offs[rank + 1]].copy_(piece)
-        ops = [dist.P2POp(dist.irecv, full[offs[r]:offs[r + 1]], r) for r in range(world) if r != root and sizes[r]]
-    else:
-        full = None
-        ops = [dist.P2POp(dist.isend, piece, root)] if sizes[rank] else []
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return full
+class ShardedBuild:
+    """One rank's share of the build as explicit phases; what travels between two phases is named in the
+    docstring of the phase that produces it."""
+
+    def __init__(self, engine, rank, world, ranges_per_gpu=1):
+        self.engine, self.rank, self.world, self.ranges = engine, rank, world, ranges_per_gpu
+        self.handle = None
+        self.text = None
+        self.marks = []
+        self._t = time.perf_counter()
+
+    def _mark(self, name):
+        if os.environ.get("DSMFM_MG_TRACE"):
+            if self.engine.tensor_device().type == "cuda":
+                torch.cuda.synchronize()
+            t = time.perf_counter()
+            self.marks.append((name, 1000 * (t - self._t)))
+            self._t = t
+
+    def stats(self, local_docs):
+        """-> this block's dsmfm_block_info record (all-gather them in rank order)."""
+        self._t = time.perf_counter()
+        self.handle = self.engine.open(local_docs, self.rank, self.world, self.ranges)
+        info = self.engine.block_stats(self.handle)
+        self._mark("stats")
+        return info
+
+    def pack(self, infos):
+        """-> (text, slot_bytes, top): the packed text with THIS rank's slot filled (all-gather the slots in place)
+        and the block's histogram of the top 12 key bits (sum them over the ranks)."""
+        self.plan, text_bytes, self.slot_bytes = self.engine.plan(infos)
+        self.n_total = int(self.plan.n)
+        self.text = self.engine.new_text(text_bytes)
+        top = self.engine.block_pack(self.handle, self.plan, self.rank, self.text)
+        self._mark("pack")
+        return self.text, self.slot_bytes, top
+
+    def sort(self, top_sum):
+        """-> (rank_begin, count, hist): this rank's slice of the global suffix order and the byte histogram of
+        its BWT slice (all-gather all three)."""
+        self._mark("exchange_text")
+        self.rank_begin, self.count = self.engine.build_packed(self.handle, self.plan, self.text, top_sum)
+        self.text = None  # the sort is done with it
+        hist = self.engine.slice_hist(self.handle)
+        if int(hist.sum()) != self.count:
+            raise RuntimeError("slice histogram of rank %d does not match its slice" % self.rank)
+        self._mark("sort")
+        return self.rank_begin, self.count, hist
+
+    def pieces(self, begins, counts, hist_all):
+        """-> this rank's dsmfm_piece_edge records (all-gather them in rank order)."""
+        check_tiling(begins, counts, self.n_total)
+        self.hist_all = np.ascontiguousarray(hist_all, dtype=np.uint64).reshape(self.world, 256)
+        edges, self.section_bytes = self.engine.pieces_build(self.handle, self.hist_all, self.rank)
+        self._mark("pieces")
+        return edges
+
+    def merge(self, edges_all):
+        self.engine.pieces_merge(self.handle, b"".join(edges_all), self.world)
+        self._mark("merge")
+
+    def write(self, prefix):
+        """Every rank writes its share into <prefix>.fmi; rank 0 adds header, node table and tail."""
+        self.engine.pieces_write(self.handle, prefix, self.rank == 0)
+
+    def build_stats(self):
+        return self.engine.stats(self.handle) if hasattr(self.engine, "stats") else None
+
+    def report(self):
+        import sys
+        s = self.build_stats()
+        extra = ""
+        if s is not None:
+            extra = " | build: sort %.1f refine %.1f wt %.1f total %.1f, wall %.1f of which alloc %.1f, count %d" % (
+                s.ms_sort, s.ms_refine, s.ms_wt, s.ms_total, s.ms_wall_build, s.ms_wall_alloc, self.count)
+        print("[multigpu rank %d] " % self.rank + " ".join("%s %.1f ms" % m for m in self.marks) + extra, file=sys.stderr)
+
+    def close(self):
+        if self.handle is not None:
+            self.engine.close(self.handle)
+            self.handle = None
+        self.text = None
 
 
-def gather_slices(dist, piece, rank_begin, n_total, device, root=0):
-    """Collects the ranks' BWT slices on `root` in global rank order.  Returns the whole BWT there, None elsewhere."""
-    counts = check_tiling(dist, rank_begin, piece.numel(), n_total, device)
-    return gather_to_root(dist, piece, counts, device, root)
+# ---- (a) one rank per process: torch.distributed ------------------------------------------------------------
 
-
-def all_gather_hist(dist, hist, device):
-    """hist: numpy uint64[256] of this rank -> numpy uint64[world, 256]."""
-    import numpy as np
-    t = torch.from_numpy(hist.astype(np.int64)).to(device)
-    out = torch.empty(dist.get_world_size() * 256, dtype=torch.int64, device=device)
+def _all_gather_bytes(dist, record, device):
+    """Fixed-size records (bytes) of every rank, in rank order."""
+    world = dist.get_world_size()
+    t = torch.frombuffer(bytearray(record), dtype=torch.uint8).to(device)
+    out = torch.empty(world * t.numel(), dtype=torch.uint8, device=device)
     dist.all_gather_into_tensor(out, t)
-    return out.cpu().numpy().astype(np.uint64).reshape(dist.get_world_size(), 256)
+    blob = out.cpu().numpy().tobytes()
+    return [blob[i * len(record):(i + 1) * len(record)] for i in range(world)]
 
 
-def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, root=0, wavelet="distributed"):
+def _all_gather_u64(dist, values, device):
+    """numpy uint64[k] of every rank -> uint64[world, k]."""
+    a = np.ascontiguousarray(values, dtype=np.uint64)
+    recs = _all_gather_bytes(dist, a.tobytes(), device)
+    return np.stack([np.frombuffer(r, dtype=np.uint64) for r in recs])
+
+
+def build_sharded(dist, local_docs, engine, ranges_per_gpu=1):
     """Builds ONE index over the documents of all ranks (rank order = document order).
 
     local_docs: uint8 tensor (pinned host or device) with this rank's '\\0'-terminated documents.
-    wavelet: "distributed" (every GPU builds its pieces of the wavelet tree) or "root" (BWT slices go to
-    the root, which builds the whole tree).
-    Returns (handle, info): on `root` handle is the engine's builder holding the assembled index
-    (fetch()/fmi()/save() as for a single-GPU build), None elsewhere; info has the slice layout.
-    """
+    Returns the rank's ShardedBuild, merged: sb.write(prefix) puts the rank's share into the `.fmi` file,
+    sb.section_bytes is what it holds in host memory.  Close it when done."""
     world, rank = dist.get_world_size(), dist.get_rank()
     device = engine.tensor_device()
-    trace = _Trace(device) if os.environ.get("DSMFM_MG_TRACE") else None
-    full, sizes = gather_text(dist, local_docs, device)
-    if trace: trace.mark("gather_text")
-    n = full.numel()
-    k = max(1, int(ranges_per_gpu))
-    if hasattr(engine, "open"):
-        opened = engine.open(full, rank * k, world * k, k)
-        big = full.numel() > (8 << 30)
-        del full  # the builder holds its own copy now
-        if big and device.type == "cuda":
-            torch.cuda.empty_cache()  # hand the gathered text's memory back before the sort buffers are allocated
-        handle, rank_begin, count = engine.sort(opened)
-    else:
-        handle, rank_begin, count = engine.sort_slice(full, rank * k, world * k, k)
-        del full
-    if trace: trace.mark("sort_slice")
-    if trace and hasattr(engine, "last_walls"): trace.marks.append(("(append %.1f build %.1f)" % engine.last_walls, 0.0))
-    info = {"n_total": n, "block_bytes": sizes, "rank_begin": rank_begin, "count": count}
-    distributed = wavelet == "distributed" and hasattr(engine, "build_pieces")
-    if distributed:
-        check_tiling(dist, rank_begin, count, n, device)
-        hist_all = all_gather_hist(dist, engine.slice_hist(handle), device)
-        if int(hist_all[rank].sum()) != count:
-            raise RuntimeError("slice histogram of rank %d does not match its slice" % rank)
-        psizes = [engine.pieces_bytes(handle, hist_all, r) for r in range(world)]
-        piece = torch.empty(psizes[rank], dtype=torch.uint8, device=device)
-        engine.build_pieces(handle, hist_all, rank, piece)
-        if trace: trace.mark("build_pieces")
-        gathered = gather_to_root(dist, piece, psizes, device, root)
-    else:
-        piece = torch.empty(count, dtype=torch.uint8, device=device)
-        engine.export_bwt(handle, piece)
-        gathered = gather_slices(dist, piece, rank_begin, n, device, root)
-    if trace: trace.mark("gather")
-    if rank != root:
-        if hasattr(engine, "stats"):
-            info["stats"] = engine.stats(handle)
-        engine.close(handle)
-        if trace: trace.report(rank, info)
-        return None, info
-    if distributed:
-        engine.assemble_pieces(handle, hist_all, gathered)
-    else:
-        engine.assemble(handle, gathered, n)
-    if trace: trace.mark("assemble")
-    if hasattr(engine, "stats"):
-        info["stats"] = engine.stats(handle)
-    if trace: trace.report(rank, info)
-    return handle, info
+    sb = ShardedBuild(engine, rank, world, ranges_per_gpu)
+    ctx = engine.stream_context() if hasattr(engine, "stream_context") else _Null()
+    try:
+        with ctx:
+            infos = _all_gather_bytes(dist, sb.stats(local_docs), device)
+            text, slot_bytes, top = sb.pack(infos)
+            if world > 1:
+                mine = text[rank * slot_bytes:(rank + 1) * slot_bytes]
+                dist.all_gather_into_tensor(text[:world * slot_bytes], mine)  # in place, over NVLink
+            top_sum = _all_gather_u64(dist, top, device).sum(axis=0, dtype=np.uint64)
+            rank_begin, count, hist = sb.sort(top_sum)
+            rec = _all_gather_u64(dist, np.concatenate([np.array([rank_begin, count], dtype=np.uint64), hist]), device)
+            edges = sb.pieces([int(x) for x in rec[:, 0]], [int(x) for x in rec[:, 1]], rec[:, 2:])
+            sb.merge(_all_gather_bytes(dist, edges, device))
+    except Exception:
+        sb.close()
+        raise
+    if os.environ.get("DSMFM_MG_TRACE"):
+        sb.report()
+    return sb
 
 
-class _Trace:
-    """DSMFM_MG_TRACE=1: wall time of every phase (with a device synchronize in between) on stderr."""
+class _Null:
+    def __enter__(self):
+        return self
 
-    def __init__(self, device):
-        import time
-        self.time = time
-        self.cuda = device.type == "cuda"
-        self.t = self._now()
-        self.marks = []
+    def __exit__(self, *a):
+        return False
 
-    def _now(self):
-        if self.cuda:
-            torch.cuda.synchronize()
-        return self.time.perf_counter()
 
-    def mark(self, name):
-        t = self._now()
-        self.marks.append((name, 1000 * (t - self.t)))
-        self.t = t
+# ---- (b) all ranks in one process, one after the other (one GPU, or the CPU model) ----------------------------
 
-    def report(self, rank, info):
-        import sys
-        s = info.get("stats")
-        extra = ""
-        if s is not None:
-            extra = " | build: pack %.1f sort %.1f refine %.1f wt %.1f total %.1f, wall %.1f of which alloc %.1f, count %d" % (
-                s.ms_pack, s.ms_sort, s.ms_refine, s.ms_wt, s.ms_total, s.ms_wall_build, s.ms_wall_alloc, info["count"])
-        print("[multigpu rank %d] " % rank + " ".join("%s %.1f ms" % m for m in self.marks) + extra, file=sys.stderr)
+def build_sharded_local(blocks, engines, ranges_per_gpu=1):
+    """blocks[r]: uint8 tensor with rank r's documents; engines[r]: its engine (they may share a device).
+    The exchanges of build_sharded become plain copies.  Returns the list of merged ShardedBuilds."""
+    world = len(blocks)
+    sbs = [ShardedBuild(engines[r], r, world, ranges_per_gpu) for r in range(world)]
+    try:
+        infos = [sb.stats(blocks[r]) for r, sb in enumerate(sbs)]
+        packed = [sb.pack(infos) for sb in sbs]
+        slot = packed[0][1]
+        for r in range(world):  # the all-gather: everybody's slot into everybody's text
+            for q in range(world):
+                if q != r:
+                    packed[q][0][r * slot:(r + 1) * slot].copy_(packed[r][0][r * slot:(r + 1) * slot])
+        for e in engines:
+            if e.tensor_device().type == "cuda":
+                torch.cuda.synchronize(e.tensor_device())
+        top_sum = np.sum(np.stack([p[2] for p in packed]), axis=0, dtype=np.uint64)
+        del packed
+        sorted_ = [sb.sort(top_sum) for sb in sbs]
+        begins, counts = [s[0] for s in sorted_], [s[1] for s in sorted_]
+        hist_all = np.stack([s[2] for s in sorted_])
+        edges = [sb.pieces(begins, counts, hist_all) for sb in sbs]
+        for sb in sbs:
+            sb.merge(edges)
+    except Exception:
+        for sb in sbs:
+            sb.close()
+        raise
+    return sbs

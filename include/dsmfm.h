@@ -244,6 +244,106 @@ DSMFM_API uint64_t dsmfm_pieces_bytes(dsmfm_builder *b, const uint64_t *hist_all
 DSMFM_API int dsmfm_build_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, void *dst_dev);
 DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, const void *pieces_dev);
 
+/* ---- one collection over several GPUs, packed-text exchange (what bench.py --gpus N and `builder --gpus N` run) ----
+ * Replaces, across GPUs, incbwt's batch merge -- RLCSABuilder::addRLCSA / getRanks / mergeRLCSA
+ * (incbwt/rlcsa_builder.cpp:245-318; incbwt/rlcsa.cpp:156-220, 307-337) -- whose result is, like everything on this
+ * path, a function of the text alone: builder r of `world` holds block r of the documents (block order = document
+ * order).  Nothing but small tables and the PACKED blocks (3 bits per symbol for reads) has to travel:
+ *   1. dsmfm_block_stats      every builder: histogram / document count / longest document of its block
+ *      -> all-gather the dsmfm_block_info records (any transport: NCCL, MPI, shared memory of a threaded host)
+ *   2. dsmfm_text_plan        pure host arithmetic, identical on every builder: alphabet, bits per symbol, the slot
+ *                             every block occupies in the packed text (equal slots, so one all-gather moves them)
+ *   3. dsmfm_block_pack       every builder packs ITS block into its slot of `text_dev` (device buffer holding the
+ *                             whole packed text) and counts the top 12 key bits of its suffixes (4096 bins)
+ *      -> all-gather the slots (in place), sum the 4096-bin histograms over the builders
+ *   4. dsmfm_build_packed     every builder sorts the key ranges dsmfm_options.shard_* name, reading the replicated
+ *                             packed text; dsmfm_shard_info / dsmfm_slice_hist describe its slice of the global BWT
+ *      -> all-gather the slice histograms
+ *   5. dsmfm_pieces_build     every builder: its slice's share of every wavelet-tree node -- bit words, Rs, Rb with
+ *                             the counts of the slices in front of it added -- built on ITS GPU and copied to ITS host
+ *      -> all-gather the dsmfm_piece_edge records (12 words per node and builder)
+ *   6. dsmfm_pieces_merge     host: words and directory entries next to a slice boundary are completed
+ *   7. dsmfm_pieces_write     every builder writes its share straight into `<prefix>.fmi` (pwrite at the offsets of
+ *                             FMIndex::save's layout, FMIndex.cpp:155-217); the builder given `header` != 0 adds the rest.
+ * No builder ever holds the whole index, no GPU the whole wavelet tree, and the device-to-host copies run in parallel. */
+#define DSMFM_MAX_BLOCKS 64
+
+typedef struct dsmfm_block_info {
+    uint64_t counts[256];       /* byte histogram of the block                                       */
+    uint64_t bytes;             /* symbols incl. terminators                                         */
+    uint64_t documents;
+    uint64_t max_text_length;   /* longest document incl. its terminator                             */
+    uint32_t empty_document;    /* the block holds an empty document (two terminators in a row)      */
+    uint32_t reserved;
+} dsmfm_block_info;
+
+typedef struct dsmfm_text_plan {
+    uint32_t world;
+    uint32_t bits;              /* bits per packed symbol: 3, 4 or 8                                 */
+    uint64_t n;                 /* symbols of the collection                                         */
+    uint64_t documents;
+    uint64_t max_text_length;
+    uint64_t slot_words;        /* 64-bit words per slot (the same for every block)                  */
+    uint64_t text_bytes;        /* size of the packed-text buffer: (world * slot_words + 8) * 8      */
+    uint64_t counts[256];       /* histogram of the collection                                       */
+    uint64_t block_bytes[DSMFM_MAX_BLOCKS];
+} dsmfm_text_plan;
+
+/* Further appends fail.  Synchronises the builder's stream. */
+DSMFM_API int dsmfm_block_stats(dsmfm_builder *b, dsmfm_block_info *out);
+/* DSMFM_EEMPTY if any block holds an empty document, DSMFM_EINVAL if world is 0 or above DSMFM_MAX_BLOCKS. */
+DSMFM_API int dsmfm_text_plan_make(const dsmfm_block_info *all, uint32_t world, dsmfm_text_plan *out);
+/* text_dev: DEVICE memory of plan->text_bytes on the builder's device; words [rank*slot_words, (rank+1)*slot_words)
+ * are written (the block, then zeros).  top_hist4096: HOST array, the block's counts are stored (not added).
+ * The builder's raw block is released.  Synchronises the builder's stream. */
+DSMFM_API int dsmfm_block_pack(dsmfm_builder *b, const dsmfm_text_plan *plan, uint32_t rank, void *text_dev,
+                               uint64_t *top_hist4096);
+/* text_dev must be complete on the builder's stream (all slots, and 8 zero words behind the last slot) and stay
+ * untouched until the call returns; top_hist4096 = the sum over all builders.  DSMFM_FLAG_KEEP_SA is not supported. */
+DSMFM_API int dsmfm_build_packed(dsmfm_builder *b, const dsmfm_text_plan *plan, const void *text_dev,
+                                 const uint64_t *top_hist4096);
+
+typedef struct dsmfm_piece_edge {   /* one per internal node of the wavelet tree and builder; all-gathered */
+    uint64_t count;                 /* members of the node in this builder's slice (0: the rest is void)   */
+    uint64_t first_word;            /* first data word the slice contributes bits to                       */
+    uint64_t first[4];              /* its contribution to words first_word .. first_word + 3              */
+    uint64_t last_word;             /* last data word it contributes bits to                               */
+    uint64_t last[4];               /* its contribution to words last_word - 3 .. last_word                */
+    uint64_t ch;                    /* first member symbol of the slice (HuffWT.cpp:8)                     */
+} dsmfm_piece_edge;
+
+typedef struct dsmfm_piece {        /* this builder's share of one internal node's BitRank (BitRank.h:19-24) */
+    uint32_t node;                  /* index in the pre-order node list of the index                        */
+    uint32_t reserved;
+    uint64_t word_first, word_count; /* data[word_first .. word_first + word_count)                          */
+    uint64_t rs_first, rs_count;     /* Rs[rs_first .. )                                                     */
+    uint64_t rb_first, rb_count;     /* Rb[rb_first .. )                                                     */
+    uint64_t *data;                  /* HOST memory, valid until dsmfm_destroy; final after dsmfm_pieces_merge */
+    uint64_t *Rs;
+    uint8_t *Rb;
+} dsmfm_piece;
+
+typedef struct dsmfm_pieces {
+    uint32_t n_internal;            /* internal nodes of the tree = entries of `piece` and `edge`           */
+    uint32_t world, rank;
+    uint32_t reserved;
+    uint64_t bytes;                 /* bytes of sections this builder holds (copied device to host)         */
+    const dsmfm_piece *piece;
+    const dsmfm_piece_edge *edge;   /* this builder's records for the exchange                              */
+} dsmfm_pieces;
+
+/* hist_all[world][256]: dsmfm_slice_hist of every builder, in slice order. */
+DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, dsmfm_pieces *out);
+/* edges_all[world][n_internal] in slice order (host). */
+DSMFM_API int dsmfm_pieces_merge(dsmfm_builder *b, const dsmfm_piece_edge *edges_all, uint32_t world);
+/* The header fields, C[], code table and node list (leaf / ch / nbits / integers; data pointers NULL) of the whole
+ * index, as every builder knows them after dsmfm_pieces_merge. */
+DSMFM_API int dsmfm_pieces_index(dsmfm_builder *b, dsmfm_index *out);
+/* Writes this builder's share into `<path_prefix>.fmi` (created if missing, never truncated: every builder of the
+ * build writes the same file, in any order).  header != 0: also everything that is not a BitRank array, and the
+ * file is cut to its final size. */
+DSMFM_API int dsmfm_pieces_write(dsmfm_builder *b, const char *path_prefix, int header);
+
 /* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
  * byte-for-byte in the reference layout (version 17). */
 DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix);

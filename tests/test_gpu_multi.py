@@ -25,6 +25,8 @@ def test_index_built_by_several_gpus_matches_the_oracle(world, lo_bits):
     env = dict(os.environ)
     if lo_bits:
         env["DSMFM_POS_LO_BITS"] = lo_bits
+    else:
+        env["DSMFM_CHECK_LARGE"] = "1"  # 400k reads per rank: the N-GPU file equals the 1-GPU build of the same documents
     port = 29500 + os.getpid() % 2000
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", str(port),

@@ -1,7 +1,9 @@
-"""Host logic of the multi-GPU build (dsm-framework_b200/multigpu.py) on CPU: world_size 2 and 3 with the
-gloo backend.  The device work is replaced by an engine backed by the oracle, so what is exercised is the
-plumbing around it: uneven document blocks, text all-gather, slice order and tiling checks, assembly on
-the root rank."""
+"""Host logic of the multi-GPU build (dsm-framework_b200/multigpu.py) on CPU: world_size 2 and 3 with the gloo
+backend, and all ranks in one process.  The device work is replaced by tests/cpu_engine.py (a numpy model over
+the oracle), so what is exercised is everything around it: uneven and empty document blocks, the exchanges of
+block records / packed slots / slice histograms / edge records, slice tiling checks, and the `.fmi` file that
+every rank writes its share of -- which must equal the oracle's byte for byte, including the words and
+directory entries that straddle slice boundaries."""
 import os
 import socket
 
@@ -13,37 +15,7 @@ import torch.multiprocessing as mp
 
 import cases
 import oracle
-
-
-class OracleEngine:
-    """Stands in for the CUDA engine: suffix order and index come from oracle/ (test infrastructure)."""
-
-    def __init__(self, shuffle_ranges=False):
-        self.shuffle = shuffle_ranges
-
-    def tensor_device(self):
-        return torch.device("cpu")
-
-    def sort_slice(self, text, shard_index, shard_count, shard_span):
-        docs = text.numpy().tobytes()
-        bwt = oracle.bwt(docs)
-        n = len(docs)
-        # any cut of [0, n) into shard_count contiguous ranges is a valid sharding
-        cuts = [n * i // shard_count for i in range(shard_count + 1)]
-        lo, hi = cuts[shard_index], cuts[shard_index + shard_span]
-        return {"docs": docs, "bwt": bwt[lo:hi]}, lo, hi - lo
-
-    def export_bwt(self, handle, out):
-        out.copy_(torch.frombuffer(bytearray(handle["bwt"]), dtype=torch.uint8))
-
-    def assemble(self, handle, bwt, n_total):
-        assert bwt.numel() == n_total
-        nd, maxlen = oracle.doc_stats(handle["docs"])
-        handle["fmi"] = oracle.fmi_from_bwt(bwt.numpy().tobytes(), 124, nd, maxlen)
-        return handle
-
-    def close(self, handle):
-        pass
+from cpu_engine import CpuEngine
 
 
 def _free_port():
@@ -54,23 +26,25 @@ def _free_port():
     return p
 
 
+def _block(doc_list, rank, world):
+    import multigpu
+    b, e = multigpu.block_of(len(doc_list), rank, world)
+    local = b"".join(d + b"\0" for d in doc_list[b:e])
+    return torch.frombuffer(bytearray(local), dtype=torch.uint8) if local else torch.empty(0, dtype=torch.uint8)
+
+
 def _worker(rank, world, port, doc_list, ranges_per_gpu, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import multigpu
-        b, e = multigpu.block_of(len(doc_list), rank, world)
-        local = b"".join(d + b"\0" for d in doc_list[b:e])
-        t = torch.frombuffer(bytearray(local), dtype=torch.uint8) if local else torch.empty(0, dtype=torch.uint8)
-        handle, info = multigpu.build_sharded(dist, t, OracleEngine(), ranges_per_gpu=ranges_per_gpu)
-        assert info["n_total"] == sum(len(d) + 1 for d in doc_list)
-        assert info["block_bytes"][rank] == len(local)
-        if rank == 0:
-            with open(os.path.join(out_dir, "out.fmi"), "wb") as f:
-                f.write(handle["fmi"])
-        else:
-            assert handle is None
+        t = _block(doc_list, rank, world)
+        sb = multigpu.build_sharded(dist, t, CpuEngine(), ranges_per_gpu=ranges_per_gpu)
+        assert sb.n_total == sum(len(d) + 1 for d in doc_list)
+        sb.write(os.path.join(out_dir, "out"))
+        sb.close()
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -82,7 +56,29 @@ def test_sharded_build_plumbing_over_gloo(world, ndocs, ranges, tmp_path):
     assert len(doc_list) == ndocs
     mp.spawn(_worker, args=(world, _free_port(), doc_list, ranges, str(tmp_path)), nprocs=world, join=True)
     got = open(tmp_path / "out.fmi", "rb").read()
-    assert got == oracle.fmi_from_docs(docs)
+    want = oracle.fmi_from_docs(docs)
+    assert got == want, oracle.diff_fmi(got, want)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("seed,kw", [(3, dict(nreads=37, maxlen=30)), (4, dict(nreads=300, maxlen=50, alpha="AC", genome=100)),
+                                     (5, dict(nreads=9, maxlen=3, minlen=1)), (6, dict(nreads=150, maxlen=35, alpha="ACGT0123.", genome=400))])
+def test_every_rank_writes_its_share_of_the_file(world, seed, kw, tmp_path):
+    """All ranks in one process (multigpu.build_sharded_local): slices of very different sizes -- down to slices
+    that fit inside one 64-bit word of a node, so that several ranks meet in one word and in one superblock --
+    must still add up to the oracle's file, whatever the order in which the ranks write."""
+    import multigpu
+    docs, _ = oracle.fasta_to_docs(cases.rnd_fasta(seed, **kw))
+    doc_list = docs.split(b"\0")[:-1]
+    blocks = [_block(doc_list, r, world) for r in range(world)]
+    sbs = multigpu.build_sharded_local(blocks, [CpuEngine() for _ in range(world)], ranges_per_gpu=1 + seed % 2)
+    prefix = str(tmp_path / "local")
+    for sb in reversed(sbs):  # header last: the file must not depend on the order
+        sb.write(prefix)
+        sb.close()
+    got = open(prefix + ".fmi", "rb").read()
+    want = oracle.fmi_from_docs(docs)
+    assert got == want, oracle.diff_fmi(got, want)
 
 
 def test_block_of_partitions_exactly():
@@ -96,19 +92,26 @@ def test_block_of_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _gap_worker(rank, world, port):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        import multigpu
-        piece = torch.zeros(5, dtype=torch.uint8)
-        # rank 1 claims to begin at 6: slices [0,5) and [6,11) leave a hole
-        with pytest.raises(RuntimeError):
-            multigpu.gather_slices(dist, piece, 0 if rank == 0 else 6, 10, torch.device("cpu"))
-    finally:
-        dist.destroy_process_group()
-
-
 def test_slices_that_do_not_tile_are_rejected():
-    mp.spawn(_gap_worker, args=(2, _free_port()), nprocs=2, join=True)
+    import multigpu
+    multigpu.check_tiling([0, 5], [5, 5], 10)
+    with pytest.raises(RuntimeError):
+        multigpu.check_tiling([0, 6], [5, 5], 10)  # a hole between the slices
+    with pytest.raises(RuntimeError):
+        multigpu.check_tiling([0, 5], [5, 4], 10)  # one suffix short
+
+
+def test_text_plan_is_host_arithmetic():
+    """dsmfm_text_plan_make needs no GPU: alphabet -> bits per symbol, equal slots of whole 128-byte lines."""
+    import ctypes as C
+    import dsmfm
+    eng = CpuEngine()
+    infos = [eng.block_stats(eng.open(torch.frombuffer(bytearray(d), dtype=torch.uint8), r, 3, 1))
+             for r, d in enumerate([b"ACGT\0GG\0", b"T-A\0", b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN\0"])]
+    plan = dsmfm.text_plan(infos)
+    assert (plan.world, plan.bits, plan.n, plan.documents, plan.max_text_length) == (3, 3, 55, 4, 43)
+    assert plan.slot_words == 16 and plan.text_bytes == (3 * 16 + 8) * 8
+    assert [plan.block_bytes[r] for r in range(3)] == [8, 4, 43]
+    bad = eng.block_stats(eng.open(torch.frombuffer(bytearray(b"AC\0\0"), dtype=torch.uint8), 0, 1, 1))
+    with pytest.raises(dsmfm.DsmfmError):
+        dsmfm.text_plan([bad])
