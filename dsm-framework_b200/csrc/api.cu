@@ -2162,6 +2162,53 @@ DSMFM_API int dsmfm_assemble_pieces(dsmfm_builder *b, const uint64_t *hist_all, 
     return DSMFM_OK;
 }
 
+DSMFM_API int dsmfm_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+DSMFM_API void *dsmfm_device_alloc(int device, size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+DSMFM_API void dsmfm_device_free(int device, void *p)
+{
+    if (p && cudaSetDevice(device) == cudaSuccess) cudaFree(p);
+}
+
+DSMFM_API int dsmfm_slot_send(dsmfm_builder *b, const dsmfm_text_plan *plan, uint32_t rank, const void *text_src_dev,
+                              int dst_device, void *text_dst_dev)
+{
+    API_GUARD(b);
+    if (!plan || rank >= plan->world || !text_src_dev || !text_dst_dev) return b->fail(DSMFM_EINVAL, "dsmfm_slot_send: bad arguments");
+    try {
+        const size_t bytes = (size_t)plan->slot_words * 8, off = (size_t)rank * bytes;
+        const uint8_t *src = static_cast<const uint8_t *>(text_src_dev) + off;
+        uint8_t *dst = static_cast<uint8_t *>(text_dst_dev) + off;
+        if (dst_device == b->device) {
+            if (src != dst) DSM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, b->stream));
+        } else {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, b->device, dst_device) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dst_device, 0); // direct stores over NVLink
+                if (e != cudaSuccess) cudaGetLastError();                         // (already enabled)
+            }
+            DSM_CUDA(cudaMemcpyPeerAsync(dst, dst_device, src, b->device, bytes, b->stream));
+        }
+        DSM_CUDA(cudaStreamSynchronize(b->stream));
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    }
+    return DSMFM_OK;
+}
+
 // ---- wavelet tree and BitRank directories built where the BWT slices are --------------------------
 // Slice r's members of node v occupy the bits [o, o + c) of the node's vector (o, c from the slices' byte
 // histograms).  Builder r OWNS the data words whose first bit lies in that range -- [ceil(o/64), ceil((o+c)/64)) --

@@ -5,6 +5,7 @@
 // (builder.cpp:60-104, 183-201); the index itself is built on the GPU behind
 // TextCollectionBuilder.  There is no CPU fallback.
 #include "TextCollectionBuilder.h"
+#include "MultiGpuBuilder.h"
 
 #include <chrono>
 #include <cstdio>
@@ -26,6 +27,7 @@ bool g_verbose = false;
 bool g_samples = false; // --samples: also write <output>.sa (the reference's dormant FMIndex::saveSamples)
 bool g_fast_exit = true;   // leave through _Exit once the files are written (DSMFM_ORDERLY_EXIT=1: normal teardown)
 bool g_host_parse = false; // --host-parse: the reference's per-read loop on the host instead of the GPU front end
+unsigned g_gpus = 1;        // --gpus N: one index built by N GPUs (MultiGpuBuilder)
 
 struct Clock
 {
@@ -92,7 +94,8 @@ void help(char const *name)
               << "     --samples                 Also write <output>.sa, the suffix array samples of" << std::endl
               << "                               FMIndex::saveSamples (extension; off in the reference)." << std::endl
               << "     --host-parse              Parse and transform the reads on the host, one InsertText" << std::endl
-              << "                               per read as the reference does (default: on the GPU)." << std::endl;
+              << "                               per read as the reference does (default: on the GPU)." << std::endl
+              << "     --gpus <int>              Build the one index on <int> GPUs of this box (extension)." << std::endl;
 }
 
 int parse_int_at_least(char const *value, int min, char const *parameter, char const *name)
@@ -319,6 +322,46 @@ void build_gpu_front_end(FILE *in, std::string const &outputfile, unsigned sampl
     delete tc;
 }
 
+// --gpus N: the whole input is read into (page-locked) host memory, cut into N blocks at record boundaries, and
+// N host threads -- one per GPU -- build the one index together (MultiGpuBuilder.h).
+void build_multi_gpu(FILE *in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
+{
+    size_t cap = (size_t)64 << 20, have = 0;
+    unsigned char *buf = (unsigned char *)std::malloc(cap);
+    while (buf)
+    {
+        const size_t got = std::fread(buf + have, 1, cap - have, in);
+        have += got;
+        if (got == 0) break;
+        if (have == cap)
+        {
+            cap *= 2;
+            buf = (unsigned char *)std::realloc(buf, cap);
+        }
+    }
+    if (!buf)
+    {
+        std::cerr << "builder: unable to allocate the input buffer" << std::endl;
+        std::exit(1);
+    }
+    if (g_verbose)
+        std::cerr << "Read " << have << " bytes of input (elapsed " << wall.seconds() << " s); building on " << g_gpus
+                  << " GPUs" << std::endl;
+    std::cerr << "Warning: not thread-safe" << std::endl;
+    MultiGpuBuilder mg(g_gpus, samplerate ? samplerate : TEXTCOLLECTION_DEFAULT_SAMPLERATE);
+    MultiGpuBuilder::Report rep;
+    mg.Build(buf, have, outputfile, rep);
+    if (rep.badHeaders) throw std::out_of_range("basic_string::substr: header line without a name");
+    if (rep.invalidRecords)
+        std::cerr << "Warning: " << rep.invalidRecords << " sequence(s) contain invalid symbols (all turned into N)" << std::endl;
+    if (g_verbose)
+        std::cerr << "Created index with " << rep.documents << " sequences, total " << rep.bases << " bytes, " << rep.symbols
+                  << " indexed symbols, in " << rep.seconds << " s on " << g_gpus << " GPU ranks:" << std::endl
+                  << rep.perGpu << "Saved to file " << outputfile << ".fmi" << std::endl
+                  << "(total wall-clock time " << wall.seconds() << " s, " << wall.seconds() / 3600 << " hours)" << std::endl;
+    std::free(buf);
+}
+
 void build(std::istream &in, std::string const &outputfile, unsigned samplerate, Clock const &wall)
 {
     TextCollectionBuilder *tcb = new TextCollectionBuilder(samplerate, 1);
@@ -399,6 +442,7 @@ int main(int argc, char **argv)
                                            {"verbose", no_argument, 0, 'v'},
                                            {"samples", no_argument, 0, 1000},
                                            {"host-parse", no_argument, 0, 1001},
+                                           {"gpus", required_argument, 0, 1002},
                                            {0, 0, 0, 0}};
     int option_index = 0, c;
     // same option string as the reference (builder.cpp:353): -c, -R and -F are accepted by getopt
@@ -415,6 +459,7 @@ int main(int argc, char **argv)
             setenv("DSMFM_KEEP_SA", "1", 1);
             break;
         case 1001: g_host_parse = true; break;
+        case 1002: g_gpus = (unsigned)parse_int_at_least(optarg, 1, "--gpus", argv[0]); break;
         case '?': usage(argv[0]); return 1;
         default: usage(argv[0]); std::abort();
         }
@@ -459,7 +504,16 @@ int main(int argc, char **argv)
     std::cerr.precision(2);
     Clock wall;
     if (g_verbose) std::cerr << "Building the forward index:" << std::endl;
-    if (g_host_parse)
+    if (g_gpus > 1)
+    {
+        if (g_host_parse || g_samples)
+        {
+            std::cerr << "builder: --gpus can not be combined with --host-parse or --samples" << std::endl;
+            return 1;
+        }
+        build_multi_gpu(fin, outputfile, samplerate, wall);
+    }
+    else if (g_host_parse)
         build(*in, outputfile, samplerate, wall);
     else
         build_gpu_front_end(fin, outputfile, samplerate, wall);

@@ -344,6 +344,16 @@ DSMFM_API int dsmfm_pieces_index(dsmfm_builder *b, dsmfm_index *out);
  * file is cut to its final size. */
 DSMFM_API int dsmfm_pieces_write(dsmfm_builder *b, const char *path_prefix, int header);
 
+/* Helpers for hosts that do not link the CUDA runtime themselves (the C++ CLI runs one thread per GPU and moves
+ * the packed slots with peer copies instead of NCCL): device memory for the packed text, and the copy of slot
+ * `rank` of this builder's text into the text buffer of another device (peer-to-peer over NVLink when the devices
+ * allow it), ordered on the builder's stream and waited for. */
+DSMFM_API int dsmfm_device_count(void);
+DSMFM_API void *dsmfm_device_alloc(int device, size_t bytes);
+DSMFM_API void dsmfm_device_free(int device, void *p);
+DSMFM_API int dsmfm_slot_send(dsmfm_builder *b, const dsmfm_text_plan *plan, uint32_t rank, const void *text_src_dev,
+                              int dst_device, void *text_dst_dev);
+
 /* Replaces: FMIndex::save (FMIndex.cpp:155-217).  Writes `<path_prefix>.fmi`
  * byte-for-byte in the reference layout (version 17). */
 DSMFM_API int dsmfm_write_fmi(const dsmfm_index *idx, const char *path_prefix);
