@@ -413,7 +413,9 @@ size_t wavelet_fill_bits(cudaStream_t st, const uint8_t *d_seq, uint64_t n, cons
     const int m = shape.n_internal;
     if (m == 0 || n == 0) return 0;
     const uint64_t ntiles = div_up(n, kWtTile);
-    const size_t tile_bytes = sizeof(uint64_t) * (size_t)m * ntiles;
+    static const bool no_sweep = std::getenv("DSMFM_WT_SWEEP") && std::atoi(std::getenv("DSMFM_WT_SWEEP")) == 0;
+    const bool sweep = wt_sweep_ok(m) && !no_sweep; // one pass (small trees) or count / scan / fill
+    const size_t tile_bytes = sizeof(uint64_t) * (sweep ? wt_sweep_status_words(ntiles) + 1 : (size_t)m * ntiles);
     uint8_t *d_info = static_cast<uint8_t *>(dev_alloc((size_t)m * 256, st));
     uint64_t *d_tile = static_cast<uint64_t *>(dev_alloc(tile_bytes, st));
     uint64_t **d_ptrs = static_cast<uint64_t **>(dev_alloc(sizeof(uint64_t *) * m, st));
@@ -422,9 +424,14 @@ size_t wavelet_fill_bits(cudaStream_t st, const uint8_t *d_seq, uint64_t n, cons
         DSM_CUDA(cudaMemcpyAsync(d_info, shape.info.data(), (size_t)m * 256, cudaMemcpyHostToDevice, st));
         DSM_CUDA(cudaMemcpyAsync(d_ptrs, ptrs.data(), sizeof(uint64_t *) * m, cudaMemcpyHostToDevice, st));
         if (d_base) DSM_CUDA(cudaMemcpyAsync(d_base, bit_base.data(), sizeof(uint64_t) * m, cudaMemcpyHostToDevice, st));
-        launch_wt_count(st, d_seq, n, d_info, m, ntiles, d_tile, launches);
-        launch_wt_scan(st, d_tile, m, ntiles, launches);
-        launch_wt_fill(st, d_seq, n, d_info, m, ntiles, d_tile, d_ptrs, d_ch, d_base, launches);
+        if (sweep) {
+            launch_wt_sweep(st, d_seq, n, d_info, m, ntiles, d_tile,
+                            reinterpret_cast<uint32_t *>(d_tile + wt_sweep_status_words(ntiles)), d_ptrs, d_ch, d_base, launches);
+        } else {
+            launch_wt_count(st, d_seq, n, d_info, m, ntiles, d_tile, launches);
+            launch_wt_scan(st, d_tile, m, ntiles, launches);
+            launch_wt_fill(st, d_seq, n, d_info, m, ntiles, d_tile, d_ptrs, d_ch, d_base, launches);
+        }
         DSM_CUDA(cudaStreamSynchronize(st)); // the host vectors are consumed
     } catch (...) {
         dev_free(d_info, st); dev_free(d_tile, st); dev_free(d_ptrs, st); dev_free(d_base, st);
@@ -706,6 +713,12 @@ struct dsmfm_builder {
         std::vector<uint64_t> bit_off, bit_count; // per internal node
         uint8_t *h_blob = nullptr;                // pinned
         size_t h_bytes = 0;
+        uint8_t *d_blob = nullptr;                // device pieces until dsmfm_pieces_fetch
+        size_t blob_bytes = 0, ch_off = 0;
+        bool built = false;
+        std::vector<uint64_t> loc_G0, loc_words, off_data, off_rs, off_rb, nbits_of;
+        std::vector<uint32_t> node_of;
+        std::vector<uint8_t> loc_last;
         uint32_t world = 0, rank = 0;
         bool merged = false;
         WtShape shape;
@@ -2267,12 +2280,14 @@ bool pwrite_all(int fd, const void *p, size_t n, uint64_t off)
 }
 } // namespace
 
+DSMFM_API int dsmfm_pieces_fetch(dsmfm_builder *b, dsmfm_pieces *out);
+
 DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, dsmfm_pieces *out)
 {
     API_GUARD(b);
-    if (!out || !hist_all || world == 0 || rank >= world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: bad arguments");
+    if (!hist_all || world == 0 || rank >= world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: bad arguments");
     if (!b->built || !b->d_bwt) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: nothing built (or already fetched)");
-    if (b->ph.h_blob) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: already built");
+    if (b->ph.built) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_build: already built");
     for (int c = 0; c < 256; ++c) { // the slices together must hold exactly the symbols of the collection
         uint64_t t = 0;
         for (uint32_t r = 0; r < world; ++r) t += hist_all[(size_t)r * 256 + c];
@@ -2351,9 +2366,6 @@ DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uin
                 launch_bitrank(st, ptrs[v], loc[v].nb, reinterpret_cast<uint64_t *>(d_blob + loc[v].off_rs),
                                d_blob + loc[v].off_rb, d_scratch, L, loc[v].B);
         DSM_CUDA(cudaEventRecord(e1, st));
-        ph.h_blob = static_cast<uint8_t *>(g_pinned.get(blob_bytes));
-        ph.h_bytes = blob_bytes;
-        DSM_CUDA(cudaMemcpyAsync(ph.h_blob, d_blob, blob_bytes, cudaMemcpyDeviceToHost, st));
         DSM_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
@@ -2361,54 +2373,103 @@ DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uin
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         b->dfree(d_scratch);
-        b->dfree(d_blob);
         b->dfree(b->d_bwt);
         b->d_bwt = nullptr;
+        ph.d_blob = d_blob;
+        ph.blob_bytes = blob_bytes;
+        ph.ch_off = blob;
+        ph.loc_G0.resize(m); ph.loc_words.resize(m); ph.loc_last.resize(m);
+        ph.off_data.resize(m); ph.off_rs.resize(m); ph.off_rb.resize(m); ph.nbits_of = nbits_of; ph.node_of = node_of;
+        for (int v = 0; v < m; ++v) {
+            ph.loc_G0[v] = loc[v].G0; ph.loc_words[v] = loc[v].words; ph.loc_last[v] = loc[v].last ? 1 : 0;
+            ph.off_data[v] = loc[v].off_data; ph.off_rs[v] = loc[v].off_rs; ph.off_rb[v] = loc[v].off_rb;
+        }
+        ph.built = true;
+        ph.merged = false;
+        if (out) {
+            const int rc = dsmfm_pieces_fetch(b, out);
+            if (rc) return rc;
+        }
+    } catch (const CudaError &e) {
+        return b->fail_cuda(e);
+    } catch (const std::bad_alloc &) {
+        return b->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+    return DSMFM_OK;
+}
 
+DSMFM_API int dsmfm_pieces_fetch(dsmfm_builder *b, dsmfm_pieces *out)
+{
+    API_GUARD(b);
+    if (!out) return DSMFM_EINVAL;
+    auto &ph = b->ph;
+    if (!ph.built) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_fetch: call dsmfm_pieces_build first");
+    try {
+        cudaStream_t st = b->stream;
+        const int m = ph.shape.n_internal;
+        if (!ph.h_blob) {
+            cudaEvent_t e0, e1;
+            DSM_CUDA(cudaEventCreate(&e0));
+            DSM_CUDA(cudaEventCreate(&e1));
+            ph.h_blob = static_cast<uint8_t *>(g_pinned.get(ph.blob_bytes));
+            ph.h_bytes = ph.blob_bytes;
+            DSM_CUDA(cudaEventRecord(e0, st));
+            DSM_CUDA(cudaMemcpyAsync(ph.h_blob, ph.d_blob, ph.blob_bytes, cudaMemcpyDeviceToHost, st));
+            DSM_CUDA(cudaEventRecord(e1, st));
+            DSM_CUDA(cudaStreamSynchronize(st));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            b->stats.ms_d2h = ms;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            b->dfree(ph.d_blob);
+            ph.d_blob = nullptr;
+        }
         uint64_t held = 0;
         for (int v = 0; v < m; ++v) {
-            const Loc &l = loc[v];
-            const uint64_t o = ph.bit_off[v], c = ph.bit_count[v], nbits = nbits_of[v];
+            const uint64_t o = ph.bit_off[v], c = ph.bit_count[v], nbits = ph.nbits_of[v];
+            const uint64_t G0 = ph.loc_G0[v], words = ph.loc_words[v];
+            const bool last = ph.loc_last[v] != 0;
             dsmfm_piece &pc = ph.piece[v];
             dsmfm_piece_edge &ed = ph.edge[v];
-            pc.node = node_of[v];
-            uint64_t *h_data = reinterpret_cast<uint64_t *>(ph.h_blob + l.off_data);
-            uint64_t *h_rs = reinterpret_cast<uint64_t *>(ph.h_blob + l.off_rs);
-            uint8_t *h_rb = ph.h_blob + l.off_rb;
+            pc = dsmfm_piece();
+            ed = dsmfm_piece_edge();
+            pc.node = ph.node_of[v];
+            uint64_t *h_data = reinterpret_cast<uint64_t *>(ph.h_blob + ph.off_data[v]);
+            uint64_t *h_rs = reinterpret_cast<uint64_t *>(ph.h_blob + ph.off_rs[v]);
+            uint8_t *h_rb = ph.h_blob + ph.off_rb[v];
             if (c) {
                 pc.word_first = div_up(o, 64);
-                const uint64_t w_end = l.last ? nbits / 64 + 1 : div_up(o + c, 64);
+                const uint64_t w_end = last ? nbits / 64 + 1 : div_up(o + c, 64);
                 pc.word_count = w_end > pc.word_first ? w_end - pc.word_first : 0;
                 pc.rb_first = pc.word_first;
                 pc.rb_count = pc.word_count;
                 pc.rs_first = div_up(o, 256);
-                const uint64_t s_end = l.last ? nbits / 256 + 1 : div_up(o + c, 256);
+                const uint64_t s_end = last ? nbits / 256 + 1 : div_up(o + c, 256);
                 pc.rs_count = s_end > pc.rs_first ? s_end - pc.rs_first : 0;
-                pc.data = h_data + (pc.word_first - l.G0);
-                pc.Rb = h_rb + (pc.word_first - l.G0);
-                pc.Rs = h_rs + (pc.rs_first - l.G0 / 4);
+                pc.data = h_data + (pc.word_first - G0);
+                pc.Rb = h_rb + (pc.word_first - G0);
+                pc.Rs = h_rs + (pc.rs_first - G0 / 4);
                 ed.count = c;
                 ed.first_word = o / 64;
                 ed.last_word = (o + c - 1) / 64;
                 for (int t = 0; t < 4; ++t) {
-                    const uint64_t fi = ed.first_word - l.G0 + t;
-                    ed.first[t] = fi < l.words ? h_data[fi] : 0ull;
-                    const int64_t li = (int64_t)(ed.last_word - l.G0) - 3 + t;
-                    ed.last[t] = li >= 0 && (uint64_t)li < l.words ? h_data[li] : 0ull;
+                    const uint64_t fi = ed.first_word - G0 + t;
+                    ed.first[t] = fi < words ? h_data[fi] : 0ull;
+                    const int64_t li = (int64_t)(ed.last_word - G0) - 3 + t;
+                    ed.last[t] = li >= 0 && (uint64_t)li < words ? h_data[li] : 0ull;
                 }
-                ed.ch = ph.h_blob[blob + v];
+                ed.ch = ph.h_blob[ph.ch_off + v];
                 held += pc.word_count * 8 + pc.rs_count * 8 + pc.rb_count;
             }
         }
-        ph.merged = false;
         out->n_internal = (uint32_t)m;
-        out->world = world;
-        out->rank = rank;
+        out->world = ph.world;
+        out->rank = ph.rank;
         out->reserved = 0;
         out->bytes = held;
         out->piece = ph.piece.data();
         out->edge = ph.edge.data();
-        b->stats.ms_d2h = 0.f;
     } catch (const CudaError &e) {
         return b->fail_cuda(e);
     } catch (const std::bad_alloc &) {
@@ -2421,7 +2482,7 @@ DSMFM_API int dsmfm_pieces_merge(dsmfm_builder *b, const dsmfm_piece_edge *edges
 {
     if (!b || !edges_all) return DSMFM_EINVAL;
     auto &ph = b->ph;
-    if (!ph.h_blob || world != ph.world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_merge: call dsmfm_pieces_build first (same world)");
+    if (!ph.h_blob || world != ph.world) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_merge: call dsmfm_pieces_build / dsmfm_pieces_fetch first (same world)");
     if (ph.merged) return b->fail(DSMFM_EINVAL, "dsmfm_pieces_merge: already merged");
     const int m = ph.shape.n_internal;
     const uint32_t rank = ph.rank;

@@ -2051,6 +2051,135 @@ wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__res
     }
 }
 
+// ---- one pass over the sequence for small trees (reads: 6 internal nodes) -----------------------------------
+// wt_count + wt_scan + wt_fill read the sequence twice, build the member masks twice, and every thread ORs its
+// bits into the node arrays with global atomics (two per node and thread).  For trees of at most 8 internal nodes
+// one kernel does it all: a CTA takes the next tile (dynamic tile id), builds the masks once, publishes its member
+// counts per node and obtains the bit offsets of its contribution by decoupled look-back over the tiles in front
+// (one warp per node, 32 predecessors per step) -- while the look-back runs nothing else is waiting, the masks are
+// already in registers.  The tile's bits of every node are then assembled in shared memory (32-bit shared atomics)
+// and leave the SM as whole 64-bit words; only the first and the last word of a tile's run, which it may share
+// with its neighbours, are OR-ed into global memory.
+constexpr int kWtRunWords = kWtTile / 64 + 2; // 64-bit words a tile's run of one node can touch
+
+__global__ void __launch_bounds__(256)
+wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
+                volatile unsigned long long *status, uint32_t *counter, uint64_t *const *__restrict__ node_data,
+                uint8_t *__restrict__ node_ch, const uint64_t *__restrict__ bit_base)
+{
+    __shared__ uint16_t s_lut16[256];
+    __shared__ uint32_t s_part[kWtSmallNodes][8];
+    __shared__ uint32_t s_total[kWtSmallNodes];
+    __shared__ unsigned long long s_off[kWtSmallNodes]; // global bit offset of the tile's run in node v
+    __shared__ uint32_t s_bits[kWtSmallNodes][2 * kWtRunWords];
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(counter, 1u);
+    wt_small_table(node_info, n_internal, s_lut16);
+    for (int i = tid; i < kWtSmallNodes * 2 * kWtRunWords; i += 256) (&s_bits[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t p0 = tile * kWtTile + (uint64_t)tid * 32;
+    uint32_t w[8];
+    wt_load32(seq, n, p0, w);
+    const uint32_t valid = wt_valid_mask(n, p0);
+    uint32_t m[kWtSmallNodes], b[kWtSmallNodes], incl[kWtSmallNodes];
+    wt_masks_small(s_lut16, w, valid, n_internal, m, b);
+#pragma unroll
+    for (int v = 0; v < kWtSmallNodes; ++v) {
+        if (v < n_internal) {
+            incl[v] = warp_incl_sum((uint32_t)__popc(m[v]));
+            if (lane == 31) s_part[v][warp] = incl[v];
+        }
+    }
+    __syncthreads();
+    // warp v: total of node v, publish, look back
+    if (warp < n_internal) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) total += s_part[warp][k];
+        volatile unsigned long long *st = status + (size_t)warp; // status[tile * 8 + node]
+        if (lane == 0) st[tile * kWtSmallNodes] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            long long t = (long long)tile - 1;
+            for (;;) {
+                const long long idx = t - lane;
+                unsigned long long x = 2ull << 62; // in front of the first tile: an empty prefix
+                if (idx >= 0) x = st[idx * kWtSmallNodes];
+                while (__any_sync(0xffffffffu, (x >> 62) == 0))
+                    if ((x >> 62) == 0) x = st[idx * kWtSmallNodes];
+                const uint32_t pm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+                const int stop = pm ? __ffs(pm) - 1 : 32;
+                unsigned long long val = lane <= stop ? (x & kSelValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                excl += val;
+                if (pm) break;
+                t -= 32;
+            }
+            if (lane == 0) st[tile * kWtSmallNodes] = kSelFlagPrefix | (excl + total);
+        }
+        if (lane == 0) {
+            s_total[warp] = total;
+            s_off[warp] = excl + (bit_base ? bit_base[warp] : 0ull);
+        }
+    }
+    __syncthreads();
+    // every thread: its bits of every node into the tile's run (bit 0 of the run buffer = bit (off & ~63) of the node)
+#pragma unroll
+    for (int v = 0; v < kWtSmallNodes; ++v) {
+        if (v < n_internal) {
+            const uint32_t c = __popc(m[v]);
+            if (c) {
+                uint32_t before = incl[v] - c;
+                for (int k = 0; k < warp; ++k) before += s_part[v][k];
+                uint32_t bits = b[v]; // all 32 symbols are members (always so at the root): nothing to compress
+                if (m[v] != 0xffffffffu) {
+                    bits = 0;
+                    uint32_t mm = m[v];
+                    int out = 0;
+                    while (mm) {
+                        const int j = __ffs(mm) - 1;
+                        bits |= ((b[v] >> j) & 1u) << out;
+                        ++out;
+                        mm &= mm - 1;
+                    }
+                }
+                const uint64_t off = s_off[v];
+                const uint32_t o = (uint32_t)(off & 63) + before; // bit position inside the run buffer
+                const int sh = (int)(o & 31);
+                if (bits << sh) atomicOr(&s_bits[v][o >> 5], bits << sh);
+                if (sh && (bits >> (32 - sh))) atomicOr(&s_bits[v][(o >> 5) + 1], bits >> (32 - sh));
+                if (off + before == (bit_base ? bit_base[v] : 0ull)) { // first symbol of the node's subsequence (HuffWT.cpp:8)
+                    const int j = __ffs(m[v]) - 1;
+                    uint32_t word = w[0];
+#pragma unroll
+                    for (int q = 1; q < 8; ++q)
+                        if ((j >> 2) == q) word = w[q];
+                    node_ch[v] = (uint8_t)((word >> (8 * (j & 3))) & 0xff);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int v = 0; v < n_internal; ++v) {
+        const uint32_t total = s_total[v];
+        if (!total) continue;
+        const uint64_t off = s_off[v];
+        const uint32_t words = (uint32_t)(((off & 63) + total + 63) >> 6);
+        unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]) + (off >> 6);
+        for (uint32_t i = tid; i < words; i += 256) {
+            const unsigned long long x = (unsigned long long)s_bits[v][2 * i] | ((unsigned long long)s_bits[v][2 * i + 1] << 32);
+            if (i == 0 || i + 1 == words) {
+                if (x) atomicOr(d + i, x);
+            } else {
+                d[i] = x;
+            }
+        }
+    }
+}
+
 // Pieces of node bit arrays built by different GPUs (each already shifted to its global bit offset modulo
 // 64) are merged into the node arrays: interior words are plain copies, the first and last word of a piece
 // may share their destination word with a neighbouring piece and are OR-ed in.
@@ -2572,6 +2701,22 @@ void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8
 {
     wt_fill_kernel<<<(unsigned)ntiles, 256, wt_info_smem(n_internal), st>>>(seq, n, node_info, n_internal, ntiles,
                                                                            tile_off, node_data, node_ch, bit_base);
+    DSM_LAUNCH_CHECK();
+    if (launches) ++*launches;
+}
+
+bool wt_sweep_ok(int n_internal) { return n_internal <= kWtSmallNodes; }
+uint64_t wt_sweep_status_words(uint64_t ntiles) { return ntiles * kWtSmallNodes; }
+
+void launch_wt_sweep(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                     uint64_t ntiles, uint64_t *status, uint32_t *counter, uint64_t *const *node_data, uint8_t *node_ch,
+                     const uint64_t *bit_base, uint32_t *launches)
+{
+    DSM_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * wt_sweep_status_words(ntiles), st));
+    DSM_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
+    wt_sweep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(seq, n, node_info, n_internal,
+                                                     reinterpret_cast<volatile unsigned long long *>(status), counter,
+                                                     node_data, node_ch, bit_base);
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

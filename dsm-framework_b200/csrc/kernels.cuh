@@ -179,6 +179,14 @@ void launch_wt_fill(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8
                     uint64_t ntiles, const uint64_t *tile_off, uint64_t *const *node_data, uint8_t *node_ch,
                     const uint64_t *bit_base, uint32_t *launches);
 
+// Trees of at most 8 internal nodes: count, scan and fill in ONE pass over the sequence (decoupled look-back over
+// the tiles, the tile's bits assembled in shared memory).  status: wt_sweep_status_words(ntiles) u64, counter: one u32.
+bool wt_sweep_ok(int n_internal);
+uint64_t wt_sweep_status_words(uint64_t ntiles);
+void launch_wt_sweep(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint8_t *node_info, int n_internal,
+                     uint64_t ntiles, uint64_t *status, uint32_t *counter, uint64_t *const *node_data, uint8_t *node_ch,
+                     const uint64_t *bit_base, uint32_t *launches);
+
 // Multi-GPU: node bit arrays arrive as pieces built on different GPUs.  nwords words from src + src_word
 // are merged into dst (first / last word OR-ed, interior copied); gridDim.y = pieces.
 struct WtPiece {

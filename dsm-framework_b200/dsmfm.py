@@ -158,6 +158,7 @@ def lib():
     L.dsmfm_block_pack.argtypes = [B, C.POINTER(TextPlan), C.c_uint32, C.c_void_p, C.c_void_p]
     L.dsmfm_build_packed.argtypes = [B, C.POINTER(TextPlan), C.c_void_p, C.c_void_p]
     L.dsmfm_pieces_build.argtypes = [B, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(Pieces)]
+    L.dsmfm_pieces_fetch.argtypes = [B, C.POINTER(Pieces)]
     L.dsmfm_pieces_merge.argtypes = [B, C.c_void_p, C.c_uint32]
     L.dsmfm_pieces_index.argtypes = [B, C.POINTER(Index)]
     L.dsmfm_pieces_write.argtypes = [B, C.c_char_p, C.c_int]
@@ -317,11 +318,20 @@ class Builder:
         top = np.ascontiguousarray(top_sum, dtype=np.uint64)
         self._check(self._L.dsmfm_build_packed(self._h, C.byref(plan), text.data_ptr(), top.ctypes.data))
 
-    def pieces_build(self, hist_all, rank):
-        """Returns (Pieces, edges) -- edges: this builder's dsmfm_piece_edge records as bytes."""
+    def pieces_build(self, hist_all, rank, fetch=True):
+        """Returns (Pieces, edges) -- edges: this builder's dsmfm_piece_edge records as bytes; (None, None) with
+        fetch=False (the sections then stay in HBM until pieces_fetch)."""
         h = self._hist_table(hist_all)
         out = Pieces()
-        self._check(self._L.dsmfm_pieces_build(self._h, h.ctypes.data, h.shape[0], rank, C.byref(out)))
+        self._check(self._L.dsmfm_pieces_build(self._h, h.ctypes.data, h.shape[0], rank, C.byref(out) if fetch else None))
+        if not fetch:
+            return None, None
+        self.pieces = out
+        return out, C.string_at(out.edge, C.sizeof(PieceEdge) * out.n_internal)
+
+    def pieces_fetch(self):
+        out = Pieces()
+        self._check(self._L.dsmfm_pieces_fetch(self._h, C.byref(out)))
         self.pieces = out
         return out, C.string_at(out.edge, C.sizeof(PieceEdge) * out.n_internal)
 

@@ -197,7 +197,7 @@ void MultiGpuBuilder::Build(uchar const *text, ulong length, std::string const &
     for (unsigned r = 0; r < world; ++r)
         if (!errors[r].empty()) die("GPU rank " + std::to_string(r) + ": " + errors[r]);
 
-    std::memset(&report, 0, sizeof(ulong) * 6);
+    report.records = report.documents = report.bases = report.symbols = report.invalidRecords = report.badHeaders = 0;
     std::ostringstream per;
     uint64_t pos = 0;
     for (unsigned r = 0; r < world; ++r)

@@ -88,9 +88,9 @@ class CudaEngine:
     def slice_hist(self, b):
         return b.slice_hist()
 
-    def pieces_build(self, b, hist_all, rank):
-        pieces, edges = b.pieces_build(hist_all, rank)
-        return edges, int(pieces.bytes)
+    def pieces_build(self, b, hist_all, rank, fetch=True):
+        pieces, edges = b.pieces_build(hist_all, rank, fetch)
+        return (edges, int(pieces.bytes)) if fetch else (None, 0)
 
     def pieces_merge(self, b, edges_all, world):
         b.pieces_merge(edges_all, world)
@@ -172,11 +172,15 @@ class ShardedBuild:
         self._mark("sort")
         return self.rank_begin, self.count, hist
 
-    def pieces(self, begins, counts, hist_all):
-        """-> this rank's dsmfm_piece_edge records (all-gather them in rank order)."""
+    def pieces(self, begins, counts, hist_all, fetch=True):
+        """-> this rank's dsmfm_piece_edge records (all-gather them in rank order); None with fetch=False: the
+        rank's share of the sections is built and stays in HBM (device-resident timing)."""
         check_tiling(begins, counts, self.n_total)
         self.hist_all = np.ascontiguousarray(hist_all, dtype=np.uint64).reshape(self.world, 256)
-        edges, self.section_bytes = self.engine.pieces_build(self.handle, self.hist_all, self.rank)
+        if fetch:
+            edges, self.section_bytes = self.engine.pieces_build(self.handle, self.hist_all, self.rank)
+        else:
+            edges, self.section_bytes = self.engine.pieces_build(self.handle, self.hist_all, self.rank, False)
         self._mark("pieces")
         return edges
 
@@ -226,12 +230,13 @@ def _all_gather_u64(dist, values, device):
     return np.stack([np.frombuffer(r, dtype=np.uint64) for r in recs])
 
 
-def build_sharded(dist, local_docs, engine, ranges_per_gpu=1):
+def build_sharded(dist, local_docs, engine, ranges_per_gpu=1, fetch=True):
     """Builds ONE index over the documents of all ranks (rank order = document order).
 
     local_docs: uint8 tensor (pinned host or device) with this rank's '\\0'-terminated documents.
     Returns the rank's ShardedBuild, merged: sb.write(prefix) puts the rank's share into the `.fmi` file,
-    sb.section_bytes is what it holds in host memory.  Close it when done."""
+    sb.section_bytes is what it holds in host memory.  fetch=False stops with every rank's share of the sections
+    in its HBM (what a device-resident measurement times).  Close it when done."""
     world, rank = dist.get_world_size(), dist.get_rank()
     device = engine.tensor_device()
     sb = ShardedBuild(engine, rank, world, ranges_per_gpu)
@@ -246,8 +251,9 @@ def build_sharded(dist, local_docs, engine, ranges_per_gpu=1):
             top_sum = _all_gather_u64(dist, top, device).sum(axis=0, dtype=np.uint64)
             rank_begin, count, hist = sb.sort(top_sum)
             rec = _all_gather_u64(dist, np.concatenate([np.array([rank_begin, count], dtype=np.uint64), hist]), device)
-            edges = sb.pieces([int(x) for x in rec[:, 0]], [int(x) for x in rec[:, 1]], rec[:, 2:])
-            sb.merge(_all_gather_bytes(dist, edges, device))
+            edges = sb.pieces([int(x) for x in rec[:, 0]], [int(x) for x in rec[:, 1]], rec[:, 2:], fetch)
+            if fetch:
+                sb.merge(_all_gather_bytes(dist, edges, device))
     except Exception:
         sb.close()
         raise

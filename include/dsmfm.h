@@ -332,8 +332,10 @@ typedef struct dsmfm_pieces {
     const dsmfm_piece_edge *edge;   /* this builder's records for the exchange                              */
 } dsmfm_pieces;
 
-/* hist_all[world][256]: dsmfm_slice_hist of every builder, in slice order. */
+/* hist_all[world][256]: dsmfm_slice_hist of every builder, in slice order.  The device work; with out != NULL the
+ * sections are copied to the host right away (dsmfm_pieces_fetch), with out == NULL they stay in HBM until then. */
 DSMFM_API int dsmfm_pieces_build(dsmfm_builder *b, const uint64_t *hist_all, uint32_t world, uint32_t rank, dsmfm_pieces *out);
+DSMFM_API int dsmfm_pieces_fetch(dsmfm_builder *b, dsmfm_pieces *out);
 /* edges_all[world][n_internal] in slice order (host). */
 DSMFM_API int dsmfm_pieces_merge(dsmfm_builder *b, const dsmfm_piece_edge *edges_all, uint32_t world);
 /* The header fields, C[], code table and node list (leaf / ch / nbits / integers; data pointers NULL) of the whole
