@@ -501,6 +501,13 @@ constexpr int kSweepSelThreads = 128;
 constexpr int kSweepSelWords = kSweepSelThreads; // one packed word per thread
 constexpr unsigned long long kSelFlagAgg = 1ull << 62, kSelFlagPrefix = 2ull << 62, kSelValueMask = (1ull << 62) - 1;
 
+// A tile is kSelSub sub-tiles of kSweepSelWords words: the selection masks of all of them are taken first (they
+// stay in registers), so that the tile publishes ONE count and runs ONE look-back -- the dynamic tile id and the
+// look-back are a few microseconds of latency each, which 128 words of work could not hide (the kernel spent 3.2 ms
+// per G symbols on them, and on G GPUs every GPU scans the whole text) -- then the sub-tiles are staged and
+// written out one after the other.
+constexpr int kSelSub = 8;
+
 template <int BITS>
 __global__ void __launch_bounds__(kSweepSelThreads)
 select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int key_bits, const uint32_t *__restrict__ lut,
@@ -509,7 +516,7 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
 {
     using P = Pack<BITS>;
     using T = TopBits<BITS>;
-    constexpr int CAP = kSweepSelWords * P::SPW; // suffixes per tile
+    constexpr int CAP = kSweepSelWords * P::SPW; // suffixes per sub-tile
     constexpr int LUT_WORDS = (1 << T::RAW) / 32;
     __shared__ uint64_t s_key[CAP];
     __shared__ uint32_t s_val[CAP];
@@ -523,53 +530,31 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
-    const uint64_t w = (uint64_t)tile * kSweepSelWords + tid;
-    // the word's block (slot) and how many of its positions are suffixes of that block
-    int valid = 0;
-    if (w < nwords) {
-        const uint64_t slot = w / geom.slot_words;
-        const uint64_t first = (w - slot * geom.slot_words) * P::SPW; // position of the word inside its block
-        const uint64_t have = slot < geom.world ? geom.bytes[slot] : 0ull;
-        valid = have > first ? (have - first >= (uint64_t)P::SPW ? P::SPW : (int)(have - first)) : 0;
-    }
-    uint32_t sel = 0;
-    if (valid) {
-        uint32_t st[4];
-        load_stream<BITS>(packed, w, nwords, st);
-        sel = select_mask_lut<BITS>(s_lut, st, valid);
+    const uint64_t w0 = (uint64_t)tile * (kSweepSelWords * kSelSub) + tid;
+    // the selection masks of this thread's word in every sub-tile
+    uint32_t sel[kSelSub];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < kSelSub; ++j) {
+        const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
+        sel[j] = 0;
+        if (w < nwords) {
+            // the word's block (slot) and how many of its positions are suffixes of that block
+            const uint64_t slot = w / geom.slot_words;
+            const uint64_t first = (w - slot * geom.slot_words) * P::SPW; // position of the word inside its block
+            const uint64_t have = slot < geom.world ? geom.bytes[slot] : 0ull;
+            const int valid = have > first ? (have - first >= (uint64_t)P::SPW ? P::SPW : (int)(have - first)) : 0;
+            if (valid) {
+                uint32_t st[4];
+                load_stream<BITS>(packed, w, nwords, st);
+                sel[j] = select_mask_lut<BITS>(s_lut, st, valid);
+            }
+        }
+        mine += __popc(sel[j]);
     }
     uint32_t total;
-    uint32_t o = block_excl_sum((uint32_t)__popc(sel), scratch, &total);
+    block_excl_sum(mine, scratch, &total);
     if (tid == 0) status[tile] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
-
-    // Keys of the selected suffixes, staged in text order.  The word and its successor hold every symbol a
-    // first key can need (first_syms <= SPW), so keys are cut out of two registers; the symbol before the
-    // suffix (the BWT symbol, which rides above the key bits) is the previous symbol of the same stream.
-    const uint64_t p0 = w * P::SPW;
-    if (sel) {
-        uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
-        uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u; // last symbol of the previous word
-        if (P::USED == 63) {
-            x0 = (x0 << 1) | (x1 >> 62);
-            x1 <<= 2;
-        }
-        const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
-        while (sel) {
-            const int j = __ffs(sel) - 1;
-            sel &= sel - 1;
-            const int b = BITS * j;
-            const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0;     // stream from symbol j on
-            uint64_t k = (v >> (64 - key_bits)) | ~kmask;                  // ones above: only real fields can be zero
-            k = cut_at_terminator<BITS>(k) & kmask;
-            const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
-            k |= (uint64_t)prev << key_bits;                               // the BWT symbol rides along
-            const uint64_t p = p0 + j;
-            if (hi_shift) k |= (p >> lo_bits) << hi_shift;
-            s_key[o] = k;
-            s_val[o] = (uint32_t)(p & lo_mask);
-            ++o;
-        }
-    }
 
     // look-back by the first warp: 32 predecessors per step
     if (tid < 32) {
@@ -596,10 +581,53 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
         if (lane == 0) s_base = excl;
     }
     __syncthreads();
-    const uint64_t base = s_base;
-    for (uint32_t i = tid; i < total; i += kSweepSelThreads) {
-        keys[base + i] = s_key[i];
-        vals[base + i] = s_val[i];
+    uint64_t base = s_base;
+
+    // Keys of the selected suffixes, staged in text order, sub-tile by sub-tile.  The word and its successor hold
+    // every symbol a first key can need (first_syms <= SPW), so keys are cut out of two registers; the symbol
+    // before the suffix (the BWT symbol, which rides above the key bits) is the previous symbol of the same stream.
+    const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
+#pragma unroll 1
+    for (int j = 0; j < kSelSub; ++j) {
+        uint32_t sj = 0; // (sel[] is indexed by a loop that is not unrolled: pick the register by comparison)
+#pragma unroll
+        for (int q = 0; q < kSelSub; ++q)
+            if (q == j) sj = sel[q];
+        uint32_t sub_total;
+        uint32_t o = block_excl_sum((uint32_t)__popc(sj), scratch, &sub_total);
+        if (sub_total == 0) continue; // (uniform)
+        const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
+        const uint64_t p0 = w * P::SPW;
+        if (sj) {
+            uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
+            uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u; // last symbol of the previous word
+            if (P::USED == 63) {
+                x0 = (x0 << 1) | (x1 >> 62);
+                x1 <<= 2;
+            }
+            while (sj) {
+                const int i = __ffs(sj) - 1;
+                sj &= sj - 1;
+                const int b = BITS * i;
+                const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0;     // stream from symbol i on
+                uint64_t k = (v >> (64 - key_bits)) | ~kmask;                  // ones above: only real fields can be zero
+                k = cut_at_terminator<BITS>(k) & kmask;
+                const uint32_t prev = i ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
+                k |= (uint64_t)prev << key_bits;                               // the BWT symbol rides along
+                const uint64_t p = p0 + i;
+                if (hi_shift) k |= (p >> lo_bits) << hi_shift;
+                s_key[o] = k;
+                s_val[o] = (uint32_t)(p & lo_mask);
+                ++o;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < sub_total; i += kSweepSelThreads) {
+            keys[base + i] = s_key[i];
+            vals[base + i] = s_val[i];
+        }
+        base += sub_total;
+        __syncthreads();
     }
 }
 
@@ -1052,6 +1080,13 @@ template <int BITS> __device__ __forceinline__ uint64_t window_of(uint64_t x0, u
 // (128-bit keys): fewer steps per suffix, and every step has a fixed cost per suffix.
 constexpr int kRwGroupMax = kRefGroupMaxWarps;
 constexpr int kRwCap = kRefWindow + kRwGroupMax;
+// Groups of at least this many members are ranked by the whole warp at once.  In repetitive collections (high
+// coverage, few errors) a tie group is the set of reads covering one locus: after the next 21 symbols most of
+// its members still agree -- they share ONE dominant key -- and only the reads that end inside the window (or
+// carry an error there) differ.  The warp counts the members below / equal to / above a candidate key with
+// ballots (the equal ones get their stable rank from the running count: no comparisons among them at all) and
+// ranks only the others against each other: (0.3 g)^2 comparisons instead of g^2.
+constexpr int kRwBigGroup = 64;
 
 template <int KW, bool WIDE> struct RwSmem {
     uint64_t khi[kRwCap];
@@ -1065,6 +1100,9 @@ template <int KW, bool WIDE> struct RwSmem {
     uint32_t mix[kRwCap / 32 + 2];     // per group head: the group's members carry different BWT symbols
     uint32_t df[kRwCap / 32 + 2];      // per slot: BWT symbol differs from the predecessor's inside a group
     uint32_t act[kRwCap / 32 + 2];     // per slot: member of a group that has to be sorted
+    uint16_t newpos[kRwCap];           // large groups: where the member at a slot goes in this step
+    uint16_t nd[kRwCap];               // large groups: the members whose key is not the dominant one, in slot order
+    uint16_t bigq[kRefThreads / 32][kRwCap / kRwBigGroup + 2]; // per warp: first slots of its large groups
     int range[2];
 };
 
@@ -1300,32 +1338,117 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         fetched += (unsigned)cnt;
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
         // carries the same key (or its key holds the terminator, which makes it unique)
-        for (int i = lane; i < cnt; i += 32) {
-            const int r = list[i];
-            const int gs = prev_set_le(s_ha, r);
-            const int ge = next_set_gt(s_ha, r);
-            const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
-            int lt = 0, eq = 0;
-            if (KW == 2) {
-                for (int j = gs; j < ge; ++j) {
-                    const uint64_t oh = s_khi[j], ol = s_klo[j];
-                    lt += (oh < mh) | ((oh == mh) & (ol < ml));
-                    eq += (oh == mh) & (ol == ml) & (j < r);
+        int nbig = 0; // large groups of this warp's range seen in this step (warp-uniform)
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            bool big_first = false;
+            int gs = 0;
+            if (i < cnt) {
+                const int r = list[i];
+                gs = prev_set_le(s_ha, r);
+                const int ge = next_set_gt(s_ha, r);
+                if (ge - gs >= kRwBigGroup) {
+                    big_first = r == gs; // the whole warp ranks this group below
+                } else {
+                    const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
+                    int lt = 0, eq = 0;
+                    if (KW == 2) {
+                        for (int j = gs; j < ge; ++j) {
+                            const uint64_t oh = s_khi[j], ol = s_klo[j];
+                            lt += (oh < mh) | ((oh == mh) & (ol < ml));
+                            eq += (oh == mh) & (ol == ml) & (j < r);
+                        }
+                    } else {
+                        for (int j = gs; j < r; ++j) {
+                            const uint64_t o = s_khi[j];
+                            lt += o < mh;
+                            eq += o == mh;
+                        }
+                        for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
+                    }
+                    const int p = gs + lt + eq;
+                    if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                    s_sa[c ^ 1][p] = s_sa[c][r];
+                    s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+                    if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                    list[i] = (uint16_t)p;       // where this suffix went
                 }
-            } else {
-                for (int j = gs; j < r; ++j) {
-                    const uint64_t o = s_khi[j];
-                    lt += o < mh;
-                    eq += o == mh;
-                }
-                for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
             }
-            const int p = gs + lt + eq;
-            if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
-            s_sa[c ^ 1][p] = s_sa[c][r];
-            s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
-            if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-            list[i] = (uint16_t)p;       // where this suffix went
+            const uint32_t bm = __ballot_sync(0xffffffffu, big_first);
+            if (big_first) S.bigq[warp][nbig + __popc(bm & lanemask_lt())] = (uint16_t)gs;
+            nbig += __popc(bm);
+        }
+        __syncwarp();
+        for (int q = 0; q < nbig; ++q) {
+            const int gs = S.bigq[warp][q];
+            const int ge = next_set_gt(s_ha, gs);
+            const int g = ge - gs;
+            // candidate for the dominant key: the member in the middle of the group
+            const uint64_t ch = s_khi[gs + (g >> 1)], cl = KW == 2 ? s_klo[gs + (g >> 1)] : 0ull;
+            int n_lt = 0, n_eq = 0, n_nd = 0;
+            for (int b0 = gs; b0 < ge; b0 += 32) {
+                const int r = b0 + lane;
+                const bool in = r < ge;
+                bool is_eq = false, is_lt = false;
+                if (in) {
+                    const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
+                    is_eq = mh == ch && ml == cl;
+                    is_lt = mh < ch || (mh == ch && ml < cl);
+                }
+                const uint32_t eqm = __ballot_sync(0xffffffffu, is_eq), ltm = __ballot_sync(0xffffffffu, is_lt);
+                const uint32_t ndm = __ballot_sync(0xffffffffu, in && !is_eq);
+                if (is_eq) S.newpos[r] = (uint16_t)(n_eq + __popc(eqm & lanemask_lt())); // rank among the equal ones
+                if (in && !is_eq) S.nd[gs + n_nd + __popc(ndm & lanemask_lt())] = (uint16_t)r;
+                n_eq += __popc(eqm);
+                n_lt += __popc(ltm);
+                n_nd += __popc(ndm);
+            }
+            __syncwarp();
+            const bool dominant = 2 * n_eq >= g;
+            // the members carrying the candidate key (none of them is ranked against anything when it dominates)
+            if (dominant) {
+                const bool term = key_terminated<BITS>(KW == 2 ? cl : ch);
+                for (int r = gs + lane; r < ge; r += 32) {
+                    const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
+                    if (mh == ch && ml == cl) {
+                        const int e = S.newpos[r];
+                        const int p = gs + n_lt + e;
+                        if (p != gs && (e == 0 || term)) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                        s_sa[c ^ 1][p] = s_sa[c][r];
+                        s_bw[c ^ 1][p] = s_bw[c][r];
+                        if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                        S.newpos[r] = (uint16_t)p;
+                    }
+                }
+            }
+            // the others -- or everybody, if no key dominates -- against each other
+            const int n_rank = dominant ? n_nd : g;
+            for (int t = lane; t < n_rank; t += 32) {
+                const int r = dominant ? (int)S.nd[gs + t] : gs + t;
+                const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
+                int lt = 0, eq = 0;
+                for (int u = 0; u < n_rank; ++u) {
+                    const int r2 = dominant ? (int)S.nd[gs + u] : gs + u;
+                    const uint64_t oh = s_khi[r2], ol = KW == 2 ? s_klo[r2] : 0ull;
+                    lt += (oh < mh) | ((oh == mh) & (ol < ml));
+                    eq += (oh == mh) & (ol == ml) & (u < t);
+                }
+                const bool above = dominant && (mh > ch || (mh == ch && ml > cl));
+                const int p = gs + lt + eq + (above ? n_eq : 0);
+                if (p != gs && (eq == 0 || key_terminated<BITS>(KW == 2 ? ml : mh))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                s_sa[c ^ 1][p] = s_sa[c][r];
+                s_bw[c ^ 1][p] = s_bw[c][r];
+                if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                S.newpos[r] = (uint16_t)p;
+            }
+            __syncwarp();
+        }
+        if (nbig) { // list entries of the members of large groups
+            for (int i = lane; i < cnt; i += 32) {
+                const int r = list[i];
+                const int gs = prev_set_le(s_ha, r);
+                if (next_set_gt(s_ha, r) - gs >= kRwBigGroup) list[i] = S.newpos[r];
+            }
         }
         __syncwarp();
         if (!ORDER) {
@@ -2377,7 +2500,7 @@ void launch_key_top_hist(cudaStream_t st, int bits, const uint64_t *packed, uint
 
 uint64_t select_tiles(uint64_t nwords, int bits, int first_syms, int top_bits)
 {
-    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(nwords, kSweepSelWords);
+    if (select_fast_ok(bits, first_syms, top_bits)) return div_up(nwords, (uint64_t)kSweepSelWords * kSelSub);
     return div_up(nwords * (uint64_t)(64 / bits), kSelTile);
 }
 

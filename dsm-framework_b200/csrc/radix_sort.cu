@@ -79,13 +79,13 @@ __global__ void __launch_bounds__(kRadix) radix_scan_kernel(uint64_t *__restrict
     h[tid] = base + incl - v;
 }
 
-struct SweepSmem {
+template <int WARPS> struct SweepSmemT {
     uint64_t keys[kSweepTile];                 // tile in sorted order
     uint32_t vals[kSweepTile];
     uint64_t goff[kRadix];                     // global offset of digit run minus its tile-local start
-    uint16_t cnt[kSweepThreads / 32][kRadix];  // per-warp digit counters -> per-warp digit bases (<= tile size)
+    uint16_t cnt[WARPS][kRadix];               // per-warp digit counters -> per-warp digit bases (<= tile size)
     uint32_t excl[kRadix];                     // tile-local start of each digit run
-    uint32_t warp_sum[kSweepThreads / 32];
+    uint32_t warp_sum[kRadix / 32];
     uint32_t tile;
 };
 
@@ -94,41 +94,44 @@ struct SweepSmem {
 // Phases of a CTA (tile of 4096 pairs): load keys -> rank inside the tile (per-warp digit counters)
 // -> publish the tile's digit counts -> stage keys in sorted order in shared memory -> fetch values
 // while the look-back over the preceding tiles resolves the global offsets -> stage values -> write
-// both out, one contiguous burst per digit.  Key registers die before the values are fetched, which
-// keeps the kernel at 64 registers and 4 CTAs (32 warps) per SM.
-template <bool IOTA, bool HW_MATCH>
-__global__ void __launch_bounds__(kSweepThreads, 4)
+// both out, one contiguous burst per digit.  Key registers die before the values are fetched.
+// Two shapes of the same tile: 256 threads x 16 pairs (64 registers, 4 CTAs = 32 warps per SM) and
+// 512 threads x 8 pairs (fewer registers per thread: 3 CTAs = 48 warps per SM); the kernel is bound by
+// latency (shared-memory round trips of the ranking, DRAM loads), not by issue slots or bandwidth,
+// so the warps in flight are what counts.  Threads 0..255 own one digit each in the scan / look-back phases.
+template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 3)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
                 int shift, uint32_t mask, const uint64_t *__restrict__ base_in, uint64_t *__restrict__ base_out,
                 volatile uint32_t *status, uint32_t *counter, uint32_t last_tile)
 {
-    static_assert(kSweepThreads == kRadix, "one thread per digit in the look-back");
-    constexpr int WARPS = kSweepThreads / 32;
+    static_assert(THREADS * ITEMS == kSweepTile && THREADS >= kRadix, "one tile, at least one thread per digit");
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SweepSmem &s = *reinterpret_cast<SweepSmem *>(smem_raw);
+    SweepSmemT<WARPS> &s = *reinterpret_cast<SweepSmemT<WARPS> *>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) s.tile = atomicAdd(counter, 1u);
-    for (int i = tid; i < WARPS * kRadix / 2; i += kSweepThreads) reinterpret_cast<uint32_t *>(&s.cnt[0][0])[i] = 0;
+    for (int i = tid; i < WARPS * kRadix / 2; i += THREADS) reinterpret_cast<uint32_t *>(&s.cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
     const uint32_t tile_base = tile * (uint32_t)kSweepTile;
     const uint32_t valid = min((uint32_t)kSweepTile, n - tile_base);
-    const uint32_t first = tile_base + warp * (32 * kSweepItems) + lane;
+    const uint32_t first = tile_base + warp * (32 * ITEMS) + lane;
 
     // warp-striped load: item k of lane l is element first + 32k, so the order
     // (warp, k, lane) is the input order and the ranking below is stable
-    uint64_t key[kSweepItems];
+    uint64_t key[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const uint32_t idx = first + 32 * k;
         key[k] = idx < n ? keys_in[idx] : ~0ull; // padding sorts to the very end of the tile
     }
 
-    uint16_t lpos[kSweepItems];
+    uint16_t lpos[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
         const uint32_t peers = HW_MATCH ? __match_any_sync(0xffffffffu, d) : match_digit(d);
         const int leader = __ffs(peers) - 1;
@@ -144,36 +147,41 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     __syncthreads();
 
     // thread d owns digit d: turn per-warp counts into per-warp bases, get the tile total
-    uint32_t total = 0;
+    uint32_t total = 0, pub = 0, excl = 0;
+    volatile uint32_t *mine = status + (size_t)tile * kRadix + (tid & (kRadix - 1));
+    if (tid < kRadix) {
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-        const uint32_t t = s.cnt[w][tid];
-        s.cnt[w][tid] = (uint16_t)total;
-        total += t;
-    }
-    // publish the tile's count of digit d as early as possible: later tiles are waiting for it
-    uint32_t pub = total;
-    if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
-    volatile uint32_t *mine = status + (size_t)tile * kRadix + tid;
-    if (tile != 0) *mine = kFlagAgg | pub;
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t t = s.cnt[w][tid];
+            s.cnt[w][tid] = (uint16_t)total;
+            total += t;
+        }
+        // publish the tile's count of digit d as early as possible: later tiles are waiting for it
+        pub = total;
+        if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
+        if (tile != 0) *mine = kFlagAgg | pub;
 
-    uint32_t incl = total;
+        uint32_t incl = total;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s.warp_sum[warp] = incl;
+        excl = incl - total;
     }
-    if (lane == 31) s.warp_sum[warp] = incl;
     __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
-    const uint32_t excl = wbase + incl - total;
-    s.excl[tid] = excl;
+    if (tid < kRadix) {
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
+        excl += wbase;
+        s.excl[tid] = excl;
+    }
     __syncthreads();
 
     // stage the keys in sorted order; afterwards only their tile-local positions stay in registers
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
         const uint32_t p = lpos[k] + s.excl[d] + s.cnt[warp][d];
         s.keys[p] = key[k];
@@ -181,9 +189,9 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 
     // values are fetched now so that their latency overlaps the look-back
-    uint32_t val[kSweepItems];
+    uint32_t val[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         const uint32_t idx = first + 32 * k;
         if (IOTA)
             val[k] = (uint32_t)(iota_base + idx);
@@ -192,41 +200,43 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 
     // decoupled look-back, one chain per digit, four predecessors in flight at a time
-    uint32_t exclusive = 0;
-    if (tile == 0) {
-        *mine = kFlagPrefix | pub;
-    } else {
-        uint32_t t = tile; // next predecessor to read is t-1
-        bool done = false;
-        while (!done) {
-            const uint32_t cnt = t < 4u ? t : 4u;
-            uint32_t w[4];
+    if (tid < kRadix) {
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            *mine = kFlagPrefix | pub;
+        } else {
+            uint32_t t = tile; // next predecessor to read is t-1
+            bool done = false;
+            while (!done) {
+                const uint32_t cnt = t < 4u ? t : 4u;
+                uint32_t w[4];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-                if (j < cnt) w[j] = status[(size_t)(t - 1 - j) * kRadix + tid];
+                for (uint32_t j = 0; j < 4; ++j)
+                    if (j < cnt) w[j] = status[(size_t)(t - 1 - j) * kRadix + tid];
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) {
-                if (j < cnt && !done) {
-                    uint32_t x = w[j];
-                    while ((x >> 30) == 0) x = status[(size_t)(t - 1 - j) * kRadix + tid];
-                    exclusive += x & kValueMask;
-                    if (x & kFlagPrefix) done = true;
+                for (uint32_t j = 0; j < 4; ++j) {
+                    if (j < cnt && !done) {
+                        uint32_t x = w[j];
+                        while ((x >> 30) == 0) x = status[(size_t)(t - 1 - j) * kRadix + tid];
+                        exclusive += x & kValueMask;
+                        if (x & kFlagPrefix) done = true;
+                    }
                 }
+                t -= cnt;
             }
-            t -= cnt;
+            *mine = kFlagPrefix | (exclusive + pub);
         }
-        *mine = kFlagPrefix | (exclusive + pub);
+        const uint64_t gbase = base_in[tid] + exclusive;
+        s.goff[tid] = gbase - excl;
+        if (tile == last_tile) base_out[tid] = gbase + pub;
     }
-    const uint64_t gbase = base_in[tid] + exclusive;
-    s.goff[tid] = gbase - excl;
-    if (tile == last_tile) base_out[tid] = gbase + pub;
 
 #pragma unroll
-    for (int k = 0; k < kSweepItems; ++k) s.vals[lpos[k]] = val[k];
+    for (int k = 0; k < ITEMS; ++k) s.vals[lpos[k]] = val[k];
     __syncthreads();
 
     // every digit run goes out as one contiguous burst
-    for (uint32_t i = tid; i < valid; i += kSweepThreads) {
+    for (uint32_t i = tid; i < valid; i += THREADS) {
         const uint64_t kk = s.keys[i];
         const uint32_t d = (uint32_t)(kk >> shift) & mask;
         const uint64_t o = s.goff[d] + i;
@@ -277,16 +287,18 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         const char *e = getenv("DSMFM_SWEEP_MATCH");
         return e && atoi(e) != 0;
     }();
+    static const bool wide_cta = [] { // 512 threads x 8 pairs instead of 256 x 16 (DSMFM_SWEEP_THREADS=256|512)
+        const char *e = getenv("DSMFM_SWEEP_THREADS");
+        return e ? atoi(e) == 512 : kSweepWideDefault;
+    }();
     attr_once.run([] {
-        const int sm = (int)sizeof(SweepSmem);
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define ATTR(I, M, T, N)                                                                                          \
+    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                  (int)sizeof(SweepSmemT<T / 32>)));                                              \
+    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+        ATTR(true, false, 256, 16); ATTR(false, false, 256, 16); ATTR(true, true, 256, 16); ATTR(false, true, 256, 16);
+        ATTR(true, false, 512, 8);  ATTR(false, false, 512, 8);  ATTR(true, true, 512, 8);  ATTR(false, true, 512, 8);
+#undef ATTR
     });
 
     if (!hist_ready) {
@@ -316,15 +328,20 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
             uint64_t *base_out = ws.carry + (size_t)flip * kRadix;
             DSM_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(uint32_t) * (size_t)tiles * kRadix, stream));
             DSM_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream));
-#define SWEEP(I, M)                                                                                              \
-    onesweep_kernel<I, M><<<tiles, kSweepThreads, sizeof(SweepSmem), stream>>>(                                  \
+#define SWEEP2(I, M, T, N)                                                                                       \
+    onesweep_kernel<I, M, T, N><<<tiles, T, sizeof(SweepSmemT<T / 32>), stream>>>(                               \
         src_k + start, (I) ? nullptr : src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, \
         base_out, ws.status, ws.counter, tiles - 1)
+#define SWEEP(I, M)                                                                                              \
+    do {                                                                                                         \
+        if (wide_cta) SWEEP2(I, M, 512, 8); else SWEEP2(I, M, 256, 16);                                          \
+    } while (0)
             if (iota) {
                 if (hw_match) SWEEP(true, true); else SWEEP(true, false);
             } else {
                 if (hw_match) SWEEP(false, true); else SWEEP(false, false);
             }
+#undef SWEEP2
 #undef SWEEP
             DSM_LAUNCH_CHECK();
             if (launches) *launches += 1;

@@ -18,10 +18,9 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 
-// Tile shape of the one-sweep kernel.
-constexpr int kSweepThreads = 256;
-constexpr int kSweepItems = 16;
-constexpr int kSweepTile = kSweepThreads * kSweepItems; // 4096 pairs
+// Tile of the one-sweep kernel: 4096 pairs, as 256 threads x 16 pairs or 512 threads x 8 pairs.
+constexpr int kSweepTile = 4096;
+constexpr bool kSweepWideDefault = false;
 // A launch handles at most this many pairs so that tile prefixes fit the
 // 30-bit payload of a status word; longer inputs run as several portions.
 constexpr uint64_t kSweepPortion = (uint64_t)kSweepTile * 131072; // 2^29
