@@ -42,6 +42,7 @@ WORKLOADS = {
     "C3": "C3",
     "C1": "C1",
     "C5": "C5",  # high repetition: 4 genomes at 200x coverage, error free (BASELINE.json configs[4])
+    "C4": "C4",  # 16 Gbp metagenome: 2000 x 1 Mbp genomes at 8x (BASELINE.json configs[3]; with --reads and --shared-genomes)
 }
 CPU_SAMPLE = dict(seed=1, pool_seed=1, pool_size=10, n_genomes=10, genome_len=100_000, n_reads=100_000,
                   read_len=100, sub=0.005, pn=0.001)  # 10 Mbp at the 10x coverage of C1
@@ -59,6 +60,8 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the FASTA front-end and query-side measurements (N=1)")
     ap.add_argument("--ranges-per-gpu", type=int, default=1, help="N>1: key ranges sorted one after the other per GPU")
     ap.add_argument("--no-full-parity", action="store_true", help="N>1: skip the one-GPU rebuild of the full collection (parity)")
+    ap.add_argument("--shared-genomes", action="store_true",
+                    help="N>1: all ranks draw their reads from the SAME genomes (strong-scaling shape of C4 / C5: --reads = total / N)")
     return ap.parse_args()
 
 
@@ -176,7 +179,8 @@ def multi_gpu_parity(args, dist, torch, dsmfm, dsmgen, multigpu, engine, host_do
     try:
         # ---- (1) reduced size ----
         small = dict(kw, n_reads=100_000, genome_len=max(10_000, kw["genome_len"] // 100))
-        kws = [dict(small, seed=small["seed"] - 1000 * rank + 1000 * r, pool_seed=small["pool_seed"] - 1000 * rank + 1000 * r)
+        pool_step = 0 if args.shared_genomes else 1000
+        kws = [dict(small, seed=small["seed"] - 1000 * rank + 1000 * r, pool_seed=small["pool_seed"] - pool_step * rank + pool_step * r)
                for r in range(world)]
         mine = torch.from_numpy(dsmgen.docs(**kws[rank])).pin_memory()
         sb = multigpu.build_sharded(dist, mine, engine, ranges_per_gpu=args.ranges_per_gpu)
@@ -208,7 +212,7 @@ def multi_gpu_parity(args, dist, torch, dsmfm, dsmgen, multigpu, engine, host_do
                     k = max(2, world)
                     with dsmfm.Builder(device=local, shard_index=0, shard_count=k, shard_span=k) as b1:
                         for r in range(world):
-                            kr = dict(kw, seed=kw["seed"] - 1000 * rank + 1000 * r, pool_seed=kw["pool_seed"] - 1000 * rank + 1000 * r)
+                            kr = dict(kw, seed=kw["seed"] - 1000 * rank + 1000 * r, pool_seed=kw["pool_seed"] - pool_step * rank + pool_step * r)
                             b1.append_batch(host_docs if r == rank else dsmgen.docs(**kr))
                         b1.build_device()
                         info = b1.shard_info()
@@ -400,7 +404,8 @@ def main():
 
     kw = dict(dsmgen.CONFIGS[WORKLOADS[args.workload]])
     kw["seed"] += 1000 * rank  # every rank holds its own block of reads, drawn from its own genomes
-    kw["pool_seed"] += 1000 * rank  # (coverage stays that of the workload as N grows, like C4 vs C3)
+    pool_step = 0 if args.shared_genomes else 1000
+    kw["pool_seed"] += pool_step * rank  # (coverage stays that of the workload as N grows, like C4 vs C3)
     if args.reads:
         kw["n_reads"] = args.reads
     n_reads, L = kw["n_reads"], kw["read_len"]

@@ -1327,7 +1327,8 @@ void dsmfm_builder::build()
             ++stats.refine_launches;
             launch_refine(st, bits, d_packed, r_sa, r_head[cur], r_head[cur ^ 1], r_m, depth, win_list, n_list,
                           d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
-                          r_bwt, multi_step, key_words, r_hi, lo_bits, full_order, round == 1 ? r_diff : nullptr, L);
+                          r_bwt, multi_step, key_words, r_hi, lo_bits, full_order, round == 1 ? r_diff : nullptr, L,
+                          /*big_groups=*/!(compact && m_act));
             uint32_t nbig = 0;
             DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
             remaining = read_remaining();

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 // over the key array (8 bytes per suffix read back from HBM).
 constexpr int kKeyTileThreads = 128; // one packed word per thread and tile
 constexpr int kMaxKeyPasses = 8;     // 64 key bits / 8-bit digits
+constexpr int kKeySub = 4;           // copies of every digit counter in make_keys_hist_kernel
 
 // cut_at_terminator without the early exit (same result; the keys of a whole word are cut back to back)
 template <int BITS> __device__ __forceinline__ uint64_t cut_at_terminator_nb(uint64_t x)
@@ -258,10 +259,15 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
     constexpr int CAP = kKeyTileThreads * P::SPW;
     constexpr int HP = NP < 0 ? kMaxKeyPasses : (NP == 0 ? 1 : NP);
     const int npass = NP < 0 ? npass_rt : NP;
+    // Read collections use few digit values (a byte of a 3-bit-per-symbol key of ACGT reads takes ~50 of its 256
+    // values), so the lanes of a warp keep hitting the same counters and same-address shared atomics serialise.
+    // Every counter therefore exists kKeySub times, picked by the lane: 4x fewer collisions for 18 KB more.
+    constexpr int SUB = (NP > 0 && NP <= 6) ? kKeySub : 1; // (the run-time variant keeps eight tables: no room for copies)
     __shared__ uint64_t s_key[CAP];
-    __shared__ uint32_t s_hist[HP][256];
-    for (int i = threadIdx.x; i < HP * 256; i += kKeyTileThreads) (&s_hist[0][0])[i] = 0;
+    __shared__ uint32_t s_hist[HP][256][SUB];
+    for (int i = threadIdx.x; i < HP * 256 * SUB; i += kKeyTileThreads) (&s_hist[0][0][0])[i] = 0;
     __syncthreads();
+    const int sub = threadIdx.x & (SUB - 1);
     const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
     const uint64_t ntiles = (nwords + kKeyTileThreads - 1) / kKeyTileThreads;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -284,7 +290,7 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
                     k = cut_at_terminator_nb<BITS>(k) & kmask;
 #pragma unroll
                     for (int q = 0; q < HP; ++q)
-                        if (NP > 0 || q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu], 1u);
+                        if (NP > 0 || q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu][sub], 1u);
                     if (carry_prev) {
                         const uint32_t prev = j ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
                         k |= (uint64_t)prev << key_bits;
@@ -300,7 +306,9 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
         __syncthreads();
     }
     for (int i = threadIdx.x; i < npass * 256; i += kKeyTileThreads) {
-        const uint32_t c = (&s_hist[0][0])[i];
+        uint32_t c = 0;
+#pragma unroll
+        for (int u = 0; u < SUB; ++u) c += (&s_hist[0][0][0])[i * SUB + u];
         if (c) atomicAdd((unsigned long long *)&ghist[i], (unsigned long long)c);
     }
 }
@@ -1100,7 +1108,8 @@ template <int KW, bool WIDE> struct RwSmem {
     uint32_t mix[kRwCap / 32 + 2];     // per group head: the group's members carry different BWT symbols
     uint32_t df[kRwCap / 32 + 2];      // per slot: BWT symbol differs from the predecessor's inside a group
     uint32_t act[kRwCap / 32 + 2];     // per slot: member of a group that has to be sorted
-    uint16_t newpos[kRwCap];           // large groups: where the member at a slot goes in this step
+    uint16_t newpos[kRwCap];           // large groups: rank of a carrier of the dominant key among the carriers
+    uint16_t lidx[kRwCap];             // large groups: list entry of the member at a slot
     uint16_t nd[kRwCap];               // large groups: the members whose key is not the dominant one, in slot order
     uint16_t bigq[kRefThreads / 32][kRwCap / kRwBigGroup + 2]; // per warp: first slots of its large groups
     int range[2];
@@ -1119,7 +1128,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                     uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
                     unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
                     uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint8_t *__restrict__ bwt,
-                    uint8_t *__restrict__ sa_hi, int lo_bits, const uint32_t *__restrict__ diff_bits)
+                    uint8_t *__restrict__ sa_hi, int lo_bits, const uint32_t *__restrict__ diff_bits, int big_thr)
 {
     using P = Pack<BITS>;
     constexpr int HW = kRwCap / 32 + 2;
@@ -1339,6 +1348,35 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
         // carries the same key (or its key holds the terminator, which makes it unique)
         int nbig = 0; // large groups of this warp's range seen in this step (warp-uniform)
+        if (big_thr > kRwCap) { // every group by its own members (all pairs)
+            for (int i = lane; i < cnt; i += 32) {
+                const int r = list[i];
+                const int gs = prev_set_le(s_ha, r);
+                const int ge = next_set_gt(s_ha, r);
+                const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
+                int lt = 0, eq = 0;
+                if (KW == 2) {
+                    for (int j = gs; j < ge; ++j) {
+                        const uint64_t oh = s_khi[j], ol = s_klo[j];
+                        lt += (oh < mh) | ((oh == mh) & (ol < ml));
+                        eq += (oh == mh) & (ol == ml) & (j < r);
+                    }
+                } else {
+                    for (int j = gs; j < r; ++j) {
+                        const uint64_t o = s_khi[j];
+                        lt += o < mh;
+                        eq += o == mh;
+                    }
+                    for (int j = r + 1; j < ge; ++j) lt += s_khi[j] < mh;
+                }
+                const int p = gs + lt + eq;
+                if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                s_sa[c ^ 1][p] = s_sa[c][r];
+                s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+                if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                list[i] = (uint16_t)p;       // where this suffix went
+            }
+        } else
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             const int i = i0 + lane;
             bool big_first = false;
@@ -1347,8 +1385,9 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 const int r = list[i];
                 gs = prev_set_le(s_ha, r);
                 const int ge = next_set_gt(s_ha, r);
-                if (ge - gs >= kRwBigGroup) {
+                if (ge - gs >= big_thr) {
                     big_first = r == gs; // the whole warp ranks this group below
+                    S.lidx[r] = (uint16_t)i; // where the member sits in the list
                 } else {
                     const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
                     int lt = 0, eq = 0;
@@ -1385,70 +1424,69 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
             const int g = ge - gs;
             // candidate for the dominant key: the member in the middle of the group
             const uint64_t ch = s_khi[gs + (g >> 1)], cl = KW == 2 ? s_klo[gs + (g >> 1)] : 0ull;
+            __syncwarp();
+            // pass 1: classes.  The members that do not carry the candidate key are compacted, in slot order, to
+            // the front of the group's own key slots (a key is read by its lane before anything of its chunk is
+            // written, and the write index never exceeds the read index), so that the ranking below reads dense keys.
             int n_lt = 0, n_eq = 0, n_nd = 0;
             for (int b0 = gs; b0 < ge; b0 += 32) {
                 const int r = b0 + lane;
                 const bool in = r < ge;
+                uint64_t mh = 0, ml = 0;
                 bool is_eq = false, is_lt = false;
                 if (in) {
-                    const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
+                    mh = s_khi[r];
+                    ml = KW == 2 ? s_klo[r] : 0ull;
                     is_eq = mh == ch && ml == cl;
-                    is_lt = mh < ch || (mh == ch && ml < cl);
+                    is_lt = mh < ch || (KW == 2 && mh == ch && ml < cl);
                 }
                 const uint32_t eqm = __ballot_sync(0xffffffffu, is_eq), ltm = __ballot_sync(0xffffffffu, is_lt);
                 const uint32_t ndm = __ballot_sync(0xffffffffu, in && !is_eq);
                 if (is_eq) S.newpos[r] = (uint16_t)(n_eq + __popc(eqm & lanemask_lt())); // rank among the equal ones
-                if (in && !is_eq) S.nd[gs + n_nd + __popc(ndm & lanemask_lt())] = (uint16_t)r;
+                if (in && !is_eq) {
+                    const int t = gs + n_nd + __popc(ndm & lanemask_lt());
+                    S.newpos[r] = 0xffffu; // not a carrier of the candidate key
+                    S.nd[t] = (uint16_t)r;
+                    s_khi[t] = mh;
+                    if (KW == 2) s_klo[t] = ml;
+                }
                 n_eq += __popc(eqm);
                 n_lt += __popc(ltm);
                 n_nd += __popc(ndm);
+                __syncwarp();
             }
-            __syncwarp();
-            const bool dominant = 2 * n_eq >= g;
-            // the members carrying the candidate key (none of them is ranked against anything when it dominates)
-            if (dominant) {
-                const bool term = key_terminated<BITS>(KW == 2 ? cl : ch);
-                for (int r = gs + lane; r < ge; r += 32) {
-                    const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
-                    if (mh == ch && ml == cl) {
-                        const int e = S.newpos[r];
-                        const int p = gs + n_lt + e;
-                        if (p != gs && (e == 0 || term)) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
-                        s_sa[c ^ 1][p] = s_sa[c][r];
-                        s_bw[c ^ 1][p] = s_bw[c][r];
-                        if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                        S.newpos[r] = (uint16_t)p;
-                    }
+            // the carriers of the candidate key: their stable rank is their running count, no comparisons at all
+            const bool term = key_terminated<BITS>(KW == 2 ? cl : ch);
+            for (int r = gs + lane; r < ge; r += 32) {
+                const int e = S.newpos[r];
+                if (e != 0xffff) {
+                    const int p = gs + n_lt + e;
+                    if (p != gs && (e == 0 || term)) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                    s_sa[c ^ 1][p] = s_sa[c][r];
+                    s_bw[c ^ 1][p] = s_bw[c][r];
+                    if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                    list[S.lidx[r]] = (uint16_t)p;
                 }
             }
-            // the others -- or everybody, if no key dominates -- against each other
-            const int n_rank = dominant ? n_nd : g;
-            for (int t = lane; t < n_rank; t += 32) {
-                const int r = dominant ? (int)S.nd[gs + t] : gs + t;
-                const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : 0ull;
+            // the others against each other (dense keys in the first n_nd key slots of the group)
+            for (int t = lane; t < n_nd; t += 32) {
+                const int r = S.nd[gs + t];
+                const uint64_t mh = s_khi[gs + t], ml = KW == 2 ? s_klo[gs + t] : 0ull;
                 int lt = 0, eq = 0;
-                for (int u = 0; u < n_rank; ++u) {
-                    const int r2 = dominant ? (int)S.nd[gs + u] : gs + u;
-                    const uint64_t oh = s_khi[r2], ol = KW == 2 ? s_klo[r2] : 0ull;
+                for (int u = 0; u < n_nd; ++u) {
+                    const uint64_t oh = s_khi[gs + u], ol = KW == 2 ? s_klo[gs + u] : 0ull;
                     lt += (oh < mh) | ((oh == mh) & (ol < ml));
                     eq += (oh == mh) & (ol == ml) & (u < t);
                 }
-                const bool above = dominant && (mh > ch || (mh == ch && ml > cl));
+                const bool above = mh > ch || (KW == 2 && mh == ch && ml > cl);
                 const int p = gs + lt + eq + (above ? n_eq : 0);
                 if (p != gs && (eq == 0 || key_terminated<BITS>(KW == 2 ? ml : mh))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
                 s_sa[c ^ 1][p] = s_sa[c][r];
                 s_bw[c ^ 1][p] = s_bw[c][r];
                 if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                S.newpos[r] = (uint16_t)p;
+                list[S.lidx[r]] = (uint16_t)p;
             }
             __syncwarp();
-        }
-        if (nbig) { // list entries of the members of large groups
-            for (int i = lane; i < cnt; i += 32) {
-                const int r = list[i];
-                const int gs = prev_set_le(s_ha, r);
-                if (next_set_gt(s_ha, r) - gs >= kRwBigGroup) list[i] = S.newpos[r];
-            }
         }
         __syncwarp();
         if (!ORDER) {
@@ -2584,7 +2622,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
                    int key_words, uint8_t *sa_hi, int lo_bits, bool full_order, const uint32_t *diff_bits,
-                   uint32_t *launches)
+                   uint32_t *launches, bool big_groups)
 {
     const uint32_t nwin = (uint32_t)div_up(n, kRefWindow);
     const int max_steps = multi_step ? (1 << 30) : 1;
@@ -2604,6 +2642,14 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
     const char *variant_env = std::getenv("DSMFM_REFINE_VARIANT"); // 0: CTA-wide steps (refine_kernel), 2: independent warps
     const int variant = variant_env ? std::atoi(variant_env) : 2;
     if (multi_step && variant == 2) {
+        // groups of at least big_thr members are ranked by the whole warp around their dominant key
+        // (DSMFM_REFINE_BIG=<members>; 0 or unset: every group by its own members)
+        // -- the default when the refinement runs in place, i.e. when most suffixes sit in groups that have to be
+        // sorted (high repetition: C5 refinement 118 -> 98 ms); on the dense arrays of a read collection with few
+        // large groups the per-member path is the faster one (C3: 25.2 vs 26.6 ms).
+        static const int big_env = std::getenv("DSMFM_REFINE_BIG") ? std::atoi(std::getenv("DSMFM_REFINE_BIG")) : -1;
+        const int big_want = big_env >= 0 ? big_env : (big_groups ? kRwBigGroup : 0);
+        const int big_thr = big_want >= 32 ? (big_want < kRwBigGroup ? kRwBigGroup : big_want) : kRwCap + 1;
         static DeviceOnce attr3_once;
         attr3_once.run([] {
 #define SET3(B, K)                                                                                                      \
@@ -2621,7 +2667,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
 #define RW2(B, K, W, O)                                                                                           \
     refine_warps_kernel<B, K, W, O><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                             \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \
-        win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits)
+        win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits, big_thr)
 #define RW(B, K, W)                                                                                               \
     do {                                                                                                          \
         if (full_order || !bwt) RW2(B, K, W, true); else RW2(B, K, W, false);                                     \

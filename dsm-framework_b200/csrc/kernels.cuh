@@ -97,12 +97,13 @@ inline uint64_t head_words_for(uint64_t n) { return div_up(n, 32) + kRefCap / 32
 // members all carry the same BWT symbol are left as they are -- their order cannot change the BWT -- so the
 // suffix array is then only sorted as far as the BWT needs it.  diff_bits: launch_heads' bitmap while it is
 // still valid (first launch after the initial sort), nullptr afterwards (the kernel then compares the bytes).
+// big_groups: groups of 64+ members are ranked by the whole warp around their dominant key (kernels.cu, kRwBigGroup).
 void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *sa, const uint32_t *head_cur,
                    uint32_t *head_next, uint64_t n, uint32_t depth, const uint32_t *win_list, uint32_t n_list,
                    uint32_t *big_heads, uint32_t big_cap, uint32_t *big_count, unsigned long long *remaining,
                    uint32_t *win_flag, uint32_t *win_next, uint32_t *win_next_count, uint8_t *bwt, bool multi_step,
                    int key_words, uint8_t *sa_hi, int lo_bits, bool full_order, const uint32_t *diff_bits,
-                   uint32_t *launches);
+                   uint32_t *launches, bool big_groups = false);
 
 // BWT-only builds: the groups with mixed BWT symbols, copied out in order so that the refinement works on dense
 // arrays.  launch_mark_active: act (zeroed, head_words words) gets the slots of those groups, tile_off

@@ -11,6 +11,10 @@ import dsmgen
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 kw = dict(dsmgen.CONFIGS[name])
+scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0  # fewer reads from proportionally shorter genomes (same coverage)
+if scale != 1.0:
+    kw["n_reads"] = int(kw["n_reads"] * scale)
+    kw["genome_len"] = int(kw["genome_len"] * scale)
 t = torch.empty(kw["n_reads"] * (2 * kw["read_len"] + 2), dtype=torch.uint8, pin_memory=True)
 dsmgen.docs(out=t, **kw)
 d = t.cuda()
