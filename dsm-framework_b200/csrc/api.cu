@@ -641,6 +641,7 @@ struct dsmfm_builder {
 
     void push_device(const void *src, size_t bytes, cudaMemcpyKind kind)
     {
+        pipeline_abandon(); // (text behind a streamed batch: plain statistics at build time)
         const uint8_t *s = static_cast<const uint8_t *>(src);
         while (bytes) {
             if (chunks.empty() || chunks.back().used == chunks.back().cap) {
@@ -683,6 +684,10 @@ struct dsmfm_builder {
         ph.h_blob = nullptr;
         delete ext;
         ext = nullptr;
+        for (cudaEvent_t e : pl.ev) cudaEventDestroy(e);
+        pl.ev.clear();
+        if (pl.copy) cudaStreamDestroy(pl.copy);
+        pl = Pipeline();
         d_raw = nullptr;
         d_sa = nullptr;
         d_sa_hi = nullptr;
@@ -726,6 +731,32 @@ struct dsmfm_builder {
         uint64_t file_bytes = 0;
     } ph;
 
+    // ---- a text that streams in from host memory (dsmfm_append_batch of a whole collection) ----
+    // The copy runs in pieces on a stream of its own; while piece k+1 crosses PCIe the build stream already
+    // histograms, scans, packs and keys piece k -- everything of the build that needs no more than the text
+    // seen so far.  The alphabet (bits per symbol, code map) is only known at the end, so the pack is SPECULATIVE:
+    // it assumes the symbols of the first piece are all there are; build() checks and redoes it otherwise.
+    struct Pipeline {
+        bool active = false;
+        cudaStream_t copy = nullptr;
+        std::vector<cudaEvent_t> ev;
+        uint64_t *d_counts = nullptr;
+        ChunkStat *d_stat = nullptr;
+        uint64_t nstat = 0, piece = 0;
+        // speculative products
+        bool spec = false;
+        int bits = 0, first_syms = 0;
+        bool carry = false;
+        uint8_t code_map[256];
+        uint64_t *d_packed = nullptr, *d_keys = nullptr, *d_hist = nullptr;
+        uint8_t *d_map = nullptr;
+        uint64_t nwords = 0;
+    } pl;
+    bool append_pipelined(const uint8_t *src, size_t bytes);
+    void pipeline_finish_stats(); // waits for the copies, fills block_info
+    void pipeline_drop_spec();    // frees the speculative buffers
+    void pipeline_abandon();      // more text arrives after all: plain statistics at build time
+
     uint32_t pre_launches = 0; // kernels launched before build() (the FASTA front end)
     // Page-locking the host buffer of the sections costs ~0.4 s per GB the first time (later builds find it in
     // the pool): a helper thread does it while the GPU sorts, as soon as the histogram fixes the size.
@@ -748,6 +779,7 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     cudaStream_t st = stream;
     uint32_t *L = &pre_launches;
     trace("append_fasta: begin");
+    pipeline_abandon();
     std::lock_guard<std::mutex> arena_lock(g_fasta_arena.mu);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // part 1 (sizes follow the text), part 2 (sizes follow the number of records, known after the first pass)
@@ -811,6 +843,169 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
     info->bad_headers = cnt[0];
     info->invalid_records = cnt[1];
     info->first_invalid_offset = cnt[2];
+}
+
+// ---------------------------------------------------------------------------
+// host text streaming in: copy pieces on one stream, work on them on the other
+// ---------------------------------------------------------------------------
+namespace {
+// first key of an unsharded build (see build()): symbols sorted by the initial radix sort, BWT symbol carried or not
+void first_key_shape(int bits, uint64_t n_idx, int *first_syms, bool *carry)
+{
+    const int spw = 64 / bits;
+    uint64_t long_key_above = 1ull << 32;
+    if (const char *e = std::getenv("DSMFM_LONG_KEY_ABOVE")) long_key_above = std::strtoull(e, nullptr, 10);
+    int first_key_bits = 48;
+    if (n_idx > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);
+    if (const char *e = std::getenv("DSMFM_FIRST_KEY_BITS")) first_key_bits = std::atoi(e);
+    if (first_key_bits < 8 || first_key_bits > spw * bits) first_key_bits = spw * bits;
+    *first_syms = std::max(1, first_key_bits / bits);
+    *carry = *first_syms * bits + bits <= 64;
+}
+} // namespace
+
+bool dsmfm_builder::append_pipelined(const uint8_t *src, size_t bytes)
+{
+    // pieces of 63 MiB: a multiple of 21, 16 and 8 symbols (whole packed words for 3-, 4- and 8-bit symbols), of the
+    // 16-byte vectors the kernels load and of the 16 KiB chunks of the document statistics
+    constexpr uint64_t kPiece = 21ull * 3145728ull;
+    static_assert(kPiece % 16 == 0 && kPiece % kStatChunk == 0, "piece alignment");
+    static const bool off = std::getenv("DSMFM_NO_PIPELINE") != nullptr;
+    if (off || n != 0 || !chunks.empty() || cur_used != 0 || shard_count > 1 || (flags & DSMFM_FLAG_KEEP_SA) ||
+        bytes < 3 * kPiece || bytes >= (1ull << 32) - 4096)
+        return false;
+    cudaStream_t st = stream;
+    uint32_t *L = &pre_launches;
+    uint8_t *d = static_cast<uint8_t *>(dmalloc(bytes + 64));
+    chunks.push_back(Chunk{d, bytes + 64, bytes});
+    n = bytes;
+    if (!pl.copy) DSM_CUDA(cudaStreamCreateWithFlags(&pl.copy, cudaStreamNonBlocking));
+    pl.piece = kPiece;
+    const uint64_t npiece = div_up(bytes, kPiece);
+    pl.ev.resize(npiece);
+    for (auto &e : pl.ev) DSM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // whatever is queued on the build stream (nothing, normally) precedes the copies
+    cudaEvent_t start;
+    DSM_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    DSM_CUDA(cudaEventRecord(start, st));
+    DSM_CUDA(cudaStreamWaitEvent(pl.copy, start, 0));
+    cudaEventDestroy(start);
+    for (uint64_t k = 0; k < npiece; ++k) {
+        const uint64_t o = k * kPiece, len = std::min<uint64_t>(kPiece, bytes - o);
+        DSM_CUDA(cudaMemcpyAsync(d + o, src + o, len, cudaMemcpyHostToDevice, pl.copy));
+        DSM_CUDA(cudaEventRecord(pl.ev[k], pl.copy));
+    }
+    pl.nstat = div_up(bytes, kStatChunk);
+    pl.d_counts = static_cast<uint64_t *>(dmalloc(256 * 8));
+    pl.d_stat = static_cast<ChunkStat *>(dmalloc(pl.nstat * sizeof(ChunkStat)));
+    DSM_CUDA(cudaMemsetAsync(pl.d_counts, 0, 256 * 8, st));
+    auto stats_of = [&](uint64_t k) {
+        const uint64_t o = k * kPiece, len = std::min<uint64_t>(kPiece, bytes - o);
+        DSM_CUDA(cudaStreamWaitEvent(st, pl.ev[k], 0));
+        launch_byte_hist(st, d + o, len, pl.d_counts, L);
+        launch_doc_stats(st, d + o, len, pl.d_stat + o / kStatChunk, L); // (positions relative to the piece)
+    };
+    pl.active = true;
+    // the alphabet of the first piece: the guess for the whole text
+    stats_of(0);
+    uint64_t first_counts[256];
+    DSM_CUDA(cudaMemcpyAsync(first_counts, pl.d_counts, sizeof first_counts, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st));
+    std::memset(pl.code_map, 0, sizeof pl.code_map);
+    uint32_t sigma = 0;
+    for (int c = 1; c < 256; ++c)
+        if (first_counts[c]) pl.code_map[c] = (uint8_t)++sigma;
+    pl.bits = sigma <= 7 ? 3 : (sigma <= 15 ? 4 : 8);
+    first_key_shape(pl.bits, bytes, &pl.first_syms, &pl.carry);
+    const int spw = 64 / pl.bits;
+    pl.spec = sigma > 0 && (pl.first_syms * pl.bits + 7) / 8 <= kMaxPasses;
+    uint64_t text_words = div_up(bytes, (uint64_t)spw);
+    if (pl.spec) {
+        pl.nwords = text_words + 8;
+        pl.d_map = static_cast<uint8_t *>(dmalloc(256));
+        pl.d_packed = static_cast<uint64_t *>(dmalloc(pl.nwords * 8));
+        pl.d_keys = static_cast<uint64_t *>(dmalloc(bytes * 8));
+        pl.d_hist = static_cast<uint64_t *>(dmalloc(sizeof(uint64_t) * kMaxPasses * kRadix));
+        DSM_CUDA(cudaMemcpyAsync(pl.d_map, pl.code_map, 256, cudaMemcpyHostToDevice, st));
+        DSM_CUDA(cudaMemsetAsync(pl.d_hist, 0, sizeof(uint64_t) * kMaxPasses * kRadix, st));
+    }
+    uint64_t keyed_to = 0; // words whose keys are built
+    for (uint64_t k = 0; k < npiece; ++k) {
+        if (k) stats_of(k);
+        if (!pl.spec) continue;
+        const uint64_t o = k * kPiece, len = std::min<uint64_t>(kPiece, bytes - o);
+        const bool last = k + 1 == npiece;
+        const uint64_t w0 = o / spw, wn = last ? pl.nwords - w0 : len / spw; // (the last piece also writes the zero words)
+        launch_pack(st, pl.bits, d + o, len, pl.d_map, pl.d_packed + w0, wn, L);
+        // keys of every word whose successor is packed by now
+        const uint64_t upto = last ? text_words : w0 + wn - 1;
+        if (upto > keyed_to) {
+            launch_make_keys_hist(st, pl.bits, pl.d_packed, bytes, pl.d_keys, pl.first_syms, pl.carry, pl.d_hist, L, keyed_to, upto);
+            keyed_to = upto;
+        }
+    }
+    return true;
+}
+
+void dsmfm_builder::pipeline_finish_stats()
+{
+    cudaStream_t st = stream;
+    std::memset(&block_info, 0, sizeof block_info);
+    block_info.bytes = n;
+    std::vector<ChunkStat> hstat(pl.nstat);
+    DSM_CUDA(cudaMemcpyAsync(block_info.counts, pl.d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaMemcpyAsync(hstat.data(), pl.d_stat, pl.nstat * sizeof(ChunkStat), cudaMemcpyDeviceToHost, st));
+    DSM_CUDA(cudaStreamSynchronize(st)); // every piece has arrived and has been looked at
+    dfree(pl.d_counts);
+    dfree(pl.d_stat);
+    pl.d_counts = nullptr;
+    pl.d_stat = nullptr;
+    uint64_t maxgap = 0, mingap = ~0ull;
+    int64_t prev = -1, lastz = -1;
+    const uint64_t per_piece = pl.piece / kStatChunk;
+    for (uint64_t i = 0; i < pl.nstat; ++i) {
+        const ChunkStat &c = hstat[i];
+        if (c.last < 0) continue;
+        const int64_t base = (int64_t)((i / per_piece) * pl.piece); // the kernel saw the piece, not the text
+        const uint64_t g = (uint64_t)(c.first + base - prev);
+        maxgap = std::max(maxgap, g);
+        mingap = std::min(mingap, g);
+        maxgap = std::max(maxgap, c.maxgap);
+        mingap = std::min(mingap, c.mingap);
+        prev = c.last + base;
+        lastz = c.last + base;
+    }
+    pl.active = false;
+    block_stats_done = true;
+    if (lastz != (int64_t)n - 1)
+        throw CudaError{cudaErrorInvalidValue, "text does not end with a document terminator", __FILE__, __LINE__};
+    block_info.documents = block_info.counts[0];
+    block_info.max_text_length = maxgap;
+    block_info.empty_document = mingap == 1 ? 1u : 0u;
+}
+
+void dsmfm_builder::pipeline_drop_spec()
+{
+    if (pl.d_packed) dfree(pl.d_packed);
+    if (pl.d_keys) dfree(pl.d_keys);
+    if (pl.d_hist) dfree(pl.d_hist);
+    if (pl.d_map) dfree(pl.d_map);
+    pl.d_packed = pl.d_keys = pl.d_hist = nullptr;
+    pl.d_map = nullptr;
+    pl.spec = false;
+}
+
+void dsmfm_builder::pipeline_abandon()
+{
+    if (!pl.active) return;
+    DSM_CUDA(cudaStreamSynchronize(pl.copy));
+    DSM_CUDA(cudaStreamSynchronize(stream));
+    pipeline_drop_spec();
+    dfree(pl.d_counts);
+    dfree(pl.d_stat);
+    pl.d_counts = nullptr;
+    pl.d_stat = nullptr;
+    pl.active = false;
 }
 
 // ---------------------------------------------------------------------------
@@ -923,6 +1118,7 @@ void dsmfm_builder::build()
     DSM_CUDA(cudaEventRecord(ev[0], st));
     if (!packed_in) {
         // ---- contiguous text, histogram, document statistics ----------------------------------
+        if (pl.active) pipeline_finish_stats(); // a streamed batch: its pieces were looked at as they arrived
         gather_raw();
         if (!block_stats_done) block_stats(L);
         std::memcpy(counts, block_info.counts, sizeof counts);
@@ -984,6 +1180,11 @@ void dsmfm_builder::build()
     std::memset(inv_map, 0, sizeof inv_map);
     for (int c = 1; c < 256; ++c)
         if (code_map[c]) inv_map[code_map[c]] = (uint8_t)c;
+    // a streamed batch was packed and keyed with the alphabet of its first piece: keep that work if the guess held
+    bool spec_ok = pl.spec && !sharded && !packed_in && pl.bits == bits && pl.first_syms == first_syms &&
+                   pl.carry == carry_bwt && std::memcmp(pl.code_map, code_map, sizeof code_map) == 0;
+    if (pl.spec && !spec_ok) pipeline_drop_spec();
+    stats.streamed = spec_ok ? 1u : 0u;
 
     if (!sharded && !host_prefetch.joinable()) {
         dsmfm_code tab[256];
@@ -1025,6 +1226,12 @@ void dsmfm_builder::build()
     uint64_t *d_packed = nullptr;
     if (packed_in) {
         d_packed = const_cast<uint64_t *>(ext->text);
+    } else if (spec_ok) {
+        d_packed = pl.d_packed; // packed piece by piece while the text streamed in (same words, same zero tail)
+        pl.d_packed = nullptr;
+        dfree(d_raw);
+        chunks.clear();
+        d_raw = nullptr;
     } else {
         d_packed = static_cast<uint64_t *>(dmalloc(nwords * 8));
         launch_pack(st, bits, d_raw, n, d_map, d_packed, nwords, L);
@@ -1108,7 +1315,8 @@ void dsmfm_builder::build()
                         "more than 2^32 suffixes in one sort range (use more shards: shard_count / shard_span)", __FILE__, __LINE__};
 
     // ---- buffers of one range (sized for the largest) -------------------------------------
-    uint64_t *d_keys_a = static_cast<uint64_t *>(dmalloc(m_max * 8));
+    uint64_t *d_keys_a = spec_ok ? pl.d_keys : static_cast<uint64_t *>(dmalloc(m_max * 8));
+    if (spec_ok) pl.d_keys = nullptr;
     uint64_t *d_keys_b = static_cast<uint64_t *>(dmalloc(m_max * 8));
     uint32_t *d_vals_a = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
     uint32_t *d_vals_b = static_cast<uint32_t *>(dmalloc(m_max * 4 + 16));
@@ -1187,8 +1395,12 @@ void dsmfm_builder::build()
         bool hist_ready = false;
         if (!sharded) {
             // keys and their digit histogram in one pass over the packed text
-            DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * kMaxPasses * kRadix, st));
-            launch_make_keys_hist(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, ws.hist, L);
+            if (spec_ok) { // keys and digit counts were made as the pieces arrived
+                DSM_CUDA(cudaMemcpyAsync(ws.hist, pl.d_hist, sizeof(uint64_t) * kMaxPasses * kRadix, cudaMemcpyDeviceToDevice, st));
+            } else {
+                DSM_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(uint64_t) * kMaxPasses * kRadix, st));
+                launch_make_keys_hist(st, bits, d_packed, n, d_keys_a, first_syms, carry_bwt, ws.hist, L);
+            }
             hist_ready = true;
         } else {
             const uint64_t twords = nwords - 8; // words that hold text
@@ -1328,7 +1540,7 @@ void dsmfm_builder::build()
             launch_refine(st, bits, d_packed, r_sa, r_head[cur], r_head[cur ^ 1], r_m, depth, win_list, n_list,
                           d_big_heads, big_cap, d_big_count, d_remaining, d_win_flag, d_win_list[wl], d_win_count,
                           r_bwt, multi_step, key_words, r_hi, lo_bits, full_order, round == 1 ? r_diff : nullptr, L,
-                          /*big_groups=*/!(compact && m_act));
+                          /*big_groups=*/!full_order && !(compact && m_act));
             uint32_t nbig = 0;
             DSM_CUDA(cudaMemcpyAsync(&nbig, d_big_count, 4, cudaMemcpyDeviceToHost, st));
             remaining = read_remaining();
@@ -1447,6 +1659,7 @@ void dsmfm_builder::build()
     trace("build: wavelet tree done");
 
     // ---- release what the sections do not need ---------------------------------------
+    pipeline_drop_spec(); // (d_hist, d_map of a streamed batch)
     dfree(d_map);
     dfree(d_inv);
     dfree(d_sel_lut);
@@ -1749,7 +1962,9 @@ static int append_bulk(dsmfm_builder *b, const void *src, size_t bytes, cudaMemc
     if (!src || bytes == 0) return b->fail(DSMFM_EINVAL, "append: empty batch");
     try {
         b->flush_stage();
-        b->push_device(src, bytes, kind);
+        b->pipeline_abandon(); // (a second batch behind a streamed one: plain statistics at build time)
+        if (kind != cudaMemcpyHostToDevice || !b->append_pipelined(static_cast<const uint8_t *>(src), bytes))
+            b->push_device(src, bytes, kind);
     } catch (const CudaError &e) {
         return b->fail_cuda(e);
     }
@@ -1868,6 +2083,10 @@ DSMFM_API int dsmfm_block_stats(dsmfm_builder *b, dsmfm_block_info *out)
     if (b->finished) return b->fail(DSMFM_EINVAL, "dsmfm_block_stats: already built");
     try {
         b->flush_stage();
+        if (b->pl.active) { // a streamed batch: statistics are ready; its pack used the LOCAL alphabet and is dropped
+            b->pipeline_finish_stats();
+            b->pipeline_drop_spec();
+        }
         if (b->n == 0) {
             std::memset(&b->block_info, 0, sizeof b->block_info);
             b->block_stats_done = true;

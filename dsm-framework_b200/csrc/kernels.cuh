@@ -33,8 +33,11 @@ void launch_make_keys(cudaStream_t st, int bits, const uint64_t *packed, uint64_
 
 // The same keys plus, in ghist[pass][256] (zeroed u64), the counts of their 8-bit digits from bit 0 up to
 // first_syms*bits -- the histogram the LSD sort needs (radix_sort_pairs with hist_ready).
+// word_begin / word_end (0 = all): only the suffixes starting in these words of the packed text -- a text that
+// streams in from the host is keyed piece by piece; the word behind the last one must already be packed.
 void launch_make_keys_hist(cudaStream_t st, int bits, const uint64_t *packed, uint64_t n, uint64_t *keys, int first_syms,
-                           bool carry_prev, uint64_t *ghist, uint32_t *launches);
+                           bool carry_prev, uint64_t *ghist, uint32_t *launches, uint64_t word_begin = 0,
+                           uint64_t word_end = 0);
 
 // Group heads after the initial sort: bit i set iff suffix i starts a new group
 // (key differs from its predecessor) or is already finished (key holds the

@@ -82,7 +82,7 @@ class Stats(C.Structure):
                 ("ms_wt", C.c_float), ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("sort_passes", C.c_uint32),
                 ("sort_launches", C.c_uint32), ("sort_pass_bytes", C.c_uint64), ("device_bytes_peak", C.c_uint64),
                 ("ms_wall_build", C.c_float), ("ms_wall_fetch", C.c_float), ("ms_wall_alloc", C.c_float),
-                ("reserved2", C.c_float), ("refine_key_fetches", C.c_uint64), ("refine_launches", C.c_uint64),
+                ("streamed", C.c_uint32), ("refine_key_fetches", C.c_uint64), ("refine_launches", C.c_uint64),
                 ("refine_members", C.c_uint64)]
 
     def as_dict(self):

@@ -139,7 +139,8 @@ typedef struct dsmfm_stats {
     float ms_wall_build;         /* host wall time of dsmfm_build_device                    */
     float ms_wall_fetch;         /* host wall time of dsmfm_fetch                           */
     float ms_wall_alloc;         /* of which: device allocation calls                       */
-    float reserved2;
+    uint32_t streamed;           /* 1: the text streamed in from the host in pieces and was packed and keyed   */
+                                 /* piece by piece behind the copy (dsmfm_append_batch of a whole collection)  */
     uint64_t refine_key_fetches; /* 8-byte keys the refinement kernel gathered from the text */
     uint64_t refine_launches;    /* refine_kernel launches                                  */
     uint64_t refine_members;     /* suffixes in the tie groups that had to be sorted: all of them when the */

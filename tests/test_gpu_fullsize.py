@@ -39,6 +39,8 @@ def test_full_size_fmi_equals_the_reference_digest(config):
             b.append_batch(docs)
             b.finish()
             got = b.fmi()
+            # batches of 3 x 63 MiB or more stream in piece by piece and are packed and keyed behind the copy
+            assert b.stats().streamed == (1 if docs.nbytes >= 3 * 21 * 3145728 and flags == 0 else 0)
         assert len(got) == want["fmi_bytes"]
         assert hashlib.sha256(got).hexdigest() == want["fmi_sha256"], "flags=%d: .fmi differs from the reference's" % flags
         del got
@@ -200,3 +202,33 @@ def test_collection_beyond_2_to_32_symbols_in_key_ranges():
     assert nxt == n
     assert np.array_equal(counts, np.bincount(docs, minlength=256))
     assert np.array_equal(head, docs.reshape(nreads, doc_len)[:, doc_len - 2])
+
+
+def test_streamed_batch_whose_alphabet_grows_late():
+    """A host batch streams in piece by piece and is packed with the alphabet of its FIRST piece; here the last
+    document brings symbols no earlier piece had (and pushes the alphabet from 3 to 4 bits per symbol), so the
+    speculative pack must be thrown away.  Reference: the same documents appended from device memory (no streaming)."""
+    import torch
+    import dsmfm
+    import dsmgen
+    kw = dict(seed=77, pool_seed=77, pool_size=4, n_genomes=4, genome_len=200_000, n_reads=1_100_000, read_len=100,
+              sub=0.002, pn=0.0)
+    docs = dsmgen.docs(**kw)
+    tail = np.frombuffer(b"0123.0123.XYZWV\0", dtype=np.uint8)
+    both = torch.from_numpy(np.concatenate([docs, tail])).pin_memory()
+    with dsmfm.Builder() as b:
+        b.append_batch(both)
+        b.finish()
+        assert b.stats().streamed == 0 and b.stats().bits_per_symbol == 4
+        got = hashlib.sha256(b.fmi()).hexdigest()
+    with dsmfm.Builder() as b:
+        b.append_batch_device(both.cuda())
+        b.finish()
+        want = hashlib.sha256(b.fmi()).hexdigest()
+    assert got == want
+    # and a second batch behind a streamed one: statistics are taken again over the whole text
+    with dsmfm.Builder() as b:
+        b.append_batch(torch.from_numpy(docs).pin_memory())
+        b.append_batch(tail)
+        b.finish()
+        assert hashlib.sha256(b.fmi()).hexdigest() == want
