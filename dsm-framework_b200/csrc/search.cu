@@ -12,6 +12,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <unistd.h>
 #include <cstring>
 #include <new>
 #include <string>
@@ -147,6 +149,191 @@ __global__ void __launch_bounds__(256) search_count_kernel(const QIndex *__restr
     }
     sp_out[q] = lo;
     ep_out[q] = hi;
+}
+
+// ---- the mining client's trie walk, level by level -----------------------------------------
+// EnumerateQuery (EnumerateQuery.cpp:9-58, 151-290) walks the trie of the substrings that occur at least fmin
+// times depth-first, one backward-search step per edge, carrying for every node the interval [sp, ep] of the
+// pattern and the four intervals of "pattern followed by A / C / G / T" (its left characters, in the orientation
+// of the reversed reads).  The same nodes level by level: one thread per (node, symbol) takes the step, the
+// surviving children are compacted in order (children of a node stay together, symbols in ACGT order), and every
+// node leaves a small record -- frequency, left-character code, symbol, children -- from which the host writes
+// the client's byte stream in the reference's depth-first order.
+struct EnumNode {
+    uint64_t sp, ep;
+    uint64_t emin[4], emax[4];
+};
+
+__device__ __forceinline__ char enum_left_char(const EnumNode &x)
+{
+    // EnumerateQuery::leftChar (EnumerateQuery.cpp:77-103)
+    bool matches = false, any = false;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (x.emin[i] <= x.emax[i]) {
+            any = true;
+            c = i;
+            if (x.emin[i] == x.sp && x.emax[i] == x.ep) matches = true;
+        }
+    }
+    const char alphabet[4] = {'A', 'C', 'G', 'T'};
+    return matches ? alphabet[c] : (any ? 'N' : '0');
+}
+
+// EnumerateQuery::pushChar for symbol c on node x; false if the pattern does not occur
+__device__ __forceinline__ bool enum_step(const QIndex *__restrict__ q, const EnumNode &x, uint32_t c, EnumNode &y)
+{
+    y.sp = fm_lf(q, c, x.sp - 1);
+    y.ep = fm_lf(q, c, x.ep) - 1;
+    if (y.sp > y.ep) return false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint64_t lo = x.emin[i], hi = x.emax[i];
+        if (lo <= hi) {
+            lo = fm_lf(q, c, lo - 1);
+            hi = fm_lf(q, c, hi) - 1;
+        }
+        y.emin[i] = lo;
+        y.emax[i] = hi;
+    }
+    return true;
+}
+
+// the root and the enforced path (EnumerateQuery::enumerate / nextEnforced): chain[d] = node of path[0..d), d = 0..len;
+// *reached = number of path symbols that could be pushed with at least fmin occurrences
+__global__ void enum_chain_kernel(const QIndex *__restrict__ q, const uint8_t *__restrict__ path, uint32_t len, uint64_t fmin,
+                                  EnumNode *__restrict__ chain, uint32_t *__restrict__ reached)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const uint8_t alphabet[4] = {'A', 'C', 'G', 'T'};
+    EnumNode x;
+    x.sp = 0;
+    x.ep = q->n - 1;
+    for (int i = 0; i < 4; ++i) {
+        x.emin[i] = fm_lf(q, alphabet[i], ~0ull);
+        x.emax[i] = fm_lf(q, alphabet[i], q->n - 1) - 1;
+    }
+    chain[0] = x;
+    uint32_t d = 0;
+    for (; d < len; ++d) {
+        EnumNode y;
+        if (!enum_step(q, x, path[d], y) || y.ep - y.sp + 1 < fmin) break;
+        chain[d + 1] = y;
+        x = y;
+    }
+    *reached = d;
+}
+
+// which of the four children of every frontier node survive
+__global__ void __launch_bounds__(256) enum_count_kernel(const QIndex *__restrict__ q, const EnumNode *__restrict__ front,
+                                                         uint64_t m, uint64_t fmin, uint8_t *__restrict__ mask)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t i = t >> 2;
+    const int c = (int)(t & 3);
+    bool ok = false;
+    if (i < m) {
+        const uint8_t alphabet[4] = {'A', 'C', 'G', 'T'};
+        const uint64_t sp = fm_lf(q, alphabet[c], front[i].sp - 1), ep = fm_lf(q, alphabet[c], front[i].ep) - 1;
+        ok = sp <= ep && ep - sp + 1 >= fmin;
+    }
+    // the four threads of a node sit in one warp (4 divides 32)
+    const uint32_t b = __ballot_sync(0xffffffffu, ok);
+    if (i < m && c == 0) mask[i] = (uint8_t)((b >> (threadIdx.x & 28)) & 15u);
+}
+
+// per-block sums of the child counts, then (after a scan of the sums) the child offsets and the children
+__global__ void __launch_bounds__(256) enum_sum_kernel(const uint8_t *__restrict__ mask, uint64_t m, uint64_t *__restrict__ block_sum)
+{
+    __shared__ uint32_t s[8];
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    uint32_t c = i < m ? __popc(mask[i]) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int k = 0; k < 8; ++k) tot += s[k];
+        block_sum[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(1024) enum_scan_kernel(uint64_t *__restrict__ v, uint64_t nblocks)
+{
+    // exclusive scan in place, total behind the last entry; one block
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nblocks; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t x = i < nblocks ? v[i] : 0;
+        uint64_t incl = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint64_t before = carry_s;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += warp_tot[w];
+        if (i < nblocks) v[i] = before + incl - x;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v[nblocks] = carry_s;
+}
+
+struct EnumRecord { // what the host needs of a node to write its part of the stream
+    uint64_t freq;
+    uint64_t child_begin; // index of its first child in the next level
+    uint8_t sym, left, mask, pad[5];
+};
+
+__global__ void __launch_bounds__(256)
+enum_write_kernel(const QIndex *__restrict__ q, const EnumNode *__restrict__ front, uint64_t m, const uint8_t *__restrict__ mask,
+                  const uint64_t *__restrict__ block_off, EnumNode *__restrict__ next, EnumRecord *__restrict__ rec_cur,
+                  EnumRecord *__restrict__ rec_next)
+{
+    __shared__ uint32_t s[8];
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t mk = i < m ? mask[i] : 0u;
+    const uint32_t c = __popc(mk);
+    // exclusive prefix of the child counts inside the block
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t before = incl - c;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s[w];
+    if (i >= m) return;
+    uint64_t j = block_off[blockIdx.x] + before;
+    rec_cur[i].child_begin = j;
+    rec_cur[i].mask = (uint8_t)mk;
+    const uint8_t alphabet[4] = {'A', 'C', 'G', 'T'};
+    const EnumNode x = front[i];
+    for (int k = 0; k < 4; ++k) {
+        if (!((mk >> k) & 1u)) continue;
+        EnumNode y;
+        enum_step(q, x, alphabet[k], y);
+        next[j] = y;
+        EnumRecord r;
+        r.freq = y.ep - y.sp + 1;
+        r.child_begin = 0;
+        r.sym = alphabet[k];
+        r.left = (uint8_t)enum_left_char(y);
+        r.mask = 0;
+        rec_next[j] = r;
+        ++j;
+    }
 }
 
 std::string g_search_create_error;
@@ -535,6 +722,226 @@ DSMFM_API int dsmfm_searcher_count(dsmfm_searcher *s, const uint8_t *patterns, c
     }
     return DSMFM_OK;
 }
+
+// ---- EnumerateQuery::enumerate as a byte stream -----------------------------------------------------------
+namespace {
+struct StreamSink {
+    int fd = -1;
+    std::vector<uint8_t> *mem = nullptr;
+    std::vector<uint8_t> buf;
+    uint64_t total = 0;
+    bool ok = true;
+    void flush()
+    {
+        if (fd >= 0 && ok) {
+            size_t done = 0;
+            while (done < buf.size()) {
+                const ssize_t w = ::write(fd, buf.data() + done, buf.size() - done);
+                if (w <= 0) { ok = false; break; }
+                done += (size_t)w;
+            }
+        } else if (mem) {
+            mem->insert(mem->end(), buf.begin(), buf.end());
+        }
+        total += buf.size();
+        buf.clear();
+    }
+    void putc(uint8_t c)
+    {
+        buf.push_back(c);
+        if (buf.size() >= (1u << 20)) flush();
+    }
+    void putulong(uint64_t u) // ClientSocket::putulong (ClientSocket.h:20-39)
+    {
+        if (u < 128) { putc((uint8_t)(u | 128u)); return; }
+        uint8_t l = 0;
+        for (uint64_t t = u; t; t >>= 8) ++l;
+        putc(l);
+        for (; u; u >>= 8) putc((uint8_t)(u & 0xff));
+    }
+};
+
+int enumerate_impl(dsmfm_searcher *s, const uint8_t *path, uint32_t path_len, uint64_t fmin, uint32_t maxdepth, StreamSink &out)
+{
+    SEARCH_GUARD(s);
+    if (fmin < 2) return s->fail(DSMFM_EINVAL, "dsmfm_searcher_enumerate: fmin must be at least 2 (fmin 1 walks unary paths one getL at a time)");
+    if (path_len && !path) return s->fail(DSMFM_EINVAL, "null path");
+    if (s->n < 2) return s->fail(DSMFM_EINVAL, "dsmfm_searcher_enumerate: index of fewer than two symbols");
+    cudaStream_t st = s->stream;
+    std::vector<std::vector<EnumRecord>> levels; // levels[0] = the node at the end of the enforced path (or the root)
+    std::vector<EnumNode> chain(path_len + 1);
+    uint32_t reached = 0;
+    EnumNode *d_front = nullptr, *d_next = nullptr;
+    EnumRecord *d_rec_cur = nullptr, *d_rec_next = nullptr;
+    uint8_t *d_mask = nullptr, *d_path = nullptr;
+    uint64_t *d_block = nullptr;
+    uint32_t *d_reached = nullptr;
+    auto release = [&]() {
+        cudaFree(d_front); cudaFree(d_next); cudaFree(d_rec_cur); cudaFree(d_rec_next); cudaFree(d_mask); cudaFree(d_path);
+        cudaFree(d_block); cudaFree(d_reached);
+    };
+    try {
+        DSM_CUDA(cudaMalloc(&d_front, sizeof(EnumNode) * (path_len + 1)));
+        DSM_CUDA(cudaMalloc(&d_path, path_len + 1));
+        DSM_CUDA(cudaMalloc(&d_reached, 4));
+        if (path_len) DSM_CUDA(cudaMemcpyAsync(d_path, path, path_len, cudaMemcpyHostToDevice, st));
+        enum_chain_kernel<<<1, 32, 0, st>>>(s->d_index, d_path, path_len, fmin, d_front, d_reached);
+        DSM_LAUNCH_CHECK();
+        DSM_CUDA(cudaMemcpyAsync(chain.data(), d_front, sizeof(EnumNode) * (path_len + 1), cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaMemcpyAsync(&reached, d_reached, 4, cudaMemcpyDeviceToHost, st));
+        DSM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_front);
+        d_front = nullptr;
+        // the subtree below the enforced path exists only if the whole path could be pushed
+        // (depth of its root = path_len; EnumerateQuery::nextSymbol returns at once at maxdepth)
+        if (reached == path_len) {
+            uint64_t m = 1;
+            DSM_CUDA(cudaMalloc(&d_front, sizeof(EnumNode)));
+            DSM_CUDA(cudaMemcpyAsync(d_front, &chain[path_len], sizeof(EnumNode), cudaMemcpyHostToDevice, st));
+            DSM_CUDA(cudaMalloc(&d_rec_cur, sizeof(EnumRecord)));
+            DSM_CUDA(cudaMemsetAsync(d_rec_cur, 0, sizeof(EnumRecord), st));
+            uint32_t depth = path_len;
+            while (m > 0) {
+                levels.emplace_back(m);
+                uint64_t next_m = 0;
+                if (depth < maxdepth) {
+                    const uint64_t nblocks = (m + 255) / 256;
+                    DSM_CUDA(cudaMalloc(&d_mask, m));
+                    DSM_CUDA(cudaMalloc(&d_block, sizeof(uint64_t) * (nblocks + 1)));
+                    enum_count_kernel<<<(unsigned)((4 * m + 255) / 256), 256, 0, st>>>(s->d_index, d_front, m, fmin, d_mask);
+                    enum_sum_kernel<<<(unsigned)nblocks, 256, 0, st>>>(d_mask, m, d_block);
+                    enum_scan_kernel<<<1, 1024, 0, st>>>(d_block, nblocks);
+                    DSM_LAUNCH_CHECK();
+                    DSM_CUDA(cudaMemcpyAsync(&next_m, d_block + nblocks, 8, cudaMemcpyDeviceToHost, st));
+                    DSM_CUDA(cudaStreamSynchronize(st));
+                    DSM_CUDA(cudaMalloc(&d_next, sizeof(EnumNode) * (next_m ? next_m : 1)));
+                    DSM_CUDA(cudaMalloc(&d_rec_next, sizeof(EnumRecord) * (next_m ? next_m : 1)));
+                    enum_write_kernel<<<(unsigned)nblocks, 256, 0, st>>>(s->d_index, d_front, m, d_mask, d_block, d_next, d_rec_cur,
+                                                                          d_rec_next);
+                    DSM_LAUNCH_CHECK();
+                }
+                DSM_CUDA(cudaMemcpyAsync(levels.back().data(), d_rec_cur, sizeof(EnumRecord) * m, cudaMemcpyDeviceToHost, st));
+                DSM_CUDA(cudaStreamSynchronize(st));
+                cudaFree(d_front); cudaFree(d_rec_cur); cudaFree(d_mask); cudaFree(d_block);
+                d_front = d_next;
+                d_rec_cur = d_rec_next;
+                d_next = nullptr; d_rec_next = nullptr; d_mask = nullptr; d_block = nullptr;
+                m = next_m;
+                ++depth;
+            }
+        }
+    } catch (const CudaError &e) {
+        release();
+        return s->fail(e.code == cudaErrorMemoryAllocation ? DSMFM_ENOMEM : DSMFM_ECUDA, "CUDA error %d (%s) at %s:%d", (int)e.code,
+                       cudaGetErrorString(e.code), e.file, e.line);
+    }
+    release();
+
+    // ---- the stream, depth first (EnumerateQuery.cpp:207-222, 273-288) ----
+    uint64_t reported = 0;
+    auto close_node = [&](uint64_t freq, uint32_t depth, uint8_t left) {
+        out.putulong(freq);
+        if (depth <= 6) {
+            out.putc('R');
+            out.putulong(reported);
+        }
+        out.putc(left);
+        out.putc(')');
+    };
+    auto left_of = [](const EnumNode &x) -> uint8_t {
+        bool matches = false, any = false;
+        int c = 0;
+        for (int i = 0; i < 4; ++i)
+            if (x.emin[i] <= x.emax[i]) {
+                any = true;
+                c = i;
+                if (x.emin[i] == x.sp && x.emax[i] == x.ep) matches = true;
+            }
+        return matches ? (uint8_t)"ACGT"[c] : (any ? 'N' : '0');
+    };
+    for (uint32_t d = 1; d <= reached; ++d) { // the enforced path opens ...
+        out.putc('(');
+        out.putc(path[d - 1]);
+        ++reported;
+    }
+    if (reached == path_len && !levels.empty()) {
+        // children of the path's last node, depth first with an explicit stack
+        struct Frame { uint32_t level; uint64_t idx; uint8_t next; };
+        std::vector<Frame> stack;
+        auto open_children = [&](uint32_t level, uint64_t idx) { stack.push_back(Frame{level, idx, 0}); };
+        open_children(0, 0);
+        while (!stack.empty()) {
+            Frame &f = stack.back();
+            const EnumRecord &r = levels[f.level][f.idx];
+            const uint32_t nchild = (uint32_t)__builtin_popcount(r.mask);
+            if (f.next < nchild) {
+                const uint64_t child = r.child_begin + f.next;
+                ++f.next;
+                const EnumRecord &c = levels[f.level + 1][child];
+                out.putc('(');
+                out.putc(c.sym);
+                ++reported;
+                open_children(f.level + 1, child);
+            } else {
+                const uint32_t level = f.level;
+                const uint64_t idx = f.idx;
+                stack.pop_back();
+                if (level > 0) { // (level 0 is the path's last node or the root: closed below)
+                    const EnumRecord &me = levels[level][idx];
+                    close_node(me.freq, path_len + level, me.left);
+                }
+            }
+        }
+    }
+    for (uint32_t d = reached; d >= 1; --d) // ... and closes, innermost first
+        close_node(chain[d].ep - chain[d].sp + 1, d, left_of(chain[d]));
+    out.flush();
+    if (!out.ok) return s->fail(DSMFM_EIO, "dsmfm_searcher_enumerate: write error");
+    return DSMFM_OK;
+}
+} // namespace
+
+DSMFM_API int dsmfm_searcher_enumerate_fd(dsmfm_searcher *s, const char *enforce_path, uint64_t fmin, uint32_t maxdepth, int fd,
+                                          uint64_t *bytes_written)
+{
+    if (!s) return DSMFM_EINVAL;
+    try {
+        StreamSink sink;
+        sink.fd = fd;
+        const size_t len = enforce_path ? std::strlen(enforce_path) : 0;
+        const int rc = enumerate_impl(s, reinterpret_cast<const uint8_t *>(enforce_path), (uint32_t)len, fmin, maxdepth ? maxdepth : ~0u, sink);
+        if (bytes_written) *bytes_written = sink.total;
+        return rc;
+    } catch (const std::bad_alloc &) {
+        return s->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+}
+
+DSMFM_API int dsmfm_searcher_enumerate(dsmfm_searcher *s, const char *enforce_path, uint64_t fmin, uint32_t maxdepth, uint8_t **out,
+                                       uint64_t *out_bytes)
+{
+    if (!s || !out || !out_bytes) return DSMFM_EINVAL;
+    *out = nullptr;
+    *out_bytes = 0;
+    try {
+        std::vector<uint8_t> mem;
+        StreamSink sink;
+        sink.mem = &mem;
+        const size_t len = enforce_path ? std::strlen(enforce_path) : 0;
+        const int rc = enumerate_impl(s, reinterpret_cast<const uint8_t *>(enforce_path), (uint32_t)len, fmin, maxdepth ? maxdepth : ~0u, sink);
+        if (rc) return rc;
+        uint8_t *p = static_cast<uint8_t *>(std::malloc(mem.size() ? mem.size() : 1));
+        if (!p) return s->fail(DSMFM_ENOMEM, "host allocation failed");
+        std::memcpy(p, mem.data(), mem.size());
+        *out = p;
+        *out_bytes = mem.size();
+        return DSMFM_OK;
+    } catch (const std::bad_alloc &) {
+        return s->fail(DSMFM_ENOMEM, "host allocation failed");
+    }
+}
+
+DSMFM_API void dsmfm_stream_free(uint8_t *p) { std::free(p); }
 
 DSMFM_API const char *dsmfm_searcher_last_error(const dsmfm_searcher *s)
 {

@@ -173,6 +173,10 @@ def lib():
     L.dsmfm_searcher_access.argtypes = [S, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.dsmfm_searcher_extend.argtypes = [S, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.dsmfm_searcher_count.argtypes = [S, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.dsmfm_searcher_enumerate.argtypes = [S, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_uint64)]
+    L.dsmfm_searcher_enumerate_fd.argtypes = [S, C.c_char_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+    L.dsmfm_stream_free.argtypes = [C.POINTER(C.c_uint8)]
+    L.dsmfm_stream_free.restype = None
     L.dsmfm_searcher_last_error.argtypes = [S]
     L.dsmfm_searcher_last_error.restype = C.c_char_p
     L.dsmfm_searcher_destroy.argtypes = [S]
@@ -496,6 +500,20 @@ class Searcher:
         self._check(self._L.dsmfm_searcher_count(self._h, blob.ctypes.data, off.ctypes.data, len(patterns),
                                                  sp.ctypes.data, ep.ctypes.data))
         return sp, ep
+
+    def enumerate(self, enforce_path, fmin=10, maxdepth=0):
+        """EnumerateQuery::enumerate: the client's byte stream (without the handshake) for the trie below enforce_path."""
+        out, n = C.POINTER(C.c_uint8)(), C.c_uint64()
+        self._check(self._L.dsmfm_searcher_enumerate(self._h, bytes(enforce_path), fmin, maxdepth, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            self._L.dsmfm_stream_free(out)
+
+    def enumerate_to_fd(self, enforce_path, fd, fmin=10, maxdepth=0):
+        n = C.c_uint64()
+        self._check(self._L.dsmfm_searcher_enumerate_fd(self._h, bytes(enforce_path), fmin, maxdepth, fd, C.byref(n)))
+        return n.value
 
     def close(self):
         if self._h:

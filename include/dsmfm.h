@@ -423,6 +423,21 @@ DSMFM_API int dsmfm_searcher_extend(dsmfm_searcher *s, const uint64_t *sp, const
  * the interval of all suffixes: [sp, ep] of its occurrences, sp > ep if there are none */
 DSMFM_API int dsmfm_searcher_count(dsmfm_searcher *s, const uint8_t *patterns, const uint64_t *offsets, uint64_t count,
                                    uint64_t *sp_out, uint64_t *ep_out);
+/* Replaces: EnumerateQuery::enumerate (EnumerateQuery.cpp:9-37) with nextEnforced / nextSymbol (151-290), pushChar /
+ * leftChar (39-103) and the encoding of ClientSocket::putc / putulong (ClientSocket.h:12-39) -- the mining client's
+ * walk of the trie of all substrings that occur at least fmin times below `enforce_path`, SURVEY 8(f) row 4.  The
+ * walk runs level by level on the GPU (one thread per node and symbol); the bytes are the reference's, in its
+ * depth-first order: node := '(' sym node* freq ['R' count] leftChar ')' (Appendix B of SURVEY.md), i.e. exactly
+ * what metaenumerate sends a metaserver after the handshake 'S' name '.' (metaenumerate.cpp:285-286), which the
+ * caller writes itself.  maxdepth 0 = unlimited.  fmin >= 2 (with fmin 1 the reference follows unary paths symbol
+ * by symbol, EnumerateQuery.cpp:105-149: not rebuilt).
+ *   _fd: the stream is written to a file descriptor (a connected socket: the drop-in for ClientSocket);
+ *   the other form returns it in memory (release with dsmfm_stream_free). */
+DSMFM_API int dsmfm_searcher_enumerate_fd(dsmfm_searcher *s, const char *enforce_path, uint64_t fmin, uint32_t maxdepth, int fd,
+                                          uint64_t *bytes_written);
+DSMFM_API int dsmfm_searcher_enumerate(dsmfm_searcher *s, const char *enforce_path, uint64_t fmin, uint32_t maxdepth, uint8_t **out,
+                                       uint64_t *out_bytes);
+DSMFM_API void dsmfm_stream_free(uint8_t *p);
 DSMFM_API const char *dsmfm_searcher_last_error(const dsmfm_searcher *s);
 DSMFM_API void dsmfm_searcher_destroy(dsmfm_searcher *s);
 

@@ -143,3 +143,50 @@ def test_large_index_lf_on_device_matches_counting():
                 sel = qc == c
                 want = occ[qi[sel]] + np.uint64(int((bwt < c).sum()))
                 assert np.array_equal(got[sel], want)
+
+
+# ---- the mining client's byte stream -------------------------------------------------------
+
+def _stream_cases():
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streams.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("key", sorted(_stream_cases()))
+def test_enumerate_stream_equals_the_reference_clients(key):
+    """tests/golden/streams.json holds what the UNMODIFIED reference client (metaenumerate: EnumerateQuery::enumerate
+    over ClientSocket) sent a recording server for a golden index, an enforced path, fmin and maxdepth
+    (tests/golden/make_stream_golden.py).  dsmfm_searcher_enumerate walks the same trie level by level on the GPU
+    and must produce the same bytes behind the handshake 'S' name '.'."""
+    import hashlib
+    import dsmfm
+    case = _stream_cases()[key]
+    fmi = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case["index"] + ".fmi")
+    with dsmfm.Searcher(fmi) as s:
+        got = b"S" + case["index"].encode() + b"." + s.enumerate(case["path"].encode(), fmin=case["fmin"], maxdepth=case["maxdepth"])
+    assert len(got) == case["bytes"]
+    assert hashlib.sha256(got).hexdigest() == case["sha256"]
+    if "hex" in case:
+        assert got == bytes.fromhex(case["hex"])
+
+
+def test_enumerate_stream_to_a_socket_and_errors():
+    import socket
+    import threading
+    import dsmfm
+    case = _stream_cases()["reads100:G:f10:m0"]
+    fmi = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reads100.fmi")
+    a, b = socket.socketpair()
+    got = []
+    t = threading.Thread(target=lambda: [got.append(x) for x in iter(lambda: b.recv(1 << 16), b"")])
+    t.start()
+    with dsmfm.Searcher(fmi) as s:
+        n = s.enumerate_to_fd(b"G", a.fileno(), fmin=10)
+        a.close()
+        t.join()
+        assert n == case["bytes"] - len(b"Sreads100.") and len(b"".join(got)) == n
+        with pytest.raises(dsmfm.DsmfmError):
+            s.enumerate(b"A", fmin=1)  # unary-path following is not rebuilt
+        # an enforced path that stops occurring half way: the nodes that were reached open and close, nothing below
+        part = s.enumerate(b"A" * 64, fmin=2)
+        assert part == b"" or (part.startswith(b"(A") and part.count(b"(") == part.count(b")"))
