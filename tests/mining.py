@@ -21,9 +21,22 @@ def _free_ports(k):
     return ports
 
 
-def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900):
+def _gpu_streams(fmi_paths, hashes, fmin):
+    """What metaenumerate would send, made on the GPU: {(sample, hash): handshake + dsmfm_searcher_enumerate stream}."""
+    import dsmfm
+    out = {}
+    for n, path in fmi_paths.items():
+        with dsmfm.Searcher(path) as s:
+            for h in hashes:
+                out[(n, h)] = b"S" + n.encode() + b"." + s.enumerate(h.encode(), fmin=int(fmin))
+    return out
+
+
+def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900, client="reference"):
     """fmi_paths: {sample name: path of <name>.<...>.fmi}.  The file's basename up to the first '.' must be the
-    sample name (metaenumerate.cpp:79-88).  Returns {hash prefix: server stdout bytes}."""
+    sample name (metaenumerate.cpp:79-88).  Returns {hash prefix: server stdout bytes}.
+    client="gpu": the reference's metaenumerate processes are replaced by the GPU trie walk (dsmfm_searcher_enumerate);
+    one thread per connection sends its stream, the unmodified metaserver processes do the rest."""
     ref = oracle.REF_DIR
     os.makedirs(workdir, exist_ok=True)
     names = sorted(fmi_paths)
@@ -45,6 +58,24 @@ def mine(fmi_paths, workdir, emax="1.2", fmin="2", timeout=900):
             sp.stdin.close()
             servers.append((sp, out, err))
         time.sleep(1.0)  # servers listen before the clients connect (wrapper-simple does the same)
+        if client == "gpu":
+            import threading
+            streams = _gpu_streams(fmi_paths, hashes, fmin)
+            errors = []
+
+            def send(port, blob):
+                try:
+                    with socket.create_connection(("127.0.0.1", port)) as c:
+                        c.sendall(blob)
+                except Exception as e:  # noqa: BLE001
+                    errors.append(e)
+            threads = [threading.Thread(target=send, args=(p, streams[(n, h)])) for n in names for p, h in zip(ports, hashes)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join(timeout)
+            assert not errors, errors
+            names = []
         for n in names:
             log = open(os.path.join(workdir, "cli.%s.log" % n), "wb")
             cp = subprocess.Popen([os.path.join(ref, "metaenumerate"), "--fmin", fmin, fmi_paths[n]],

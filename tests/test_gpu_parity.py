@@ -610,3 +610,7 @@ def test_five_samples_and_identical_mining_output(tmp_path):
     assert sum(len(v) for v in want.values()) > 1000, "the mining run printed nothing"
     for h in want:
         assert hashlib.sha256(got[h]).hexdigest() == hashlib.sha256(want[h]).hexdigest(), "server %s output differs" % h
+    # and with the mining CLIENT on the GPU as well: dsmfm_searcher_enumerate streams to the unmodified servers
+    gpu = mining.mine(ours, str(tmp_path / "mine_gpu_client"), emax="2.4", client="gpu")
+    for h in want:
+        assert hashlib.sha256(gpu[h]).hexdigest() == hashlib.sha256(want[h]).hexdigest(), "server %s output differs (GPU client)" % h
