@@ -531,7 +531,7 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
     __shared__ uint64_t s_key[CAP];
     __shared__ uint32_t s_val[CAP];
     __shared__ uint32_t s_lut[LUT_WORDS];
-    __shared__ uint32_t scratch[kSweepSelThreads / 32 + 1];
+    __shared__ uint32_t s_w[kSelSub][kSweepSelThreads / 32];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -562,8 +562,31 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
         }
         mine += __popc(sel[j]);
     }
-    uint32_t total;
-    block_excl_sum(mine, scratch, &total);
+    // tile-local position of this thread's first selected suffix in every sub-tile (text order: sub-tile, then thread):
+    // one scan for all sub-tiles, two barriers for the whole tile
+    uint32_t off[kSelSub];
+#pragma unroll
+    for (int j = 0; j < kSelSub; ++j) {
+        const uint32_t c = __popc(sel[j]);
+        const uint32_t incl = warp_incl_sum(c);
+        if (lane == 31) s_w[j][tid >> 5] = incl;
+        off[j] = incl - c;
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < kSelSub; ++j) {
+        uint32_t before = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSweepSelThreads / 32; ++w) {
+            const uint32_t x = s_w[j][w];
+            before += w < (tid >> 5) ? x : 0u;
+            tot += x;
+        }
+        off[j] += before + total;
+        total += tot;
+    }
+    (void)mine;
     if (tid == 0) status[tile] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
 
     // look-back by the first warp: 32 predecessors per step
@@ -591,52 +614,53 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
         if (lane == 0) s_base = excl;
     }
     __syncthreads();
-    uint64_t base = s_base;
+    const uint64_t base = s_base;
 
-    // Keys of the selected suffixes, staged in text order, sub-tile by sub-tile.  The word and its successor hold
-    // every symbol a first key can need (first_syms <= SPW), so keys are cut out of two registers; the symbol
-    // before the suffix (the BWT symbol, which rides above the key bits) is the previous symbol of the same stream.
+    // Keys of the selected suffixes, staged in text order, CAP pairs per round (one round when an eighth of the
+    // suffixes is selected, as on eight GPUs).  The word and its successor hold every symbol a first key can need
+    // (first_syms <= SPW), so keys are cut out of two registers; the symbol before the suffix (the BWT symbol,
+    // which rides above the key bits) is the previous symbol of the same stream.
     const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
-#pragma unroll 1
-    for (int j = 0; j < kSelSub; ++j) {
-        uint32_t sj = 0; // (sel[] is indexed by a loop that is not unrolled: pick the register by comparison)
+    for (uint32_t lo = 0; lo < total; lo += CAP) {
+        const uint32_t hi = lo + CAP;
 #pragma unroll
-        for (int q = 0; q < kSelSub; ++q)
-            if (q == j) sj = sel[q];
-        uint32_t sub_total;
-        uint32_t o = block_excl_sum((uint32_t)__popc(sj), scratch, &sub_total);
-        if (sub_total == 0) continue; // (uniform)
-        const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
-        const uint64_t p0 = w * P::SPW;
-        if (sj) {
+        for (int j = 0; j < kSelSub; ++j) {
+            uint32_t sj = sel[j];
+            const uint32_t c = __popc(sj);
+            if (c == 0 || off[j] >= hi || off[j] + c <= lo) continue;
+            const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
+            const uint64_t p0 = w * P::SPW;
             uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
-            uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u; // last symbol of the previous word
+            const uint32_t before = w ? (uint32_t)(__ldg(packed + w - 1) & P::FIELD) : 0u; // last symbol of the previous word
             if (P::USED == 63) {
                 x0 = (x0 << 1) | (x1 >> 62);
                 x1 <<= 2;
             }
+            uint32_t pos = off[j];
             while (sj) {
                 const int i = __ffs(sj) - 1;
                 sj &= sj - 1;
-                const int b = BITS * i;
-                const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0;     // stream from symbol i on
-                uint64_t k = (v >> (64 - key_bits)) | ~kmask;                  // ones above: only real fields can be zero
-                k = cut_at_terminator<BITS>(k) & kmask;
-                const uint32_t prev = i ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
-                k |= (uint64_t)prev << key_bits;                               // the BWT symbol rides along
-                const uint64_t p = p0 + i;
-                if (hi_shift) k |= (p >> lo_bits) << hi_shift;
-                s_key[o] = k;
-                s_val[o] = (uint32_t)(p & lo_mask);
-                ++o;
+                if (pos >= lo && pos < hi) {
+                    const int b = BITS * i;
+                    const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0;     // stream from symbol i on
+                    uint64_t k = (v >> (64 - key_bits)) | ~kmask;                  // ones above: only real fields can be zero
+                    k = cut_at_terminator<BITS>(k) & kmask;
+                    const uint32_t prev = i ? (uint32_t)((x0 >> (64 - b)) & P::FIELD) : before;
+                    k |= (uint64_t)prev << key_bits;                               // the BWT symbol rides along
+                    const uint64_t p = p0 + i;
+                    if (hi_shift) k |= (p >> lo_bits) << hi_shift;
+                    s_key[pos - lo] = k;
+                    s_val[pos - lo] = (uint32_t)(p & lo_mask);
+                }
+                ++pos;
             }
         }
         __syncthreads();
-        for (uint32_t i = tid; i < sub_total; i += kSweepSelThreads) {
-            keys[base + i] = s_key[i];
-            vals[base + i] = s_val[i];
+        const uint32_t cnt = total - lo < (uint32_t)CAP ? total - lo : (uint32_t)CAP;
+        for (uint32_t i = tid; i < cnt; i += kSweepSelThreads) {
+            keys[base + lo + i] = s_key[i];
+            vals[base + lo + i] = s_val[i];
         }
-        base += sub_total;
         __syncthreads();
     }
 }

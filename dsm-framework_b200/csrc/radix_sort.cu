@@ -99,7 +99,7 @@ template <int WARPS> struct SweepSmemT {
 // 512 threads x 8 pairs (fewer registers per thread: 3 CTAs = 48 warps per SM); the kernel is bound by
 // latency (shared-memory round trips of the ranking, DRAM loads), not by issue slots or bandwidth,
 // so the warps in flight are what counts.  Threads 0..255 own one digit each in the scan / look-back phases.
-template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS>
+template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS, bool HINTS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 3)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
@@ -126,7 +126,9 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t idx = first + 32 * k;
-        key[k] = idx < n ? keys_in[idx] : ~0ull; // padding sorts to the very end of the tile
+        // (HINTS: every pair is read once and written once per pass -- evict-first loads, streaming stores)
+        key[k] = idx < n ? (HINTS ? __ldcs(reinterpret_cast<const unsigned long long *>(keys_in) + idx) : keys_in[idx])
+                         : ~0ull; // padding sorts to the very end of the tile
     }
 
     uint16_t lpos[ITEMS];
@@ -196,7 +198,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         if (IOTA)
             val[k] = (uint32_t)(iota_base + idx);
         else
-            val[k] = idx < n ? vals_in[idx] : 0u;
+            val[k] = idx < n ? (HINTS ? __ldcs(vals_in + idx) : vals_in[idx]) : 0u;
     }
 
     // decoupled look-back, one chain per digit, four predecessors in flight at a time
@@ -240,8 +242,13 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         const uint64_t kk = s.keys[i];
         const uint32_t d = (uint32_t)(kk >> shift) & mask;
         const uint64_t o = s.goff[d] + i;
-        keys_out[o] = kk;
-        vals_out[o] = s.vals[i];
+        if (HINTS) {
+            __stcs(reinterpret_cast<unsigned long long *>(keys_out) + o, (unsigned long long)kk);
+            __stcs(vals_out + o, s.vals[i]);
+        } else {
+            keys_out[o] = kk;
+            vals_out[o] = s.vals[i];
+        }
     }
 }
 
@@ -287,18 +294,24 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         const char *e = getenv("DSMFM_SWEEP_MATCH");
         return e && atoi(e) != 0;
     }();
+    static const bool hints = [] { // evict-first loads and streaming stores (DSMFM_SWEEP_HINTS=0|1)
+        const char *e = getenv("DSMFM_SWEEP_HINTS");
+        return e ? atoi(e) != 0 : kSweepHintsDefault;
+    }();
     static const bool wide_cta = [] { // 512 threads x 8 pairs instead of 256 x 16 (DSMFM_SWEEP_THREADS=256|512)
         const char *e = getenv("DSMFM_SWEEP_THREADS");
         return e ? atoi(e) == 512 : kSweepWideDefault;
     }();
     attr_once.run([] {
-#define ATTR(I, M, T, N)                                                                                          \
-    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+#define ATTR1(I, M, T, N, H)                                                                                      \
+    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)sizeof(SweepSmemT<T / 32>)));                                              \
-    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+    DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N, H>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
+#define ATTR(I, M, T, N) ATTR1(I, M, T, N, false); ATTR1(I, M, T, N, true)
         ATTR(true, false, 256, 16); ATTR(false, false, 256, 16); ATTR(true, true, 256, 16); ATTR(false, true, 256, 16);
         ATTR(true, false, 512, 8);  ATTR(false, false, 512, 8);  ATTR(true, true, 512, 8);  ATTR(false, true, 512, 8);
 #undef ATTR
+#undef ATTR1
     });
 
     if (!hist_ready) {
@@ -328,10 +341,14 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
             uint64_t *base_out = ws.carry + (size_t)flip * kRadix;
             DSM_CUDA(cudaMemsetAsync(ws.status, 0, sizeof(uint32_t) * (size_t)tiles * kRadix, stream));
             DSM_CUDA(cudaMemsetAsync(ws.counter, 0, sizeof(uint32_t), stream));
-#define SWEEP2(I, M, T, N)                                                                                       \
-    onesweep_kernel<I, M, T, N><<<tiles, T, sizeof(SweepSmemT<T / 32>), stream>>>(                               \
+#define SWEEP3(I, M, T, N, H)                                                                                    \
+    onesweep_kernel<I, M, T, N, H><<<tiles, T, sizeof(SweepSmemT<T / 32>), stream>>>(                            \
         src_k + start, (I) ? nullptr : src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, \
         base_out, ws.status, ws.counter, tiles - 1)
+#define SWEEP2(I, M, T, N)                                                                                       \
+    do {                                                                                                         \
+        if (hints) SWEEP3(I, M, T, N, true); else SWEEP3(I, M, T, N, false);                                     \
+    } while (0)
 #define SWEEP(I, M)                                                                                              \
     do {                                                                                                         \
         if (wide_cta) SWEEP2(I, M, 512, 8); else SWEEP2(I, M, 256, 16);                                          \
@@ -342,6 +359,7 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
                 if (hw_match) SWEEP(false, true); else SWEEP(false, false);
             }
 #undef SWEEP2
+#undef SWEEP3
 #undef SWEEP
             DSM_LAUNCH_CHECK();
             if (launches) *launches += 1;

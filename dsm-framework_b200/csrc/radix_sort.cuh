@@ -21,6 +21,7 @@ constexpr int kMaxPasses = 8;
 // Tile of the one-sweep kernel: 4096 pairs, as 256 threads x 16 pairs or 512 threads x 8 pairs.
 constexpr int kSweepTile = 4096;
 constexpr bool kSweepWideDefault = false;
+constexpr bool kSweepHintsDefault = false;
 // A launch handles at most this many pairs so that tile prefixes fit the
 // 30-bit payload of a status word; longer inputs run as several portions.
 constexpr uint64_t kSweepPortion = (uint64_t)kSweepTile * 131072; // 2^29
