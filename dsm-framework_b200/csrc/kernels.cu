@@ -541,17 +541,17 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
     const uint32_t tile = s_tile;
     const uint64_t lo_mask = lo_bits >= 32 ? 0xffffffffull : ((1ull << lo_bits) - 1);
     const uint64_t w0 = (uint64_t)tile * (kSweepSelWords * kSelSub) + tid;
-    // the selection masks of this thread's word in every sub-tile
+    // the selection masks of this thread's word in every sub-tile.  (Block and position inside the block by ONE
+    // 64-bit division per thread; the other sub-tiles follow by adding the stride.)
     uint32_t sel[kSelSub];
     uint32_t mine = 0;
+    uint64_t slot = w0 / geom.slot_words, rem = w0 - slot * geom.slot_words; // word rem of block `slot`
 #pragma unroll
     for (int j = 0; j < kSelSub; ++j) {
         const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
         sel[j] = 0;
         if (w < nwords) {
-            // the word's block (slot) and how many of its positions are suffixes of that block
-            const uint64_t slot = w / geom.slot_words;
-            const uint64_t first = (w - slot * geom.slot_words) * P::SPW; // position of the word inside its block
+            const uint64_t first = rem * P::SPW; // position of the word inside its block
             const uint64_t have = slot < geom.world ? geom.bytes[slot] : 0ull;
             const int valid = have > first ? (have - first >= (uint64_t)P::SPW ? P::SPW : (int)(have - first)) : 0;
             if (valid) {
@@ -561,6 +561,11 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
             }
         }
         mine += __popc(sel[j]);
+        rem += kSweepSelWords;
+        while (rem >= geom.slot_words) {
+            rem -= geom.slot_words;
+            ++slot;
+        }
     }
     // tile-local position of this thread's first selected suffix in every sub-tile (text order: sub-tile, then thread):
     // one scan for all sub-tiles, two barriers for the whole tile
@@ -623,11 +628,17 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
     const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
     for (uint32_t lo = 0; lo < total; lo += CAP) {
         const uint32_t hi = lo + CAP;
+#pragma unroll 1
+        for (int j = 0; j < kSelSub; ++j) { // (not unrolled: eight copies of the key extraction do not fit the instruction cache)
+            uint32_t sj = 0, oj = 0;
 #pragma unroll
-        for (int j = 0; j < kSelSub; ++j) {
-            uint32_t sj = sel[j];
+            for (int q = 0; q < kSelSub; ++q)
+                if (q == j) {
+                    sj = sel[q];
+                    oj = off[q];
+                }
             const uint32_t c = __popc(sj);
-            if (c == 0 || off[j] >= hi || off[j] + c <= lo) continue;
+            if (c == 0 || oj >= hi || oj + c <= lo) continue;
             const uint64_t w = w0 + (uint64_t)j * kSweepSelWords;
             const uint64_t p0 = w * P::SPW;
             uint64_t x0 = __ldg(packed + w), x1 = w + 1 < nwords ? __ldg(packed + w + 1) : 0ull;
@@ -636,7 +647,7 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
                 x0 = (x0 << 1) | (x1 >> 62);
                 x1 <<= 2;
             }
-            uint32_t pos = off[j];
+            uint32_t pos = oj;
             while (sj) {
                 const int i = __ffs(sj) - 1;
                 sj &= sj - 1;

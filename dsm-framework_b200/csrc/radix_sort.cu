@@ -87,7 +87,32 @@ template <int WARPS> struct SweepSmemT {
     uint32_t excl[kRadix];                     // tile-local start of each digit run
     uint32_t warp_sum[kRadix / 32];
     uint32_t tile;
+    alignas(8) uint64_t mbar[2];               // TMA ingest: completion barriers of the tile's bulk copies (keys, values)
 };
+
+// ---- TMA (bulk async copy) helpers: cp.async.bulk + mbarrier, sm_90+ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(phase)
+                     : "memory");
+}
 
 // One LSD pass over one portion (<= kSweepPortion pairs) of the input.
 //
@@ -99,7 +124,10 @@ template <int WARPS> struct SweepSmemT {
 // 512 threads x 8 pairs (fewer registers per thread: 3 CTAs = 48 warps per SM); the kernel is bound by
 // latency (shared-memory round trips of the ranking, DRAM loads), not by issue slots or bandwidth,
 // so the warps in flight are what counts.  Threads 0..255 own one digit each in the scan / look-back phases.
-template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS, bool HINTS>
+// TMA: a whole tile's keys arrive by ONE bulk asynchronous copy (cp.async.bulk, the 1-D form of TMA) into the very
+// staging buffer the sorted keys overwrite later, signalled through an mbarrier; the threads then take their keys
+// from shared memory (16 conflict-free LDS.64 instead of 16 predicated LDG.64 with their address arithmetic).
+template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS, bool HINTS, bool TMA = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 3)
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
@@ -112,7 +140,18 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     SweepSmemT<WARPS> &s = *reinterpret_cast<SweepSmemT<WARPS> *>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) s.tile = atomicAdd(counter, 1u);
+    if (tid == 0) {
+        s.tile = atomicAdd(counter, 1u);
+        if (TMA) {
+            mbar_init(&s.mbar[0], 1);
+            mbar_init(&s.mbar[1], 1);
+            const uint32_t t0 = s.tile * (uint32_t)kSweepTile;
+            if (n - t0 >= (uint32_t)kSweepTile) { // whole tiles only
+                bulk_load(s.keys, keys_in + t0, kSweepTile * 8, &s.mbar[0]);
+                if (!IOTA) bulk_load(s.vals, vals_in + t0, kSweepTile * 4, &s.mbar[1]); // needed much later: fully hidden
+            }
+        }
+    }
     for (int i = tid; i < WARPS * kRadix / 2; i += THREADS) reinterpret_cast<uint32_t *>(&s.cnt[0][0])[i] = 0;
     __syncthreads();
     const uint32_t tile = s.tile;
@@ -123,6 +162,11 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     // warp-striped load: item k of lane l is element first + 32k, so the order
     // (warp, k, lane) is the input order and the ranking below is stable
     uint64_t key[ITEMS];
+    if (TMA && valid == (uint32_t)kSweepTile) {
+        mbar_wait(&s.mbar[0], 0);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) key[k] = s.keys[warp * (32 * ITEMS) + 32 * k + lane];
+    } else
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t idx = first + 32 * k;
@@ -192,6 +236,12 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 
     // values are fetched now so that their latency overlaps the look-back
     uint32_t val[ITEMS];
+    const bool vals_in_smem = TMA && !IOTA && valid == (uint32_t)kSweepTile; // the values came with the bulk copy
+    if (vals_in_smem) {
+        mbar_wait(&s.mbar[1], 0);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) val[k] = s.vals[warp * (32 * ITEMS) + 32 * k + lane];
+    } else
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t idx = first + 32 * k;
@@ -233,6 +283,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         if (tile == last_tile) base_out[tid] = gbase + pub;
     }
 
+    if (vals_in_smem) __syncthreads(); // everybody has taken its values out of the buffer they are now permuted into
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) s.vals[lpos[k]] = val[k];
     __syncthreads();
@@ -298,6 +349,10 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
         const char *e = getenv("DSMFM_SWEEP_HINTS");
         return e ? atoi(e) != 0 : kSweepHintsDefault;
     }();
+    static const bool tma = [] { // the tile's keys by one bulk asynchronous copy (DSMFM_SWEEP_TMA=0|1)
+        const char *e = getenv("DSMFM_SWEEP_TMA");
+        return e ? atoi(e) != 0 : kSweepTmaDefault;
+    }();
     static const bool wide_cta = [] { // 512 threads x 8 pairs instead of 256 x 16 (DSMFM_SWEEP_THREADS=256|512)
         const char *e = getenv("DSMFM_SWEEP_THREADS");
         return e ? atoi(e) == 512 : kSweepWideDefault;
@@ -308,6 +363,12 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
                                   (int)sizeof(SweepSmemT<T / 32>)));                                              \
     DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N, H>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
 #define ATTR(I, M, T, N) ATTR1(I, M, T, N, false); ATTR1(I, M, T, N, true)
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, 256, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmemT<8>)));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, 256, 16, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, 256, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmemT<8>)));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, 256, 16, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         ATTR(true, false, 256, 16); ATTR(false, false, 256, 16); ATTR(true, true, 256, 16); ATTR(false, true, 256, 16);
         ATTR(true, false, 512, 8);  ATTR(false, false, 512, 8);  ATTR(true, true, 512, 8);  ATTR(false, true, 512, 8);
 #undef ATTR
@@ -353,7 +414,19 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
     do {                                                                                                         \
         if (wide_cta) SWEEP2(I, M, 512, 8); else SWEEP2(I, M, 256, 16);                                          \
     } while (0)
-            if (iota) {
+            // bulk copies need 16-byte aligned sources: portions start at multiples of 2^29 pairs
+            const bool use_tma = tma && !hw_match && !wide_cta && !hints && (reinterpret_cast<uintptr_t>(src_k + start) & 15) == 0 &&
+                                 (iota || (reinterpret_cast<uintptr_t>(src_v + start) & 15) == 0);
+            if (use_tma) {
+                if (iota)
+                    onesweep_kernel<true, false, 256, 16, false, true><<<tiles, 256, sizeof(SweepSmemT<8>), stream>>>(
+                        src_k + start, nullptr, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out, ws.status,
+                        ws.counter, tiles - 1);
+                else
+                    onesweep_kernel<false, false, 256, 16, false, true><<<tiles, 256, sizeof(SweepSmemT<8>), stream>>>(
+                        src_k + start, src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out, ws.status,
+                        ws.counter, tiles - 1);
+            } else if (iota) {
                 if (hw_match) SWEEP(true, true); else SWEEP(true, false);
             } else {
                 if (hw_match) SWEEP(false, true); else SWEEP(false, false);
