@@ -10,6 +10,7 @@
 #include "radix_sort.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <fcntl.h>
 #include <unistd.h>
@@ -41,6 +42,7 @@ double now_ms()
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 thread_local double g_alloc_ms = 0.0;
+std::atomic<unsigned long long> g_guard_violations{0};
 
 // DSMFM_TRACE=1: wall-clock milestones of a process on stderr (cold-start costs -- context creation, first
 // device allocations, pinned buffers -- are invisible to the CUDA-event timers in dsmfm_stats)
@@ -619,13 +621,52 @@ struct dsmfm_builder {
 
     // every device allocation of the builder is tracked so that a failed build leaks nothing
     std::vector<std::pair<void *, size_t>> allocs;
+    // DSMFM_GUARD=1 (tests; compute-sanitizer is closed on the pool this was developed on): every device buffer of
+    // the builder gets 4 KB of pattern in front and behind, checked when it is released -- a kernel that writes
+    // outside its buffer is reported (dsmfm_dbg_guard_violations) instead of silently corrupting a neighbour.
+    static constexpr size_t kGuard = 4096;
+    static bool guard_on()
+    {
+        static const bool on = std::getenv("DSMFM_GUARD") != nullptr;
+        return on;
+    }
     void *dmalloc(size_t bytes)
     {
-        void *p = dev_alloc(bytes, stream);
+        const bool g = guard_on();
+        uint8_t *raw = static_cast<uint8_t *>(dev_alloc(bytes + (g ? 2 * kGuard : 0), stream));
+        if (g) {
+            DSM_CUDA(cudaMemsetAsync(raw, 0xA5, kGuard, stream));
+            DSM_CUDA(cudaMemsetAsync(raw + kGuard + bytes, 0xA5, kGuard, stream));
+        }
+        void *p = raw + (g ? kGuard : 0);
         allocs.emplace_back(p, bytes);
         dev_now += bytes;
         dev_peak = std::max(dev_peak, dev_now);
         return p;
+    }
+    void check_guard(void *p, size_t bytes)
+    {
+        uint8_t h[2 * kGuard];
+        uint8_t *raw = static_cast<uint8_t *>(p) - kGuard;
+        if (cudaStreamSynchronize(stream) != cudaSuccess || cudaMemcpy(h, raw, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(h + kGuard, raw + kGuard + bytes, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return; // (a failed stream: the error is reported where it happened)
+        for (size_t i = 0; i < 2 * kGuard; ++i)
+            if (h[i] != 0xA5) {
+                std::fprintf(stderr, "[dsmfm guard] write outside a %zu-byte device buffer: %s it, offset %zu\n", bytes,
+                             i < kGuard ? "in front of" : "behind", i < kGuard ? kGuard - i : i - kGuard);
+                ++g_guard_violations;
+                break;
+            }
+    }
+    void free_one(void *p, size_t bytes)
+    {
+        if (guard_on()) {
+            check_guard(p, bytes);
+            dev_free(static_cast<uint8_t *>(p) - kGuard, stream);
+        } else {
+            dev_free(p, stream);
+        }
     }
     void dfree(void *p)
     {
@@ -633,8 +674,9 @@ struct dsmfm_builder {
         for (size_t i = 0; i < allocs.size(); ++i) {
             if (allocs[i].first != p) continue;
             dev_now -= std::min(dev_now, allocs[i].second);
+            const size_t bytes = allocs[i].second;
             allocs.erase(allocs.begin() + i);
-            dev_free(p, stream);
+            free_one(p, bytes);
             return;
         }
     }
@@ -677,7 +719,7 @@ struct dsmfm_builder {
             g_pinned.put(host_ready);
             host_ready = nullptr;
         }
-        for (auto &a : allocs) dev_free(a.first, stream);
+        for (auto &a : allocs) free_one(a.first, a.second);
         allocs.clear();
         chunks.clear();
         g_pinned.put(ph.h_blob);
@@ -2941,6 +2983,8 @@ DSMFM_API const char *dsmfm_last_error(const dsmfm_builder *b)
 {
     return b ? b->err.c_str() : g_create_error.c_str();
 }
+
+DSMFM_API uint64_t dsmfm_dbg_guard_violations(void) { return g_guard_violations.load(); }
 
 DSMFM_API int dsmfm_release_cached(int device)
 {

@@ -22,6 +22,7 @@ constexpr int kMaxPasses = 8;
 constexpr int kSweepTile = 4096;
 constexpr bool kSweepWideDefault = false;
 constexpr bool kSweepHintsDefault = false;
+constexpr bool kSweepTmaVals = false;
 constexpr bool kSweepTmaDefault = true; // measured: 3.08 -> 2.98 ms per launch with the keys, see DESIGN.md section 5
 // A launch handles at most this many pairs so that tile prefixes fit the
 // 30-bit payload of a status word; longer inputs run as several portions.

@@ -181,6 +181,7 @@ def lib():
     L.dsmfm_searcher_last_error.restype = C.c_char_p
     L.dsmfm_searcher_destroy.argtypes = [S]
     L.dsmfm_searcher_destroy.restype = None
+    L.dsmfm_dbg_guard_violations.restype = C.c_uint64
     L.dsmfm_dbg_radix_sort.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
     L.dsmfm_dbg_wavelet.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.POINTER(Index), C.POINTER(C.c_void_p)]
     L.dsmfm_dbg_free_index.argtypes = [C.c_void_p]

@@ -448,6 +448,10 @@ DSMFM_API void dsmfm_free_pinned(void *p);
 
 /* ---- kernel-level entry points used by the unit tests (host buffers in/out) ---- */
 
+/* With DSMFM_GUARD=1 in the environment every device buffer of a builder carries 4 KB of pattern in front and
+ * behind, checked when it is released: the number of buffers found overwritten so far (0 = clean). */
+DSMFM_API uint64_t dsmfm_dbg_guard_violations(void);
+
 /* Stable LSD radix sort of (key, value) pairs on bits [begin_bit, end_bit) with
  * the same onesweep kernels the build uses.  Sorts in place. */
 DSMFM_API int dsmfm_dbg_radix_sort(int device, uint64_t *keys, uint32_t *vals, uint64_t n, int begin_bit, int end_bit);
