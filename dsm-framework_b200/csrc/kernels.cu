@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 // per suffix; they are staged in shared memory and leave the SM as one contiguous burst.  While the keys
 // are in registers the kernel also counts their radix digits, which saves the sort's own histogram pass
 // over the key array (8 bytes per suffix read back from HBM).
+constexpr int kHeadsU = 8;           // head words per warp iteration of heads_kernel (8: 5.9 -> 5.3 ms on C3)
 constexpr int kKeyTileThreads = 128; // one packed word per thread and tile
 constexpr int kMaxKeyPasses = 8;     // 64 key bits / 8-bit digits
 constexpr int kKeySub = 1;           // copies of every digit counter in make_keys_hist_kernel (4 copies: no gain measured)
@@ -685,7 +686,7 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
 // whether its BWT symbol differs.  "Next rank opens a group" is the head bit of the next rank, so the count of
 // suffixes left in groups of >= 2 falls out of the head words themselves.  Chunks that lie entirely inside
 // the array take a path without bounds checks and with 32-bit offsets from the chunk's base pointers.
-template <int BITS>
+template <int BITS, int U>
 __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
                                                     unsigned long long *__restrict__ remaining, int key_bits,
@@ -693,7 +694,6 @@ __global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__
                                                     uint8_t *__restrict__ pos_hi, int hi_shift,
                                                     uint32_t *__restrict__ diff)
 {
-    constexpr int U = 4;
     constexpr uint64_t FIELD = Pack<BITS>::FIELD;
     __shared__ unsigned long long s_cnt[8];
     __shared__ uint8_t s_inv[256];
@@ -2647,9 +2647,17 @@ void launch_heads(cudaStream_t st, int bits, const uint64_t *sorted_keys, uint64
                   uint64_t head_words, unsigned long long *remaining, int key_bits, const uint8_t *inv_map,
                   uint8_t *bwt, uint8_t *pos_hi, int hi_shift, uint32_t *diff, uint32_t *launches)
 {
-#define CALL(B)                                                                                                 \
-    heads_kernel<B><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
-                                                                  key_bits, inv_map, bwt, pos_hi, hi_shift, diff)
+    // ranks per warp iteration: 128 or 256 (DSMFM_HEADS_U=4|8: eight key loads in flight per lane instead of four)
+    static const int u_env = std::getenv("DSMFM_HEADS_U") ? std::atoi(std::getenv("DSMFM_HEADS_U")) : kHeadsU;
+#define CALL(B)                                                                                                      \
+    do {                                                                                                             \
+        if (u_env == 8)                                                                                              \
+            heads_kernel<B, 8><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
+                                                                             key_bits, inv_map, bwt, pos_hi, hi_shift, diff); \
+        else                                                                                                         \
+            heads_kernel<B, 4><<<grid_for(head_words, 8 * 16), 256, 0, st>>>(sorted_keys, n, head, head_words, remaining, \
+                                                                             key_bits, inv_map, bwt, pos_hi, hi_shift, diff); \
+    } while (0)
     DISPATCH_BITS(bits, CALL);
 #undef CALL
     DSM_LAUNCH_CHECK();

@@ -192,16 +192,13 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
     }
     __syncthreads();
 
-    // thread d owns digit d: turn per-warp counts into per-warp bases, get the tile total
+    // thread d owns digit d: the tile's count of its digit, then -- once the scan over the digits has placed the
+    // digit's run inside the tile -- the position where every warp's members of the digit start
     uint32_t total = 0, pub = 0, excl = 0;
     volatile uint32_t *mine = status + (size_t)tile * kRadix + (tid & (kRadix - 1));
     if (tid < kRadix) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t t = s.cnt[w][tid];
-            s.cnt[w][tid] = (uint16_t)total;
-            total += t;
-        }
+        for (int w = 0; w < WARPS; ++w) total += s.cnt[w][tid];
         // publish the tile's count of digit d as early as possible: later tiles are waiting for it
         pub = total;
         if ((uint32_t)tid == mask) pub -= (uint32_t)kSweepTile - valid; // do not publish the padding
@@ -222,6 +219,13 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
         for (int w = 0; w < warp; ++w) wbase += s.warp_sum[w];
         excl += wbase;
         s.excl[tid] = excl;
+        uint32_t run = excl; // per-warp counts -> absolute tile positions (one shared-memory read less per key below)
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t t = s.cnt[w][tid];
+            s.cnt[w][tid] = (uint16_t)run;
+            run += t;
+        }
     }
     __syncthreads();
 
@@ -229,7 +233,7 @@ onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-        const uint32_t p = lpos[k] + s.excl[d] + s.cnt[warp][d];
+        const uint32_t p = lpos[k] + s.cnt[warp][d];
         s.keys[p] = key[k];
         lpos[k] = (uint16_t)p;
     }
