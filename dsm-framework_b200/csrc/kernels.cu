@@ -2249,6 +2249,28 @@ wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__res
     }
 }
 
+// the bits of x selected by m, moved together to the low end (parallel suffix method, Hacker's Delight 7-4): 5 rounds
+// of straight-line code whatever the mask
+__device__ __forceinline__ uint32_t compress_bits(uint32_t x, uint32_t m)
+{
+    x &= m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2;
+        mp ^= mp << 4;
+        mp ^= mp << 8;
+        mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        m = (m ^ mv) | (mv >> (1 << i));
+        const uint32_t t = x & mv;
+        x = (x ^ t) | (t >> (1 << i));
+        mk &= ~mp;
+    }
+    return x;
+}
+
 // ---- one pass over the sequence for small trees (reads: 6 internal nodes) -----------------------------------
 // wt_count + wt_scan + wt_fill read the sequence twice, build the member masks twice, and every thread ORs its
 // bits into the node arrays with global atomics (two per node and thread).  For trees of at most 8 internal nodes
@@ -2260,11 +2282,15 @@ wt_fill_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__res
 // with its neighbours, are OR-ed into global memory.
 constexpr int kWtRunWords = kWtTile / 64 + 2; // 64-bit words a tile's run of one node can touch
 
+// NI: the number of internal nodes at compile time (reads: 6), 0 = run time.  With a run-time count the per-node loops
+// are unrolled to 8 and predicated: a quarter of the issued instructions does nothing for a six-node tree.
+template <int NI>
 __global__ void __launch_bounds__(256)
-wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal,
+wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__restrict__ node_info, int n_internal_rt,
                 volatile unsigned long long *status, uint32_t *counter, uint64_t *const *__restrict__ node_data,
                 uint8_t *__restrict__ node_ch, const uint64_t *__restrict__ bit_base)
 {
+    const int n_internal = NI ? NI : n_internal_rt;
     __shared__ uint16_t s_lut16[256];
     __shared__ uint32_t s_part[kWtSmallNodes][8];
     __shared__ uint32_t s_total[kWtSmallNodes];
@@ -2329,19 +2355,26 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
     for (int v = 0; v < kWtSmallNodes; ++v) {
         if (v < n_internal) {
             const uint32_t c = __popc(m[v]);
+            // many members somewhere in the warp (the two nodes under the root of a read collection): compress
+            // without a loop, whose trip count would be the warp's maximum
+            const bool dense = __any_sync(0xffffffffu, c > 12u && m[v] != 0xffffffffu);
             if (c) {
                 uint32_t before = incl[v] - c;
                 for (int k = 0; k < warp; ++k) before += s_part[v][k];
                 uint32_t bits = b[v]; // all 32 symbols are members (always so at the root): nothing to compress
                 if (m[v] != 0xffffffffu) {
-                    bits = 0;
-                    uint32_t mm = m[v];
-                    int out = 0;
-                    while (mm) {
-                        const int j = __ffs(mm) - 1;
-                        bits |= ((b[v] >> j) & 1u) << out;
-                        ++out;
-                        mm &= mm - 1;
+                    if (dense) {
+                        bits = compress_bits(b[v], m[v]);
+                    } else {
+                        bits = 0;
+                        uint32_t mm = m[v];
+                        int out = 0;
+                        while (mm) {
+                            const int j = __ffs(mm) - 1;
+                            bits |= ((b[v] >> j) & 1u) << out;
+                            ++out;
+                            mm &= mm - 1;
+                        }
                     }
                 }
                 const uint64_t off = s_off[v];
@@ -2930,9 +2963,15 @@ void launch_wt_sweep(cudaStream_t st, const uint8_t *seq, uint64_t n, const uint
 {
     DSM_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * wt_sweep_status_words(ntiles), st));
     DSM_CUDA(cudaMemsetAsync(counter, 0, sizeof(uint32_t), st));
-    wt_sweep_kernel<<<(unsigned)ntiles, 256, 0, st>>>(seq, n, node_info, n_internal,
-                                                     reinterpret_cast<volatile unsigned long long *>(status), counter,
-                                                     node_data, node_ch, bit_base);
+#define WT_SWEEP(NI)                                                                                              \
+    wt_sweep_kernel<NI><<<(unsigned)ntiles, 256, 0, st>>>(seq, n, node_info, n_internal,                          \
+                                                         reinterpret_cast<volatile unsigned long long *>(status), \
+                                                         counter, node_data, node_ch, bit_base)
+    if (n_internal == 6) WT_SWEEP(6); // seven symbols: reads over ACGTN with the separator and the terminator
+    else if (n_internal == 5) WT_SWEEP(5);
+    else if (n_internal == 4) WT_SWEEP(4);
+    else WT_SWEEP(0);
+#undef WT_SWEEP
     DSM_LAUNCH_CHECK();
     if (launches) ++*launches;
 }

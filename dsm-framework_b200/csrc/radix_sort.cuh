@@ -19,7 +19,11 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr int kMaxPasses = 8;
 
 // Tile of the one-sweep kernel: 4096 pairs, as 256 threads x 16 pairs or 512 threads x 8 pairs.
-constexpr int kSweepTile = 4096;
+#ifndef DSMFM_SWEEP_TILE
+#define DSMFM_SWEEP_TILE 4096
+#endif
+constexpr int kSweepTile = DSMFM_SWEEP_TILE; // pairs per CTA (a multiple of 512)
+constexpr int kSweepCtasPerSm = kSweepTile <= 3072 ? 5 : 4;
 constexpr bool kSweepWideDefault = false;
 constexpr bool kSweepHintsDefault = false;
 constexpr bool kSweepTmaVals = false;

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsmfm.so")
+LIB_PATH = os.environ.get("DSMFM_LIB") or os.path.join(_HERE, "libdsmfm.so")  # (DSMFM_LIB: a variant build, for A/B measurements)
 
 OK, EINVAL, ECUDA, ENOMEM, EEMPTY, ELIMIT, EIO = 0, -1, -2, -3, -4, -5, -6
 FLAG_KEEP_BWT, FLAG_KEEP_SA, FLAG_DEFAULT_STREAM = 1, 2, 4
