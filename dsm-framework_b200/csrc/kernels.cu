@@ -1158,14 +1158,19 @@ template <int KW, bool WIDE> struct RwSmem {
 // from reads overlapping the same stretch of a genome, and they agree on the symbol in front of it too.  Only
 // groups with mixed symbols are loaded and refined, and a group that becomes uniform after a split is dropped
 // at once.  (ORDER = true, DSMFM_FLAG_KEEP_SA: the full order, as needed for the .sa samples.)
+#ifndef DSMFM_RW_CTAS
+#define DSMFM_RW_CTAS 4
+#endif
+constexpr int kRwCtas = DSMFM_RW_CTAS; // resident CTAs per SM the compiler budgets registers for
 template <int BITS, int KW, bool WIDE, bool ORDER>
-__global__ void __launch_bounds__(kRefThreads, 4)
+__global__ void __launch_bounds__(kRefThreads, kRwCtas)
 refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
                     uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
                     uint32_t *__restrict__ big_heads, uint32_t big_cap, uint32_t *__restrict__ big_count,
                     unsigned long long *__restrict__ remaining, uint32_t *__restrict__ win_flag,
                     uint32_t *__restrict__ win_next, uint32_t *__restrict__ win_next_count, uint8_t *__restrict__ bwt,
-                    uint8_t *__restrict__ sa_hi, int lo_bits, const uint32_t *__restrict__ diff_bits, int big_thr)
+                    uint8_t *__restrict__ sa_hi, int lo_bits, const uint32_t *__restrict__ diff_bits, int big_thr,
+                    bool chunked)
 {
     using P = Pack<BITS>;
     constexpr int HW = kRwCap / 32 + 2;
@@ -1385,7 +1390,81 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
         // carries the same key (or its key holds the terminator, which makes it unique)
         int nbig = 0; // large groups of this warp's range seen in this step (warp-uniform)
-        if (big_thr > kRwCap) { // every group by its own members (all pairs)
+        if (big_thr > kRwCap && chunked) {
+            // Whole groups, as many as fit the 32 lanes, one member per lane.  The list holds whole groups in slot
+            // order (it starts that way, and the classification below compacts it in order), so a group is a run of
+            // lanes between two head flags; match.any finds the lanes that carry
+            // a lane's key (its class), the count of earlier ones is its rank among equals, and the members with
+            // smaller keys are counted class by class -- a group rarely holds more than a few distinct keys.
+            for (int i0 = 0; i0 < cnt;) {
+                const int i = i0 + lane;
+                const bool valid = i < cnt;
+                const int r = valid ? list[i] : 0;
+                const uint32_t hb = __ballot_sync(0xffffffffu, valid && ((s_ha[r >> 5] >> (r & 31)) & 1u)) | 1u;
+                int take = cnt - i0 < 32 ? cnt - i0 : 32;
+                if (i0 + 32 < cnt) { // the group at the end of the window may go on behind it
+                    const int rn = list[i0 + 32];
+                    if (!((s_ha[rn >> 5] >> (rn & 31)) & 1u)) take = 31 - __clz(hb);
+                }
+                if (take == 0) {
+                    // a group of more than 32 members: every member against all others
+                    const int gs = list[i0];
+                    const int ge = next_set_gt(s_ha, gs);
+                    for (int ii = i0 + lane; ii < i0 + (ge - gs); ii += 32) {
+                        const int rr = list[ii];
+                        const uint64_t mh = s_khi[rr], ml = KW == 2 ? s_klo[rr] : mh;
+                        int lt = 0, eq = 0;
+                        for (int j = gs; j < ge; ++j) {
+                            const uint64_t oh = s_khi[j], ol = KW == 2 ? s_klo[j] : oh;
+                            lt += (oh < mh) | ((oh == mh) & (ol < ml));
+                            eq += (oh == mh) & (ol == ml) & (j < rr);
+                        }
+                        const int p = gs + lt + eq;
+                        if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                        s_sa[c ^ 1][p] = s_sa[c][rr];
+                        s_bw[c ^ 1][p] = s_bw[c][rr];
+                        if (WIDE) s_hi[c ^ 1][p] = s_hi[c][rr];
+                    }
+                    i0 += ge - gs;
+                    continue;
+                }
+                const bool in = lane < take;
+                const uint32_t takemask = take >= 32 ? 0xffffffffu : ((1u << take) - 1);
+                const uint32_t upto = 0xffffffffu >> (31 - lane);               // lanes <= this one
+                const int sl = 31 - __clz(hb & upto);                            // lane of my group's head
+                const uint32_t above = hb & ~upto & takemask;
+                const int el = above ? __ffs(above) - 1 : take;                  // one behind my group's last lane
+                const uint32_t gmask = (el >= 32 ? 0xffffffffu : ((1u << el) - 1)) & ~((1u << sl) - 1);
+                const uint64_t mh = valid ? s_khi[r] : 0ull, ml = KW == 2 ? (valid ? s_klo[r] : 0ull) : mh;
+                uint32_t E = __match_any_sync(0xffffffffu, mh);
+                if (KW == 2) E &= __match_any_sync(0xffffffffu, ml);
+                E &= gmask;
+                const int eq = __popc(E & lanemask_lt());
+                int lt = 0;
+                uint32_t rem = in ? (gmask & ~E) : 0u; // members of my group with other keys
+                while (__any_sync(0xffffffffu, rem != 0)) {
+                    const int l = rem ? __ffs(rem) - 1 : lane;
+                    const uint64_t kh = __shfl_sync(0xffffffffu, mh, l);
+                    const uint64_t kl = KW == 2 ? __shfl_sync(0xffffffffu, ml, l) : kh;
+                    const uint32_t El = __shfl_sync(0xffffffffu, E, l);
+                    if (rem) {
+                        if ((kh < mh) | ((kh == mh) & (kl < ml))) lt += __popc(El);
+                        rem &= ~El;
+                    }
+                }
+                const int gs = __shfl_sync(0xffffffffu, r, sl);
+                if (in) {
+                    const int p = gs + lt + eq;
+                    if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                    s_sa[c ^ 1][p] = s_sa[c][r];
+                    s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
+                    if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
+                    // (the list stays as it is: the group's members went to the group's slots, and the steps below
+                    // only need the set of slots -- in slot order, which the next step's lane runs rely on)
+                }
+                i0 += take;
+            }
+        } else if (big_thr > kRwCap) { // every group by its own members (all pairs)
             for (int i = lane; i < cnt; i += 32) {
                 const int r = list[i];
                 const int gs = prev_set_le(s_ha, r);
@@ -2730,6 +2809,9 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
         static const int big_env = std::getenv("DSMFM_REFINE_BIG") ? std::atoi(std::getenv("DSMFM_REFINE_BIG")) : -1;
         const int big_want = big_env >= 0 ? big_env : (big_groups ? kRwBigGroup : 0);
         const int big_thr = big_want >= 32 ? (big_want < kRwBigGroup ? kRwBigGroup : big_want) : kRwCap + 1;
+        // groups of up to 32 members are ranked a warp-load of whole groups at a time (match.any; DSMFM_REFINE_RANK=0:
+        // every member loops over its group)
+        static const bool chunked = !(std::getenv("DSMFM_REFINE_RANK") && std::atoi(std::getenv("DSMFM_REFINE_RANK")) == 0);
         static DeviceOnce attr3_once;
         attr3_once.run([] {
 #define SET3(B, K)                                                                                                      \
@@ -2747,7 +2829,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
 #define RW2(B, K, W, O)                                                                                           \
     refine_warps_kernel<B, K, W, O><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                             \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \
-        win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits, big_thr)
+        win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits, big_thr, chunked)
 #define RW(B, K, W)                                                                                               \
     do {                                                                                                          \
         if (full_order || !bwt) RW2(B, K, W, true); else RW2(B, K, W, false);                                     \

@@ -128,7 +128,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 // staging buffer the sorted keys overwrite later, signalled through an mbarrier; the threads then take their keys
 // from shared memory (16 conflict-free LDS.64 instead of 16 predicated LDG.64 with their address arithmetic).
 template <bool IOTA, bool HW_MATCH, int THREADS, int ITEMS, bool HINTS, bool TMA = false>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? kSweepCtasPerSm : 3)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? kSweepCtasPerSm : (kSweepTile > 4096 ? 2 : 3))
 onesweep_kernel(const uint64_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, uint64_t iota_base,
                 int shift, uint32_t mask, const uint64_t *__restrict__ base_in, uint64_t *__restrict__ base_out,
@@ -369,13 +369,14 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
                                   (int)sizeof(SweepSmemT<T / 32>)));                                              \
     DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<I, M, T, N, H>, cudaFuncAttributePreferredSharedMemoryCarveout, 100))
 #define ATTR(I, M, T, N) ATTR1(I, M, T, N, false); ATTR1(I, M, T, N, true)
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, 256, kSweepTile / 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SweepSmemT<8>)));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, 256, kSweepTile / 256, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, 256, kSweepTile / 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)sizeof(SweepSmemT<8>)));
-        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, 256, kSweepTile / 256, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        ATTR(true, false, 256, kSweepTile / 256); ATTR(false, false, 256, kSweepTile / 256); ATTR(true, true, 256, kSweepTile / 256); ATTR(false, true, 256, kSweepTile / 256);
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmemT<kSweepTmaThreads / 32>)));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<false, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(SweepSmemT<kSweepTmaThreads / 32>)));
+        DSM_CUDA(cudaFuncSetAttribute(onesweep_kernel<true, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        ATTR(true, false, kSweepNarrow, kSweepTile / kSweepNarrow); ATTR(false, false, kSweepNarrow, kSweepTile / kSweepNarrow);
+        ATTR(true, true, kSweepNarrow, kSweepTile / kSweepNarrow); ATTR(false, true, kSweepNarrow, kSweepTile / kSweepNarrow);
         ATTR(true, false, 512, kSweepTile / 512);  ATTR(false, false, 512, kSweepTile / 512);  ATTR(true, true, 512, kSweepTile / 512);  ATTR(false, true, 512, kSweepTile / 512);
 #undef ATTR
 #undef ATTR1
@@ -418,18 +419,18 @@ int radix_sort_pairs(cudaStream_t stream, RadixWorkspace &ws, uint64_t *keys_a, 
     } while (0)
 #define SWEEP(I, M)                                                                                              \
     do {                                                                                                         \
-        if (wide_cta) SWEEP2(I, M, 512, kSweepTile / 512); else SWEEP2(I, M, 256, kSweepTile / 256);                                          \
+        if (wide_cta) SWEEP2(I, M, 512, kSweepTile / 512); else SWEEP2(I, M, kSweepNarrow, kSweepTile / kSweepNarrow);       \
     } while (0)
             // bulk copies need 16-byte aligned sources: portions start at multiples of 2^29 pairs
             const bool use_tma = tma && !hw_match && !wide_cta && !hints && (reinterpret_cast<uintptr_t>(src_k + start) & 15) == 0 &&
                                  (iota || (reinterpret_cast<uintptr_t>(src_v + start) & 15) == 0);
             if (use_tma) {
                 if (iota)
-                    onesweep_kernel<true, false, 256, kSweepTile / 256, false, true><<<tiles, 256, sizeof(SweepSmemT<8>), stream>>>(
+                    onesweep_kernel<true, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true><<<tiles, kSweepTmaThreads, sizeof(SweepSmemT<kSweepTmaThreads / 32>), stream>>>(
                         src_k + start, nullptr, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out, ws.status,
                         ws.counter, tiles - 1);
                 else
-                    onesweep_kernel<false, false, 256, kSweepTile / 256, false, true><<<tiles, 256, sizeof(SweepSmemT<8>), stream>>>(
+                    onesweep_kernel<false, false, kSweepTmaThreads, kSweepTile / kSweepTmaThreads, false, true><<<tiles, kSweepTmaThreads, sizeof(SweepSmemT<kSweepTmaThreads / 32>), stream>>>(
                         src_k + start, src_v + start, dst_k, dst_v, (uint32_t)cnt, start, shift, mask, base_in, base_out, ws.status,
                         ws.counter, tiles - 1);
             } else if (iota) {

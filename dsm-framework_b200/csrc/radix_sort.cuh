@@ -30,7 +30,9 @@ constexpr bool kSweepTmaVals = false;
 constexpr bool kSweepTmaDefault = true; // measured: 3.08 -> 2.98 ms per launch with the keys, see DESIGN.md section 5
 // A launch handles at most this many pairs so that tile prefixes fit the
 // 30-bit payload of a status word; longer inputs run as several portions.
-constexpr uint64_t kSweepPortion = (uint64_t)kSweepTile * 131072; // 2^29
+constexpr uint64_t kSweepPortion = (uint64_t)kSweepTile * (kSweepTile > 4096 ? 65536 : 131072); // 2^29 for tiles of 4096 / 8192
+constexpr int kSweepTmaThreads = kSweepTile > 4096 ? 512 : 256; // threads of the default (bulk-copy ingest) kernel: 16 pairs each
+constexpr int kSweepNarrow = kSweepTile > 4096 ? 512 : 256;     // the narrower of the two switchable shapes
 
 struct RadixWorkspace {
     uint64_t *hist = nullptr;     // [kMaxPasses][256] digit counts, then exclusive bases
