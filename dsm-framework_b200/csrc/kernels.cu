@@ -233,6 +233,10 @@ __global__ void __launch_bounds__(256) make_keys_kernel(const uint64_t *__restri
 // are in registers the kernel also counts their radix digits, which saves the sort's own histogram pass
 // over the key array (8 bytes per suffix read back from HBM).
 constexpr int kHeadsU = 8;           // head words per warp iteration of heads_kernel (8: 5.9 -> 5.3 ms on C3)
+#ifndef DSMFM_HEADS_CTAS
+#define DSMFM_HEADS_CTAS 4
+#endif
+constexpr int kHeadsCtas = DSMFM_HEADS_CTAS; // resident CTAs per SM the registers of heads_kernel are budgeted for
 constexpr int kKeyTileThreads = 128; // one packed word per thread and tile
 constexpr int kMaxKeyPasses = 8;     // 64 key bits / 8-bit digits
 constexpr int kKeySub = 1;           // copies of every digit counter in make_keys_hist_kernel (4 copies: no gain measured)
@@ -248,6 +252,16 @@ template <int BITS> __device__ __forceinline__ uint64_t cut_at_terminator_nb(uin
     const int top = 64 - __clzll((long long)z) + BITS - 1; // one past the most significant zero field (BITS - 1 if none)
     const uint64_t keep = z == 0 ? ~0ull : (top >= 64 ? 0ull : ~((1ull << top) - 1));
     return x & keep;
+}
+
+// Most significant bits of the fields of a 128-bit stream of BITS-bit symbols (half 0: stream bits 0..63, the first
+// symbol at the top; half 1: bits 64..127).  Three-bit fields run across the two halves (the stream has its gap closed).
+template <int BITS> __host__ __device__ constexpr uint64_t stream_field_msb(int half)
+{
+    uint64_t m = 0;
+    for (int o = 0; o < 128; o += BITS)
+        if (o / 64 == half) m |= 1ull << (63 - o % 64);
+    return m;
 }
 
 // NP: number of 8-bit digits counted, fixed at compile time (6 for the 48-bit first key), or -1: `npass` at run time
@@ -269,7 +283,7 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
     for (int i = threadIdx.x; i < HP * 256 * SUB; i += kKeyTileThreads) (&s_hist[0][0][0])[i] = 0;
     __syncthreads();
     const int sub = threadIdx.x & (SUB - 1);
-    const uint64_t kmask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1);
+    const uint64_t zkeep = key_bits >= 64 ? ~0ull : ~(~0ull >> key_bits); // the top key_bits bits
     // the words [word_begin, nwords) of the packed text (a text that streams in is keyed piece by piece)
     const uint64_t ntiles = (nwords - word_begin + kKeyTileThreads - 1) / kKeyTileThreads;
     const uint64_t n_lim = nwords * (uint64_t)P::SPW < n ? nwords * (uint64_t)P::SPW : n; // keys of later words: later calls
@@ -284,13 +298,24 @@ make_keys_hist_kernel(const uint64_t *__restrict__ packed, uint64_t n, uint64_t 
             }
             const uint64_t p0 = w * P::SPW;
             const int have = p0 + P::SPW <= n ? P::SPW : (int)(n - p0); // positions of this word inside the text
+            // where the stream's fields are zero (terminators, and the zero words behind the text), once per thread:
+            // a flag at the most significant bit of every zero field.  A key is cut at its first flag.
+            uint64_t z0 = x0, z1 = x1;
+#pragma unroll
+            for (int i = 1; i < BITS; ++i) {
+                z0 |= (x0 << i) | (x1 >> (64 - i));
+                z1 |= x1 << i;
+            }
+            z0 = ~z0 & stream_field_msb<BITS>(0);
+            z1 = ~z1 & stream_field_msb<BITS>(1);
 #pragma unroll
             for (int j = 0; j < P::SPW; ++j) {
                 if (j < have) {
                     const int b = BITS * j;
-                    const uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0; // stream from symbol j on
-                    uint64_t k = (v >> (64 - key_bits)) | ~kmask;                // ones above: only real fields can be zero
-                    k = cut_at_terminator_nb<BITS>(k) & kmask;
+                    uint64_t v = b ? ((x0 << b) | (x1 >> (64 - b))) : x0; // stream from symbol j on
+                    const uint64_t zj = (b ? ((z0 << b) | (z1 >> (64 - b))) : z0) & zkeep; // zero fields among the key's
+                    if (zj) v &= ~(~0ull >> __clzll((long long)zj)); // nothing from the first terminator on
+                    uint64_t k = v >> (64 - key_bits);
 #pragma unroll
                     for (int q = 0; q < HP; ++q)
                         if (NP > 0 || q < npass) atomicAdd(&s_hist[q][(uint32_t)(k >> (8 * q)) & 0xffu][sub], 1u);
@@ -687,7 +712,7 @@ select_sweep_kernel(const uint64_t *__restrict__ packed, uint64_t nwords, int ke
 // suffixes left in groups of >= 2 falls out of the head words themselves.  Chunks that lie entirely inside
 // the array take a path without bounds checks and with 32-bit offsets from the chunk's base pointers.
 template <int BITS, int U>
-__global__ void __launch_bounds__(256) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+__global__ void __launch_bounds__(256, kHeadsCtas) heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                     uint32_t *__restrict__ head, uint64_t head_words,
                                                     unsigned long long *__restrict__ remaining, int key_bits,
                                                     const uint8_t *__restrict__ inv_map, uint8_t *__restrict__ bwt,
@@ -2398,9 +2423,15 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
     __syncthreads();
     // warp v: total of node v, publish, look back
     if (warp < n_internal) {
-        uint32_t total = 0;
+        uint32_t total = 0, mine = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) total += s_part[warp][k];
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t pk = s_part[warp][k];
+            if (k < lane) mine += pk;
+            total += pk;
+        }
+        __syncwarp();
+        if (lane < 8) s_part[warp][lane] = mine; // from here on: members of node `warp` in the warps in front of warp `lane`
         volatile unsigned long long *st = status + (size_t)warp; // status[tile * 8 + node]
         if (lane == 0) st[tile * kWtSmallNodes] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
         unsigned long long excl = 0;
@@ -2438,8 +2469,7 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
             // without a loop, whose trip count would be the warp's maximum
             const bool dense = __any_sync(0xffffffffu, c > 12u && m[v] != 0xffffffffu);
             if (c) {
-                uint32_t before = incl[v] - c;
-                for (int k = 0; k < warp; ++k) before += s_part[v][k];
+                const uint32_t before = incl[v] - c + s_part[v][warp];
                 uint32_t bits = b[v]; // all 32 symbols are members (always so at the root): nothing to compress
                 if (m[v] != 0xffffffffu) {
                     if (dense) {
