@@ -1187,7 +1187,9 @@ template <int KW, bool WIDE> struct RwSmem {
 #define DSMFM_RW_CTAS 4
 #endif
 constexpr int kRwCtas = DSMFM_RW_CTAS; // resident CTAs per SM the compiler budgets registers for
-template <int BITS, int KW, bool WIDE, bool ORDER>
+// COOP: groups of big_thr members or more are ranked by the whole warp around their dominant key (a separate
+// instantiation: with both ranking schemes in one kernel the whole-warp path lost 10 % to the other's code).
+template <int BITS, int KW, bool WIDE, bool ORDER, bool COOP>
 __global__ void __launch_bounds__(kRefThreads, kRwCtas)
 refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ sa, const uint32_t *__restrict__ head_cur,
                     uint32_t *__restrict__ head_next, uint64_t n, uint32_t depth, const uint32_t *__restrict__ win_list,
@@ -1410,12 +1412,16 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
 
     int c = 0;
     unsigned long long fetched = 0;
+    // Where no group is ranked by the whole warp, the ranking notes for every slot the first slot of the group it put
+    // the suffix in (in the array the whole-warp ranking would use), which saves the steps below their bit scans.
+    constexpr bool heads_kept = !COOP;
+    uint16_t *ghead = S.newpos;
     while (cnt > 0) {
         fetched += (unsigned)cnt;
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
         // carries the same key (or its key holds the terminator, which makes it unique)
         int nbig = 0; // large groups of this warp's range seen in this step (warp-uniform)
-        if (big_thr > kRwCap && chunked) {
+        if (!COOP && chunked) {
             // Whole groups, as many as fit the 32 lanes, one member per lane.  The list holds whole groups in slot
             // order (it starts that way, and the classification below compacts it in order), so a group is a run of
             // lanes between two head flags; match.any finds the lanes that carry
@@ -1446,6 +1452,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                         }
                         const int p = gs + lt + eq;
                         if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                        ghead[p] = (uint16_t)(key_terminated<BITS>(ml) ? p : gs + lt);
                         s_sa[c ^ 1][p] = s_sa[c][rr];
                         s_bw[c ^ 1][p] = s_bw[c][rr];
                         if (WIDE) s_hi[c ^ 1][p] = s_hi[c][rr];
@@ -1481,6 +1488,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 if (in) {
                     const int p = gs + lt + eq;
                     if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                    ghead[p] = (uint16_t)(key_terminated<BITS>(ml) ? p : gs + lt); // the equal ones start at gs + lt
                     s_sa[c ^ 1][p] = s_sa[c][r];
                     s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
                     if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
@@ -1489,7 +1497,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 }
                 i0 += take;
             }
-        } else if (big_thr > kRwCap) { // every group by its own members (all pairs)
+        } else if (!COOP) { // every group by its own members (all pairs)
             for (int i = lane; i < cnt; i += 32) {
                 const int r = list[i];
                 const int gs = prev_set_le(s_ha, r);
@@ -1512,6 +1520,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 }
                 const int p = gs + lt + eq;
                 if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                ghead[p] = (uint16_t)(key_terminated<BITS>(ml) ? p : gs + lt); // the equal ones start at gs + lt
                 s_sa[c ^ 1][p] = s_sa[c][r];
                 s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
                 if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
@@ -1636,7 +1645,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
             __syncwarp();
             for (int i = lane; i < cnt; i += 32) {
                 const int p = list[i];
-                const int g = prev_set_le(s_hb, p);
+                const int g = heads_kept ? ghead[p] : prev_set_le(s_hb, p);
                 if (g != p && s_bw[c ^ 1][p] != s_bw[c ^ 1][g]) atomicOr(&s_mix[g >> 5], 1u << (g & 31));
             }
             __syncwarp();
@@ -1653,7 +1662,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 const bool h0 = (s_hb[p >> 5] >> (p & 31)) & 1u;
                 const bool h1 = (s_hb[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u;
                 again = !(h0 && h1);
-                if (!ORDER && again) again = mixed(prev_set_le(s_hb, p));
+                if (!ORDER && again) again = mixed(heads_kept ? ghead[p] : prev_set_le(s_hb, p));
                 if (!again) {
                     sa[win + p] = s_sa[c ^ 1][p];
                     if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
@@ -2845,21 +2854,24 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
         static DeviceOnce attr3_once;
         attr3_once.run([] {
 #define SET3(B, K)                                                                                                      \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)sizeof(RwSmem<K, false>)));                                                      \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)sizeof(RwSmem<K, true>)));                                                       \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)sizeof(RwSmem<K, false>)));                                                      \
-    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                  (int)sizeof(RwSmem<K, true>)))
+    SET4(B, K, false, false); SET4(B, K, true, false); SET4(B, K, false, true); SET4(B, K, true, true)
+#define SET4(B, K, W, O)                                                                                                \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, W, O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)sizeof(RwSmem<K, W>)));                                                          \
+    DSM_CUDA(cudaFuncSetAttribute(refine_warps_kernel<B, K, W, O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                  (int)sizeof(RwSmem<K, W>)))
             SET3(3, 1); SET3(4, 1); SET3(8, 1); SET3(3, 2); SET3(4, 2); SET3(8, 2);
+#undef SET4
 #undef SET3
         });
-#define RW2(B, K, W, O)                                                                                           \
-    refine_warps_kernel<B, K, W, O><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                             \
+#define RW3(B, K, W, O, C)                                                                                        \
+    refine_warps_kernel<B, K, W, O, C><<<grid, kRefThreads, sizeof(RwSmem<K, W>), st>>>(                          \
         packed, sa, head_cur, head_next, n, depth, win_list, big_heads, big_cap, big_count, remaining, win_flag,  \
         win_next, win_next_count, bwt, sa_hi, lo_bits, diff_bits, big_thr, chunked)
+#define RW2(B, K, W, O)                                                                                           \
+    do {                                                                                                          \
+        if (big_thr <= kRwCap) RW3(B, K, W, O, true); else RW3(B, K, W, O, false);                                \
+    } while (0)
 #define RW(B, K, W)                                                                                               \
     do {                                                                                                          \
         if (full_order || !bwt) RW2(B, K, W, true); else RW2(B, K, W, false);                                     \
@@ -2876,6 +2888,7 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
 #undef CALL3
 #undef RW
 #undef RW2
+#undef RW3
         DSM_LAUNCH_CHECK();
         if (launches) ++*launches;
         return;
