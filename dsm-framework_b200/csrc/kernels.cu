@@ -1171,7 +1171,7 @@ template <int KW, bool WIDE> struct RwSmem {
     uint32_t df[kRwCap / 32 + 2];      // per slot: BWT symbol differs from the predecessor's inside a group
     uint32_t act[kRwCap / 32 + 2];     // per slot: member of a group that has to be sorted
     uint16_t newpos[kRwCap];           // large groups: rank of a carrier of the dominant key among the carriers
-    uint16_t lidx[kRwCap];             // large groups: list entry of the member at a slot
+    uint16_t ghead[kRwCap];            // per slot: first slot of the group the last ranking step put its suffix in
     uint16_t nd[kRwCap];               // large groups: the members whose key is not the dominant one, in slot order
     uint16_t bigq[kRefThreads / 32][kRwCap / kRwBigGroup + 2]; // per warp: first slots of its large groups
     int range[2];
@@ -1412,10 +1412,10 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
 
     int c = 0;
     unsigned long long fetched = 0;
-    // Where no group is ranked by the whole warp, the ranking notes for every slot the first slot of the group it put
-    // the suffix in (in the array the whole-warp ranking would use), which saves the steps below their bit scans.
-    constexpr bool heads_kept = !COOP;
-    uint16_t *ghead = S.newpos;
+    // The ranking notes for every slot the first slot of the group it put the suffix in, which saves the steps after
+    // it their bit scans.  It leaves the list alone: a group's members go to the group's own slots, so as a set of
+    // slots -- all the later steps need -- the list is the same before and after, and it stays in slot order.
+    uint16_t *ghead = S.ghead;
     while (cnt > 0) {
         fetched += (unsigned)cnt;
         // rank: stable position inside the group; a suffix opens a new group iff no earlier member
@@ -1524,7 +1524,6 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 s_sa[c ^ 1][p] = s_sa[c][r];
                 s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
                 if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                list[i] = (uint16_t)p;       // where this suffix went
             }
         } else
         for (int i0 = 0; i0 < cnt; i0 += 32) {
@@ -1537,7 +1536,6 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 const int ge = next_set_gt(s_ha, r);
                 if (ge - gs >= big_thr) {
                     big_first = r == gs; // the whole warp ranks this group below
-                    S.lidx[r] = (uint16_t)i; // where the member sits in the list
                 } else {
                     const uint64_t mh = s_khi[r], ml = KW == 2 ? s_klo[r] : mh;
                     int lt = 0, eq = 0;
@@ -1557,10 +1555,10 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                     }
                     const int p = gs + lt + eq;
                     if (p != gs && (eq == 0 || key_terminated<BITS>(ml))) atomicOr(&s_hb[p >> 5], 1u << (p & 31));
+                    ghead[p] = (uint16_t)(key_terminated<BITS>(ml) ? p : gs + lt);
                     s_sa[c ^ 1][p] = s_sa[c][r];
                     s_bw[c ^ 1][p] = s_bw[c][r]; // the BWT symbol moves with its suffix
                     if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                    list[i] = (uint16_t)p;       // where this suffix went
                 }
             }
             const uint32_t bm = __ballot_sync(0xffffffffu, big_first);
@@ -1615,7 +1613,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                     s_sa[c ^ 1][p] = s_sa[c][r];
                     s_bw[c ^ 1][p] = s_bw[c][r];
                     if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                    list[S.lidx[r]] = (uint16_t)p;
+                    ghead[p] = (uint16_t)(term ? p : gs + n_lt);
                 }
             }
             // the others against each other (dense keys in the first n_nd key slots of the group)
@@ -1634,7 +1632,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 s_sa[c ^ 1][p] = s_sa[c][r];
                 s_bw[c ^ 1][p] = s_bw[c][r];
                 if (WIDE) s_hi[c ^ 1][p] = s_hi[c][r];
-                list[S.lidx[r]] = (uint16_t)p;
+                ghead[p] = (uint16_t)(key_terminated<BITS>(KW == 2 ? ml : mh) ? p : p - eq);
             }
             __syncwarp();
         }
@@ -1645,7 +1643,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
             __syncwarp();
             for (int i = lane; i < cnt; i += 32) {
                 const int p = list[i];
-                const int g = heads_kept ? ghead[p] : prev_set_le(s_hb, p);
+                const int g = ghead[p];
                 if (g != p && s_bw[c ^ 1][p] != s_bw[c ^ 1][g]) atomicOr(&s_mix[g >> 5], 1u << (g & 31));
             }
             __syncwarp();
@@ -1662,7 +1660,7 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
                 const bool h0 = (s_hb[p >> 5] >> (p & 31)) & 1u;
                 const bool h1 = (s_hb[(p + 1) >> 5] >> ((p + 1) & 31)) & 1u;
                 again = !(h0 && h1);
-                if (!ORDER && again) again = mixed(heads_kept ? ghead[p] : prev_set_le(s_hb, p));
+                if (!ORDER && again) again = mixed(ghead[p]);
                 if (!again) {
                     sa[win + p] = s_sa[c ^ 1][p];
                     if (bwt) bwt[win + p] = s_bw[c ^ 1][p];
