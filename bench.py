@@ -68,59 +68,110 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks / throttle reasons / power DURING the timed region (B200_PROFILING.md's clocks line).
+
+    The counters are the ones `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.*` prints,
+    read through NVML from a thread of this process every 100 ms (more samples per timed region than a child process
+    polling every 250 ms, and nothing else competing for the driver).  An `nvidia-smi -lms 250` child process is the
+    fallback when pynvml is missing; BENCH_CLOCKS=smi selects it.  (In one run the steps that coincided with a sample
+    of the child process were 10 ms longer, profiles/r2c_bench_1gpu_smi.json; a repeat showed no such effect.)"""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, pci_bus_id=None):
         self.index = index
+        self.pci_bus_id = pci_bus_id
         self.proc = None
-        self.lines = []
+        self.thread = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+        self.lines = []      # nvidia-smi csv lines
+        self.samples = []    # (sm_mhz, max_mhz, watts, reason names)
+        self.source = None
 
     def start(self):
+        if os.environ.get("BENCH_CLOCKS", "nvml") != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                handle = None
+                if self.pci_bus_id:
+                    try:
+                        handle = pynvml.nvmlDeviceGetHandleByPciBusId(self.pci_bus_id.encode())
+                    except Exception:
+                        handle = None
+                if handle is None:
+                    handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                self.nvml, self.handle, self.source = pynvml, handle, "nvml"
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 250"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while True:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((sm, self.max_mhz, watts, [nm for bit, nm in bits if mask & bit]))
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.1):
+                return
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=5)
+        elif self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    self.samples.append((float(f[0]), float(f[1]), float(f[2]),
+                                         [nm for nm, v in zip(self.NAMES, f[3:7]) if v.lower().startswith("active")]))
+                except ValueError:
+                    continue
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"]}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "source": self.source}
+        reasons = set()
+        for smp in self.samples:
+            reasons.update(smp[3])
         # median over the samples taken under load (the upper half by power draw)
-        idx = sorted(range(len(sm)), key=lambda i: power[i])[len(sm) // 2:]
-        load = sorted(sm[i] for i in idx)
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        under_load = sorted(self.samples, key=lambda x: x[2])[len(self.samples) // 2:]
+        load = sorted(x[0] for x in under_load)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(x[1] for x in self.samples), "reasons": sorted(reasons),
+                "samples": len(self.samples), "power_w_max": round(max(x[2] for x in self.samples), 2), "source": self.source}
 
 
 def section_bytes(idx):
@@ -459,7 +510,12 @@ def main():
     # ---- device-resident throughput ("value") ------------------------------------------------------
     for _ in range(args.warmup):
         device_step()
-    sampler = ClockSampler(local)
+    try:  # the NVML handle by PCI address: NVML's indices need not be CUDA's
+        pr = torch.cuda.get_device_properties(local)
+        pci = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        pci = None
+    sampler = ClockSampler(local, pci)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
