@@ -1764,17 +1764,27 @@ __global__ void __launch_bounds__(256) count_active_kernel(const uint32_t *__res
     }
 }
 
-// exclusive scan of u64 counts in place, total behind the last entry; one block
+// exclusive scan of u64 counts in place, total behind the last entry; one block, eight consecutive entries per thread
 __global__ void __launch_bounds__(1024) scan_tiles_kernel(uint64_t *__restrict__ v, uint64_t n)
 {
+    constexpr int ITEMS = 8;
     __shared__ uint64_t scratch[33];
     uint64_t carry = 0;
-    for (uint64_t base = 0; base < n; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t x = i < n ? v[i] : 0;
+    for (uint64_t base = 0; base < n; base += 1024 * ITEMS) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * ITEMS;
+        uint64_t x[ITEMS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            x[k] = i0 + k < n ? v[i0 + k] : 0;
+            sum += x[k];
+        }
         uint64_t total;
-        const uint64_t e = block_excl_sum(x, scratch, &total);
-        if (i < n) v[i] = carry + e;
+        uint64_t e = carry + block_excl_sum(sum, scratch, &total);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            if (i0 + k < n) v[i0 + k] = e;
+            e += x[k];
+        }
         carry += total;
     }
     if (threadIdx.x == 0) v[n] = carry;
@@ -1788,43 +1798,52 @@ compact_active_kernel(const uint32_t *__restrict__ act, const uint32_t *__restri
                       const uint8_t *__restrict__ sa_hi, uint32_t *__restrict__ csa, uint8_t *__restrict__ cbw,
                       uint8_t *__restrict__ chi, uint32_t *__restrict__ corig, uint32_t *__restrict__ chead)
 {
+    // A warp owns 32 words (1024 slots) of the tile.  Its active slots are handled 32 at a time, one per lane and in
+    // order: the lane finds the word of its slot in the warp's prefix sums (five shuffles), the bit inside the word
+    // (find-nth-set), and copies -- reads that follow the runs of active slots, writes that are dense.
     __shared__ uint32_t scratch[9];
+    const int lane = threadIdx.x & 31;
     const uint64_t t = (uint64_t)blockIdx.x * kActTileWords + threadIdx.x;
-    uint32_t a = t < nwords ? act[t] : 0u;
+    const uint32_t a = t < nwords ? act[t] : 0u;
     const uint32_t hd = t < nwords ? head[t] : 0u;
     const uint32_t c = __popc(a);
     uint32_t total;
     const uint32_t e = block_excl_sum(c, scratch, &total);
-    if (c == 0) return;
-    uint64_t j = tile_off[blockIdx.x] + e;
-    // head bits of the active slots, compressed, at bit offset j of chead
-    uint64_t hb = 0;
-    {
-        uint32_t aa = a;
-        int out = 0;
-        while (aa) {
-            const int b = __ffs(aa) - 1;
-            aa &= aa - 1;
-            hb |= (uint64_t)((hd >> b) & 1u) << out;
-            ++out;
+    const uint32_t ex = e - __shfl_sync(0xffffffffu, e, 0);           // active slots of the warp's words in front of mine
+    const uint32_t T = __shfl_sync(0xffffffffu, ex + c, 31);          // active slots of the warp
+    if (T == 0) return;
+    const uint64_t j0 = tile_off[blockIdx.x] + __shfl_sync(0xffffffffu, e, 0); // dense index of the warp's first active slot
+    const uint64_t word0 = t - lane;
+    for (uint32_t k0 = 0; k0 < T; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool valid = k < T;
+        // the last word whose prefix does not exceed k holds the k-th active slot
+        int L = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t ec = __shfl_sync(0xffffffffu, ex, (L + step) & 31);
+            if (L + step < 32 && ec <= k) L += step;
         }
-    }
-    if (hb) {
-        const int sh = (int)(j & 31);
-        const uint64_t lo = hb << sh;
-        atomicOr(&chead[j >> 5], (uint32_t)lo);
-        if (lo >> 32) atomicOr(&chead[(j >> 5) + 1], (uint32_t)(lo >> 32));
-        if (sh && (hb >> (64 - sh))) atomicOr(&chead[(j >> 5) + 2], (uint32_t)(hb >> (64 - sh)));
-    }
-    while (a) {
-        const int b = __ffs(a) - 1;
-        a &= a - 1;
-        const uint64_t slot = t * 32 + b;
-        csa[j] = sa[slot];
-        cbw[j] = bwt[slot];
-        if (chi) chi[j] = sa_hi[slot];
-        corig[j] = (uint32_t)slot;
-        ++j;
+        const uint32_t aL = __shfl_sync(0xffffffffu, a, L);
+        const uint32_t hL = __shfl_sync(0xffffffffu, hd, L);
+        const uint32_t exL = __shfl_sync(0xffffffffu, ex, L);
+        bool hbit = false;
+        if (valid) {
+            const int b = (int)__fns(aL, 0, (int)(k - exL) + 1);
+            const uint64_t slot = (word0 + L) * 32 + b;
+            const uint64_t j = j0 + k;
+            hbit = (hL >> b) & 1u;
+            csa[j] = sa[slot];
+            cbw[j] = bwt[slot];
+            if (chi) chi[j] = sa_hi[slot];
+            corig[j] = (uint32_t)slot;
+        }
+        // head bits of these 32 entries, at bit offset j0 + k0 of chead (words shared with the neighbours: OR)
+        const uint32_t hbm = __ballot_sync(0xffffffffu, hbit);
+        const uint64_t o = j0 + k0;
+        const int sh = (int)(o & 31);
+        if (lane == 0 && (hbm << sh)) atomicOr(&chead[o >> 5], hbm << sh);
+        if (lane == 1 && sh && (hbm >> (32 - sh))) atomicOr(&chead[(o >> 5) + 1], hbm >> (32 - sh));
     }
 }
 
