@@ -2425,7 +2425,8 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
     __shared__ uint32_t s_part[kWtSmallNodes][8];
     __shared__ uint32_t s_total[kWtSmallNodes];
     __shared__ unsigned long long s_off[kWtSmallNodes]; // global bit offset of the tile's run in node v
-    __shared__ uint32_t s_bits[kWtSmallNodes][2 * kWtRunWords];
+    __shared__ uint32_t s_bits[kWtSmallNodes][2 * kWtRunWords]; // the tile's bits of node v, from bit 0
+    __shared__ uint8_t s_first[kWtSmallNodes];          // first member symbol of node v in this tile
     __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(counter, 1u);
@@ -2447,9 +2448,12 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
         }
     }
     __syncthreads();
-    // warp v: total of node v, publish, look back
+    // warp v: total of node v -- published at once, so that the tiles behind can go on; this tile's own look-back
+    // comes last, after its bits are assembled, when the tiles in front have long published theirs
+    uint32_t total = 0;
+    volatile unsigned long long *st = status + (size_t)warp; // status[tile * 8 + node]
     if (warp < n_internal) {
-        uint32_t total = 0, mine = 0;
+        uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const uint32_t pk = s_part[warp][k];
@@ -2458,35 +2462,13 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
         }
         __syncwarp();
         if (lane < 8) s_part[warp][lane] = mine; // from here on: members of node `warp` in the warps in front of warp `lane`
-        volatile unsigned long long *st = status + (size_t)warp; // status[tile * 8 + node]
-        if (lane == 0) st[tile * kWtSmallNodes] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
-        unsigned long long excl = 0;
-        if (tile != 0) {
-            long long t = (long long)tile - 1;
-            for (;;) {
-                const long long idx = t - lane;
-                unsigned long long x = 2ull << 62; // in front of the first tile: an empty prefix
-                if (idx >= 0) x = st[idx * kWtSmallNodes];
-                while (__any_sync(0xffffffffu, (x >> 62) == 0))
-                    if ((x >> 62) == 0) x = st[idx * kWtSmallNodes];
-                const uint32_t pm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
-                const int stop = pm ? __ffs(pm) - 1 : 32;
-                unsigned long long val = lane <= stop ? (x & kSelValueMask) : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                excl += val;
-                if (pm) break;
-                t -= 32;
-            }
-            if (lane == 0) st[tile * kWtSmallNodes] = kSelFlagPrefix | (excl + total);
-        }
         if (lane == 0) {
+            st[tile * kWtSmallNodes] = (tile == 0 ? kSelFlagPrefix : kSelFlagAgg) | total;
             s_total[warp] = total;
-            s_off[warp] = excl + (bit_base ? bit_base[warp] : 0ull);
         }
     }
     __syncthreads();
-    // every thread: its bits of every node into the tile's run (bit 0 of the run buffer = bit (off & ~63) of the node)
+    // every thread: its bits of every node into the tile's run (bit 0 of the run buffer = the tile's first member)
 #pragma unroll
     for (int v = 0; v < kWtSmallNodes; ++v) {
         if (v < n_internal) {
@@ -2512,31 +2494,62 @@ wt_sweep_kernel(const uint8_t *__restrict__ seq, uint64_t n, const uint8_t *__re
                         }
                     }
                 }
-                const uint64_t off = s_off[v];
-                const uint32_t o = (uint32_t)(off & 63) + before; // bit position inside the run buffer
-                const int sh = (int)(o & 31);
-                if (bits << sh) atomicOr(&s_bits[v][o >> 5], bits << sh);
-                if (sh && (bits >> (32 - sh))) atomicOr(&s_bits[v][(o >> 5) + 1], bits >> (32 - sh));
-                if (off + before == (bit_base ? bit_base[v] : 0ull)) { // first symbol of the node's subsequence (HuffWT.cpp:8)
+                const int sh = (int)(before & 31);
+                if (bits << sh) atomicOr(&s_bits[v][before >> 5], bits << sh);
+                if (sh && (bits >> (32 - sh))) atomicOr(&s_bits[v][(before >> 5) + 1], bits >> (32 - sh));
+                if (before == 0) { // the tile's first member of the node: the node's first symbol if the tile is its first (HuffWT.cpp:8)
                     const int j = __ffs(m[v]) - 1;
                     uint32_t word = w[0];
 #pragma unroll
                     for (int q = 1; q < 8; ++q)
                         if ((j >> 2) == q) word = w[q];
-                    node_ch[v] = (uint8_t)((word >> (8 * (j & 3))) & 0xff);
+                    s_first[v] = (uint8_t)((word >> (8 * (j & 3))) & 0xff);
                 }
             }
         }
     }
+    // warp v: look back for the bit offset of the tile's run in node v
+    if (warp < n_internal) {
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            long long t = (long long)tile - 1;
+            for (;;) {
+                const long long idx = t - lane;
+                unsigned long long x = 2ull << 62; // in front of the first tile: an empty prefix
+                if (idx >= 0) x = st[idx * kWtSmallNodes];
+                while (__any_sync(0xffffffffu, (x >> 62) == 0))
+                    if ((x >> 62) == 0) x = st[idx * kWtSmallNodes];
+                const uint32_t pm = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+                const int stop = pm ? __ffs(pm) - 1 : 32;
+                unsigned long long val = lane <= stop ? (x & kSelValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                excl += val;
+                if (pm) break;
+                t -= 32;
+            }
+            if (lane == 0) st[tile * kWtSmallNodes] = kSelFlagPrefix | (excl + total);
+        }
+        if (lane == 0) s_off[warp] = excl + (bit_base ? bit_base[warp] : 0ull);
+    }
     __syncthreads();
+    // the runs leave as whole 64-bit words, shifted to their bit offset; the first and the last word of a run may be
+    // shared with the neighbouring tiles and are OR-ed in
     for (int v = 0; v < n_internal; ++v) {
-        const uint32_t total = s_total[v];
-        if (!total) continue;
+        const uint32_t tot = s_total[v];
+        if (!tot) continue;
         const uint64_t off = s_off[v];
-        const uint32_t words = (uint32_t)(((off & 63) + total + 63) >> 6);
+        const int sh = (int)(off & 63);
+        if (tid == 0 && off == (bit_base ? bit_base[v] : 0ull)) node_ch[v] = s_first[v];
+        const uint32_t words = (uint32_t)((sh + tot + 63) >> 6);
         unsigned long long *d = reinterpret_cast<unsigned long long *>(node_data[v]) + (off >> 6);
         for (uint32_t i = tid; i < words; i += 256) {
-            const unsigned long long x = (unsigned long long)s_bits[v][2 * i] | ((unsigned long long)s_bits[v][2 * i + 1] << 32);
+            const unsigned long long cur = (unsigned long long)s_bits[v][2 * i] | ((unsigned long long)s_bits[v][2 * i + 1] << 32);
+            unsigned long long x = cur << sh;
+            if (sh && i) {
+                const unsigned long long prv = (unsigned long long)s_bits[v][2 * i - 2] | ((unsigned long long)s_bits[v][2 * i - 1] << 32);
+                x |= prv >> (64 - sh);
+            }
             if (i == 0 || i + 1 == words) {
                 if (x) atomicOr(d + i, x);
             } else {
