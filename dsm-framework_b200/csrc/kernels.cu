@@ -1717,12 +1717,9 @@ refine_warps_kernel(const uint64_t *__restrict__ packed, uint32_t *__restrict__ 
 constexpr int kActTileWords = 256; // head words per CTA in the compaction passes (8192 slots)
 
 // act bit i = slot i belongs to a group holding a diff bit; act is zeroed by the caller.
-__global__ void __launch_bounds__(256) mark_active_kernel(const uint32_t *__restrict__ head, const uint32_t *__restrict__ diff,
-                                                          uint64_t nwords, uint32_t *__restrict__ act)
+// word t of the difference bitmap: every group that holds one of its bits is marked from its head to its last slot
+__device__ __forceinline__ void mark_word(const uint32_t *__restrict__ head, uint64_t t, uint32_t dw, uint32_t *__restrict__ act)
 {
-    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= nwords) return;
-    uint32_t dw = diff[t];
     uint64_t done_to = 0; // slots below this are already marked by this thread
     while (dw) {
         const int b = __ffs(dw) - 1;
@@ -1746,6 +1743,25 @@ __global__ void __launch_bounds__(256) mark_active_kernel(const uint32_t *__rest
         }
         done_to = e;
     }
+}
+
+// four words of the difference bitmap per thread, fetched as one 16-byte load (most of them are zero)
+__global__ void __launch_bounds__(256) mark_active_kernel(const uint32_t *__restrict__ head, const uint32_t *__restrict__ diff,
+                                                          uint64_t nwords, uint32_t *__restrict__ act)
+{
+    const uint64_t t0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (t0 >= nwords) return;
+    uint32_t dv[4] = {0u, 0u, 0u, 0u};
+    if (t0 + 4 <= nwords) {
+        const uint4 x = *reinterpret_cast<const uint4 *>(diff + t0);
+        dv[0] = x.x; dv[1] = x.y; dv[2] = x.z; dv[3] = x.w;
+    } else {
+        for (int u = 0; u < 4; ++u)
+            if (t0 + u < nwords) dv[u] = diff[t0 + u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (dv[u]) mark_word(head, t0 + u, dv[u], act);
 }
 
 __global__ void __launch_bounds__(256) count_active_kernel(const uint32_t *__restrict__ act, uint64_t nwords,
@@ -2949,7 +2965,7 @@ void launch_mark_active(cudaStream_t st, const uint32_t *head, const uint32_t *d
 {
     const uint64_t nwords = div_up(n, 32);
     const unsigned tiles = (unsigned)active_tiles(nwords);
-    mark_active_kernel<<<(unsigned)div_up(nwords, 256), 256, 0, st>>>(head, diff, nwords, act);
+    mark_active_kernel<<<(unsigned)div_up(nwords, 256 * 4), 256, 0, st>>>(head, diff, nwords, act);
     count_active_kernel<<<tiles, 256, 0, st>>>(act, nwords, tile_off);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_off, tiles);
     DSM_LAUNCH_CHECK();
