@@ -891,11 +891,12 @@ void dsmfm_builder::append_fasta(const uint8_t *text, size_t m, dsmfm_fasta_info
 // host text streaming in: copy pieces on one stream, work on them on the other
 // ---------------------------------------------------------------------------
 namespace {
+constexpr uint64_t kLongKeyAbove = 3500000000ull; // indexed symbols above which the first key is 18 symbols (build())
 // first key of an unsharded build (see build()): symbols sorted by the initial radix sort, BWT symbol carried or not
 void first_key_shape(int bits, uint64_t n_idx, int *first_syms, bool *carry)
 {
     const int spw = 64 / bits;
-    uint64_t long_key_above = 1ull << 32;
+    uint64_t long_key_above = kLongKeyAbove;
     if (const char *e = std::getenv("DSMFM_LONG_KEY_ABOVE")) long_key_above = std::strtoull(e, nullptr, 10);
     int first_key_bits = 48;
     if (n_idx > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);
@@ -1188,10 +1189,12 @@ void dsmfm_builder::build()
     // no extra refinement work.  That stops being true when the collection is large: with L distinct loci the
     // chance that a 16-mer also occurs at an unrelated locus is about L / 4^16, and unrelated loci in one tie
     // group carry different BWT symbols, so the group has to be refined (8 GPUs x 1 Gbp: 3.2 G loci, 75 %;
-    // the refinement took 75 ms per GPU instead of 24).  Collections beyond 2^32 symbols therefore sort 18
-    // symbols (54 bits, a seventh pass of 6 bits): 16x fewer chance matches for about 13 ms of sorting.
+    // the refinement took 75 ms per GPU instead of 24).  Collections beyond 3.5 G symbols therefore sort 18
+    // symbols (54 bits, a seventh pass of 6 bits): 16x fewer chance matches for about 13 ms of sorting.  (The
+    // threshold sits between the 1 Gbp sample -- 2.02 G symbols, where the seventh pass costs what it saves -- and two
+    // of them, 4.04 G, where the refinement takes 36 ms with 16 symbols.)
     // DSMFM_FIRST_KEY_BITS overrides (any multiple of bits/symbol); DSMFM_LONG_KEY_ABOVE moves the threshold (tests).
-    uint64_t long_key_above = 1ull << 32;
+    uint64_t long_key_above = kLongKeyAbove;
     if (const char *e = std::getenv("DSMFM_LONG_KEY_ABOVE")) long_key_above = std::strtoull(e, nullptr, 10);
     int first_key_bits = 48;
     if (n_idx > long_key_above) first_key_bits = bits == 3 ? 54 : (bits == 4 ? 56 : 48);

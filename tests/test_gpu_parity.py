@@ -165,7 +165,7 @@ def test_suffix_array_bwt_and_index_match_oracle(seed, kw):
 
 
 def test_long_first_key_of_large_collections(monkeypatch):
-    """Collections beyond 2^32 symbols sort 18 symbols (54 bits, 7 passes) instead of 16; with the threshold moved
+    """Collections beyond 3.5 G symbols sort 18 symbols (54 bits, 7 passes) instead of 16; with the threshold moved
     down the same schedule runs on small inputs, unsharded and as key-range shards with wide positions."""
     import dsmfm
     monkeypatch.setenv("DSMFM_LONG_KEY_ABOVE", "1000")
