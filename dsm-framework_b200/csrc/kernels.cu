@@ -2891,12 +2891,14 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
         // -- the default when the refinement runs in place, i.e. when most suffixes sit in groups that have to be
         // sorted (high repetition: C5 refinement 118 -> 98 ms); on the dense arrays of a read collection with few
         // large groups the per-member path is the faster one (C3: 25.2 vs 26.6 ms).
-        static const int big_env = std::getenv("DSMFM_REFINE_BIG") ? std::atoi(std::getenv("DSMFM_REFINE_BIG")) : -1;
+        const char *big_str = std::getenv("DSMFM_REFINE_BIG"); // (read per launch: the tests switch it)
+        const int big_env = big_str ? std::atoi(big_str) : -1;
         const int big_want = big_env >= 0 ? big_env : (big_groups ? kRwBigGroup : 0);
         const int big_thr = big_want >= 32 ? (big_want < kRwBigGroup ? kRwBigGroup : big_want) : kRwCap + 1;
         // groups of up to 32 members are ranked a warp-load of whole groups at a time (match.any; DSMFM_REFINE_RANK=0:
         // every member loops over its group)
-        static const bool chunked = !(std::getenv("DSMFM_REFINE_RANK") && std::atoi(std::getenv("DSMFM_REFINE_RANK")) == 0);
+        const char *rank_str = std::getenv("DSMFM_REFINE_RANK");
+        const bool chunked = !(rank_str && std::atoi(rank_str) == 0);
         static DeviceOnce attr3_once;
         attr3_once.run([] {
 #define SET3(B, K)                                                                                                      \

@@ -209,10 +209,16 @@ def test_single_step_refinement_schedule(monkeypatch, key_words):
 
 @pytest.mark.parametrize("env", [{"DSMFM_REFINE_COMPACT": "0"}, {"DSMFM_REFINE_FULL_ORDER": "1"}, {"DSMFM_REFINE_VARIANT": "0"},
                                  {"DSMFM_REFINE_VARIANT": "0", "DSMFM_REFINE_FULL_ORDER": "1"},
-                                 {"DSMFM_REFINE_COMPACT": "0", "DSMFM_REFINE_KEY_WORDS": "2"}])
+                                 {"DSMFM_REFINE_COMPACT": "0", "DSMFM_REFINE_KEY_WORDS": "2"},
+                                 {"DSMFM_REFINE_RANK": "0"}, {"DSMFM_REFINE_RANK": "0", "DSMFM_REFINE_FULL_ORDER": "1"},
+                                 {"DSMFM_REFINE_BIG": "64"}, {"DSMFM_REFINE_BIG": "64", "DSMFM_REFINE_COMPACT": "0"},
+                                 {"DSMFM_REFINE_BIG": "0", "DSMFM_REFINE_COMPACT": "0"},
+                                 {"DSMFM_REFINE_BIG": "64", "DSMFM_REFINE_KEY_WORDS": "2", "DSMFM_REFINE_FULL_ORDER": "1"}])
 def test_refinement_schedules_give_the_same_index(monkeypatch, env):
     """BWT-only refinement on dense copies of the mixed groups (default), in place with the difference bitmap, the
-    full suffix order, and the schedule with CTA-wide steps: one index."""
+    full suffix order, the schedule with CTA-wide steps, and the three ranking schemes of the independent-warps kernel
+    (whole groups per warp-load with match.any -- the default --, every member over its group, large groups by the
+    whole warp around their dominant key): one index."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for name in ("reads100", "duplicates", "poly_a", "mixed_alphabet", "one_base_reads"):
