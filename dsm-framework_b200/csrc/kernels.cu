@@ -2420,12 +2420,12 @@ __device__ __forceinline__ uint32_t compress_bits(uint32_t x, uint32_t m)
 // ---- one pass over the sequence for small trees (reads: 6 internal nodes) -----------------------------------
 // wt_count + wt_scan + wt_fill read the sequence twice, build the member masks twice, and every thread ORs its
 // bits into the node arrays with global atomics (two per node and thread).  For trees of at most 8 internal nodes
-// one kernel does it all: a CTA takes the next tile (dynamic tile id), builds the masks once, publishes its member
-// counts per node and obtains the bit offsets of its contribution by decoupled look-back over the tiles in front
-// (one warp per node, 32 predecessors per step) -- while the look-back runs nothing else is waiting, the masks are
-// already in registers.  The tile's bits of every node are then assembled in shared memory (32-bit shared atomics)
-// and leave the SM as whole 64-bit words; only the first and the last word of a tile's run, which it may share
-// with its neighbours, are OR-ed into global memory.
+// one kernel does it all: a CTA takes the next tile (dynamic tile id), builds the masks once and publishes its member
+// counts per node at once; the tile's bits of every node are assembled in shared memory from bit 0 (32-bit shared
+// atomics), which needs no global offset; only then does the CTA obtain the bit offsets of its runs by decoupled
+// look-back over the tiles in front (one warp per node, 32 predecessors per step) -- they published long ago, so
+// the look-back hardly ever waits -- and the runs leave the SM as whole 64-bit words, shifted to their offset; only
+// the first and the last word of a run, which it may share with its neighbours, are OR-ed into global memory.
 constexpr int kWtRunWords = kWtTile / 64 + 2; // 64-bit words a tile's run of one node can touch
 
 // NI: the number of internal nodes at compile time (reads: 6), 0 = run time.  With a run-time count the per-node loops

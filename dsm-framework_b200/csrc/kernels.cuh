@@ -109,7 +109,8 @@ void launch_refine(cudaStream_t st, int bits, const uint64_t *packed, uint32_t *
                    uint32_t *launches, bool big_groups = false);
 
 // BWT-only builds: the groups with mixed BWT symbols, copied out in order so that the refinement works on dense
-// arrays.  launch_mark_active: act (zeroed, head_words words) gets the slots of those groups, tile_off
+// arrays.  launch_mark_active: act (zeroed, head_words words) gets the slots of those groups (diff is read 16 bytes
+// at a time: aligned like every allocation of the builder), tile_off
 // (active_tiles(words of n) + 1 entries) their running counts per tile, the total behind the last entry.
 // launch_compact_active: fills the dense arrays (m_act entries; chi/sa_hi may be nullptr) and the compact
 // head bitmap chead (zeroed by the caller, chead_words words, bits from m_act on set).
