@@ -2213,25 +2213,75 @@ __device__ __forceinline__ void wt_small_table(const uint8_t *__restrict__ node_
     lut16[threadIdx.x] = (uint16_t)e;
 }
 
+// 8x8 bit matrix in two words (byte s = row s, rows 0..3 in lo), transposed in place: afterwards bit s of byte v is
+// what bit v of byte s was (Hacker's Delight 7-3, on 32-bit halves: only the last step crosses the halves)
+__device__ __forceinline__ void transpose8x8(uint32_t &lo, uint32_t &hi)
+{
+    uint32_t t;
+    t = (lo ^ (lo >> 7)) & 0x00AA00AAu;
+    lo ^= t ^ (t << 7);
+    t = (hi ^ (hi >> 7)) & 0x00AA00AAu;
+    hi ^= t ^ (t << 7);
+    t = (lo ^ (lo >> 14)) & 0x0000CCCCu;
+    lo ^= t ^ (t << 14);
+    t = (hi ^ (hi >> 14)) & 0x0000CCCCu;
+    hi ^= t ^ (t << 14);
+    t = (lo ^ ((lo >> 28) | (hi << 4))) & 0xF0F0F0F0u;
+    lo ^= t ^ (t << 28);
+    hi ^= t >> 4;
+}
+
+// byte (V & 3) of src into byte G of dst
+template <int G, int V> __device__ __forceinline__ uint32_t put_byte(uint32_t dst, uint32_t src)
+{
+    constexpr uint32_t sel = (0x3210u & ~(0xfu << (4 * G))) | ((4u + (V & 3)) << (4 * G));
+    return __byte_perm(dst, src, sel);
+}
+
+template <int G>
+__device__ __forceinline__ void wt_put_group(uint32_t lo, uint32_t hi, int n_internal, uint32_t (&out)[kWtSmallNodes])
+{
+    out[0] = put_byte<G, 0>(out[0], lo);
+    if (1 < n_internal) out[1] = put_byte<G, 1>(out[1], lo);
+    if (2 < n_internal) out[2] = put_byte<G, 2>(out[2], lo);
+    if (3 < n_internal) out[3] = put_byte<G, 3>(out[3], lo);
+    if (4 < n_internal) out[4] = put_byte<G, 4>(out[4], hi);
+    if (5 < n_internal) out[5] = put_byte<G, 5>(out[5], hi);
+    if (6 < n_internal) out[6] = put_byte<G, 6>(out[6], hi);
+    if (7 < n_internal) out[7] = put_byte<G, 7>(out[7], hi);
+}
+
+// Member / branch masks of a thread's 32 symbols for every node.  The table gives a symbol's member byte and branch
+// byte (bit v = node v); eight symbols' bytes are an 8x8 bit matrix whose transpose holds, in byte v, node v's bits of
+// those eight symbols -- 24 instructions per matrix instead of a multiply-gather per node and four symbols.
+template <int G>
+__device__ __forceinline__ void wt_masks_group(const uint16_t *lut16, uint32_t w0, uint32_t w1, int n_internal,
+                                               uint32_t (&m)[kWtSmallNodes], uint32_t (&b)[kWtSmallNodes])
+{
+    uint32_t M[2], B[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t w = h ? w1 : w0;
+        const uint32_t e0 = lut16[w & 0xff], e1 = lut16[(w >> 8) & 0xff], e2 = lut16[(w >> 16) & 0xff], e3 = lut16[w >> 24];
+        const uint32_t lo = e0 | (e1 << 16), hi = e2 | (e3 << 16); // [mem0 br0 mem1 br1], [mem2 br2 mem3 br3]
+        M[h] = __byte_perm(lo, hi, 0x6420);
+        B[h] = __byte_perm(lo, hi, 0x7531);
+    }
+    transpose8x8(M[0], M[1]);
+    transpose8x8(B[0], B[1]);
+    wt_put_group<G>(M[0], M[1], n_internal, m);
+    wt_put_group<G>(B[0], B[1], n_internal, b);
+}
+
 __device__ __forceinline__ void wt_masks_small(const uint16_t *lut16, const uint32_t (&w)[8], uint32_t valid, int n_internal,
                                                uint32_t (&m)[kWtSmallNodes], uint32_t (&b)[kWtSmallNodes])
 {
 #pragma unroll
     for (int v = 0; v < kWtSmallNodes; ++v) m[v] = b[v] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t e0 = lut16[w[i] & 0xff], e1 = lut16[(w[i] >> 8) & 0xff], e2 = lut16[(w[i] >> 16) & 0xff],
-                       e3 = lut16[w[i] >> 24];
-        const uint32_t lo = e0 | (e1 << 16), hi = e2 | (e3 << 16); // [mem0 br0 mem1 br1], [mem2 br2 mem3 br3]
-        const uint32_t M4 = __byte_perm(lo, hi, 0x6420), B4 = __byte_perm(lo, hi, 0x7531);
-#pragma unroll
-        for (int v = 0; v < kWtSmallNodes; ++v) {
-            if (v < n_internal) {
-                m[v] |= ((((M4 >> v) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
-                b[v] |= ((((B4 >> v) & 0x01010101u) * 0x10204080u) >> 28) << (4 * i);
-            }
-        }
-    }
+    wt_masks_group<0>(lut16, w[0], w[1], n_internal, m, b);
+    wt_masks_group<1>(lut16, w[2], w[3], n_internal, m, b);
+    wt_masks_group<2>(lut16, w[4], w[5], n_internal, m, b);
+    wt_masks_group<3>(lut16, w[6], w[7], n_internal, m, b);
 #pragma unroll
     for (int v = 0; v < kWtSmallNodes; ++v) {
         m[v] &= valid;
