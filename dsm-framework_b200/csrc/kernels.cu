@@ -2197,9 +2197,9 @@ __device__ __forceinline__ uint32_t wt_valid_mask(uint64_t n, uint64_t p0)
 }
 
 // Trees with at most 8 internal nodes (reads: 6): one table lookup per symbol yields its membership and branch
-// bit for every node at once (low byte: member of node v, high byte: branch taken there); four symbols are
-// packed into one word per byte lane, and a multiply gathers one node's four bits -- instead of one lookup
-// per (symbol, node).
+// bit for every node at once (low byte: member of node v, high byte: branch taken there); the bytes of eight symbols
+// form an 8x8 bit matrix whose transpose holds every node's bits of those symbols (wt_masks_group) -- instead of
+// one lookup per (symbol, node).
 constexpr int kWtSmallNodes = 8;
 
 __device__ __forceinline__ void wt_small_table(const uint8_t *__restrict__ node_info, int n_internal, uint16_t *lut16)
